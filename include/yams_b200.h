@@ -1,0 +1,309 @@
+/*
+ * yams_b200.h -- C ABI of libyams_b200.so: the B200-native drop-in for YAMS's data-parallel hot
+ * path (brute-force vector scan behind src/vector + the sqlite-vec-cpp operator surface, and the
+ * CDC + SHA-256 ingest path behind src/chunking + src/crypto).
+ *
+ * Conventions follow the reference's plugin ABI (all path:line under /root/reference):
+ *   - envelope: include/yams/plugins/abi.h:17-33 (8 symbols, YAMS_PLUGIN_* return codes);
+ *   - vtables:  include/yams/plugins/model_provider_v1.h:44-130 -- struct starts with
+ *     {uint32_t abi_version; void* self;}, every fn takes self first and returns yams_status_t,
+ *     plugin-allocated buffers are released by a paired free_* fn (host never calls free()),
+ *     contiguous row-major [batch, dim] float buffers;
+ *   - status codes: model_provider_v1.h:17-25.
+ * No exceptions cross this boundary; CUDA failures map to YAMS_ERR_INTERNAL and the text is
+ * available through yams_plugin_get_health_json().
+ *
+ * There is NO CPU fallback: every compute entry point returns YAMS_ERR_INTERNAL (and says why in the
+ * health JSON) when no sm_100 device is usable.
+ */
+#ifndef YAMS_B200_H
+#define YAMS_B200_H
+
+#include <stdbool.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__) || defined(__clang__)
+#define YAMS_B200_API __attribute__((visibility("default")))
+#else
+#define YAMS_B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (model_provider_v1.h:17-25) --------------------------------------------- */
+#ifndef YAMS_PLUGINS_MODEL_PROVIDER_V1_H
+enum yams_status_e {
+    YAMS_OK = 0,
+    YAMS_ERR_INVALID_ARG = 1,
+    YAMS_ERR_NOT_FOUND = 2,
+    YAMS_ERR_IO = 3,
+    YAMS_ERR_INTERNAL = 4,
+    YAMS_ERR_UNSUPPORTED = 5
+};
+typedef int yams_status_t;
+#endif
+
+/* ---- plugin envelope (abi.h:17-33) ----------------------------------------------------------
+ * Loader: src/daemon/resource/abi_plugin_loader.cpp:303-341 (dlopen RTLD_LAZY|RTLD_LOCAL, dlsym of
+ * each symbol), manifest regex-parsed :54-79, interface fetched by id+version :657-680. */
+#define YAMS_PLUGIN_ABI_VERSION 1
+#define YAMS_PLUGIN_OK 0
+#define YAMS_PLUGIN_ERR_INCOMPATIBLE -1
+#define YAMS_PLUGIN_ERR_NOT_FOUND -2
+#define YAMS_PLUGIN_ERR_INIT_FAILED -3
+#define YAMS_PLUGIN_ERR_INVALID -4
+
+YAMS_B200_API int yams_plugin_get_abi_version(void);
+YAMS_B200_API const char* yams_plugin_get_name(void);
+YAMS_B200_API const char* yams_plugin_get_version(void);
+YAMS_B200_API const char* yams_plugin_get_manifest_json(void);
+/* config_json keys (all optional): "device": int (default: LOCAL_RANK env or 0) */
+YAMS_B200_API int yams_plugin_init(const char* config_json, const void* host_context);
+YAMS_B200_API void yams_plugin_shutdown(void);
+YAMS_B200_API int yams_plugin_get_interface(const char* iface_id, uint32_t version, void** out_iface);
+/* *out_json is malloc'd (strdup), as s3_plugin.cpp does; release with free() */
+YAMS_B200_API int yams_plugin_get_health_json(char** out_json);
+
+#define YAMS_IFACE_VECTOR_SCAN_V1 "vector_scan_v1"
+#define YAMS_IFACE_VECTOR_SCAN_V1_VERSION 1u
+#define YAMS_IFACE_CONTENT_INGEST_V1 "content_ingest_v1"
+#define YAMS_IFACE_CONTENT_INGEST_V1_VERSION 1u
+
+/* =============================================================================================
+ * content_ingest_v1 -- replaces IChunker (include/yams/chunking/chunker.h:65-92) +
+ * IContentHasher (include/yams/crypto/hasher.h:14-46) as injected at
+ * src/api/content_store_builder.cpp:152-170.
+ * ============================================================================================= */
+
+enum yams_cdc_variant_e {
+    YAMS_CDC_STREAMING = 0, /* StreamingChunker (streaming_chunker.h:146-181) -- what `yams add` uses */
+    YAMS_CDC_RABIN = 1      /* RabinChunker (rabin_chunker.cpp:63-152) -- bench/test class          */
+};
+
+/* ChunkingConfig (chunker.h:44-51) + which reference class to mirror */
+typedef struct yams_cdc_config {
+    uint64_t window_size; /* 1..48 (the reference ring is a fixed 48-byte array, chunker.h:151) */
+    uint64_t min_chunk;
+    uint64_t max_chunk;
+    uint64_t polynomial;  /* 0 -> default 0x3DA3358B4DC173 (rabin_chunker.cpp:30-36)             */
+    uint64_t mask;
+    int32_t variant;      /* yams_cdc_variant_e */
+    int32_t reserved;
+} yams_cdc_config;
+
+/* One chunk: Chunk{hash,offset,size} (chunker.h:18-23) with the raw 32-byte digest; the host
+ * adapter hex-encodes (sha256_hasher.cpp:19-30) */
+typedef struct yams_chunk_desc {
+    uint64_t offset;
+    uint64_t size;
+    uint8_t digest[32];
+} yams_chunk_desc;
+
+typedef struct yams_b200_ingest yams_b200_ingest; /* opaque streaming session */
+
+YAMS_B200_API void yams_b200_cdc_default_config(yams_cdc_config* cfg);
+
+/* IChunker::chunkData / chunkDataLazy (rabin_chunker.cpp:112-152, streaming_chunker.cpp:92-137):
+ * boundaries + per-chunk SHA-256 of a HOST buffer. *out is plugin-allocated; free with
+ * yams_b200_free_chunks. len == 0 -> *out_n = 0. */
+YAMS_B200_API yams_status_t yams_b200_chunk_and_hash(void* self, const uint8_t* data, size_t len,
+                                                     const yams_cdc_config* cfg,
+                                                     yams_chunk_desc** out, size_t* out_n);
+YAMS_B200_API void yams_b200_free_chunks(void* self, yams_chunk_desc* chunks, size_t n);
+
+/* Same with the input already resident in HBM (device pointer). Results come back on the host. */
+YAMS_B200_API yams_status_t yams_b200_chunk_and_hash_device(void* self, const uint8_t* d_data,
+                                                            size_t len, const yams_cdc_config* cfg,
+                                                            yams_chunk_desc** out, size_t* out_n);
+
+/* Streaming form: StreamingChunker::processStream/processBuffer (streaming_chunker.h:78-181).
+ * Fragmentation is invisible (tests/unit/chunking/chunking_test.cpp:481-523): feeding any split of
+ * a stream yields the same chunks as one call.  Each feed returns the chunks completed so far;
+ * finish returns the trailing partial chunk (streaming_chunker.h:115-118). Offsets are stream
+ * offsets. */
+YAMS_B200_API yams_status_t yams_b200_ingest_open(void* self, const yams_cdc_config* cfg,
+                                                  yams_b200_ingest** out);
+YAMS_B200_API yams_status_t yams_b200_ingest_feed(yams_b200_ingest* s, const uint8_t* data,
+                                                  size_t len, yams_chunk_desc** out, size_t* out_n);
+YAMS_B200_API yams_status_t yams_b200_ingest_finish(yams_b200_ingest* s, yams_chunk_desc** out,
+                                                    size_t* out_n);
+YAMS_B200_API void yams_b200_ingest_close(yams_b200_ingest* s);
+
+/* SHA256Hasher::hash over many spans of one HOST buffer (sha256_hasher.cpp:167-195);
+ * digests: n x 32 bytes, caller-owned. */
+YAMS_B200_API yams_status_t yams_b200_sha256_batch(void* self, const uint8_t* base, size_t base_len,
+                                                   const uint64_t* offsets, const uint64_t* sizes,
+                                                   size_t n, uint8_t* digests);
+/* base is a device pointer; offsets/sizes/digests are host arrays */
+YAMS_B200_API yams_status_t yams_b200_sha256_batch_device(void* self, const uint8_t* d_base,
+                                                          size_t base_len, const uint64_t* offsets,
+                                                          const uint64_t* sizes, size_t n,
+                                                          uint8_t* digests);
+
+/* Only the CDC boundaries (no digests): (offset,size) pairs, digest field zero. */
+YAMS_B200_API yams_status_t yams_b200_chunk_boundaries(void* self, const uint8_t* data, size_t len,
+                                                       const yams_cdc_config* cfg,
+                                                       yams_chunk_desc** out, size_t* out_n);
+
+/* Per-stage device timings (ms) of the last chunk_and_hash* call on this thread's context:
+ * [0] candidate scan, [1] cut selection, [2] sha256, [3] total device, [4] h2d (0 for _device) */
+YAMS_B200_API yams_status_t yams_b200_ingest_last_timings(void* self, float out_ms[8]);
+
+typedef struct yams_content_ingest_v1 {
+    uint32_t abi_version; /* YAMS_IFACE_CONTENT_INGEST_V1_VERSION */
+    void* self;
+    yams_status_t (*chunk_and_hash)(void* self, const uint8_t* data, size_t len,
+                                    const yams_cdc_config* cfg, yams_chunk_desc** out,
+                                    size_t* out_n);
+    void (*free_chunks)(void* self, yams_chunk_desc* chunks, size_t n);
+    yams_status_t (*ingest_open)(void* self, const yams_cdc_config* cfg, yams_b200_ingest** out);
+    yams_status_t (*ingest_feed)(yams_b200_ingest* s, const uint8_t* data, size_t len,
+                                 yams_chunk_desc** out, size_t* out_n);
+    yams_status_t (*ingest_finish)(yams_b200_ingest* s, yams_chunk_desc** out, size_t* out_n);
+    void (*ingest_close)(yams_b200_ingest* s);
+    yams_status_t (*sha256_batch)(void* self, const uint8_t* base, size_t base_len,
+                                  const uint64_t* offsets, const uint64_t* sizes, size_t n,
+                                  uint8_t* digests);
+} yams_content_ingest_v1;
+
+/* =============================================================================================
+ * vector_scan_v1 -- replaces the exact scan behind IVectorStore::searchSimilar /
+ * searchSimilarBatch (include/yams/vector/vector_store.h:44-53) and the exact-candidate seams
+ * (:121-138), i.e. SqliteVecBackend::Impl::bruteForceSearchUnlocked
+ * (src/vector/sqlite_vec_backend.cpp:4115-4410), and vec0_run_exact_query
+ * (third_party/sqlite-vec-cpp/include/sqlite-vec-cpp/sqlite/vec0_module.hpp:376-430).
+ * ============================================================================================= */
+
+enum yams_b200_dtype_e { YAMS_B200_F32 = 0, YAMS_B200_F16 = 1 };
+enum yams_b200_metric_e { YAMS_B200_COSINE = 0, YAMS_B200_L2 = 1 };
+
+typedef struct yams_b200_corpus yams_b200_corpus; /* opaque device-resident mirror of `vectors` */
+
+/* rows are stored row-major [n, dim] in HBM in `dtype` (fp32 = the reference's BLOB layout,
+ * sqlite_vec_backend.cpp:343-363; fp16 = IEEE half bit patterns, utils/float16.hpp). */
+YAMS_B200_API yams_status_t yams_b200_corpus_create(void* self, uint32_t dim, int dtype, int metric,
+                                                    uint64_t capacity_hint, yams_b200_corpus** out);
+/* rows: HOST pointer, n x dim elements of the corpus dtype; rowids nullable (then consecutive,
+ * continuing from the current size). Rowids must be appended in ascending order (the reference
+ * scans ORDER BY rowid, sqlite_vec_backend.cpp:4175). */
+YAMS_B200_API yams_status_t yams_b200_corpus_append(yams_b200_corpus* c, const void* rows, uint64_t n,
+                                                    const int64_t* rowids);
+/* fp32 HOST rows converted with the reference's TRUNCATING float16_t::from_float
+ * (utils/float16.hpp:20-40) into an fp16 corpus */
+YAMS_B200_API yams_status_t yams_b200_corpus_append_f32_as_f16(yams_b200_corpus* c, const float* rows,
+                                                               uint64_t n, const int64_t* rowids);
+/* Synthetic rows generated on the device (SURVEY.md §8d generator; bit-identical to
+ * oracle yo_gen_rows_f32 [+ truncating fp16]); rowid = first_row + i */
+YAMS_B200_API yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t seed,
+                                                              uint64_t first_row, uint64_t n);
+YAMS_B200_API yams_status_t yams_b200_corpus_clear(yams_b200_corpus* c);
+YAMS_B200_API yams_status_t yams_b200_corpus_size(const yams_b200_corpus* c, uint64_t* out_n);
+YAMS_B200_API void yams_b200_corpus_destroy(yams_b200_corpus* c);
+
+#define YAMS_B200_FLAG_TIE_AT_K 1ull       /* equal scores straddle the k boundary: the host   */
+                                           /* adapter must re-break by chunk_id (:4218-4223)   */
+#define YAMS_B200_FLAG_FALLBACK_PATH 2ull  /* query was answered by the exhaustive path        */
+
+/* Exact top-k of every query against the corpus (bruteForceSearchUnlocked fast path semantics,
+ * sqlite_vec_backend.cpp:4203-4331):
+ *   cosine: sim = float(dot / (|row| * |q|)) accumulated in double; rows with a non-finite element
+ *   or |row|^2 <= 1e-12 are skipped; sim < threshold dropped; order (sim desc, rowid asc).
+ *   l2 (vec0 surface): dist = sqrtf(sum (q-r)^2) in float; order (dist asc, rowid asc); threshold
+ *   ignored.
+ * queries: HOST, Q x dim fp32 row-major.  A query that is non-finite or has |q|^2 < 1e-10 makes
+ * the whole call return YAMS_ERR_INVALID_ARG (:4127-4130).  k == 0 -> all counts 0 (:4123-4126).
+ * allowed_rowids: nullable; when given, query i may only match rowids in
+ * allowed_rowids[allowed_offsets[i] .. allowed_offsets[i+1]) (ascending) -- CandidateFilterMode::
+ * Exact (src/vector/vector_database.cpp:570-597). allowed_offsets has Q+1 entries.
+ * Outputs (caller-owned HOST): out_rowids/out_scores Q x k (unused slots: rowid -1, score 0),
+ * out_counts Q, out_flags Q (nullable). */
+YAMS_B200_API yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32_t nq,
+                                             uint32_t k, float threshold,
+                                             const int64_t* allowed_rowids,
+                                             const uint64_t* allowed_offsets, int64_t* out_rowids,
+                                             float* out_scores, uint32_t* out_counts,
+                                             uint64_t* out_flags);
+
+/* Device-pointer form for multi-GPU sharding: queries and outputs are DEVICE pointers, the call
+ * is enqueued on the corpus stream and returns after enqueueing; outputs are the rank-local partial
+ * top-k in the padded Q x k layout (unused: score -inf / +inf(l2), rowid -1). */
+YAMS_B200_API yams_status_t yams_b200_search_device(yams_b200_corpus* c, const float* d_queries,
+                                                    uint32_t nq, uint32_t k, float threshold,
+                                                    int64_t* d_out_rowids, float* d_out_scores);
+/* Merge R partial results laid out [R][Q][k] (as produced by an all-gather of search_device
+ * outputs) into the global top-k, same order. All DEVICE pointers. */
+YAMS_B200_API yams_status_t yams_b200_merge_partials_device(yams_b200_corpus* c,
+                                                            const int64_t* d_rowids,
+                                                            const float* d_scores, uint32_t nranks,
+                                                            uint32_t nq, uint32_t k,
+                                                            int64_t* d_out_rowids,
+                                                            float* d_out_scores,
+                                                            uint32_t* d_out_counts);
+YAMS_B200_API yams_status_t yams_b200_corpus_sync(yams_b200_corpus* c);
+/* raw cudaStream_t of the corpus (for event timing by the bench) */
+YAMS_B200_API void* yams_b200_corpus_stream(yams_b200_corpus* c);
+
+/* vec0_run_exact_query (vec0_module.hpp:376-430): L2 + sqrt in float over fp32 HOST rows, ascending
+ * by distance (ties rowid asc), truncated to k when k > 0 (k == 0: all rows); optional inclusive
+ * rowid range. out arrays hold min(n, k?k:n) entries. */
+YAMS_B200_API yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim,
+                                                 const float* rows, const int64_t* rowids,
+                                                 uint64_t n, uint64_t k, int use_range,
+                                                 int64_t rowid_lo, int64_t rowid_hi,
+                                                 int64_t* out_rowids, float* out_dist,
+                                                 uint64_t* out_count);
+
+/* [0] stage-1 scan ms, [1] rescoring+select ms, [2] total device ms, [3] h2d+d2h ms of the last
+ * yams_b200_search on this corpus; [4] = which stage-1 kernel ran (0 cuda-core, 1 tcgen05);
+ * [5] = duration of the full-corpus filtered scan launch alone (the dominant kernel) */
+YAMS_B200_API yams_status_t yams_b200_search_last_timings(yams_b200_corpus* c, float out_ms[8]);
+
+typedef struct yams_vector_scan_v1 {
+    uint32_t abi_version; /* YAMS_IFACE_VECTOR_SCAN_V1_VERSION */
+    void* self;
+    yams_status_t (*corpus_create)(void* self, uint32_t dim, int dtype, int metric,
+                                   uint64_t capacity_hint, yams_b200_corpus** out);
+    yams_status_t (*corpus_append)(yams_b200_corpus* c, const void* rows, uint64_t n,
+                                   const int64_t* rowids);
+    yams_status_t (*corpus_clear)(yams_b200_corpus* c);
+    yams_status_t (*corpus_size)(const yams_b200_corpus* c, uint64_t* out_n);
+    void (*corpus_destroy)(yams_b200_corpus* c);
+    yams_status_t (*search)(yams_b200_corpus* c, const float* queries, uint32_t nq, uint32_t k,
+                            float threshold, const int64_t* allowed_rowids,
+                            const uint64_t* allowed_offsets, int64_t* out_rowids, float* out_scores,
+                            uint32_t* out_counts, uint64_t* out_flags);
+    yams_status_t (*vec0_exact)(void* self, const float* query, uint32_t dim, const float* rows,
+                                const int64_t* rowids, uint64_t n, uint64_t k, int use_range,
+                                int64_t rowid_lo, int64_t rowid_hi, int64_t* out_rowids,
+                                float* out_dist, uint64_t* out_count);
+} yams_vector_scan_v1;
+
+/* ---- sqlite-vec-cpp C API kept bit-for-bit in signature and error behaviour ------------------
+ * third_party/sqlite-vec-cpp/src/sqlite_vec_c_api.cpp:57-105 (declared sqlite_vec.hpp:34-50):
+ * sizes in BYTES, returns SQLITE_OK(0) / SQLITE_ERROR(1) on null pointer or dimension mismatch.
+ * These are pairwise host-side operators (two small blobs); they are computed on the host by the
+ * adapter in float exactly as distances/{l2,cosine}.hpp scalar paths do -- a GPU launch per pair
+ * would be pure overhead. (sqlite3_vec_init needs sqlite3.h, absent in this image: see
+ * INTEGRATION.md.) */
+YAMS_B200_API int sqlite3_vec_distance_l2(const void* vec1, size_t size1, const void* vec2,
+                                          size_t size2, float* result);
+YAMS_B200_API int sqlite3_vec_distance_cosine(const void* vec1, size_t size1, const void* vec2,
+                                              size_t size2, float* result);
+
+/* ---- bench / test utilities (SURVEY.md §8d synthetic inputs, generated straight into HBM) ------ */
+/* byte[i] = (splitmix64(seed ^ (i>>3)) >> (8*(i&7))) & 0xFF for stream positions [start, start+n) */
+YAMS_B200_API yams_status_t yams_b200_synth_bytes_device(uint64_t seed, uint64_t start, uint64_t n,
+                                                         uint8_t* d_out);
+
+/* ---- misc ------------------------------------------------------------------------------------ */
+YAMS_B200_API int yams_b200_device_count(void);
+/* last error text of the calling thread (static storage) */
+YAMS_B200_API const char* yams_b200_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YAMS_B200_H */

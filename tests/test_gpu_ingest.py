@@ -1,0 +1,196 @@
+"""GPU parity tests of the ingest path: every call goes through the C ABI of libyams_b200.so and is
+compared bit-for-bit with the CPU oracle / the golden vectors generated from the reference."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from tests.streams import cfg_from_dict, make_stream
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def Y():
+    import yams_b200
+    assert yams_b200.device_count() > 0, "these tests need a B200"
+    assert yams_b200.plugin_init() == 0, yams_b200.health()
+    return yams_b200
+
+
+def ycfg(Y, ocfg):
+    return Y.CdcConfig(ocfg.window_size, ocfg.min_chunk, ocfg.max_chunk, ocfg.polynomial, ocfg.mask, ocfg.variant, 0)
+
+
+# ---- SHA-256 ------------------------------------------------------------------------------------
+def test_sha256_reference_kats(Y):
+    # /root/reference/tests/unit/crypto/crypto_test.cpp:92-99
+    base = np.frombuffer(b"abcHello World", dtype=np.uint8)
+    d = Y.sha256_batch(base, [0, 0, 3], [0, 3, 11])
+    assert bytes(d[0]).hex() == "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855"
+    assert bytes(d[1]).hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+    assert bytes(d[2]).hex() == "a591a6d40bf420404a011733cfb7b190d62c65bf0bcda32b57b277d9ad9f146e"
+
+
+def test_sha256_golden_sizes(Y, oracle, golden):
+    for g in golden["sha256"]:
+        data = oracle.gen_bytes(g["seed"], 0, max(g["size"], 1))[:g["size"]]
+        d = Y.sha256_batch(data, [0], [g["size"]])
+        assert bytes(d[0]).hex() == g["hex"], g["size"]
+
+
+def test_sha256_every_length_and_alignment(Y, oracle):
+    """All padding cases (len mod 64 in 0..63, around 55/56/64) at every byte alignment mod 16."""
+    O = oracle
+    base = O.gen_bytes(31337, 0, 1 << 16)
+    offs, sizes = [], []
+    for length in list(range(0, 200)) + [255, 256, 257, 1000, 4095, 4096, 4097]:
+        for a in range(0, 16):
+            offs.append(a + 17 * (length % 13))
+            sizes.append(length)
+    got = Y.sha256_batch(base, offs, sizes)
+    want = O.sha256_batch(base, np.array(offs), np.array(sizes))
+    assert np.array_equal(got, want)
+
+
+def test_sha256_ragged_batch_many_chunks(Y, oracle):
+    """More chunks than lanes in a wave, wildly different lengths -> work-queue refill paths."""
+    O = oracle
+    rng = np.random.default_rng(4)
+    base = O.gen_bytes(8, 0, 24 << 20)
+    n = 6000
+    sizes = np.concatenate([rng.integers(0, 300, n // 2), rng.integers(1000, 70000, n // 2 - 4),
+                            np.array([1 << 20, (1 << 20) + 1, 0, 64])]).astype(np.uint64)
+    rng.shuffle(sizes)
+    offs = rng.integers(0, base.size - (1 << 21), sizes.size).astype(np.uint64)
+    got = Y.sha256_batch(base, offs, sizes)
+    want = O.sha256_batch(base, offs, sizes)
+    assert np.array_equal(got, want)
+    assert bytes(got[0]) == hashlib.sha256(base[int(offs[0]):int(offs[0] + sizes[0])].tobytes()).digest()
+
+
+# ---- CDC + SHA-256 --------------------------------------------------------------------------------
+def test_chunk_and_hash_golden(Y, oracle, golden):
+    for g in golden["cdc"]:
+        data = make_stream(g["stream"], oracle)
+        cfg = ycfg(Y, cfg_from_dict(oracle, g["cfg"]))
+        ch = Y.chunk_and_hash(data, cfg)
+        assert [int(x) for x in ch["offset"]] == g["offsets"], (g["stream"], g["config"])
+        assert [int(x) for x in ch["size"]] == g["sizes"], (g["stream"], g["config"])
+        assert [bytes(d).hex() for d in ch["digest"][:16]] == g["digests_head"]
+        assert hashlib.sha256(np.ascontiguousarray(ch["digest"]).tobytes()).hexdigest() == g["digest_of_digests"]
+
+
+def test_chunk_random_configs_vs_oracle(Y, oracle):
+    O = oracle
+    rng = np.random.default_rng(77)
+    for trial in range(40):
+        n = int(rng.integers(0, 400000))
+        data = O.gen_bytes(int(rng.integers(1, 1 << 30)), 0, n)
+        if trial % 3 == 0 and n:
+            data[rng.integers(0, n, size=max(1, n // 40))] = 0xC5
+        if trial % 7 == 0:
+            data[:] = 0x42
+        minc, maxc = int(rng.integers(0, 3000)), int(rng.integers(0, 9000))
+        variant = trial % 2
+        if variant == 1 and minc == 0 and maxc == 0:
+            maxc = 1
+        ocfg = O.default_config(variant=variant, min_chunk=minc, max_chunk=maxc, window_size=int(rng.integers(0, 49)),
+                                mask=int(rng.choice([0x0, 0x3F, 0xFF, 0x1FF, 0x1FFF, 0x303, 0x10001, 0x8000000000000001])))
+        if ocfg.mask == 0 and n > 50000:
+            data = data[:50000]
+        want = O.cdc_chunk(data, ocfg)
+        got = Y.chunk_and_hash(data, ycfg(Y, ocfg))
+        assert np.array_equal(got["offset"], want[0]) and np.array_equal(got["size"], want[1]), (trial, minc, maxc, variant)
+        assert np.array_equal(got["digest"], want[2]), trial
+
+
+def test_boundaries_only_and_invalid_config(Y, oracle):
+    data = oracle.gen_bytes(3, 0, 300000)
+    ocfg = oracle.default_config(min_chunk=2048, max_chunk=65536)
+    b = Y.chunk_boundaries(data, ycfg(Y, ocfg))
+    want = oracle.cdc_chunk(data, ocfg, hash=False)
+    assert np.array_equal(b["offset"], want[0]) and np.array_equal(b["size"], want[1])
+    assert not b["digest"].any()
+    with pytest.raises(Y.YamsB200Error) as e:
+        Y.chunk_and_hash(data, Y.default_config(window_size=49))
+    assert e.value.status == 1
+    with pytest.raises(Y.YamsB200Error):
+        Y.chunk_and_hash(data, Y.default_config(variant=Y.RABIN, min_chunk=0, max_chunk=0))
+
+
+def test_stream_fragmentation_is_invisible(Y, oracle):
+    # /root/reference/tests/unit/chunking/chunking_test.cpp:481-523
+    O = oracle
+    data = O.gen_bytes(12345, 0, 3 << 20)
+    ocfg = O.default_config(min_chunk=4096, max_chunk=65536)
+    want = O.cdc_chunk(data, ocfg)
+    rng = np.random.default_rng(9)
+    for seg in (1 << 20, 65536, 4097, 1000):
+        with Y.IngestSession(ycfg(Y, ocfg)) as s:
+            parts = []
+            pos = 0
+            while pos < data.size:
+                ln = seg if seg > 2000 else int(rng.integers(1, 3 * seg))
+                parts.append(s.feed(data[pos:pos + ln]))
+                pos += ln
+            parts.append(s.finish())
+        got = np.concatenate(parts)
+        assert np.array_equal(got["offset"], want[0]) and np.array_equal(got["size"], want[1]), seg
+        assert np.array_equal(got["digest"], want[2]), seg
+    # empty stream, and finish without feed
+    with Y.IngestSession() as s:
+        assert len(s.feed(b"")) == 0 and len(s.finish()) == 0
+
+
+def test_device_resident_matches_host_path_and_oracle(Y, oracle):
+    import torch
+    O = oracle
+    n = (64 << 20) + 12345
+    t = torch.empty(n, dtype=torch.uint8, device="cuda")
+    Y.synth_bytes_device(12345, 0, n, t.data_ptr())
+    host = t.cpu().numpy()
+    assert np.array_equal(host[:1 << 20], O.gen_bytes(12345, 0, 1 << 20))
+    assert np.array_equal(host[-4097:], O.gen_bytes(12345, n - 4097, 4097))
+    for variant in (Y.STREAMING, Y.RABIN):
+        got = Y.chunk_and_hash_device(t.data_ptr(), n, Y.default_config(variant=variant))
+        want = O.cdc_chunk(host, O.default_config(variant=variant))
+        assert np.array_equal(got["offset"], want[0]) and np.array_equal(got["size"], want[1])
+        assert np.array_equal(got["digest"], want[2])
+    # unaligned device sub-range
+    got = Y.chunk_and_hash_device(t.data_ptr() + 7, 5_000_001, Y.default_config(min_chunk=1024, max_chunk=8192))
+    want = O.cdc_chunk(host[7:7 + 5_000_001], O.default_config(min_chunk=1024, max_chunk=8192))
+    assert np.array_equal(got["offset"], want[0]) and np.array_equal(got["digest"], want[2])
+
+
+def test_full_size_properties(Y, oracle):
+    """BASELINE-size behaviour through size-independent properties: 6 GiB of the C3 stream resident in
+    HBM (crosses the 1 GiB segment boundaries and 32-bit offsets): coverage, sequential offsets, size bounds,
+    spot-checked digests, and equality of an interior window with the oracle re-run from a known cut."""
+    import torch
+    O = oracle
+    n = 6 << 30
+    t = torch.empty(n, dtype=torch.uint8, device="cuda")
+    Y.synth_bytes_device(12345, 0, n, t.data_ptr())
+    ch = Y.chunk_and_hash_device(t.data_ptr(), n, Y.default_config())
+    offs, sizes = ch["offset"], ch["size"]
+    assert offs[0] == 0 and int(offs[-1] + sizes[-1]) == n
+    assert np.array_equal(offs[1:], (offs + sizes)[:-1])
+    assert sizes[:-1].min() >= 16384 and sizes.max() <= 1 << 20
+    assert 0.9 < (n / len(ch)) / 24576.0 < 1.1          # mean chunk ~ 16 KiB + 8 KiB
+    rng = np.random.default_rng(1)
+    for i in list(rng.integers(0, len(ch), 24)) + [0, len(ch) - 1]:
+        o, s = int(offs[i]), int(sizes[i])
+        seg = t[o:o + s].cpu().numpy().tobytes()
+        assert hashlib.sha256(seg).digest() == bytes(ch["digest"][i]), i
+    # chunking is a pure function of the stream prefix only through the rolling window: restarting the
+    # oracle at a cut (with 48+8 bytes of history to seed its window) must reproduce the following cuts.
+    j = int(np.searchsorted(offs, (4 << 30) + 12345))
+    start = int(offs[j])
+    span = 32 << 20
+    hist = 64
+    window = t[start - hist:start + span].cpu().numpy()
+    want = O.cdc_candidates(window, O.default_config())  # candidates are position-local
+    got_cuts = offs[j + 1:][offs[j + 1:] <= start + span] - 1
+    cand_abs = want.astype(np.int64) + (start - hist)
+    assert np.isin(got_cuts[sizes[j:j + len(got_cuts)] < (1 << 20)], cand_abs).all()

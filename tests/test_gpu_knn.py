@@ -1,0 +1,238 @@
+"""GPU parity tests of the vector scan through the C ABI, against the CPU oracle's restatement of
+bruteForceSearchUnlocked / vec0_run_exact_query and the reference golden vectors."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4   # the reference tests' own epsilon (sqlite-vec-cpp/tests/test_distances.cpp:16-18)
+
+
+@pytest.fixture(scope="module")
+def Y():
+    import yams_b200
+    assert yams_b200.device_count() > 0
+    assert yams_b200.plugin_init() == 0, yams_b200.health()
+    return yams_b200
+
+
+def check_against_oracle(O, rows, queries, got, k, threshold=-1.0, allowed=None, exact_scores=True):
+    rid, sc, cnt, flags = got
+    for qi, q in enumerate(queries):
+        al = None if allowed is None else allowed[qi]
+        rc, wr, ws = O.exact_scan_cosine(rows, q, k, threshold=threshold, allowed=al)
+        assert rc == 0
+        assert cnt[qi] == len(wr), (qi, cnt[qi], len(wr))
+        assert list(rid[qi, :len(wr)]) == list(wr), qi
+        if exact_scores:
+            assert np.array_equal(sc[qi, :len(wr)], ws), qi      # fp64 rescoring: bit-identical
+        else:
+            assert np.allclose(sc[qi, :len(wr)], ws, atol=TOL)
+        assert (rid[qi, len(wr):] == -1).all()
+
+
+def test_c1_config_exact(Y, oracle, golden):
+    """BASELINE config 1: 1k x 128 fp32, 16 queries, cosine top-10."""
+    O = oracle
+    rows = O.gen_rows_f32(42, 0, 1000, 128)
+    queries = O.gen_rows_f32(43, 0, 16, 128)
+    c = Y.Corpus(128, Y.F32, Y.COSINE)
+    c.append(rows)
+    got = c.search(queries, 10, threshold=-1.0)
+    check_against_oracle(O, rows, queries, got, 10)
+    for qi, g in enumerate(golden["c1_cosine_top10"]):           # ids the reference itself returns
+        assert [int(x) for x in got[0][qi]] == g["idx"]
+        assert np.allclose(1.0 - got[1][qi], g["dist"], atol=1e-5)
+    assert len(c) == 1000
+    c.close()
+
+
+def test_exact_scan_contract(Y, oracle):
+    # /root/reference/tests/unit/vector/vector_smoke_catch2_test.cpp:188-340
+    rows = np.zeros((6, 4), dtype=np.float32)
+    rows[0] = [1, 0, 0, 0]; rows[1] = [0.9, 0.1, 0, 0]; rows[2] = 0
+    rows[3] = [np.nan, 1, 0, 0]; rows[4] = [1e19, 0, 0, 0]; rows[5] = [-1, 0, 0, 0]
+    q = np.array([[1, 0, 0, 0]], dtype=np.float32)
+    c = Y.Corpus(4, Y.F32, Y.COSINE)
+    c.append(rows, rowids=[10, 11, 12, 13, 14, 15])
+    rid, sc, cnt, flags = c.search(q, 10, threshold=-1.0)
+    assert cnt[0] == 4 and list(rid[0, :4]) == [10, 14, 11, 15]
+    assert sc[0, 0] == 1.0 and sc[0, 1] == 1.0 and sc[0, 3] == -1.0
+    rid, sc, cnt, flags = c.search(q, 1, threshold=-1.0)
+    assert list(rid[0]) == [10] and (flags[0] & 1) == 1          # tie straddles k -> host re-breaks by chunk_id
+    rid, sc, cnt, flags = c.search(q, 10, threshold=0.5)
+    assert cnt[0] == 3 and list(rid[0, :3]) == [10, 14, 11]
+    assert c.search(q, 0)[2][0] == 0                              # k == 0 -> empty (:4123)
+    for bad in ([0, 0, 0, 0], [np.nan, 0, 0, 0], [np.inf, 0, 0, 0], [1e-6, 0, 0, 0]):
+        with pytest.raises(Y.YamsB200Error) as e:
+            c.search(np.array([bad], dtype=np.float32), 3)
+        assert e.value.status == 1                                # InvalidArgument (:4127)
+    # candidate set (CandidateFilterMode::Exact)
+    rid, sc, cnt, flags = c.search(q, 5, threshold=-1.0, allowed=[[11, 15, 99]])
+    assert cnt[0] == 2 and list(rid[0, :2]) == [11, 15]
+    c.clear()
+    assert len(c) == 0 and c.search(q, 3)[2][0] == 0
+    c.close()
+
+
+@pytest.mark.parametrize("dtype", ["f16", "f32"])
+def test_sampled_threshold_path_vs_oracle(Y, oracle, dtype):
+    """n > 65536 rows: thresholds from a strided sample + filtered scan + exact rescoring."""
+    O = oracle
+    n, d, nq, k = 150_000, 96, 24, 10
+    rows32 = O.gen_rows_f32(42, 0, n, d)
+    queries = O.gen_rows_f32(43, 0, nq, d)
+    if dtype == "f16":
+        rows = O.f16_from_float(rows32).reshape(n, d)             # reference truncating conversion
+        c = Y.Corpus(d, Y.F16, Y.COSINE)
+        c.append(rows32)                                          # device-side truncating conversion
+    else:
+        rows = rows32
+        c = Y.Corpus(d, Y.F32, Y.COSINE)
+        c.append(rows)
+    got = c.search(queries, k, threshold=-1.0)
+    check_against_oracle(O, rows, queries, got, k)
+    got = c.search(queries[:3], 100, threshold=0.1)
+    check_against_oracle(O, rows, queries[:3], got, 100, threshold=0.1)
+    c.close()
+
+
+def test_odd_dim_duplicates_and_ties(Y, oracle):
+    O = oracle
+    n, d = 3000, 37                                               # dim % 8 != 0 -> scalar load path
+    rows = O.gen_rows_f32(7, 0, n, d)
+    rows[100:140] = rows[5]                                       # 41 identical rows -> equal scores
+    rows[2000] = 0
+    c = Y.Corpus(d, Y.F32, Y.COSINE)
+    c.append(rows)
+    queries = np.stack([rows[5], rows[17] + 0.01, -rows[9]])
+    for k in (1, 10, 50):
+        got = c.search(queries, k, threshold=-1.0)
+        check_against_oracle(O, rows, queries, got, k)
+    assert c.search(queries[:1], 10)[3][0] & 1                    # ties at the k boundary flagged
+    c.close()
+
+
+def test_candidate_sets_vs_oracle(Y, oracle):
+    """BASELINE config 5 shape, scaled down: per-query allowed rowid lists."""
+    O = oracle
+    n, d, nq, k = 90_000, 64, 12, 10
+    rows32 = O.gen_rows_f32(42, 0, n, d)
+    rows = O.f16_from_float(rows32).reshape(n, d)
+    rowids = np.arange(n, dtype=np.int64) * 3 + 1000              # sparse, non-dense rowids
+    c = Y.Corpus(d, Y.F16, Y.COSINE)
+    c.append(rows.view(np.float16), rowids=rowids)
+    queries = O.gen_rows_f32(43, 0, nq, d)
+    rng = np.random.default_rng(5)
+    allowed = []
+    for qi in range(nq):
+        frac = [0.001, 0.01, 0.1][qi % 3]
+        sel = np.sort(rng.choice(n, size=max(1, int(n * frac)), replace=False))
+        allowed.append(rowids[sel])
+    allowed[3] = np.zeros(0, dtype=np.int64)                      # empty candidate list
+    rid, sc, cnt, flags = c.search(queries, k, threshold=-1.0, allowed=allowed)
+    for qi in range(nq):
+        rc, wr, ws = O.exact_scan_cosine(rows, queries[qi], k, threshold=-1.0, rowids=rowids, allowed=allowed[qi])
+        assert cnt[qi] == len(wr) and list(rid[qi, :len(wr)]) == list(wr), qi
+        assert np.array_equal(sc[qi, :len(wr)], ws)
+    c.close()
+
+
+def test_synthetic_corpus_bits_match_oracle(Y, oracle):
+    """Device generator == oracle generator, incl. truncating fp16: identical scores."""
+    O = oracle
+    n, d = 70_000, 128
+    rows = O.f16_from_float(O.gen_rows_f32(42, 1000, n, d)).reshape(n, d)
+    c = Y.Corpus(d, Y.F16, Y.COSINE)
+    c.append_synthetic(42, 1000, n)
+    queries = O.gen_rows_f32(43, 0, 8, d)
+    got = c.search(queries, 10, threshold=-1.0)
+    rid, sc, cnt, _ = got
+    for qi, q in enumerate(queries):
+        rc, wr, ws = O.exact_scan_cosine(rows, q, 10, threshold=-1.0, rowids=np.arange(1000, 1000 + n))
+        assert list(rid[qi]) == list(wr) and np.array_equal(sc[qi], ws)
+    c.close()
+
+
+def test_vec0_exact_and_l2_surface(Y, oracle):
+    O = oracle
+    # third_party/sqlite-vec-cpp/tests/test_sqlite_functions.cpp:1261-1399 (exact plans)
+    rows = np.array([[0, 0], [3, 4], [1, 0], [0, 2]], dtype=np.float32)
+    rid, dist = Y.vec0_exact(np.zeros(2, dtype=np.float32), rows, k=0, rowids=[10, 11, 12, 13])
+    assert list(rid) == [10, 12, 13, 11] and np.allclose(dist, [0, 1, 2, 5])
+    rid, dist = Y.vec0_exact(np.zeros(2, dtype=np.float32), rows, k=2, rowids=[10, 11, 12, 13])
+    assert list(rid) == [10, 12]
+    rid, dist = Y.vec0_exact(np.zeros(2, dtype=np.float32), rows, k=0, rowids=[10, 11, 12, 13], rowid_range=(11, 12))
+    assert list(rid) == [12, 11]
+    # larger random case incl. ties
+    big = O.gen_rows_f32(3, 0, 5000, 48)
+    big[77] = big[5]
+    q = O.gen_rows_f32(4, 0, 1, 48)[0]
+    for k in (0, 25):
+        wr, wd = O.vec0_exact(big, q, k=k)
+        rid, dist = Y.vec0_exact(q, big, k=k)
+        assert np.allclose(dist, wd, atol=TOL)
+        order_ok = list(rid) == list(wr)
+        if not order_ok:   # float summation order may swap near-equal neighbours: distances must agree
+            assert np.allclose(np.sort(dist), np.sort(wd), atol=TOL)
+    # corpus with the L2 metric (top-k ascending by distance)
+    c = Y.Corpus(48, Y.F32, Y.L2)
+    c.append(big)
+    rid, sc, cnt, _ = c.search(q[None, :], 10)
+    wr, wd = O.vec0_exact(big, q, k=10)
+    assert cnt[0] == 10 and np.allclose(sc[0], wd, atol=TOL)
+    c.close()
+    # test_batch_distance.cpp:19-104 KATs through the same surface
+    rows = np.array([[1, 2, 3], [2, 3, 4], [0, 0, 0], [4, 5, 6]], dtype=np.float32)
+    rid, dist = Y.vec0_exact(np.array([1, 2, 3], dtype=np.float32), rows, k=2)
+    assert list(rid) == [0, 1] and np.allclose(dist, [0, np.sqrt(3.0)], atol=TOL)
+
+
+def test_pairwise_c_api(Y):
+    # /root/reference/tests/unit/vector/sqlite_vec_c_api_smoke_catch2_test.cpp:19-75
+    rc, v = Y.vec_distance_l2(np.ones(16), np.ones(16))
+    assert rc == 0 and abs(v) < 1e-6
+    a = np.array([1, 2, 3, 4, 5, 6, 7, 8] * 2, dtype=np.float32)
+    b = np.array([1, 2, 3, 4, 5, 6, 7, 8, 2, 3, 4, 5, 6, 7, 8, 9], dtype=np.float32)
+    rc, v = Y.vec_distance_l2(a, b)
+    assert rc == 0 and abs(v - np.sqrt(8.0)) < 1e-5
+    rc, v = Y.vec_distance_cosine(np.full(16, 0.5), np.full(16, 0.5))
+    assert rc == 0 and abs(v) < 1e-5
+    assert Y.vec_distance_l2(np.ones(8), np.ones(16))[0] != 0
+    assert Y.vec_distance_cosine(np.ones(8), np.ones(16))[0] != 0
+    # test_distances.cpp:20-53 / distance_metrics_test.cpp:254-292 KATs
+    assert abs(Y.vec_distance_l2([1, 2, 3, 4], [2, 3, 4, 5])[1] - 2.0) < TOL
+    assert abs(Y.vec_distance_cosine([1, 2, 3], [-1, -2, -3])[1] - 2.0) < 1e-5
+    assert abs(Y.vec_distance_cosine([0.6, 0.8], [0.8, 0.6])[1] - 0.04) < 1e-5
+    assert Y.vec_distance_cosine([0, 0, 0], [1, 2, 3])[1] == 1.0
+
+
+def test_partial_topk_merge_like_allgather(Y, oracle):
+    """Row-sharded scan on one GPU: R shard corpora -> search_device partials laid out [R][Q][k] (what an
+    all-gather produces) -> merge_partials_device == single-corpus answer."""
+    import torch
+    O = oracle
+    n, d, nq, k, R = 80_000, 64, 16, 10, 4
+    rows = O.f16_from_float(O.gen_rows_f32(42, 0, n, d)).reshape(n, d)
+    queries = O.gen_rows_f32(43, 0, nq, d)
+    dq = torch.from_numpy(queries).cuda()
+    part_r = torch.empty((R, nq, k), dtype=torch.int64, device="cuda")
+    part_s = torch.empty((R, nq, k), dtype=torch.float32, device="cuda")
+    shards = []
+    per = n // R
+    for r in range(R):
+        c = Y.Corpus(d, Y.F16, Y.COSINE)
+        c.append(rows[r * per:(r + 1) * per].view(np.float16), rowids=np.arange(r * per, (r + 1) * per))
+        c.search_device(dq.data_ptr(), nq, k, -1.0, part_r[r].data_ptr(), part_s[r].data_ptr())
+        c.sync()
+        shards.append(c)
+    out_r = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    out_s = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    shards[0].merge_partials_device(part_r.data_ptr(), part_s.data_ptr(), R, nq, k, out_r.data_ptr(), out_s.data_ptr())
+    shards[0].sync()
+    for qi in range(nq):
+        rc, wr, ws = O.exact_scan_cosine(rows, queries[qi], k, threshold=-1.0)
+        assert list(out_r[qi].cpu().numpy()) == list(wr)
+        assert np.array_equal(out_s[qi].cpu().numpy(), ws)
+    for c in shards:
+        c.close()

@@ -1,0 +1,380 @@
+"""ctypes binding of include/yams_b200.h (every exported symbol is bound here; tests check that)."""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(HERE, "libyams_b200.so")
+
+STREAMING, RABIN = 0, 1
+F32, F16 = 0, 1
+COSINE, L2 = 0, 1
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+u64p = C.POINTER(C.c_uint64)
+i64p = C.POINTER(C.c_int64)
+f32p = C.POINTER(C.c_float)
+
+
+class YamsB200Error(RuntimeError):
+    def __init__(self, status: int, where: str, text: str):
+        super().__init__(f"{where}: status {status}: {text}")
+        self.status = status
+
+
+class CdcConfig(C.Structure):
+    """yams_cdc_config == ChunkingConfig (/root/reference/include/yams/chunking/chunker.h:44-51)."""
+    _fields_ = [("window_size", C.c_uint64), ("min_chunk", C.c_uint64), ("max_chunk", C.c_uint64),
+                ("polynomial", C.c_uint64), ("mask", C.c_uint64), ("variant", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class ChunkDesc(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("size", C.c_uint64), ("digest", C.c_uint8 * 32)]
+
+
+CHUNK_DTYPE = np.dtype([("offset", "<u8"), ("size", "<u8"), ("digest", "u1", (32,))])
+assert CHUNK_DTYPE.itemsize == C.sizeof(ChunkDesc) == 48
+
+# every symbol include/yams_b200.h declares: name -> (restype, argtypes)
+_descpp = C.POINTER(C.POINTER(ChunkDesc))
+_szp = C.POINTER(C.c_size_t)
+SYMBOLS = {
+    "yams_plugin_get_abi_version": (C.c_int, []),
+    "yams_plugin_get_name": (C.c_char_p, []),
+    "yams_plugin_get_version": (C.c_char_p, []),
+    "yams_plugin_get_manifest_json": (C.c_char_p, []),
+    "yams_plugin_init": (C.c_int, [C.c_char_p, C.c_void_p]),
+    "yams_plugin_shutdown": (None, []),
+    "yams_plugin_get_interface": (C.c_int, [C.c_char_p, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "yams_plugin_get_health_json": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "yams_b200_cdc_default_config": (None, [C.POINTER(CdcConfig)]),
+    "yams_b200_chunk_and_hash": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CdcConfig), _descpp, _szp]),
+    "yams_b200_free_chunks": (None, [C.c_void_p, C.POINTER(ChunkDesc), C.c_size_t]),
+    "yams_b200_chunk_and_hash_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CdcConfig), _descpp, _szp]),
+    "yams_b200_ingest_open": (C.c_int, [C.c_void_p, C.POINTER(CdcConfig), C.POINTER(C.c_void_p)]),
+    "yams_b200_ingest_feed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, _descpp, _szp]),
+    "yams_b200_ingest_finish": (C.c_int, [C.c_void_p, _descpp, _szp]),
+    "yams_b200_ingest_close": (None, [C.c_void_p]),
+    "yams_b200_sha256_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p, C.c_size_t, u8p]),
+    "yams_b200_sha256_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p, C.c_size_t, u8p]),
+    "yams_b200_chunk_boundaries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CdcConfig), _descpp, _szp]),
+    "yams_b200_ingest_last_timings": (C.c_int, [C.c_void_p, f32p]),
+    "yams_b200_corpus_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "yams_b200_corpus_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, i64p]),
+    "yams_b200_corpus_append_f32_as_f16": (C.c_int, [C.c_void_p, f32p, C.c_uint64, i64p]),
+    "yams_b200_corpus_append_synthetic": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "yams_b200_corpus_clear": (C.c_int, [C.c_void_p]),
+    "yams_b200_corpus_size": (C.c_int, [C.c_void_p, u64p]),
+    "yams_b200_corpus_destroy": (None, [C.c_void_p]),
+    "yams_b200_search": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_float, i64p, u64p, i64p, f32p, u32p, u64p]),
+    "yams_b200_search_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]),
+    "yams_b200_merge_partials_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p]),
+    "yams_b200_corpus_sync": (C.c_int, [C.c_void_p]),
+    "yams_b200_corpus_stream": (C.c_void_p, [C.c_void_p]),
+    "yams_b200_vec0_exact": (C.c_int, [C.c_void_p, f32p, C.c_uint32, f32p, i64p, C.c_uint64, C.c_uint64, C.c_int,
+                                       C.c_int64, C.c_int64, i64p, f32p, u64p]),
+    "yams_b200_search_last_timings": (C.c_int, [C.c_void_p, f32p]),
+    "sqlite3_vec_distance_l2": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, f32p]),
+    "sqlite3_vec_distance_cosine": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, f32p]),
+    "yams_b200_synth_bytes_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "yams_b200_device_count": (C.c_int, []),
+    "yams_b200_last_error": (C.c_char_p, []),
+}
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _SO
+
+
+def lib():
+    """The loaded shared library. Fails loudly when it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_SO):
+            raise ImportError(
+                f"{_SO} is missing: build it with `python -c \"import __graft_entry__ as g; g.build()\"` "
+                "(nvcc, sm_100a). yams_b200 has no CPU or PyTorch fallback.")
+        L = C.CDLL(_SO)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, where: str):
+    if rc != 0:
+        raise YamsB200Error(rc, where, (lib().yams_b200_last_error() or b"").decode(errors="replace"))
+
+
+def device_count() -> int:
+    return lib().yams_b200_device_count()
+
+
+def plugin_init(config: Optional[dict] = None) -> int:
+    return lib().yams_plugin_init(json.dumps(config or {}).encode(), None)
+
+
+def health() -> dict:
+    p = C.c_void_p()
+    lib().yams_plugin_get_health_json(C.byref(p))
+    s = C.cast(p, C.c_char_p).value.decode()
+    C.CDLL(None).free(p)
+    return json.loads(s)
+
+
+def default_config(variant: int = STREAMING, **kw) -> CdcConfig:
+    cfg = CdcConfig()
+    lib().yams_b200_cdc_default_config(C.byref(cfg))
+    cfg.variant = variant
+    for k, v in kw.items():
+        setattr(cfg, k, v)
+    return cfg
+
+
+def _as_u8(data) -> np.ndarray:
+    if isinstance(data, np.ndarray):
+        return np.ascontiguousarray(data, dtype=np.uint8)
+    return np.frombuffer(bytes(data), dtype=np.uint8)
+
+
+def _take(out_p, out_n) -> np.ndarray:
+    n = out_n.value
+    if n == 0:
+        return np.zeros(0, dtype=CHUNK_DTYPE)
+    buf = (ChunkDesc * n).from_address(C.addressof(out_p.contents))
+    arr = np.frombuffer(buf, dtype=CHUNK_DTYPE).copy()
+    lib().yams_b200_free_chunks(None, out_p, n)
+    return arr
+
+
+def _chunks(fn_name: str, ptr, length: int, cfg: CdcConfig) -> np.ndarray:
+    out_p = C.POINTER(ChunkDesc)()
+    out_n = C.c_size_t(0)
+    rc = getattr(lib(), fn_name)(None, ptr, length, C.byref(cfg), C.byref(out_p), C.byref(out_n))
+    _check(rc, fn_name)
+    return _take(out_p, out_n)
+
+
+def chunk_and_hash(data, cfg: Optional[CdcConfig] = None) -> np.ndarray:
+    """IChunker::chunkDataLazy over a host buffer -> structured array (offset, size, digest[32])."""
+    a = _as_u8(data)
+    return _chunks("yams_b200_chunk_and_hash", a.ctypes.data if a.size else None, a.size, cfg or default_config())
+
+
+def chunk_boundaries(data, cfg: Optional[CdcConfig] = None) -> np.ndarray:
+    a = _as_u8(data)
+    return _chunks("yams_b200_chunk_boundaries", a.ctypes.data if a.size else None, a.size, cfg or default_config())
+
+
+def chunk_and_hash_device(dev_ptr: int, length: int, cfg: Optional[CdcConfig] = None) -> np.ndarray:
+    """Input already resident in HBM (e.g. ``tensor.data_ptr()``)."""
+    return _chunks("yams_b200_chunk_and_hash_device", dev_ptr, length, cfg or default_config())
+
+
+def ingest_last_timings() -> dict:
+    ms = (C.c_float * 8)()
+    lib().yams_b200_ingest_last_timings(None, ms)
+    return {"scan_ms": ms[0], "select_ms": ms[1], "sha256_ms": ms[2], "total_ms": ms[3]}
+
+
+class IngestSession:
+    """StreamingChunker::processStream shaped session (open / feed... / finish)."""
+
+    def __init__(self, cfg: Optional[CdcConfig] = None):
+        self._h = C.c_void_p()
+        self._cfg = cfg or default_config()
+        _check(lib().yams_b200_ingest_open(None, C.byref(self._cfg), C.byref(self._h)), "ingest_open")
+
+    def feed(self, data) -> np.ndarray:
+        a = _as_u8(data)
+        out_p = C.POINTER(ChunkDesc)()
+        out_n = C.c_size_t(0)
+        _check(lib().yams_b200_ingest_feed(self._h, a.ctypes.data if a.size else None, a.size, C.byref(out_p),
+                                           C.byref(out_n)), "ingest_feed")
+        return _take(out_p, out_n)
+
+    def finish(self) -> np.ndarray:
+        out_p = C.POINTER(ChunkDesc)()
+        out_n = C.c_size_t(0)
+        _check(lib().yams_b200_ingest_finish(self._h, C.byref(out_p), C.byref(out_n)), "ingest_finish")
+        return _take(out_p, out_n)
+
+    def close(self):
+        if self._h:
+            lib().yams_b200_ingest_close(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def sha256_batch(base, offsets, sizes) -> np.ndarray:
+    a = _as_u8(base)
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    szs = np.ascontiguousarray(sizes, dtype=np.uint64)
+    out = np.zeros((len(offs), 32), dtype=np.uint8)
+    _check(lib().yams_b200_sha256_batch(None, a.ctypes.data if a.size else None, a.size, offs.ctypes.data_as(u64p),
+                                        szs.ctypes.data_as(u64p), len(offs), out.ctypes.data_as(u8p)), "sha256_batch")
+    return out
+
+
+def sha256_batch_device(dev_ptr: int, base_len: int, offsets, sizes) -> np.ndarray:
+    offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+    szs = np.ascontiguousarray(sizes, dtype=np.uint64)
+    out = np.zeros((len(offs), 32), dtype=np.uint8)
+    _check(lib().yams_b200_sha256_batch_device(None, dev_ptr, base_len, offs.ctypes.data_as(u64p), szs.ctypes.data_as(u64p),
+                                               len(offs), out.ctypes.data_as(u8p)), "sha256_batch_device")
+    return out
+
+
+def synth_bytes_device(seed: int, start: int, n: int, dev_ptr: int):
+    _check(lib().yams_b200_synth_bytes_device(seed, start, n, dev_ptr), "synth_bytes_device")
+
+
+class Corpus:
+    """Device-resident mirror of the `vectors` table (row-major [n, dim], fp32 or fp16)."""
+
+    def __init__(self, dim: int, dtype: int = F16, metric: int = COSINE, capacity_hint: int = 0):
+        self._h = C.c_void_p()
+        self.dim, self.dtype, self.metric = dim, dtype, metric
+        _check(lib().yams_b200_corpus_create(None, dim, dtype, metric, capacity_hint, C.byref(self._h)), "corpus_create")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def append(self, rows: np.ndarray, rowids=None):
+        rows = np.ascontiguousarray(rows)
+        n = rows.shape[0]
+        rid = np.ascontiguousarray(rowids, dtype=np.int64) if rowids is not None else None
+        ridp = rid.ctypes.data_as(i64p) if rid is not None else None
+        if self.dtype == F16 and rows.dtype == np.float32:
+            _check(lib().yams_b200_corpus_append_f32_as_f16(self._h, rows.ctypes.data_as(f32p), n, ridp), "corpus_append_f32_as_f16")
+        else:
+            want = np.uint16 if self.dtype == F16 else np.float32
+            if self.dtype == F16 and rows.dtype == np.float16:
+                rows = rows.view(np.uint16)
+            assert rows.dtype == want, (rows.dtype, want)
+            _check(lib().yams_b200_corpus_append(self._h, rows.ctypes.data, n, ridp), "corpus_append")
+
+    def append_synthetic(self, seed: int, first_row: int, n: int):
+        _check(lib().yams_b200_corpus_append_synthetic(self._h, seed, first_row, n), "corpus_append_synthetic")
+
+    def clear(self):
+        _check(lib().yams_b200_corpus_clear(self._h), "corpus_clear")
+
+    def __len__(self):
+        n = C.c_uint64(0)
+        _check(lib().yams_b200_corpus_size(self._h, C.byref(n)), "corpus_size")
+        return n.value
+
+    def search(self, queries: np.ndarray, k: int, threshold: float = -1.0, allowed=None):
+        """-> (rowids i64[Q,k], scores f32[Q,k], counts u32[Q], flags u64[Q]).
+        allowed: optional list (len Q) of ascending rowid arrays (CandidateFilterMode::Exact)."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq = q.shape[0]
+        out_r = np.full((nq, max(k, 1)), -1, dtype=np.int64)
+        out_s = np.zeros((nq, max(k, 1)), dtype=np.float32)
+        out_c = np.zeros(nq, dtype=np.uint32)
+        out_f = np.zeros(nq, dtype=np.uint64)
+        al_p = of_p = None
+        if allowed is not None:
+            offs = np.zeros(nq + 1, dtype=np.uint64)
+            offs[1:] = np.cumsum([len(a) for a in allowed])
+            al = np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.int64) for a in allowed])
+                                      if nq and int(offs[-1]) else np.zeros(1, dtype=np.int64), dtype=np.int64)
+            al_p, of_p = al.ctypes.data_as(i64p), offs.ctypes.data_as(u64p)
+        rc = lib().yams_b200_search(self._h, q.ctypes.data_as(f32p), nq, k, threshold, al_p, of_p,
+                                    out_r.ctypes.data_as(i64p), out_s.ctypes.data_as(f32p), out_c.ctypes.data_as(u32p),
+                                    out_f.ctypes.data_as(u64p))
+        _check(rc, "search")
+        return out_r[:, :k], out_s[:, :k], out_c, out_f
+
+    def search_device(self, d_queries: int, nq: int, k: int, threshold: float, d_out_rowids: int, d_out_scores: int):
+        _check(lib().yams_b200_search_device(self._h, d_queries, nq, k, threshold, d_out_rowids, d_out_scores), "search_device")
+
+    def merge_partials_device(self, d_rowids: int, d_scores: int, nranks: int, nq: int, k: int, d_out_rowids: int,
+                              d_out_scores: int, d_out_counts: int = 0):
+        _check(lib().yams_b200_merge_partials_device(self._h, d_rowids, d_scores, nranks, nq, k, d_out_rowids, d_out_scores,
+                                                     d_out_counts or None), "merge_partials_device")
+
+    def sync(self):
+        _check(lib().yams_b200_corpus_sync(self._h), "corpus_sync")
+
+    @property
+    def stream(self) -> int:
+        return lib().yams_b200_corpus_stream(self._h) or 0
+
+    def last_timings(self) -> dict:
+        ms = (C.c_float * 8)()
+        lib().yams_b200_search_last_timings(self._h, ms)
+        return {"stage1_ms": ms[0], "stage2_ms": ms[1], "total_ms": ms[2], "scan_kernel_ms": ms[5],
+                "engine": "tcgen05" if ms[4] else "cuda-core"}
+
+    def close(self):
+        if self._h:
+            lib().yams_b200_corpus_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def vec0_exact(query, rows, k: int = 0, rowids=None, rowid_range=None):
+    """vec0_run_exact_query: (rowids, distances) ascending by L2 distance."""
+    rows = np.ascontiguousarray(rows, dtype=np.float32)
+    q = np.ascontiguousarray(query, dtype=np.float32)
+    n, d = rows.shape if rows.ndim == 2 else (0, q.size)
+    out_r = np.zeros(max(n, 1), dtype=np.int64)
+    out_d = np.zeros(max(n, 1), dtype=np.float32)
+    cnt = C.c_uint64(0)
+    rid = np.ascontiguousarray(rowids, dtype=np.int64) if rowids is not None else None
+    lo, hi = rowid_range if rowid_range is not None else (0, 0)
+    rc = lib().yams_b200_vec0_exact(None, q.ctypes.data_as(f32p), d, rows.ctypes.data_as(f32p),
+                                    rid.ctypes.data_as(i64p) if rid is not None else None, n, k,
+                                    int(rowid_range is not None), lo, hi, out_r.ctypes.data_as(i64p),
+                                    out_d.ctypes.data_as(f32p), C.byref(cnt))
+    _check(rc, "vec0_exact")
+    return out_r[:cnt.value].copy(), out_d[:cnt.value].copy()
+
+
+def _pair(fn, a, b):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    out = C.c_float(0)
+    rc = fn(a.ctypes.data, a.nbytes, b.ctypes.data, b.nbytes, C.byref(out))
+    return rc, out.value
+
+
+def vec_distance_l2(a, b):
+    return _pair(lib().sqlite3_vec_distance_l2, a, b)
+
+
+def vec_distance_cosine(a, b):
+    return _pair(lib().sqlite3_vec_distance_cosine, a, b)

@@ -1,0 +1,447 @@
+// cdc.cu -- content-defined chunk boundary detection on the GPU (candidates + exact cut selection).
+//
+// Replaces the byte loops of the reference chunkers
+//   /root/reference/src/chunking/rabin_chunker.cpp:63-152   (RabinChunker)
+//   /root/reference/include/yams/chunking/streaming_chunker.h:146-204 (StreamingChunker)
+// with a data-parallel formulation:
+//   1. candidate scan   -- HBM-bound; every byte position is tested independently with the
+//                          closed-form masked rolling value (cdc_logic.h is_candidate); a SIMD
+//                          low-byte prefilter keeps the common case at ~1 instr/byte;
+//   2. ordered compaction of candidate positions (count -> scan -> write);
+//   3. next-cut per candidate (parallel), block-wise chain resolution, chunk emission.
+// All results are bit-identical to the sequential reference; the logic lives in cdc_logic.h so the
+// same lines are unit-tested on the CPU against the oracle.
+#include "cdc_kernels.cuh"
+
+namespace yb {
+
+// 16-bit mask of positions (within the 16 bytes at stream position p0) that pass the low-byte
+// prefilter.  word i covers bytes 4i..4i+3 (little endian).
+__device__ __forceinline__ uint32_t prefilter16(const uint4& v, const CdcParams& P,
+                                                const uint8_t* pass_s) {
+    uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+    uint32_t mask = 0;
+    if (P.nfast) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t z = 0;
+            for (uint32_t f = 0; f < P.nfast; ++f) {
+                uint32_t m = wv[i] ^ (0x01010101u * P.fast[f]);
+                // exact per-byte zero detect (no borrow false positives): bit7 of each byte set
+                // iff that byte of m is zero
+                uint32_t t = (m & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+                z |= ~(t | m | 0x7f7f7f7fu);
+            }
+            // compress 0x80 flags of 4 bytes into 4 bits
+            uint32_t bits = ((z >> 7) & 1u) | ((z >> 14) & 2u) | ((z >> 21) & 4u) | ((z >> 28) & 8u);
+            mask |= bits << (4 * i);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                uint32_t byte = (wv[i] >> (8 * b)) & 0xffu;
+                mask |= (uint32_t)pass_s[byte] << (4 * i + b);
+            }
+        }
+    }
+    return mask;
+}
+
+// Tests the 16-byte unit at stream position p0 (whose address is 16-byte aligned by construction
+// of `origin`); positions outside [scan_lo, scan_hi) are masked.  Returns a 16-bit hit mask.
+__device__ __forceinline__ uint32_t scan16(const ScanArgs& A, const uint64_t* T_s, const uint8_t* pass_s,
+                                           uint64_t p0) {
+    uint64_t lo = p0 > A.scan_lo ? p0 : A.scan_lo;
+    uint64_t hi = p0 + 16 < A.scan_hi ? p0 + 16 : A.scan_hi;
+    if (lo >= hi) return 0;
+    uint4 v;
+    uint32_t valid = 0xffffu;
+    if (lo == p0 && hi == p0 + 16) {
+        v = ldg_stream_u4(A.data + (p0 - A.base_pos));
+    } else {
+        // ragged first / last unit: byte loads of the in-range positions only
+        uint32_t wv[4] = {0, 0, 0, 0};
+        valid = 0;
+        for (uint64_t q = lo; q < hi; ++q) {
+            uint32_t b = (uint32_t)(q - p0);
+            wv[b >> 2] |= (uint32_t)A.data[q - A.base_pos] << (8 * (b & 3));
+            valid |= 1u << b;
+        }
+        v = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+    }
+    uint32_t pre = prefilter16(v, A.P, pass_s) & valid;
+    uint32_t hits = 0;
+    ByteView view{A.data, A.base_pos, A.lowest};
+    while (pre) {
+        int b = __ffs(pre) - 1;
+        pre &= pre - 1;
+        if (is_candidate(view, T_s, A.P, p0 + (uint64_t)b)) hits |= 1u << b;
+    }
+    return hits;
+}
+
+__device__ __forceinline__ void load_tables(const ScanArgs& A, uint64_t* T_s, uint8_t* pass_s) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        uint64_t t = A.table[i];
+        T_s[i] = t;
+        uint64_t m0 = A.P.mask & 0xffull;
+        pass_s[i] = ((t & m0) == m0) ? 1 : 0;
+    }
+    __syncthreads();
+}
+
+// pass 1: number of candidates per 16 KiB tile
+__global__ void __launch_bounds__(kScanThreads) cdc_count_kernel(ScanArgs A, uint32_t ntiles,
+                                                                 uint32_t* __restrict__ tile_counts) {
+    __shared__ uint64_t T_s[256];
+    __shared__ uint8_t pass_s[256];
+    __shared__ uint32_t warp_sums[kScanThreads / 32];
+    load_tables(A, T_s, pass_s);
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        uint64_t tile_pos = A.origin + (uint64_t)tile * kTileBytes;
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int it = 0; it < kScanIters; ++it) {
+            uint64_t p0 = tile_pos + ((uint64_t)it * kScanThreads + threadIdx.x) * 16;
+            cnt += __popc(scan16(A, T_s, pass_s, p0));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = cnt;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t s = 0;
+#pragma unroll
+            for (int w = 0; w < kScanThreads / 32; ++w) s += warp_sums[w];
+            tile_counts[tile] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// pass 2: ordered write of candidate stream positions at the scanned tile offsets
+__global__ void __launch_bounds__(kScanThreads) cdc_write_kernel(ScanArgs A, uint32_t ntiles,
+                                                                 const uint32_t* __restrict__ tile_counts,
+                                                                 const uint32_t* __restrict__ tile_offsets,
+                                                                 uint64_t* __restrict__ cand) {
+    __shared__ uint64_t T_s[256];
+    __shared__ uint8_t pass_s[256];
+    __shared__ uint32_t warp_sums[kScanThreads / 32];
+    load_tables(A, T_s, pass_s);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        if (tile_counts[tile] == 0) continue;  // block-uniform
+        uint64_t tile_pos = A.origin + (uint64_t)tile * kTileBytes;
+        uint32_t running = tile_offsets[tile];
+        for (int it = 0; it < kScanIters; ++it) {
+            uint64_t p0 = tile_pos + ((uint64_t)it * kScanThreads + threadIdx.x) * 16;
+            uint32_t hits = scan16(A, T_s, pass_s, p0);
+            uint32_t c = __popc(hits);
+            // block-wide exclusive prefix of c in thread order
+            uint32_t incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += nb;
+            }
+            if (lane == 31) warp_sums[warp] = incl;
+            __syncthreads();
+            uint32_t wbase = 0, total = 0;
+#pragma unroll
+            for (int w = 0; w < kScanThreads / 32; ++w) {
+                uint32_t s = warp_sums[w];
+                if (w < warp) wbase += s;
+                total += s;
+            }
+            uint32_t o = running + wbase + incl - c;
+            while (hits) {
+                int b = __ffs(hits) - 1;
+                hits &= hits - 1;
+                cand[o++] = p0 + (uint64_t)b;
+            }
+            running += total;
+            __syncthreads();
+        }
+    }
+}
+
+// ---- cut selection ----------------------------------------------------------------------------
+
+__global__ void cdc_next_kernel(SelectArgs S, uint32_t* __restrict__ next, uint32_t* __restrict__ forced) {
+    uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node > S.ncand) return;
+    uint64_t s = node_start(S.cand, node, S.root_start);
+    NextCut r = next_cut(S.cand, S.ncand, node, s, S.P);
+    next[node] = r.j + 1;  // node index; END = ncand + 1
+    forced[node] = (uint32_t)r.forced;
+}
+
+// one warp per block of kNodeBlock nodes; lanes load coalesced, lane 0 does the backward pass
+__global__ void __launch_bounds__(32) cdc_exit_kernel(const uint32_t* __restrict__ next, uint32_t nnodes,
+                                                      uint32_t* __restrict__ exit_out) {
+    __shared__ uint32_t nx[kNodeBlock];
+    __shared__ uint32_t ex[kNodeBlock];
+    uint32_t blk_start = blockIdx.x * kNodeBlock;
+    uint32_t blk_end = min(blk_start + kNodeBlock, nnodes);
+    for (uint32_t i = threadIdx.x; i < blk_end - blk_start; i += 32) nx[i] = next[blk_start + i];
+    __syncwarp();
+    if (threadIdx.x == 0) block_exit_seq(nx, blk_start, blk_end, ex);
+    __syncwarp();
+    for (uint32_t i = threadIdx.x; i < blk_end - blk_start; i += 32) exit_out[blk_start + i] = ex[i];
+}
+
+// single thread: hop block to block from the root, recording where the chain enters each block
+__global__ void cdc_walk_kernel(const uint32_t* __restrict__ exit_in, uint32_t nnodes,
+                                uint32_t* __restrict__ entry) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    uint32_t cur = 0;
+    while (cur < nnodes) {
+        entry[cur / kNodeBlock] = cur;
+        cur = exit_in[cur];
+    }
+}
+
+__global__ void __launch_bounds__(32) cdc_mark_kernel(const uint32_t* __restrict__ next, uint32_t nnodes,
+                                                      const uint32_t* __restrict__ entry,
+                                                      uint8_t* __restrict__ onchain) {
+    __shared__ uint32_t nx[kNodeBlock];
+    __shared__ uint8_t oc[kNodeBlock];
+    uint32_t blk_start = blockIdx.x * kNodeBlock;
+    uint32_t blk_end = min(blk_start + kNodeBlock, nnodes);
+    uint32_t ent = entry[blockIdx.x];
+    for (uint32_t i = threadIdx.x; i < blk_end - blk_start; i += 32) {
+        nx[i] = next[blk_start + i];
+        oc[i] = 0;
+    }
+    __syncwarp();
+    if (threadIdx.x == 0 && ent != kNoEntry) block_mark_seq(nx, blk_start, blk_end, ent, oc);
+    __syncwarp();
+    for (uint32_t i = threadIdx.x; i < blk_end - blk_start; i += 32) onchain[blk_start + i] = oc[i];
+}
+
+__global__ void cdc_emit_count_kernel(SelectArgs S, const uint32_t* __restrict__ next,
+                                      const uint32_t* __restrict__ forced,
+                                      const uint8_t* __restrict__ onchain, uint32_t* __restrict__ counts) {
+    uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node > S.ncand) return;
+    uint32_t c = 0;
+    if (onchain[node]) {
+        uint64_t s = node_start(S.cand, node, S.root_start);
+        c = (uint32_t)node_emit_count(next[node], forced[node], S.ncand + 1, s, S.end_pos, S.final != 0, S.P);
+    }
+    counts[node] = c;
+}
+
+// scalars[0] = new open-chunk start (written by the END node)
+__global__ void cdc_emit_kernel(SelectArgs S, const uint32_t* __restrict__ next,
+                                const uint32_t* __restrict__ forced, const uint8_t* __restrict__ onchain,
+                                const uint32_t* __restrict__ offsets, yams_chunk_desc* __restrict__ out,
+                                uint64_t out_base, uint64_t* __restrict__ scalars) {
+    uint32_t node = blockIdx.x * blockDim.x + threadIdx.x;
+    if (node > S.ncand || !onchain[node]) return;
+    const uint32_t END = S.ncand + 1;
+    uint64_t s = node_start(S.cand, node, S.root_start);
+    uint32_t nx = next[node];
+    uint64_t cnt = node_emit_count(nx, forced[node], END, s, S.end_pos, S.final != 0, S.P);
+    yams_chunk_desc* o = out + out_base + offsets[node];
+    if (nx != END) {
+        uint64_t F = forced[node];
+        for (uint64_t t = 0; t < F; ++t) {
+            o[t].offset = s + t * S.P.force;
+            o[t].size = S.P.force;
+        }
+        uint64_t ls = s + F * S.P.force;
+        o[F].offset = ls;
+        o[F].size = S.cand[nx - 1] + 1 - ls;
+    } else {
+        for (uint64_t t = 0; t < cnt; ++t) {
+            uint64_t cs = s + t * S.P.force;
+            uint64_t sz = S.end_pos - cs < S.P.force ? S.end_pos - cs : S.P.force;
+            o[t].offset = cs;
+            o[t].size = sz;
+        }
+        uint64_t ns = s + cnt * S.P.force;
+        scalars[0] = ns < S.end_pos ? ns : (S.final ? S.end_pos : ns);
+    }
+}
+
+// ---- generic exclusive scan (u32) ----------------------------------------------------------------
+constexpr int kScanBlock = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kScanBlock * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_s, uint32_t* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += nb;
+    }
+    if (lane == 31) warp_s[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < kScanBlock / 32; ++w) {
+        uint32_t s = warp_s[w];
+        if (w < warp) wbase += s;
+        tot += s;
+    }
+    __syncthreads();
+    *total = tot;
+    return wbase + incl - v;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_reduce_kernel(const uint32_t* __restrict__ in, size_t n,
+                                                                 uint64_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_s[kScanBlock / 32];
+    size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i)
+        if (base + i < n) s += in[base + i];
+    uint32_t tot;
+    block_exclusive_scan(s, warp_s, &tot);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = tot;
+}
+
+// single block: exclusive scan of block_sums (u64) in place, total to *d_total
+__global__ void __launch_bounds__(kScanBlock) scan_sums_kernel(uint64_t* __restrict__ block_sums, size_t nb,
+                                                               uint64_t* __restrict__ d_total) {
+    __shared__ uint64_t sh[kScanBlock];
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (size_t base = 0; base < nb; base += kScanBlock) {
+        size_t i = base + threadIdx.x;
+        uint64_t v = i < nb ? block_sums[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        // Hillis-Steele inclusive scan in shared memory
+        for (int o = 1; o < kScanBlock; o <<= 1) {
+            uint64_t add = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += add;
+            __syncthreads();
+        }
+        uint64_t carry = carry_s;
+        if (i < nb) block_sums[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == kScanBlock - 1) carry_s = carry + sh[kScanBlock - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *d_total = carry_s;
+}
+
+__global__ void __launch_bounds__(kScanBlock) scan_apply_kernel(const uint32_t* __restrict__ in,
+                                                                uint32_t* __restrict__ out, size_t n,
+                                                                const uint64_t* __restrict__ block_sums) {
+    __shared__ uint32_t warp_s[kScanBlock / 32];
+    size_t base = (size_t)blockIdx.x * kScanChunk + (size_t)threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        v[i] = base + i < n ? in[base + i] : 0;
+        s += v[i];
+    }
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(s, warp_s, &tot);
+    uint32_t run = (uint32_t)block_sums[blockIdx.x] + ex;
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+}
+
+yams_status_t exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, uint64_t* d_total,
+                                 DevBuf& scratch, cudaStream_t st) {
+    if (n == 0) {
+        YB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(uint64_t), st));
+        return YAMS_OK;
+    }
+    size_t nb = (n + kScanChunk - 1) / kScanChunk;
+    yams_status_t rc = scratch.reserve(nb * sizeof(uint64_t));
+    if (rc != YAMS_OK) return rc;
+    uint64_t* sums = scratch.as<uint64_t>();
+    scan_reduce_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(d_in, n, sums);
+    scan_sums_kernel<<<1, kScanBlock, 0, st>>>(sums, nb, d_total);
+    scan_apply_kernel<<<(unsigned)nb, kScanBlock, 0, st>>>(d_in, d_out, n, sums);
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
+// ---- synthetic byte stream: byte[i] = (splitmix64(seed ^ (i>>3)) >> (8*(i&7))) ----
+__global__ void synth_bytes_kernel(uint64_t seed, uint64_t start, uint64_t n, uint8_t* __restrict__ out) {
+    // one thread per aligned 8-byte group of the STREAM
+    uint64_t g0 = start >> 3;
+    uint64_t ngroups = ((start + n + 7) >> 3) - g0;
+    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g < ngroups;
+         g += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t grp = g0 + g;
+        uint64_t v = splitmix64(seed ^ grp);
+        uint64_t pos = grp << 3;
+        if (pos >= start && pos + 8 <= start + n && (((uintptr_t)(out + (pos - start))) & 7) == 0) {
+            *reinterpret_cast<uint64_t*>(out + (pos - start)) = v;
+        } else {
+            for (int b = 0; b < 8; ++b) {
+                uint64_t q = pos + b;
+                if (q >= start && q < start + n) out[q - start] = (uint8_t)(v >> (8 * b));
+            }
+        }
+    }
+}
+
+yams_status_t launch_synth_bytes(uint64_t seed, uint64_t start, uint64_t n, uint8_t* d_out, int sm_count,
+                                 cudaStream_t st) {
+    if (n == 0) return YAMS_OK;
+    synth_bytes_kernel<<<sm_count * 8, 256, 0, st>>>(seed, start, n, d_out);
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
+// ---- host orchestration ---------------------------------------------------------------------------
+
+yams_status_t resolve_params(const yams_cdc_config* cfg, CdcParams* P, uint64_t table[256]) {
+    YB_ARG(cfg != nullptr, "cfg is null");
+    YB_ARG(cfg->variant == YAMS_CDC_STREAMING || cfg->variant == YAMS_CDC_RABIN, "unknown cdc variant");
+    YB_ARG(cfg->window_size <= (uint64_t)kMaxWindow,
+           "window_size must be <= 48 (the reference ring buffer is a fixed 48-byte array)");
+    memset(P, 0, sizeof(*P));
+    uint64_t poly = cfg->polynomial ? cfg->polynomial : kDefaultPoly;
+    for (int b = 0; b < 256; ++b) table[b] = table_entry(poly, (uint32_t)b);
+    P->mask = cfg->mask;
+    P->window = cfg->window_size ? (uint32_t)cfg->window_size : 1u;  // streaming_chunker.cpp:44-46
+    P->steps = mask_steps(cfg->mask);
+    uint64_t force = cfg->min_chunk > cfg->max_chunk ? cfg->min_chunk : cfg->max_chunk;
+    if (cfg->variant == YAMS_CDC_STREAMING) {
+        P->lo = (cfg->min_chunk > 1 ? cfg->min_chunk : 1) - 1;
+        if (force == 0) force = 1;
+    } else {
+        P->lo = cfg->min_chunk;
+        YB_ARG(force != 0, "RabinChunker with min_chunk == max_chunk == 0 never terminates");
+    }
+    P->force = force;
+    // low-byte prefilter: byte values whose table entry has all of (mask & 0xff) set
+    uint64_t m0 = cfg->mask & 0xffull;
+    uint32_t npass = 0;
+    uint8_t vals[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 256; ++b) {
+        if ((table[b] & m0) == m0) {
+            if (npass < 4) vals[npass] = (uint8_t)b;
+            ++npass;
+        }
+    }
+    if (npass >= 1 && npass <= 4) {
+        P->nfast = npass;
+        memcpy(P->fast, vals, 4);
+    } else {
+        P->nfast = 0;
+    }
+    return YAMS_OK;
+}
+
+}  // namespace yb

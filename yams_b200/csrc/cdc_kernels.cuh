@@ -1,0 +1,53 @@
+// cdc_kernels.cuh -- kernel argument blocks and declarations shared by cdc.cu / sha256.cu / ingest.cu
+#pragma once
+#include "cdc_logic.h"
+#include "common.cuh"
+
+namespace yb {
+
+struct ScanArgs {
+    const uint8_t* data;   // data[0] is stream position base_pos
+    uint64_t base_pos;
+    uint64_t lowest;       // lowest readable stream position
+    uint64_t origin;       // tile origin: <= scan_lo, address of `origin` is 16-byte aligned
+    uint64_t scan_lo;      // first stream position to test
+    uint64_t scan_hi;      // one past the last stream position to test
+    const uint64_t* table; // 256 x u64 (device)
+    CdcParams P;
+};
+
+struct SelectArgs {
+    const uint64_t* cand;
+    uint32_t ncand;
+    uint64_t root_start;   // start of the open chunk
+    uint64_t end_pos;      // one past the last available stream byte
+    int final;             // stream ends at end_pos
+    CdcParams P;
+};
+
+
+__global__ void cdc_count_kernel(ScanArgs A, uint32_t ntiles, uint32_t* tile_counts);
+__global__ void cdc_write_kernel(ScanArgs A, uint32_t ntiles, const uint32_t* tile_counts,
+                                 const uint32_t* tile_offsets, uint64_t* cand);
+__global__ void cdc_next_kernel(SelectArgs S, uint32_t* next, uint32_t* forced);
+__global__ void cdc_exit_kernel(const uint32_t* next, uint32_t nnodes, uint32_t* exit_out);
+__global__ void cdc_walk_kernel(const uint32_t* exit_in, uint32_t nnodes, uint32_t* entry);
+__global__ void cdc_mark_kernel(const uint32_t* next, uint32_t nnodes, const uint32_t* entry, uint8_t* onchain);
+__global__ void cdc_emit_count_kernel(SelectArgs S, const uint32_t* next, const uint32_t* forced,
+                                      const uint8_t* onchain, uint32_t* counts);
+__global__ void cdc_emit_kernel(SelectArgs S, const uint32_t* next, const uint32_t* forced,
+                                const uint8_t* onchain, const uint32_t* offsets, yams_chunk_desc* out,
+                                uint64_t out_base, uint64_t* scalars);
+
+constexpr int kScanThreads = 256;
+constexpr int kScanIters = 4;                                     // 16-byte loads per thread per tile
+constexpr uint32_t kTileBytes = kScanThreads * 16 * kScanIters;   // 16 KiB
+
+yams_status_t resolve_params(const yams_cdc_config* cfg, CdcParams* P, uint64_t table[256]);
+yams_status_t launch_sha256_chunks(const uint8_t* d_data, uint64_t base_pos, yams_chunk_desc* d_descs,
+                                   uint32_t first, uint32_t n, unsigned int* d_counter, int sm_count,
+                                   cudaStream_t st);
+yams_status_t launch_synth_bytes(uint64_t seed, uint64_t start, uint64_t n, uint8_t* d_out, int sm_count,
+                                 cudaStream_t st);
+
+}  // namespace yb

@@ -1,0 +1,560 @@
+// ingest.cu -- host orchestration of the content-ingest path: CDC boundaries + per-chunk SHA-256.
+// Implements the content_ingest_v1 entry points of include/yams_b200.h.
+//
+// Reference call sites this replaces (paths under /root/reference):
+//   StreamingChunker::chunkData       src/chunking/streaming_chunker.cpp:92-137
+//   StreamingChunker::processStream   include/yams/chunking/streaming_chunker.h:78-121
+//   RabinChunker::chunkDataImpl       src/chunking/rabin_chunker.cpp:120-152
+//   ContentStore::store / storeBytes  src/api/content_store_impl.cpp:216-220, 510-545 (callers)
+#include <stdlib.h>
+
+#include <algorithm>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#include "cdc_kernels.cuh"
+
+namespace yb {
+
+constexpr uint32_t kTileBytesHost = kTileBytes;
+constexpr uint64_t kSegmentBytes = 1ull << 30;     // device-resident data is processed 1 GiB at a time
+constexpr uint64_t kFeedSlice = 256ull << 20;      // host feeds are staged 256 MiB at a time
+
+// All device-side working state of one chunking stream.
+struct CdcStream {
+    DeviceCtx* dev = nullptr;
+    cudaStream_t st = nullptr;
+    CdcParams P{};
+    bool no_candidates = false;  // lo >= force: no candidate can ever cut
+    DevBuf table, tile_counts, tile_offsets, cand, next, forced, exit_, entry, onchain, emit_counts,
+        emit_offsets, scan_scratch, descs, scalars;
+    HostBuf h_scalars;           // pinned: [0] ncand/ntotal, [1] new chunk start
+    uint64_t ndescs = 0;         // chunks accumulated in `descs`
+    uint64_t chunk_start = 0;    // stream position where the open chunk starts
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    float ms_scan = 0, ms_select = 0;
+
+    yams_status_t init(const yams_cdc_config* cfg) {
+        yams_status_t rc = ensure_device(&dev);
+        if (rc != YAMS_OK) return rc;
+        uint64_t tbl[256];
+        rc = resolve_params(cfg, &P, tbl);
+        if (rc != YAMS_OK) return rc;
+        no_candidates = P.lo >= P.force;
+        YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (auto& e : ev) YB_CUDA(cudaEventCreate(&e));
+        if ((rc = table.reserve(256 * 8)) != YAMS_OK) return rc;
+        if ((rc = scalars.reserve(64)) != YAMS_OK) return rc;
+        if ((rc = h_scalars.reserve(64)) != YAMS_OK) return rc;
+        YB_CUDA(cudaMemcpyAsync(table.p, tbl, sizeof tbl, cudaMemcpyHostToDevice, st));
+        YB_CUDA(cudaStreamSynchronize(st));
+        return YAMS_OK;
+    }
+    void destroy() {
+        for (DevBuf* b : {&table, &tile_counts, &tile_offsets, &cand, &next, &forced, &exit_, &entry, &onchain,
+                          &emit_counts, &emit_offsets, &scan_scratch, &descs, &scalars})
+            b->release();
+        h_scalars.release();
+        for (auto& e : ev)
+            if (e) cudaEventDestroy(e);
+        if (st) cudaStreamDestroy(st);
+        st = nullptr;
+    }
+
+    // Scan stream positions [scan_lo, scan_hi) (bytes readable from `lowest`), select cuts from the
+    // open chunk at chunk_start, append the completed chunks to descs. `data[0]` is stream position
+    // base_pos.  When final, the trailing partial chunk is emitted too.
+    yams_status_t process(const uint8_t* data, uint64_t base_pos, uint64_t lowest, uint64_t scan_lo,
+                          uint64_t scan_hi, bool final) {
+        yams_status_t rc;
+        uint64_t* d_sc = scalars.as<uint64_t>();
+        volatile uint64_t* h_sc = h_scalars.as<uint64_t>();
+        uint32_t ncand = 0;
+        YB_CUDA(cudaEventRecord(ev[0], st));
+        if (!no_candidates && scan_hi > scan_lo) {
+            // tiles start at the 16-byte-aligned address at or below scan_lo; the positions in
+            // [origin, scan_lo) are masked and never dereferenced (ragged-unit path of scan16)
+            uintptr_t addr_lo = reinterpret_cast<uintptr_t>(data) + (scan_lo - base_pos);
+            uint64_t origin = scan_lo - (uint64_t)(addr_lo & 15);
+            uint64_t span = scan_hi - origin;
+            uint64_t ntiles64 = (span + kTileBytesHost - 1) / kTileBytesHost;
+            YB_ARG(ntiles64 < (1ull << 31), "segment too large");
+            uint32_t ntiles = (uint32_t)ntiles64;
+            if ((rc = tile_counts.reserve((size_t)ntiles * 4)) != YAMS_OK) return rc;
+            if ((rc = tile_offsets.reserve((size_t)ntiles * 4)) != YAMS_OK) return rc;
+            ScanArgs A{data, base_pos, lowest, origin, scan_lo, scan_hi, table.as<uint64_t>(), P};
+            uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)dev->sm_count * 8u);
+            cdc_count_kernel<<<grid, 256, 0, st>>>(A, ntiles, tile_counts.as<uint32_t>());
+            if ((rc = exclusive_scan_u32(tile_counts.as<uint32_t>(), tile_offsets.as<uint32_t>(), ntiles,
+                                         d_sc + 0, scan_scratch, st)) != YAMS_OK)
+                return rc;
+            YB_CUDA(cudaMemcpyAsync((void*)h_sc, d_sc, 8, cudaMemcpyDeviceToHost, st));
+            YB_CUDA(cudaStreamSynchronize(st));
+            uint64_t nc = h_sc[0];
+            YB_ARG(nc < 0xFFFFFFF0ull, "too many boundary candidates in one segment");
+            ncand = (uint32_t)nc;
+            if (ncand) {
+                if ((rc = cand.reserve((size_t)ncand * 8)) != YAMS_OK) return rc;
+                cdc_write_kernel<<<grid, 256, 0, st>>>(A, ntiles, tile_counts.as<uint32_t>(),
+                                                       tile_offsets.as<uint32_t>(), cand.as<uint64_t>());
+            }
+        }
+        YB_CUDA(cudaEventRecord(ev[1], st));
+        // ---- selection ------------------------------------------------------------------------
+        uint32_t nnodes = ncand + 1;
+        uint32_t nblocks = (nnodes + kNodeBlock - 1) / kNodeBlock;
+        if ((rc = next.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+        if ((rc = forced.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+        if ((rc = exit_.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+        if ((rc = entry.reserve((size_t)nblocks * 4)) != YAMS_OK) return rc;
+        if ((rc = onchain.reserve((size_t)nnodes)) != YAMS_OK) return rc;
+        if ((rc = emit_counts.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+        if ((rc = emit_offsets.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+        if (!cand.p && (rc = cand.reserve(8)) != YAMS_OK) return rc;
+        SelectArgs S{cand.as<uint64_t>(), ncand, chunk_start, scan_hi, final ? 1 : 0, P};
+        uint32_t tgrid = (nnodes + 255) / 256;
+        cdc_next_kernel<<<tgrid, 256, 0, st>>>(S, next.as<uint32_t>(), forced.as<uint32_t>());
+        cdc_exit_kernel<<<nblocks, 32, 0, st>>>(next.as<uint32_t>(), nnodes, exit_.as<uint32_t>());
+        YB_CUDA(cudaMemsetAsync(entry.p, 0xFF, (size_t)nblocks * 4, st));
+        cdc_walk_kernel<<<1, 32, 0, st>>>(exit_.as<uint32_t>(), nnodes, entry.as<uint32_t>());
+        cdc_mark_kernel<<<nblocks, 32, 0, st>>>(next.as<uint32_t>(), nnodes, entry.as<uint32_t>(),
+                                                onchain.as<uint8_t>());
+        cdc_emit_count_kernel<<<tgrid, 256, 0, st>>>(S, next.as<uint32_t>(), forced.as<uint32_t>(),
+                                                     onchain.as<uint8_t>(), emit_counts.as<uint32_t>());
+        if ((rc = exclusive_scan_u32(emit_counts.as<uint32_t>(), emit_offsets.as<uint32_t>(), nnodes, d_sc + 0,
+                                     scan_scratch, st)) != YAMS_OK)
+            return rc;
+        YB_CUDA(cudaMemcpyAsync((void*)h_sc, d_sc, 8, cudaMemcpyDeviceToHost, st));
+        YB_CUDA(cudaStreamSynchronize(st));
+        uint64_t nnew = h_sc[0];
+        if ((rc = descs.reserve((size_t)(ndescs + nnew + 1) * sizeof(yams_chunk_desc), true, st)) != YAMS_OK)
+            return rc;
+        cdc_emit_kernel<<<tgrid, 256, 0, st>>>(S, next.as<uint32_t>(), forced.as<uint32_t>(),
+                                               onchain.as<uint8_t>(), emit_offsets.as<uint32_t>(),
+                                               descs.as<yams_chunk_desc>(), ndescs, d_sc + 1);
+        YB_CUDA(cudaGetLastError());
+        YB_CUDA(cudaMemcpyAsync((void*)(h_sc + 1), d_sc + 1, 8, cudaMemcpyDeviceToHost, st));
+        YB_CUDA(cudaEventRecord(ev[2], st));
+        YB_CUDA(cudaStreamSynchronize(st));
+        chunk_start = h_sc[1];
+        ndescs += nnew;
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, ev[0], ev[1]);
+        cudaEventElapsedTime(&b, ev[1], ev[2]);
+        ms_scan += a;
+        ms_select += b;
+        return YAMS_OK;
+    }
+};
+
+static thread_local float g_last_ms[8] = {0};
+
+static yams_status_t copy_out(CdcStream& cs, uint64_t first, uint64_t n, yams_chunk_desc** out, size_t* out_n) {
+    *out = nullptr;
+    *out_n = 0;
+    if (n == 0) return YAMS_OK;
+    yams_chunk_desc* h = static_cast<yams_chunk_desc*>(malloc((size_t)n * sizeof(yams_chunk_desc)));
+    if (!h) {
+        set_last_error("out of host memory for %llu chunk descriptors", (unsigned long long)n);
+        return YAMS_ERR_INTERNAL;
+    }
+    cudaError_t e = cudaMemcpyAsync(h, cs.descs.as<yams_chunk_desc>() + first, (size_t)n * sizeof(yams_chunk_desc),
+                                    cudaMemcpyDeviceToHost, cs.st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(cs.st);
+    if (e != cudaSuccess) {
+        free(h);
+        set_last_error("D2H of chunk descriptors failed: %s", cudaGetErrorString(e));
+        return YAMS_ERR_INTERNAL;
+    }
+    *out = h;
+    *out_n = (size_t)n;
+    return YAMS_OK;
+}
+
+// One-shot over device-resident data.
+static yams_status_t run_device(const uint8_t* d_data, size_t len, const yams_cdc_config* cfg, bool hash,
+                                yams_chunk_desc** out, size_t* out_n) {
+    CdcStream cs;
+    yams_status_t rc = cs.init(cfg);
+    if (rc == YAMS_OK) {
+        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
+        cudaEventRecord(e0, cs.st);
+        for (uint64_t lo = 0; lo < len && rc == YAMS_OK; lo += kSegmentBytes) {
+            uint64_t hi = std::min<uint64_t>(len, lo + kSegmentBytes);
+            rc = cs.process(d_data, 0, 0, lo, hi, hi == len);
+        }
+        cudaEventRecord(e1, cs.st);
+        if (rc == YAMS_OK && hash && cs.ndescs) {
+            if (cs.ndescs >= 0xFFFFFFFFull) {
+                set_last_error("too many chunks");
+                rc = YAMS_ERR_INVALID_ARG;
+            } else {
+                rc = launch_sha256_chunks(d_data, 0, cs.descs.as<yams_chunk_desc>(), 0, (uint32_t)cs.ndescs,
+                                          reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4),
+                                          cs.dev->sm_count, cs.st);
+            }
+        }
+        cudaEventRecord(e2, cs.st);
+        if (rc == YAMS_OK) rc = copy_out(cs, 0, cs.ndescs, out, out_n);
+        float t_sha = 0, t_all = 0;
+        cudaEventElapsedTime(&t_sha, e1, e2);
+        cudaEventElapsedTime(&t_all, e0, e2);
+        g_last_ms[0] = cs.ms_scan; g_last_ms[1] = cs.ms_select; g_last_ms[2] = t_sha; g_last_ms[3] = t_all;
+        g_last_ms[4] = 0;
+        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
+    }
+    cs.destroy();
+    return rc;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+// Streaming session: host bytes are staged [carry | slice] into one of two device buffers; the H2D copy
+// of slice i+1 overlaps the kernels of slice i (when the host memory is pinned).
+struct yams_b200_ingest {
+    CdcStream cs;
+    cudaStream_t copy_st = nullptr;
+    DevBuf stage[2];
+    cudaEvent_t copied[2] = {nullptr, nullptr};  // H2D into stage[b] complete
+    cudaEvent_t freed[2] = {nullptr, nullptr};   // everything that reads stage[b] has been enqueued+ordered
+    uint64_t head = 0;            // bytes reserved in front of a slice for the carry
+    uint64_t stream_pos = 0;      // bytes fed so far
+    uint64_t keep_from = 0;       // lowest stream position still resident on the device
+    const uint8_t* res_ptr = nullptr;  // device address of stream position keep_from
+    int cur = -1;                 // stage buffer holding the resident bytes (-1: none yet)
+    bool hash = true;
+    bool finished = false;
+    float ms_sha = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+static yams_status_t session_open(const yams_cdc_config* cfg, bool hash, yams_b200_ingest** out) {
+    yams_b200_ingest* s = new (std::nothrow) yams_b200_ingest();
+    if (!s) return YAMS_ERR_INTERNAL;
+    s->hash = hash;
+    yams_status_t rc = s->cs.init(cfg);
+    if (rc != YAMS_OK) {
+        s->cs.destroy();
+        delete s;
+        return rc;
+    }
+    // the open chunk is always shorter than `force`, and a position needs <= kHistory bytes behind it
+    uint64_t need = std::max<uint64_t>(s->cs.P.force, (uint64_t)kHistory) + 16;
+    s->head = (need + 255) & ~255ull;
+    cudaStreamCreateWithFlags(&s->copy_st, cudaStreamNonBlocking);
+    for (int b = 0; b < 2; ++b) {
+        cudaEventCreateWithFlags(&s->copied[b], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&s->freed[b], cudaEventDisableTiming);
+    }
+    cudaEventCreate(&s->t0);
+    cudaEventCreate(&s->t1);
+    *out = s;
+    return YAMS_OK;
+}
+
+static void session_close(yams_b200_ingest* s) {
+    if (!s) return;
+    if (s->cs.st) cudaStreamSynchronize(s->cs.st);
+    if (s->copy_st) cudaStreamSynchronize(s->copy_st);
+    for (int b = 0; b < 2; ++b) {
+        s->stage[b].release();
+        if (s->copied[b]) cudaEventDestroy(s->copied[b]);
+        if (s->freed[b]) cudaEventDestroy(s->freed[b]);
+    }
+    if (s->t0) cudaEventDestroy(s->t0);
+    if (s->t1) cudaEventDestroy(s->t1);
+    if (s->copy_st) cudaStreamDestroy(s->copy_st);
+    s->cs.destroy();
+    delete s;
+}
+
+static yams_status_t session_sha(yams_b200_ingest* s, const uint8_t* data, uint64_t base_pos, uint64_t first) {
+    CdcStream& cs = s->cs;
+    if (!s->hash || cs.ndescs <= first) return YAMS_OK;
+    YB_ARG(cs.ndescs - first < 0xFFFFFFFFull, "too many chunks in one slice");
+    YB_CUDA(cudaEventRecord(s->t0, cs.st));
+    yams_status_t rc = launch_sha256_chunks(data, base_pos, cs.descs.as<yams_chunk_desc>(), (uint32_t)first,
+                                            (uint32_t)(cs.ndescs - first),
+                                            reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4),
+                                            cs.dev->sm_count, cs.st);
+    if (rc != YAMS_OK) return rc;
+    YB_CUDA(cudaEventRecord(s->t1, cs.st));
+    YB_CUDA(cudaEventSynchronize(s->t1));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, s->t0, s->t1);
+    s->ms_sha += ms;
+    return YAMS_OK;
+}
+
+// Feed `len` host bytes; when `final`, also close the stream.  Newly completed chunks are appended to
+// cs.descs (digests included when hashing is on).
+static yams_status_t session_feed(yams_b200_ingest* s, const uint8_t* data, size_t len, bool final) {
+    CdcStream& cs = s->cs;
+    yams_status_t rc;
+    YB_ARG(!s->finished, "ingest session already finished");
+    const size_t nslices = (size_t)((len + kFeedSlice - 1) / kFeedSlice);
+    if (nslices == 0) {
+        if (final) {
+            uint64_t first = cs.ndescs;
+            rc = cs.process(s->res_ptr, s->keep_from, s->keep_from, s->stream_pos, s->stream_pos, true);
+            if (rc != YAMS_OK) return rc;
+            if ((rc = session_sha(s, s->res_ptr, s->keep_from, first)) != YAMS_OK) return rc;
+            s->finished = true;
+        }
+        return YAMS_OK;
+    }
+    auto slice_len = [&](size_t i) { return (size_t)std::min<uint64_t>(kFeedSlice, (uint64_t)len - i * kFeedSlice); };
+    auto issue_copy = [&](size_t i, int b) -> yams_status_t {
+        size_t sl = slice_len(i);
+        yams_status_t r = s->stage[b].reserve((size_t)s->head + sl + 64);
+        if (r != YAMS_OK) return r;
+        YB_CUDA(cudaStreamWaitEvent(s->copy_st, s->freed[b], 0));
+        YB_CUDA(cudaMemcpyAsync(s->stage[b].as<uint8_t>() + s->head, data + i * kFeedSlice, sl,
+                                cudaMemcpyHostToDevice, s->copy_st));
+        YB_CUDA(cudaEventRecord(s->copied[b], s->copy_st));
+        return YAMS_OK;
+    };
+    int b = s->cur < 0 ? 0 : (s->cur ^ 1);
+    if ((rc = issue_copy(0, b)) != YAMS_OK) return rc;
+    for (size_t i = 0; i < nslices; ++i) {
+        const size_t sl = slice_len(i);
+        const uint64_t carry = s->stream_pos - s->keep_from;
+        uint8_t* dst0 = s->stage[b].as<uint8_t>() + s->head;  // device address of stream position stream_pos
+        if (carry) {
+            YB_CUDA(cudaMemcpyAsync(dst0 - carry, s->res_ptr, (size_t)carry, cudaMemcpyDeviceToDevice, cs.st));
+        }
+        if (s->cur >= 0) YB_CUDA(cudaEventRecord(s->freed[s->cur], cs.st));
+        if (i + 1 < nslices) {
+            if ((rc = issue_copy(i + 1, b ^ 1)) != YAMS_OK) return rc;
+        }
+        YB_CUDA(cudaStreamWaitEvent(cs.st, s->copied[b], 0));
+        const uint64_t new_pos = s->stream_pos + sl;
+        const uint64_t first = cs.ndescs;
+        const uint8_t* view = dst0 - carry;  // stream position keep_from
+        const bool last = final && (i + 1 == nslices);
+        rc = cs.process(view, s->keep_from, s->keep_from, s->stream_pos, new_pos, last);
+        if (rc != YAMS_OK) return rc;
+        if ((rc = session_sha(s, view, s->keep_from, first)) != YAMS_OK) return rc;
+        s->stream_pos = new_pos;
+        uint64_t nk = std::min<uint64_t>(cs.chunk_start, new_pos > (uint64_t)kHistory ? new_pos - kHistory : 0);
+        if (nk < s->keep_from) nk = s->keep_from;
+        s->res_ptr = view + (nk - s->keep_from);
+        s->keep_from = nk;
+        s->cur = b;
+        b ^= 1;
+    }
+    if (final) s->finished = true;
+    return YAMS_OK;
+}
+
+static yams_status_t session_take(yams_b200_ingest* s, yams_chunk_desc** out, size_t* out_n) {
+    yams_status_t rc = copy_out(s->cs, 0, s->cs.ndescs, out, out_n);
+    if (rc == YAMS_OK) s->cs.ndescs = 0;  // descriptors handed over; reuse the device table
+    return rc;
+}
+
+static yams_status_t run_host(const uint8_t* data, size_t len, const yams_cdc_config* cfg, bool hash,
+                              yams_chunk_desc** out, size_t* out_n) {
+    yams_b200_ingest* s = nullptr;
+    yams_status_t rc = session_open(cfg, hash, &s);
+    if (rc != YAMS_OK) return rc;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, s->cs.st);
+    rc = session_feed(s, data, len, true);
+    if (rc == YAMS_OK) rc = session_take(s, out, out_n);
+    cudaEventRecord(e1, s->cs.st);
+    cudaEventSynchronize(e1);
+    float t = 0;
+    cudaEventElapsedTime(&t, e0, e1);
+    g_last_ms[0] = s->cs.ms_scan; g_last_ms[1] = s->cs.ms_select; g_last_ms[2] = s->ms_sha; g_last_ms[3] = t;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    session_close(s);
+    return rc;
+}
+
+extern "C" {
+
+void yams_b200_cdc_default_config(yams_cdc_config* cfg) {
+    // /root/reference/include/yams/chunking/chunker.h:44-51, include/yams/core/types.h:280-285;
+    // `yams add` uses StreamingChunker: src/api/content_store_builder.cpp:152-165
+    if (!cfg) return;
+    cfg->window_size = 48;
+    cfg->min_chunk = 16 * 1024;
+    cfg->max_chunk = 1024 * 1024;
+    cfg->polynomial = kDefaultPoly;
+    cfg->mask = 0x1FFF;
+    cfg->variant = YAMS_CDC_STREAMING;
+    cfg->reserved = 0;
+}
+
+yams_status_t yams_b200_chunk_and_hash(void* self, const uint8_t* data, size_t len, const yams_cdc_config* cfg,
+                                       yams_chunk_desc** out, size_t* out_n) {
+    (void)self;
+    YB_ARG(out && out_n, "out / out_n is null");
+    *out = nullptr;
+    *out_n = 0;
+    YB_ARG(data || len == 0, "data is null");
+    YB_ARG(cfg, "cfg is null");
+    return run_host(data, len, cfg, true, out, out_n);
+}
+
+yams_status_t yams_b200_chunk_boundaries(void* self, const uint8_t* data, size_t len, const yams_cdc_config* cfg,
+                                         yams_chunk_desc** out, size_t* out_n) {
+    (void)self;
+    YB_ARG(out && out_n, "out / out_n is null");
+    *out = nullptr;
+    *out_n = 0;
+    YB_ARG(data || len == 0, "data is null");
+    YB_ARG(cfg, "cfg is null");
+    yams_status_t rc = run_host(data, len, cfg, false, out, out_n);
+    if (rc == YAMS_OK)
+        for (size_t i = 0; i < *out_n; ++i) memset((*out)[i].digest, 0, 32);
+    return rc;
+}
+
+yams_status_t yams_b200_chunk_and_hash_device(void* self, const uint8_t* d_data, size_t len,
+                                              const yams_cdc_config* cfg, yams_chunk_desc** out, size_t* out_n) {
+    (void)self;
+    YB_ARG(out && out_n, "out / out_n is null");
+    *out = nullptr;
+    *out_n = 0;
+    YB_ARG(d_data || len == 0, "d_data is null");
+    YB_ARG(cfg, "cfg is null");
+    return run_device(d_data, len, cfg, true, out, out_n);
+}
+
+void yams_b200_free_chunks(void* self, yams_chunk_desc* chunks, size_t n) {
+    (void)self;
+    (void)n;
+    free(chunks);
+}
+
+yams_status_t yams_b200_ingest_open(void* self, const yams_cdc_config* cfg, yams_b200_ingest** out) {
+    (void)self;
+    YB_ARG(out, "out is null");
+    *out = nullptr;
+    YB_ARG(cfg, "cfg is null");
+    return session_open(cfg, true, out);
+}
+
+yams_status_t yams_b200_ingest_feed(yams_b200_ingest* s, const uint8_t* data, size_t len, yams_chunk_desc** out,
+                                    size_t* out_n) {
+    YB_ARG(s && out && out_n, "null argument");
+    *out = nullptr;
+    *out_n = 0;
+    YB_ARG(data || len == 0, "data is null");
+    yams_status_t rc = session_feed(s, data, len, false);
+    if (rc != YAMS_OK) return rc;
+    return session_take(s, out, out_n);
+}
+
+yams_status_t yams_b200_ingest_finish(yams_b200_ingest* s, yams_chunk_desc** out, size_t* out_n) {
+    YB_ARG(s && out && out_n, "null argument");
+    *out = nullptr;
+    *out_n = 0;
+    yams_status_t rc = session_feed(s, nullptr, 0, true);
+    if (rc != YAMS_OK) return rc;
+    return session_take(s, out, out_n);
+}
+
+void yams_b200_ingest_close(yams_b200_ingest* s) { session_close(s); }
+
+static yams_status_t sha_batch_impl(const uint8_t* d_base, size_t base_len, const uint64_t* offsets,
+                                    const uint64_t* sizes, size_t n, uint8_t* digests, DeviceCtx* dev,
+                                    cudaStream_t st) {
+    YB_ARG(n < 0xFFFFFFFFull, "too many spans");
+    std::vector<yams_chunk_desc> h(n);
+    for (size_t i = 0; i < n; ++i) {
+        YB_ARG(offsets[i] <= base_len && sizes[i] <= base_len - offsets[i], "span outside the base buffer");
+        h[i].offset = offsets[i];
+        h[i].size = sizes[i];
+    }
+    DevBuf d_descs, d_cnt;
+    yams_status_t rc = d_descs.reserve(n * sizeof(yams_chunk_desc));
+    if (rc == YAMS_OK) rc = d_cnt.reserve(16);
+    if (rc == YAMS_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_descs.p, h.data(), n * sizeof(yams_chunk_desc), cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { set_last_error("H2D failed: %s", cudaGetErrorString(e)); rc = YAMS_ERR_INTERNAL; }
+    }
+    if (rc == YAMS_OK)
+        rc = launch_sha256_chunks(d_base, 0, d_descs.as<yams_chunk_desc>(), 0, (uint32_t)n,
+                                  d_cnt.as<unsigned int>(), dev->sm_count, st);
+    if (rc == YAMS_OK) {
+        cudaError_t e = cudaMemcpyAsync(h.data(), d_descs.p, n * sizeof(yams_chunk_desc), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { set_last_error("sha256 batch failed: %s", cudaGetErrorString(e)); rc = YAMS_ERR_INTERNAL; }
+    }
+    if (rc == YAMS_OK)
+        for (size_t i = 0; i < n; ++i) memcpy(digests + 32 * i, h[i].digest, 32);
+    d_descs.release();
+    d_cnt.release();
+    return rc;
+}
+
+yams_status_t yams_b200_sha256_batch_device(void* self, const uint8_t* d_base, size_t base_len,
+                                            const uint64_t* offsets, const uint64_t* sizes, size_t n,
+                                            uint8_t* digests) {
+    (void)self;
+    if (n == 0) return YAMS_OK;
+    YB_ARG(offsets && sizes && digests, "null argument");
+    YB_ARG(d_base || base_len == 0, "d_base is null");
+    DeviceCtx* dev = nullptr;
+    yams_status_t rc = ensure_device(&dev);
+    if (rc != YAMS_OK) return rc;
+    cudaStream_t st;
+    YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    rc = sha_batch_impl(d_base, base_len, offsets, sizes, n, digests, dev, st);
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+yams_status_t yams_b200_sha256_batch(void* self, const uint8_t* base, size_t base_len, const uint64_t* offsets,
+                                     const uint64_t* sizes, size_t n, uint8_t* digests) {
+    (void)self;
+    if (n == 0) return YAMS_OK;
+    YB_ARG(offsets && sizes && digests, "null argument");
+    YB_ARG(base || base_len == 0, "base is null");
+    DeviceCtx* dev = nullptr;
+    yams_status_t rc = ensure_device(&dev);
+    if (rc != YAMS_OK) return rc;
+    cudaStream_t st;
+    YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    DevBuf d_base;
+    rc = d_base.reserve(base_len + 64);
+    if (rc == YAMS_OK && base_len) {
+        cudaError_t e = cudaMemcpyAsync(d_base.p, base, base_len, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { set_last_error("H2D failed: %s", cudaGetErrorString(e)); rc = YAMS_ERR_INTERNAL; }
+    }
+    if (rc == YAMS_OK) rc = sha_batch_impl(d_base.as<uint8_t>(), base_len, offsets, sizes, n, digests, dev, st);
+    d_base.release();
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+yams_status_t yams_b200_ingest_last_timings(void* self, float out_ms[8]) {
+    (void)self;
+    YB_ARG(out_ms, "out_ms is null");
+    for (int i = 0; i < 8; ++i) out_ms[i] = g_last_ms[i];
+    return YAMS_OK;
+}
+
+// bench / test utility: SURVEY.md §8d byte stream generated straight into HBM
+yams_status_t yams_b200_synth_bytes_device(uint64_t seed, uint64_t start, uint64_t n, uint8_t* d_out) {
+    DeviceCtx* dev = nullptr;
+    yams_status_t rc = ensure_device(&dev);
+    if (rc != YAMS_OK) return rc;
+    YB_ARG(d_out || n == 0, "d_out is null");
+    rc = launch_synth_bytes(seed, start, n, d_out, dev->sm_count, 0);
+    if (rc != YAMS_OK) return rc;
+    YB_CUDA(cudaStreamSynchronize(0));
+    return YAMS_OK;
+}
+
+}  // extern "C"

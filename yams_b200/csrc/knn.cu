@@ -1,0 +1,1261 @@
+// knn.cu -- exact brute-force vector scan: CUDA-core stage-1 engine, top-K' selection, fp64
+// rescoring, final ordering, L2 / vec0 surface, corpus mirror and the vector_scan_v1 entry points.
+//
+// Reference semantics matched (paths under /root/reference):
+//   bruteForceSearchUnlocked fast path   src/vector/sqlite_vec_backend.cpp:4203-4331
+//   isFinite / isZeroNorm query checks   src/vector/sqlite_vec_backend.cpp:204-235, 4127-4130
+//   vec0_run_exact_query                 third_party/sqlite-vec-cpp/.../sqlite/vec0_module.hpp:376-430
+//   float16_t::from_float (truncating)   third_party/sqlite-vec-cpp/.../utils/float16.hpp:20-40
+//
+// Pipeline:
+//   stage 1  approximate fp32/fp16 scores of every row against every query (GEMM-shaped; this file
+//            holds the CUDA-core engine, knn_umma.cu the tcgen05 engine) with a fused per-query
+//            threshold filter -> short candidate lists; thresholds come from a strided row sample;
+//   select   exact top-K' (K' = k + slack) of each candidate list (radix select + bitonic sort);
+//   stage 2  the K' survivors are re-scored exactly like the reference (sequential double
+//            accumulation, skip rules, float cast) -> scores are bit-identical to the CPU path;
+//   final    order by (similarity desc, rowid asc), apply the threshold, keep k, flag ties at k.
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "knn.cuh"
+
+namespace yb {
+
+// ---------------------------------------------------------------------------------------------------
+// element helpers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float load_elem(const void* rows, int dtype, uint64_t idx) {
+    if (dtype == YAMS_B200_F16) return __half2float(reinterpret_cast<const __half*>(rows)[idx]);
+    return reinterpret_cast<const float*>(rows)[idx];
+}
+
+// reference truncating fp32 -> fp16 (utils/float16.hpp:20-40), restated on integer bits
+__host__ __device__ __forceinline__ uint16_t f16_from_float_trunc(float f) {
+    uint32_t x;
+#if defined(__CUDA_ARCH__)
+    x = __float_as_uint(f);
+#else
+    memcpy(&x, &f, 4);
+#endif
+    uint32_t sign = (x >> 16) & 0x8000u;
+    int32_t e = (int32_t)((x >> 23) & 0xFFu) - 127 + 15;
+    uint32_t m = x & 0x7FFFFFu;
+    if (e <= 0) {
+        if (e < -10) return (uint16_t)sign;
+        m = (m | 0x800000u) >> (1 - e);
+        return (uint16_t)(sign | (m >> 13));
+    }
+    if (e >= 31) return (uint16_t)(sign | 0x7C00u);
+    return (uint16_t)(sign | ((uint32_t)e << 10) | (m >> 13));
+}
+
+__global__ void convert_f32_to_f16_trunc_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = f16_from_float_trunc(in[i]);
+}
+
+// SURVEY.md §8d generator: x = (splitmix64(seed ^ (row*d + c)) >> 40) * 2^-23 - 1
+__device__ __forceinline__ float synth_value(uint64_t seed, uint64_t row, uint32_t d, uint32_t c) {
+    uint64_t u = splitmix64(seed ^ (row * (uint64_t)d + (uint64_t)c));
+    return (float)(u >> 40) * 1.1920928955078125e-07f - 1.0f;
+}
+
+// one thread per row: sequential double sum of squares (bit-identical to oracle yo_gen_rows_f32)
+__global__ void synth_rownorm_kernel(uint64_t seed, uint64_t first_row, uint64_t n, uint32_t d, float* __restrict__ inv) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    double ss = 0.0;
+    for (uint32_t c = 0; c < d; ++c) {
+        float x = synth_value(seed, first_row + r, d, c);
+        ss += (double)x * (double)x;
+    }
+    inv[r] = ss > 0.0 ? (float)(1.0 / sqrt(ss)) : 0.0f;
+}
+
+__global__ void synth_fill_kernel(uint64_t seed, uint64_t first_row, uint64_t n, uint32_t d, const float* __restrict__ inv,
+                                  void* __restrict__ out, int dtype) {
+    uint64_t total = n * (uint64_t)d;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t r = i / d;
+        uint32_t c = (uint32_t)(i - r * d);
+        float v = synth_value(seed, first_row + r, d, c) * inv[r];
+        if (dtype == YAMS_B200_F16) reinterpret_cast<uint16_t*>(out)[i] = f16_from_float_trunc(v);
+        else reinterpret_cast<float*>(out)[i] = v;
+    }
+}
+
+// per-row validity + 1/|row| exactly as the reference evaluates it (sqlite_vec_backend.cpp:4253-4269):
+// sequential double accumulation; rows with a non-finite element or |row|^2 <= 1e-12 get 0
+__global__ void row_stats_kernel(const void* __restrict__ rows, int dtype, uint32_t d, uint64_t first, uint64_t n,
+                                 float* __restrict__ inv_norm) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    uint64_t base = (first + r) * (uint64_t)d;
+    double ss = 0.0;
+    bool finite = true;
+    for (uint32_t c = 0; c < d; ++c) {
+        float v = load_elem(rows, dtype, base + c);
+        if (!isfinite(v)) { finite = false; break; }
+        ss += (double)v * (double)v;
+    }
+    inv_norm[first + r] = (finite && ss > 1e-12) ? (float)(1.0 / sqrt(ss)) : 0.0f;
+}
+
+// queries: flags[q] = 1 if non-finite or |q|^2 < 1e-10 (sqlite_vec_backend.cpp:204-235,4127);
+// qnorm[q] = sqrt(sum (double)q^2) (:4204-4209), qinv[q] = 1/qnorm as float
+__global__ void query_prep_kernel(const float* __restrict__ q, uint32_t nq, uint32_t d, double* __restrict__ qnorm,
+                                  float* __restrict__ qinv, uint32_t* __restrict__ flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    double ss = 0.0;
+    bool finite = true;
+    for (uint32_t c = 0; c < d; ++c) {
+        float v = q[(uint64_t)i * d + c];
+        if (!isfinite(v)) finite = false;
+        ss += (double)v * (double)v;
+    }
+    bool bad = !finite || ss < 1e-10;
+    flags[i] = bad ? 1u : 0u;
+    double nrm = sqrt(ss);
+    qnorm[i] = nrm;
+    qinv[i] = bad ? 0.0f : (float)(1.0 / nrm);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 1, CUDA-core engine: tiled fp32 GEMM [rows x dim] x [dim x queries] with fused epilogue
+// ---------------------------------------------------------------------------------------------------
+constexpr int CC_BM = 128, CC_BN = 64, CC_BK = 32, CC_THREADS = 256;
+constexpr int CC_AS = CC_BM + 1;  // padded k-major A tile: conflict-free transposed stores
+
+template <bool FILTER>
+__global__ void __launch_bounds__(CC_THREADS, 2) stage1_cc_kernel(Stage1Args a, uint32_t nqt) {
+    __shared__ float As[CC_BK][CC_AS];
+    __shared__ __align__(16) float Bs[CC_BK][CC_BN];
+    const uint32_t qt = blockIdx.x % nqt;
+    const uint64_t rt = blockIdx.x / nqt;
+    const uint64_t row0 = rt * CC_BM;   // tile-local row index base (within this launch)
+    const uint32_t q0 = qt * CC_BN;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    const bool vec_ok = a.dtype == YAMS_B200_F16 ? (a.dim % 8 == 0) : (a.dim % 4 == 0);
+    for (uint32_t k0 = 0; k0 < a.dim; k0 += CC_BK) {
+        // ---- A tile: CC_BM rows x CC_BK k, transposed into As[k][m] ----
+        if (a.dtype == YAMS_B200_F16) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                int idx = tid + CC_THREADS * j;  // 512 segments of 8 halves
+                int m = idx >> 2, seg = idx & 3;
+                uint64_t li = row0 + m;
+                uint32_t kk = k0 + seg * 8;
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = 0.f;
+                if (li < a.nrows) {
+                    uint64_t grow = a.row_start + li * a.row_stride;
+                    const __half* src = reinterpret_cast<const __half*>(a.rows) + grow * a.dim + kk;
+                    if (vec_ok && kk + 8 <= a.dim) {
+                        uint4 raw = *reinterpret_cast<const uint4*>(src);
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            float2 f = __half22float2(h2[e]);
+                            v[2 * e] = f.x;
+                            v[2 * e + 1] = f.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e)
+                            if (kk + e < a.dim) v[e] = __half2float(src[e]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 8; ++e) As[seg * 8 + e][m] = v[e];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                int idx = tid + CC_THREADS * j;  // 1024 segments of 4 floats
+                int m = idx >> 3, seg = idx & 7;
+                uint64_t li = row0 + m;
+                uint32_t kk = k0 + seg * 4;
+                float v[4] = {0.f, 0.f, 0.f, 0.f};
+                if (li < a.nrows) {
+                    uint64_t grow = a.row_start + li * a.row_stride;
+                    const float* src = reinterpret_cast<const float*>(a.rows) + grow * a.dim + kk;
+                    if (vec_ok && kk + 4 <= a.dim) {
+                        float4 f = *reinterpret_cast<const float4*>(src);
+                        v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 4; ++e)
+                            if (kk + e < a.dim) v[e] = src[e];
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) As[seg * 4 + e][m] = v[e];
+            }
+        }
+        // ---- B tile: CC_BK k x CC_BN queries (queries are row-major [q][dim]) ----
+#pragma unroll
+        for (int j = 0; j < (CC_BK * CC_BN) / CC_THREADS; ++j) {
+            int idx = tid + CC_THREADS * j;
+            int kk = idx & (CC_BK - 1), qn = idx / CC_BK;
+            uint32_t q = q0 + qn, k = k0 + kk;
+            Bs[kk][qn] = (q < a.nq && k < a.dim) ? a.q32[(uint64_t)q * a.dim + k] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CC_BK; ++kk) {
+            float av[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) av[i] = As[kk][ty * 8 + i];
+            float4 b4 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+            float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    // ---- epilogue ----
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        uint64_t li = row0 + ty * 8 + i;
+        if (li >= a.nrows) continue;
+        uint64_t grow = a.row_start + li * a.row_stride;
+        float inr = a.inv_norm[grow];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t q = q0 + tx * 4 + j;
+            if (q >= a.nq) continue;
+            float s = inr > 0.f ? acc[i][j] * inr * a.qinv[q] : -INFINITY;
+            if (FILTER) {
+                bool pass = s > a.tau[q];
+                if (pass && a.mask) pass = (a.mask[(uint64_t)q * a.mask_ld + (grow >> 5)] >> (grow & 31)) & 1u;
+                if (pass) {
+                    uint32_t pos = atomicAdd(&a.counts[q], 1u);
+                    if (pos < a.cap) {
+                        Cand c;
+                        c.score = s;
+                        c.row = (uint32_t)grow;
+                        a.cands[(uint64_t)q * a.cap + pos] = c;
+                    }
+                }
+            } else {
+                a.out_scores[(uint64_t)q * a.ld + li] = s;
+            }
+        }
+    }
+}
+
+yams_status_t stage1_cuda_core(const Stage1Args& a, bool filter, cudaStream_t st) {
+    if (a.nrows == 0 || a.nq == 0) return YAMS_OK;
+    uint32_t nqt = (a.nq + CC_BN - 1) / CC_BN;
+    uint64_t nrt = (a.nrows + CC_BM - 1) / CC_BM;
+    uint64_t grid = nrt * nqt;
+    YB_ARG(grid < (1ull << 31), "scan too large for one launch");
+    if (filter) stage1_cc_kernel<true><<<(unsigned)grid, CC_THREADS, 0, st>>>(a, nqt);
+    else stage1_cc_kernel<false><<<(unsigned)grid, CC_THREADS, 0, st>>>(a, nqt);
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// top-K selection (one CTA per query): radix select on monotone keys, gather, bitonic sort
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t fkey(float f) {
+    if (f != f) return 0u;  // NaN ranks last
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7FFFFFFFu) : ~k;
+    return __uint_as_float(b);
+}
+
+constexpr int SEL_THREADS = 256;
+constexpr int SEL_MAXK = 1024;
+
+struct SelectIn {
+    const float* dense;     // mode dense: scores[q * ld + i], row = row_start + i * row_stride
+    uint64_t ld;
+    uint64_t row_start, row_stride;
+    uint64_t dense_len;
+    const Cand* cands;      // mode list: cands[q * cap + i], length min(counts[q], cap)
+    const uint32_t* counts;
+    uint32_t cap;
+    const uint32_t* qmap;   // nullable: CTA b handles query qmap[b] for the list/out side
+};
+
+__device__ __forceinline__ uint64_t sel_key(const SelectIn& in, uint32_t qsrc, uint64_t i) {
+    float s;
+    uint32_t row;
+    if (in.dense) {
+        s = in.dense[(uint64_t)qsrc * in.ld + i];
+        row = (uint32_t)(in.row_start + i * in.row_stride);
+    } else {
+        Cand c = in.cands[(uint64_t)qsrc * in.cap + i];
+        s = c.score;
+        row = c.row;
+    }
+    return ((uint64_t)fkey(s) << 32) | (uint64_t)(0xFFFFFFFFu - row);
+}
+
+// tau_only: writes the K-th largest score to out_tau[q] (-inf when fewer than K items)
+// else    : writes the top-K (sorted desc; ties -> smaller row first) to out_sel[q*K ..], count to out_n[q]
+__global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, uint32_t K, int tau_only, float* __restrict__ out_tau,
+                                                                  Cand* __restrict__ out_sel, uint32_t* __restrict__ out_n) {
+    __shared__ uint32_t hist[256];
+    __shared__ uint64_t s_prefix;
+    __shared__ uint32_t s_want;
+    __shared__ uint32_t s_cnt;
+    __shared__ uint64_t buf[SEL_MAXK];
+    const uint32_t b = blockIdx.x;
+    const uint32_t qdst = in.qmap ? in.qmap[b] : b;
+    const uint32_t qsrc = in.dense ? b : qdst;
+    uint64_t L = in.dense ? in.dense_len : (uint64_t)min(in.counts[qsrc], in.cap);
+    // radix select of the K-th largest key among L > K items; result in s_prefix
+    auto radix_select = [&](int npass) {
+        if (threadIdx.x == 0) { s_prefix = 0; s_want = K; }
+        __syncthreads();
+        for (int p = 0; p < npass; ++p) {
+            const int shift = 56 - 8 * p;
+            for (int i = threadIdx.x; i < 256; i += SEL_THREADS) hist[i] = 0;
+            __syncthreads();
+            const uint64_t prefix = s_prefix;
+            for (uint64_t i = threadIdx.x; i < L; i += SEL_THREADS) {
+                uint64_t key = sel_key(in, qsrc, i);
+                if (p == 0 || (key >> (shift + 8)) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t want = s_want, cum = 0;
+                int bsel = 0;
+                for (int bk = 255; bk >= 0; --bk) {
+                    uint32_t h = hist[bk];
+                    if (cum + h >= want) { bsel = bk; break; }
+                    cum += h;
+                }
+                s_want = want - cum;
+                s_prefix = (prefix << 8) | (uint64_t)bsel;
+            }
+            __syncthreads();
+        }
+    };
+    if (tau_only) {
+        if (L < K || K == 0) {
+            if (threadIdx.x == 0) out_tau[qdst] = -INFINITY;
+        } else if (L == K) {
+            if (threadIdx.x == 0) s_want = 0xFFFFFFFFu;
+            __syncthreads();
+            uint32_t mn = 0xFFFFFFFFu;
+            for (uint64_t i = threadIdx.x; i < L; i += SEL_THREADS) mn = min(mn, (uint32_t)(sel_key(in, qsrc, i) >> 32));
+            atomicMin(&s_want, mn);
+            __syncthreads();
+            if (threadIdx.x == 0) out_tau[qdst] = fkey_inv(s_want);
+        } else {
+            radix_select(4);
+            if (threadIdx.x == 0) out_tau[qdst] = fkey_inv((uint32_t)s_prefix);
+        }
+        return;
+    }
+    uint64_t kth = 0;  // keys >= kth are selected
+    if (L > K) {
+        radix_select(8);
+        kth = s_prefix;
+    }
+    if (threadIdx.x == 0) s_cnt = 0;
+    for (int i = threadIdx.x; i < SEL_MAXK; i += SEL_THREADS) buf[i] = 0;
+    __syncthreads();
+    for (uint64_t i = threadIdx.x; i < L; i += SEL_THREADS) {
+        uint64_t key = sel_key(in, qsrc, i);
+        if (key >= kth) {
+            uint32_t pos = atomicAdd(&s_cnt, 1u);
+            if (pos < SEL_MAXK) buf[pos] = key;
+        }
+    }
+    __syncthreads();
+    uint32_t cnt = min(s_cnt, (uint32_t)SEL_MAXK);
+    uint32_t np2 = 1;
+    while (np2 < cnt) np2 <<= 1;
+    // bitonic sort descending on buf[0..np2)
+    for (uint32_t size = 2; size <= np2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < np2 / 2; t += SEL_THREADS) {
+                uint32_t lo = (t / stride) * (stride * 2) + (t % stride);
+                uint32_t hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t x = buf[lo], y = buf[hi];
+                if ((x < y) == desc) { buf[lo] = y; buf[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    uint32_t nout = min(cnt, K);
+    for (uint32_t i = threadIdx.x; i < nout; i += SEL_THREADS) {
+        uint64_t key = buf[i];
+        Cand c;
+        c.score = fkey_inv((uint32_t)(key >> 32));
+        c.row = 0xFFFFFFFFu - (uint32_t)key;
+        out_sel[(uint64_t)qdst * K + i] = c;
+    }
+    if (threadIdx.x == 0) out_n[qdst] = nout;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// stage 2: exact re-scoring + final ordering
+// ---------------------------------------------------------------------------------------------------
+struct Exact {
+    float sim;       // reference similarity (float cast of the double quotient); NaN marks "skipped"
+    uint32_t row;
+};
+
+// one thread per (query, survivor): sqlite_vec_backend.cpp:4253-4279 evaluated in the same order
+__global__ void rescore_kernel(const void* __restrict__ rows, int dtype, uint32_t d, const float* __restrict__ q32,
+                               const double* __restrict__ qnorm, const Cand* __restrict__ sel, const uint32_t* __restrict__ sel_n,
+                               uint32_t Kp, uint32_t nq, float threshold, Exact* __restrict__ out) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nq * Kp) return;
+    uint32_t q = t / Kp, j = t % Kp;
+    Exact e;
+    e.sim = __int_as_float(0x7FC00000);
+    e.row = 0xFFFFFFFFu;
+    if (j < sel_n[q]) {
+        uint32_t row = sel[(uint64_t)q * Kp + j].row;
+        uint64_t base = (uint64_t)row * d;
+        const float* qv = q32 + (uint64_t)q * d;
+        double norm_sq = 0.0, dot = 0.0;
+        bool finite = true;
+        for (uint32_t c = 0; c < d; ++c) {
+            float v = load_elem(rows, dtype, base + c);
+            if (!isfinite(v)) { finite = false; break; }
+            double sv = (double)v, qd = (double)qv[c];
+            norm_sq += sv * sv;
+            dot += sv * qd;
+        }
+        if (finite && norm_sq > 1e-12) {
+            double denom = sqrt(norm_sq) * qnorm[q];
+            double simd = denom > 0.0 ? dot / denom : 0.0;
+            if (isfinite(simd)) {
+                float sim = (float)simd;
+                if (!(sim < threshold)) {
+                    e.sim = sim;
+                    e.row = row;
+                }
+            }
+        }
+    }
+    out[(uint64_t)q * Kp + j] = e;
+}
+
+// one CTA per query: order survivors by (sim desc, row asc), emit k
+__global__ void __launch_bounds__(SEL_THREADS) final_kernel(const Exact* __restrict__ ex, const uint32_t* __restrict__ ex_n,
+                                                            uint32_t Kp, uint32_t k,
+                                                            const int64_t* __restrict__ rowids, int negate,
+                                                            int64_t* __restrict__ out_rowids, float* __restrict__ out_scores,
+                                                            uint32_t* __restrict__ out_counts, uint64_t* __restrict__ out_flags,
+                                                            float pad_score) {
+    __shared__ uint64_t buf[SEL_MAXK];
+    const uint32_t q = blockIdx.x;
+    uint32_t np2 = 1;
+    while (np2 < Kp) np2 <<= 1;
+    for (uint32_t i = threadIdx.x; i < np2; i += SEL_THREADS) {
+        uint64_t key = 0;
+        if (i < Kp && (!ex_n || i < ex_n[q])) {
+            Exact e = ex[(uint64_t)q * Kp + i];
+            if (e.sim == e.sim) key = ((uint64_t)fkey(e.sim) << 32) | (uint64_t)(0xFFFFFFFFu - e.row);
+        }
+        buf[i] = key;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= np2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < np2 / 2; t += SEL_THREADS) {
+                uint32_t lo = (t / stride) * (stride * 2) + (t % stride);
+                uint32_t hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                uint64_t x = buf[lo], y = buf[hi];
+                if ((x < y) == desc) { buf[lo] = y; buf[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    // valid entries are the non-zero keys at the front
+    __shared__ uint32_t s_valid;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    uint32_t local = 0;
+    for (uint32_t i = threadIdx.x; i < np2; i += SEL_THREADS) local += buf[i] != 0 ? 1u : 0u;
+    atomicAdd(&s_valid, local);
+    __syncthreads();
+    uint32_t valid = s_valid;
+    uint32_t nout = min(valid, k);
+    for (uint32_t i = threadIdx.x; i < k; i += SEL_THREADS) {
+        if (i < nout) {
+            uint64_t key = buf[i];
+            uint32_t row = 0xFFFFFFFFu - (uint32_t)key;
+            float s = fkey_inv((uint32_t)(key >> 32));
+            out_rowids[(uint64_t)q * k + i] = rowids[row];
+            out_scores[(uint64_t)q * k + i] = negate ? -s : s;
+        } else {
+            out_rowids[(uint64_t)q * k + i] = -1;
+            out_scores[(uint64_t)q * k + i] = pad_score;
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (out_counts) out_counts[q] = nout;
+        if (out_flags) {
+            uint64_t f = 0;
+            if (valid > k && k > 0 && (buf[k - 1] >> 32) == (buf[k] >> 32)) f |= YAMS_B200_FLAG_TIE_AT_K;
+            out_flags[q] |= f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// candidate-set mask: bit (q, row) set when rowids[row] is in query q's allowed list
+// ---------------------------------------------------------------------------------------------------
+__global__ void build_mask_kernel(const int64_t* __restrict__ allowed, const uint64_t* __restrict__ offsets, uint32_t nq,
+                                  const int64_t* __restrict__ rowids, uint64_t n, uint32_t* __restrict__ mask, uint64_t mask_ld,
+                                  uint32_t* __restrict__ per_query) {
+    uint32_t q = blockIdx.y;
+    uint64_t lo = offsets[q], hi = offsets[q + 1];
+    for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t want = allowed[i];
+        uint64_t a = 0, b = n;
+        while (a < b) {
+            uint64_t m = a + ((b - a) >> 1);
+            if (rowids[m] < want) a = m + 1; else b = m;
+        }
+        if (a < n && rowids[a] == want) {
+            uint32_t old = atomicOr(&mask[(uint64_t)q * mask_ld + (a >> 5)], 1u << (a & 31));
+            if (!((old >> (a & 31)) & 1u)) atomicAdd(&per_query[q], 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// L2 surface (vec0_run_exact_query): float accumulation + sqrt; warp per row
+// ---------------------------------------------------------------------------------------------------
+__global__ void l2_dense_kernel(const void* __restrict__ rows, int dtype, uint32_t d, uint64_t n, const float* __restrict__ q32,
+                                uint32_t nq, float* __restrict__ out /* [q][n], NEGATED distance */) {
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    uint32_t q = blockIdx.y;
+    if (warp >= n || q >= nq) return;
+    const float* qv = q32 + (uint64_t)q * d;
+    float s = 0.f;
+    for (uint32_t c = lane; c < d; c += 32) {
+        float df = qv[c] - load_elem(rows, dtype, warp * d + c);
+        s = fmaf(df, df, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[(uint64_t)q * n + warp] = -sqrtf(s);
+}
+
+// global-memory bitonic sort (descending) of 64-bit keys, n a power of two
+__global__ void bitonic_step_kernel(uint64_t* __restrict__ keys, uint64_t n, uint64_t size, uint64_t stride) {
+    for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n / 2; t += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t lo = (t / stride) * (stride * 2) + (t % stride);
+        uint64_t hi = lo + stride;
+        bool desc = ((lo & size) == 0);
+        uint64_t x = keys[lo], y = keys[hi];
+        if ((x < y) == desc) { keys[lo] = y; keys[hi] = x; }
+    }
+}
+__global__ void make_keys_kernel(const float* __restrict__ neg_dist, uint64_t n, uint64_t np2, uint64_t* __restrict__ keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np2; i += (uint64_t)gridDim.x * blockDim.x)
+        keys[i] = i < n ? (((uint64_t)fkey(neg_dist[i]) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)i)) : 0ull;
+}
+__global__ void unpack_keys_kernel(const uint64_t* __restrict__ keys, uint64_t m, const int64_t* __restrict__ rowids,
+                                   int64_t* __restrict__ out_rowids, float* __restrict__ out_dist) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t key = keys[i];
+        uint32_t row = 0xFFFFFFFFu - (uint32_t)key;
+        out_rowids[i] = rowids ? rowids[row] : (int64_t)row;
+        out_dist[i] = -fkey_inv((uint32_t)(key >> 32));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// multi-GPU: merge R partial top-k lists per query
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SEL_THREADS) merge_partials_kernel(const int64_t* __restrict__ rowids, const float* __restrict__ scores,
+                                                                     uint32_t R, uint32_t nq, uint32_t k, int l2,
+                                                                     int64_t* __restrict__ out_rowids, float* __restrict__ out_scores,
+                                                                     uint32_t* __restrict__ out_counts) {
+    extern __shared__ unsigned char smraw[];
+    float* ks = reinterpret_cast<float*>(smraw);                 // np2 scores (as "bigger is better")
+    int64_t* kr = reinterpret_cast<int64_t*>(smraw + 0);         // placed after scores, see below
+    const uint32_t q = blockIdx.x;
+    uint32_t total = R * k, np2 = 1;
+    while (np2 < total) np2 <<= 1;
+    kr = reinterpret_cast<int64_t*>(smraw + (((size_t)np2 * 4 + 7) & ~(size_t)7));
+    for (uint32_t i = threadIdx.x; i < np2; i += SEL_THREADS) {
+        float s = -INFINITY;
+        int64_t r = INT64_MAX;
+        if (i < total) {
+            uint32_t rk = i / k, j = i % k;
+            size_t idx = ((size_t)rk * nq + q) * k + j;
+            r = rowids[idx];
+            s = scores[idx];
+            if (l2) s = -s;
+            if (r < 0) { s = -INFINITY; r = INT64_MAX; }
+        }
+        ks[i] = s;
+        kr[i] = r;
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= np2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = threadIdx.x; t < np2 / 2; t += SEL_THREADS) {
+                uint32_t lo = (t / stride) * (stride * 2) + (t % stride);
+                uint32_t hi = lo + stride;
+                bool desc = ((lo & size) == 0);
+                float xs = ks[lo], ys = ks[hi];
+                int64_t xr = kr[lo], yr = kr[hi];
+                // "x is worse than y": lower score, or equal score and larger rowid
+                bool x_worse = (xs < ys) || (xs == ys && xr > yr);
+                if (x_worse == desc) { ks[lo] = ys; ks[hi] = xs; kr[lo] = yr; kr[hi] = xr; }
+            }
+            __syncthreads();
+        }
+    }
+    __shared__ uint32_t s_valid;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    uint32_t local = 0;
+    for (uint32_t i = threadIdx.x; i < np2; i += SEL_THREADS) local += (kr[i] != INT64_MAX) ? 1u : 0u;
+    atomicAdd(&s_valid, local);
+    __syncthreads();
+    uint32_t nout = min(s_valid, k);
+    for (uint32_t i = threadIdx.x; i < k; i += SEL_THREADS) {
+        if (i < nout) {
+            out_rowids[(size_t)q * k + i] = kr[i];
+            out_scores[(size_t)q * k + i] = l2 ? -ks[i] : ks[i];
+        } else {
+            out_rowids[(size_t)q * k + i] = -1;
+            out_scores[(size_t)q * k + i] = l2 ? INFINITY : -INFINITY;
+        }
+    }
+    if (threadIdx.x == 0 && out_counts) out_counts[q] = nout;
+}
+
+__global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void tau_margin_kernel(float* tau, uint32_t nq, float margin, float floor_) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) {
+        float t = tau[i] - margin;
+        tau[i] = t > floor_ ? t : floor_;
+    }
+}
+__global__ void iota_rowids_kernel(int64_t* p, uint64_t n, int64_t first) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        p[i] = first + (int64_t)i;
+}
+
+}  // namespace yb
+
+// ===================================================================================================
+// host side: corpus mirror + search orchestration
+// ===================================================================================================
+struct yams_b200_corpus : public yb::Corpus {};
+
+namespace yb {
+
+// tcgen05 engine (knn_umma.cu); returns YAMS_ERR_UNSUPPORTED when the shape is not covered
+yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaStream_t st);
+bool tcgen05_supported(const Corpus* c, uint32_t nq);
+
+constexpr uint32_t kSampleRows = 65536;   // strided sample that calibrates the per-query thresholds
+constexpr uint32_t kSampleRank = 8;       // threshold = 8th best score of the sample
+constexpr float kTauMargin = 2e-3f;       // absorbs stage-1 rounding (fp16 queries on the tensor path)
+constexpr uint32_t kCandCap = 8192;       // candidate list capacity per query
+constexpr uint32_t kDenseLimit = 65536;   // corpora up to this many rows are scored densely
+
+static uint32_t survivors_for(uint32_t k) {
+    uint32_t slack = std::max<uint32_t>(16, k / 4);
+    uint32_t kp = ((k + slack + 31) / 32) * 32;
+    return std::min<uint32_t>(kp, SEL_MAXK);
+}
+
+static yams_status_t corpus_reserve(Corpus* c, uint64_t n_total) {
+    yams_status_t rc;
+    if ((rc = c->rows.reserve((size_t)n_total * c->dim * c->elem() + 256, true, c->st)) != YAMS_OK) return rc;
+    if ((rc = c->rowids.reserve((size_t)n_total * 8 + 256, true, c->st)) != YAMS_OK) return rc;
+    if ((rc = c->inv_norm.reserve((size_t)n_total * 4 + 256, true, c->st)) != YAMS_OK) return rc;
+    return YAMS_OK;
+}
+
+static yams_status_t corpus_finish_append(Corpus* c, uint64_t n_new, const int64_t* rowids_host) {
+    // rowids
+    int64_t* d_rid = c->rowids.as<int64_t>() + c->n;
+    if (rowids_host) {
+        for (uint64_t i = 0; i < n_new; ++i) {
+            YB_ARG(rowids_host[i] > c->last_rowid, "rowids must be appended in strictly ascending order");
+            if (c->n + i > 0 && rowids_host[i] != c->last_rowid + 1) c->rowids_dense = false;
+            c->last_rowid = rowids_host[i];
+        }
+        YB_CUDA(cudaMemcpyAsync(d_rid, rowids_host, (size_t)n_new * 8, cudaMemcpyHostToDevice, c->st));
+    } else {
+        int64_t first = c->n == 0 ? 0 : c->last_rowid + 1;
+        iota_rowids_kernel<<<(unsigned)std::min<uint64_t>((n_new + 255) / 256, 4096), 256, 0, c->st>>>(d_rid, n_new, first);
+        c->last_rowid = first + (int64_t)n_new - 1;
+    }
+    row_stats_kernel<<<(unsigned)((n_new + 127) / 128), 128, 0, c->st>>>(c->rows.p, c->dtype, c->dim, c->n, n_new,
+                                                                       c->inv_norm.as<float>());
+    YB_CUDA(cudaGetLastError());
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    c->n += n_new;
+    return YAMS_OK;
+}
+
+// Runs the whole cosine pipeline for nq queries already resident at c->q32 (device) and writes the
+// padded [nq][k] result into device buffers.
+static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, float threshold, const uint32_t* d_mask,
+                                          uint64_t mask_ld, uint32_t mask_max, int64_t* d_out_rowids, float* d_out_scores,
+                                          uint32_t* d_out_counts, uint64_t* d_out_flags, bool use_tensor) {
+    yams_status_t rc;
+    cudaStream_t st = c->st;
+    const uint32_t Kp = survivors_for(k);
+    const uint64_t n = c->n;
+    c->scan_timed = false;
+    float* d_qinv = c->qinv.as<float>();
+    double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());           // nq doubles
+    uint32_t* d_counts = c->counts.as<uint32_t>();
+    Stage1Args a{};
+    a.rows = c->rows.p;
+    a.inv_norm = c->inv_norm.as<float>();
+    a.dim = c->dim;
+    a.dtype = c->dtype;
+    a.q32 = c->q32.as<float>();
+    a.qinv = d_qinv;
+    a.nq = nq;
+    auto run_stage1 = [&](const Stage1Args& args, bool filter) -> yams_status_t {
+        if (use_tensor) {
+            yams_status_t r = stage1_tcgen05(c, args, filter, st);
+            if (r != YAMS_ERR_UNSUPPORTED) return r;
+        }
+        return stage1_cuda_core(args, filter, st);
+    };
+    if ((rc = c->sel.reserve((size_t)nq * Kp * sizeof(Cand) + (size_t)nq * 4)) != YAMS_OK) return rc;
+    Cand* d_sel = c->sel.as<Cand>();
+    uint32_t* d_sel_n = reinterpret_cast<uint32_t*>(d_sel + (size_t)nq * Kp);
+    YB_CUDA(cudaMemsetAsync(d_sel_n, 0, (size_t)nq * 4, st));
+    if (d_out_flags) YB_CUDA(cudaMemsetAsync(d_out_flags, 0, (size_t)nq * 8, st));
+
+    std::vector<uint32_t> bad;  // queries that need the exhaustive path
+    if (n == 0) {
+        // nothing to score
+    } else if (!d_mask && n <= kDenseLimit) {
+        // ---- dense: every score materialised, exact top-K' straight from the matrix ----
+        if ((rc = c->dense.reserve((size_t)nq * n * 4)) != YAMS_OK) return rc;
+        a.row_start = 0; a.row_stride = 1; a.nrows = n;
+        a.out_scores = c->dense.as<float>(); a.ld = n;
+        if ((rc = run_stage1(a, false)) != YAMS_OK) return rc;
+        SelectIn in{};
+        in.dense = c->dense.as<float>(); in.ld = n; in.row_start = 0; in.row_stride = 1; in.dense_len = n;
+        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
+    } else {
+        uint32_t cap;
+        if ((rc = c->tau.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
+        float* d_tau = c->tau.as<float>();
+        if (d_mask) {
+            // ---- candidate-set mode: every allowed row is a candidate ----
+            cap = std::max<uint32_t>(mask_max, 1);
+            fill_f32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_tau, nq, -INFINITY);
+        } else {
+            // ---- thresholds from a strided sample ----
+            uint64_t S = std::min<uint64_t>(n, kSampleRows);
+            uint64_t stride = n / S;
+            // the sample rank is chosen so that ~4*K' rows are expected above the threshold
+            uint32_t m = (uint32_t)std::max<uint64_t>(kSampleRank, (4ull * Kp + stride - 1) / stride);
+            uint64_t expected = (uint64_t)m * stride;
+            cap = (uint32_t)std::max<uint64_t>(kCandCap, ((3 * expected + 1023) / 1024) * 1024);
+            if ((rc = c->sample_scores.reserve((size_t)nq * S * 4)) != YAMS_OK) return rc;
+            Stage1Args s1 = a;
+            s1.row_start = 0; s1.row_stride = stride; s1.nrows = S;
+            s1.out_scores = c->sample_scores.as<float>(); s1.ld = S;
+            if ((rc = run_stage1(s1, false)) != YAMS_OK) return rc;
+            SelectIn in{};
+            in.dense = c->sample_scores.as<float>(); in.ld = S; in.row_start = 0; in.row_stride = stride; in.dense_len = S;
+            topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, m, 1, d_tau, nullptr, nullptr);
+            // never filter above what the caller's own threshold would keep
+            tau_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_tau, nq, kTauMargin, -INFINITY);
+        }
+        if ((rc = c->cands.reserve((size_t)nq * cap * sizeof(Cand))) != YAMS_OK) return rc;
+        YB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, st));
+        Stage1Args f = a;
+        f.row_start = 0; f.row_stride = 1; f.nrows = n;
+        f.tau = d_tau; f.cands = c->cands.as<Cand>(); f.cap = cap; f.counts = d_counts;
+        f.mask = d_mask; f.mask_ld = mask_ld;
+        YB_CUDA(cudaEventRecord(c->ev_scan[0], st));
+        if ((rc = run_stage1(f, true)) != YAMS_OK) return rc;
+        YB_CUDA(cudaEventRecord(c->ev_scan[1], st));
+        c->scan_timed = true;
+        SelectIn in{};
+        in.cands = c->cands.as<Cand>(); in.counts = d_counts; in.cap = cap;
+        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
+        if (!d_mask) {
+            // verify every list: overflow or too few survivors -> exhaustive path for that query
+            uint32_t* h_counts = c->h_pin.as<uint32_t>();
+            YB_CUDA(cudaMemcpyAsync(h_counts, d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+            YB_CUDA(cudaStreamSynchronize(st));
+            uint64_t need = std::min<uint64_t>(Kp, n);
+            for (uint32_t q = 0; q < nq; ++q)
+                if (h_counts[q] > cap || h_counts[q] < need) bad.push_back(q);
+        }
+    }
+    // ---- exhaustive path for the (rare) queries whose threshold was off ----
+    if (!bad.empty()) {
+        const uint32_t G = 8;  // queries per group: G * n floats of scratch
+        if ((rc = c->dense.reserve((size_t)G * n * 4 + (size_t)G * c->dim * 4 + (size_t)G * 8)) != YAMS_OK) return rc;
+        float* d_scores = c->dense.as<float>();
+        float* d_qg = d_scores + (size_t)G * n;
+        float* d_qinv_g = d_qg + (size_t)G * c->dim;
+        uint32_t* d_qmap = reinterpret_cast<uint32_t*>(d_qinv_g + G);
+        for (size_t g0 = 0; g0 < bad.size(); g0 += G) {
+            uint32_t g = (uint32_t)std::min<size_t>(G, bad.size() - g0);
+            for (uint32_t i = 0; i < g; ++i) {
+                YB_CUDA(cudaMemcpyAsync(d_qg + (size_t)i * c->dim, a.q32 + (size_t)bad[g0 + i] * c->dim, (size_t)c->dim * 4,
+                                        cudaMemcpyDeviceToDevice, st));
+                YB_CUDA(cudaMemcpyAsync(d_qinv_g + i, d_qinv + bad[g0 + i], 4, cudaMemcpyDeviceToDevice, st));
+            }
+            YB_CUDA(cudaMemcpyAsync(d_qmap, bad.data() + g0, (size_t)g * 4, cudaMemcpyHostToDevice, st));
+            Stage1Args e = a;
+            e.q32 = d_qg; e.qinv = d_qinv_g; e.nq = g;
+            e.row_start = 0; e.row_stride = 1; e.nrows = n; e.out_scores = d_scores; e.ld = n;
+            if ((rc = stage1_cuda_core(e, false, st)) != YAMS_OK) return rc;
+            SelectIn in{};
+            in.dense = d_scores; in.ld = n; in.row_start = 0; in.row_stride = 1; in.dense_len = n; in.qmap = d_qmap;
+            topk_select_kernel<<<g, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
+            YB_CUDA(cudaStreamSynchronize(st));  // d_qmap / bad.data() reuse
+        }
+        if (d_out_flags) {
+            std::vector<uint64_t> hf(nq, 0);
+            for (uint32_t q : bad) hf[q] = YAMS_B200_FLAG_FALLBACK_PATH;
+            YB_CUDA(cudaMemcpyAsync(d_out_flags, hf.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
+            YB_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    YB_CUDA(cudaEventRecord(c->ev[1], st));
+    // ---- stage 2 ----
+    if ((rc = c->outbuf.reserve((size_t)nq * Kp * sizeof(Exact))) != YAMS_OK) return rc;
+    Exact* d_ex = c->outbuf.as<Exact>();
+    uint32_t tot = nq * Kp;
+    rescore_kernel<<<(tot + 127) / 128, 128, 0, st>>>(c->rows.p, c->dtype, c->dim, a.q32, d_qnorm, d_sel, d_sel_n, Kp, nq,
+                                                      threshold, d_ex);
+    final_kernel<<<nq, SEL_THREADS, 0, st>>>(d_ex, nullptr, Kp, k, c->rowids.as<int64_t>(), 0, d_out_rowids, d_out_scores,
+                                             d_out_counts, d_out_flags, -INFINITY);
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
+// L2 (vec0 semantics) over the corpus: dense distances + exact top-k (k <= SEL_MAXK)
+static yams_status_t search_l2_device(Corpus* c, uint32_t nq, uint32_t k, int64_t* d_out_rowids, float* d_out_scores,
+                                      uint32_t* d_out_counts) {
+    yams_status_t rc;
+    cudaStream_t st = c->st;
+    const uint64_t n = c->n;
+    YB_ARG(k <= SEL_MAXK, "k too large for the L2 top-k path");
+    if ((rc = c->dense.reserve((size_t)nq * std::max<uint64_t>(n, 1) * 4)) != YAMS_OK) return rc;
+    if ((rc = c->sel.reserve((size_t)nq * std::max<uint32_t>(k, 1) * sizeof(Cand) + (size_t)nq * 4)) != YAMS_OK) return rc;
+    Cand* d_sel = c->sel.as<Cand>();
+    uint32_t* d_sel_n = reinterpret_cast<uint32_t*>(d_sel + (size_t)nq * std::max<uint32_t>(k, 1));
+    YB_CUDA(cudaMemsetAsync(d_sel_n, 0, (size_t)nq * 4, st));
+    if (n) {
+        dim3 grid((unsigned)((n * 32 + 255) / 256), nq);
+        l2_dense_kernel<<<grid, 256, 0, st>>>(c->rows.p, c->dtype, c->dim, n, c->q32.as<float>(), nq, c->dense.as<float>());
+        SelectIn in{};
+        in.dense = c->dense.as<float>(); in.ld = n; in.row_start = 0; in.row_stride = 1; in.dense_len = n;
+        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, k, 0, nullptr, d_sel, d_sel_n);
+    }
+    // reuse final_kernel: Exact has the same layout as Cand (score, row); scores are negated distances
+    static_assert(sizeof(Exact) == sizeof(Cand), "layout");
+    final_kernel<<<nq, SEL_THREADS, 0, st>>>(reinterpret_cast<const Exact*>(d_sel), d_sel_n, std::max<uint32_t>(k, 1), k,
+                                             c->rowids.as<int64_t>(), 1, d_out_rowids, d_out_scores, d_out_counts, nullptr,
+                                             INFINITY);
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" {
+
+yams_status_t yams_b200_corpus_create(void* self, uint32_t dim, int dtype, int metric, uint64_t capacity_hint,
+                                      yams_b200_corpus** out) {
+    (void)self;
+    YB_ARG(out, "out is null");
+    *out = nullptr;
+    YB_ARG(dim > 0 && dim <= 65536, "dim must be in 1..65536");  // vec0_module.hpp:109
+    YB_ARG(dtype == YAMS_B200_F32 || dtype == YAMS_B200_F16, "unknown dtype");
+    YB_ARG(metric == YAMS_B200_COSINE || metric == YAMS_B200_L2, "unknown metric");
+    DeviceCtx* dev = nullptr;
+    yams_status_t rc = ensure_device(&dev);
+    if (rc != YAMS_OK) return rc;
+    yams_b200_corpus* c = new (std::nothrow) yams_b200_corpus();
+    if (!c) return YAMS_ERR_INTERNAL;
+    c->dev = dev;
+    c->dim = dim;
+    c->dtype = dtype;
+    c->metric = metric;
+    if (cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking) != cudaSuccess) {
+        delete c;
+        set_last_error("cudaStreamCreate failed");
+        return YAMS_ERR_INTERNAL;
+    }
+    for (auto& e : c->ev) cudaEventCreate(&e);
+    for (auto& e : c->ev_scan) cudaEventCreate(&e);
+    if (capacity_hint) {
+        rc = corpus_reserve(c, capacity_hint);
+        if (rc != YAMS_OK) {
+            yams_b200_corpus_destroy(c);
+            return rc;
+        }
+    }
+    *out = c;
+    return YAMS_OK;
+}
+
+void yams_b200_corpus_destroy(yams_b200_corpus* c) {
+    if (!c) return;
+    if (c->st) cudaStreamSynchronize(c->st);
+    for (DevBuf* b : {&c->rows, &c->rowids, &c->inv_norm, &c->q32, &c->q16, &c->qinv, &c->tau, &c->counts, &c->cands,
+                      &c->sample_scores, &c->sel, &c->outbuf, &c->dense, &c->mask, &c->misc, &c->dout})
+        b->release();
+    c->h_pin.release();
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_scan)
+        if (e) cudaEventDestroy(e);
+    if (c->st) cudaStreamDestroy(c->st);
+    delete c;
+}
+
+yams_status_t yams_b200_corpus_append(yams_b200_corpus* c, const void* rows, uint64_t n, const int64_t* rowids) {
+    YB_ARG(c, "corpus is null");
+    if (n == 0) return YAMS_OK;
+    YB_ARG(rows, "rows is null");
+    YB_ARG(c->n + n < 0xFFFFFFFFull, "corpus is limited to 2^32-1 rows per GPU");
+    yams_status_t rc = corpus_reserve(c, c->n + n);
+    if (rc != YAMS_OK) return rc;
+    size_t rb = (size_t)c->dim * c->elem();
+    YB_CUDA(cudaMemcpyAsync(c->rows.as<uint8_t>() + (size_t)c->n * rb, rows, (size_t)n * rb, cudaMemcpyHostToDevice, c->st));
+    return corpus_finish_append(c, n, rowids);
+}
+
+yams_status_t yams_b200_corpus_append_f32_as_f16(yams_b200_corpus* c, const float* rows, uint64_t n, const int64_t* rowids) {
+    YB_ARG(c, "corpus is null");
+    YB_ARG(c->dtype == YAMS_B200_F16, "corpus is not fp16");
+    if (n == 0) return YAMS_OK;
+    YB_ARG(rows, "rows is null");
+    YB_ARG(c->n + n < 0xFFFFFFFFull, "corpus is limited to 2^32-1 rows per GPU");
+    yams_status_t rc = corpus_reserve(c, c->n + n);
+    if (rc != YAMS_OK) return rc;
+    size_t cnt = (size_t)n * c->dim;
+    if ((rc = c->dense.reserve(cnt * 4)) != YAMS_OK) return rc;
+    YB_CUDA(cudaMemcpyAsync(c->dense.p, rows, cnt * 4, cudaMemcpyHostToDevice, c->st));
+    convert_f32_to_f16_trunc_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 65535), 256, 0, c->st>>>(
+        c->dense.as<float>(), c->rows.as<uint16_t>() + (size_t)c->n * c->dim, cnt);
+    return corpus_finish_append(c, n, rowids);
+}
+
+yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t seed, uint64_t first_row, uint64_t n) {
+    YB_ARG(c, "corpus is null");
+    if (n == 0) return YAMS_OK;
+    YB_ARG(c->n + n < 0xFFFFFFFFull, "corpus is limited to 2^32-1 rows per GPU");
+    yams_status_t rc = corpus_reserve(c, c->n + n);
+    if (rc != YAMS_OK) return rc;
+    if ((rc = c->misc.reserve((size_t)n * 4)) != YAMS_OK) return rc;
+    float* d_inv = c->misc.as<float>();
+    synth_rownorm_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->st>>>(seed, first_row, n, c->dim, d_inv);
+    size_t rb = (size_t)c->dim * c->elem();
+    synth_fill_kernel<<<c->dev->sm_count * 16, 256, 0, c->st>>>(seed, first_row, n, c->dim, d_inv,
+                                                               c->rows.as<uint8_t>() + (size_t)c->n * rb, c->dtype);
+    YB_CUDA(cudaGetLastError());
+    // rowid = first_row + i
+    std::vector<int64_t> none;
+    int64_t first = (int64_t)first_row;
+    YB_ARG(first > c->last_rowid, "rowids must be appended in strictly ascending order");
+    if (c->n > 0 && first != c->last_rowid + 1) c->rowids_dense = false;
+    iota_rowids_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, c->st>>>(c->rowids.as<int64_t>() + c->n, n, first);
+    c->last_rowid = first + (int64_t)n - 1;
+    row_stats_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->st>>>(c->rows.p, c->dtype, c->dim, c->n, n, c->inv_norm.as<float>());
+    YB_CUDA(cudaGetLastError());
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    c->n += n;
+    return YAMS_OK;
+}
+
+yams_status_t yams_b200_corpus_clear(yams_b200_corpus* c) {
+    YB_ARG(c, "corpus is null");
+    c->n = 0;
+    c->last_rowid = INT64_MIN;
+    c->rowids_dense = true;
+    return YAMS_OK;
+}
+
+yams_status_t yams_b200_corpus_size(const yams_b200_corpus* c, uint64_t* out_n) {
+    YB_ARG(c && out_n, "null argument");
+    *out_n = c->n;
+    return YAMS_OK;
+}
+
+yams_status_t yams_b200_corpus_sync(yams_b200_corpus* c) {
+    YB_ARG(c, "corpus is null");
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    return YAMS_OK;
+}
+
+void* yams_b200_corpus_stream(yams_b200_corpus* c) { return c ? (void*)c->st : nullptr; }
+
+// uploads / validates queries; leaves q32, qinv, qnorm(misc) on the device
+static yams_status_t prepare_queries(yams_b200_corpus* c, const float* q_src, bool src_is_device, uint32_t nq) {
+    yams_status_t rc;
+    size_t qb = (size_t)nq * c->dim * 4;
+    if ((rc = c->q32.reserve(qb)) != YAMS_OK) return rc;
+    if ((rc = c->qinv.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
+    if ((rc = c->misc.reserve((size_t)nq * 8 + (size_t)nq * 4)) != YAMS_OK) return rc;
+    if ((rc = c->counts.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
+    if ((rc = c->h_pin.reserve((size_t)nq * 16)) != YAMS_OK) return rc;
+    YB_CUDA(cudaMemcpyAsync(c->q32.p, q_src, qb, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
+    double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());
+    uint32_t* d_flags = reinterpret_cast<uint32_t*>(c->misc.as<uint8_t>() + (size_t)nq * 8);
+    query_prep_kernel<<<(nq + 63) / 64, 64, 0, c->st>>>(c->q32.as<float>(), nq, c->dim, d_qnorm, c->qinv.as<float>(), d_flags);
+    uint32_t* h_flags = c->h_pin.as<uint32_t>();
+    YB_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->st));
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    for (uint32_t q = 0; q < nq; ++q)
+        YB_ARG(h_flags[q] == 0, "exact vector search requires a finite, non-zero query embedding");
+    return YAMS_OK;
+}
+
+yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32_t nq, uint32_t k, float threshold,
+                               const int64_t* allowed_rowids, const uint64_t* allowed_offsets, int64_t* out_rowids,
+                               float* out_scores, uint32_t* out_counts, uint64_t* out_flags) {
+    YB_ARG(c, "corpus is null");
+    if (nq == 0) return YAMS_OK;
+    YB_ARG(queries && out_counts, "null argument");
+    YB_ARG(!allowed_rowids || allowed_offsets, "allowed_offsets missing");
+    YB_ARG(!allowed_offsets || allowed_rowids || allowed_offsets[nq] == 0, "allowed_rowids missing");
+    for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+    if (out_flags) for (uint32_t q = 0; q < nq; ++q) out_flags[q] = 0;
+    yams_status_t rc;
+    cudaEvent_t w0 = c->ev[3];
+    YB_CUDA(cudaEventRecord(w0, c->st));
+    // the reference validates the query before looking at k (sqlite_vec_backend.cpp:4123-4130 checks
+    // k == 0 first and returns empty): mirror that order
+    if (k == 0) return YAMS_OK;
+    YB_ARG(out_rowids && out_scores, "null output");
+    YB_ARG(k <= 768, "k > 768 is not supported by the fused top-k path");
+    if ((rc = prepare_queries(c, queries, false, nq)) != YAMS_OK) return rc;
+    YB_CUDA(cudaEventRecord(c->ev[0], c->st));
+    // device outputs
+    size_t ob = (size_t)nq * k * 12 + (size_t)nq * 4 + (size_t)nq * 8 + 64;
+    DevBuf& dout = c->dout;
+    if ((rc = dout.reserve(ob)) != YAMS_OK) return rc;
+    int64_t* d_or = dout.as<int64_t>();
+    uint64_t* d_of = reinterpret_cast<uint64_t*>(d_or + (size_t)nq * k);
+    float* d_os = reinterpret_cast<float*>(d_of + nq);
+    uint32_t* d_oc = reinterpret_cast<uint32_t*>(d_os + (size_t)nq * k);
+    const bool tensor = tcgen05_supported(c, nq);
+    if (c->metric == YAMS_B200_COSINE) {
+        const uint32_t* d_mask = nullptr;
+        uint64_t mask_ld = 0;
+        uint32_t mask_max = 0;
+        if (allowed_offsets && c->n) {
+            uint64_t total = allowed_offsets[nq];
+            mask_ld = (c->n + 31) / 32;
+            size_t mb = (size_t)nq * mask_ld * 4;
+            if ((rc = c->mask.reserve(mb + (size_t)total * 8 + (size_t)(nq + 1) * 8 + (size_t)nq * 4 + 64)) != YAMS_OK) {
+                return rc;
+            }
+            uint32_t* dm = c->mask.as<uint32_t>();
+            int64_t* d_allowed = reinterpret_cast<int64_t*>(c->mask.as<uint8_t>() + ((mb + 7) & ~(size_t)7));
+            uint64_t* d_offs = reinterpret_cast<uint64_t*>(d_allowed + total);
+            uint32_t* d_pq = reinterpret_cast<uint32_t*>(d_offs + nq + 1);
+            cudaMemsetAsync(dm, 0, mb, c->st);
+            cudaMemsetAsync(d_pq, 0, (size_t)nq * 4, c->st);
+            if (total) cudaMemcpyAsync(d_allowed, allowed_rowids, (size_t)total * 8, cudaMemcpyHostToDevice, c->st);
+            cudaMemcpyAsync(d_offs, allowed_offsets, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->st);
+            dim3 grid(64, nq);
+            build_mask_kernel<<<grid, 256, 0, c->st>>>(d_allowed, d_offs, nq, c->rowids.as<int64_t>(), c->n, dm, mask_ld, d_pq);
+            uint32_t* h_pq = c->h_pin.as<uint32_t>();
+            cudaMemcpyAsync(h_pq, d_pq, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->st);
+            if (cudaStreamSynchronize(c->st) != cudaSuccess) {
+                set_last_error("mask build failed");
+                return YAMS_ERR_INTERNAL;
+            }
+            for (uint32_t q = 0; q < nq; ++q) mask_max = std::max(mask_max, h_pq[q]);
+            d_mask = dm;
+        }
+        rc = search_cosine_device(c, nq, k, threshold, d_mask, mask_ld, mask_max, d_or, d_os, d_oc, d_of, tensor);
+    } else {
+        YB_ARG(!allowed_offsets, "candidate sets are only supported for the cosine metric");
+        cudaMemsetAsync(d_of, 0, (size_t)nq * 8, c->st);
+        YB_CUDA(cudaEventRecord(c->ev[1], c->st));
+        rc = search_l2_device(c, nq, k, d_or, d_os, d_oc);
+    }
+    if (rc == YAMS_OK) {
+        cudaEventRecord(c->ev[2], c->st);
+        cudaError_t e = cudaMemcpyAsync(out_rowids, d_or, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, d_oc, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->st);
+        if (e == cudaSuccess && out_flags) e = cudaMemcpyAsync(out_flags, d_of, (size_t)nq * 8, cudaMemcpyDeviceToHost, c->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
+        if (e != cudaSuccess) {
+            set_last_error("search failed: %s", cudaGetErrorString(e));
+            rc = YAMS_ERR_INTERNAL;
+        } else {
+            cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
+            cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]);
+            cudaEventElapsedTime(&c->last_ms[2], c->ev[0], c->ev[2]);
+            c->last_ms[4] = tensor ? 1.f : 0.f;
+        }
+    }
+    return rc;
+}
+
+yams_status_t yams_b200_search_device(yams_b200_corpus* c, const float* d_queries, uint32_t nq, uint32_t k, float threshold,
+                                      int64_t* d_out_rowids, float* d_out_scores) {
+    YB_ARG(c && d_queries && d_out_rowids && d_out_scores, "null argument");
+    YB_ARG(k > 0 && k <= 768, "k must be in 1..768");
+    if (nq == 0) return YAMS_OK;
+    yams_status_t rc;
+    if ((rc = prepare_queries(c, d_queries, true, nq)) != YAMS_OK) return rc;
+    YB_CUDA(cudaEventRecord(c->ev[0], c->st));
+    const bool tensor = tcgen05_supported(c, nq);
+    if (c->metric == YAMS_B200_COSINE)
+        rc = search_cosine_device(c, nq, k, threshold, nullptr, 0, 0, d_out_rowids, d_out_scores, nullptr, nullptr, tensor);
+    else {
+        YB_CUDA(cudaEventRecord(c->ev[1], c->st));
+        rc = search_l2_device(c, nq, k, d_out_rowids, d_out_scores, nullptr);
+    }
+    if (rc != YAMS_OK) return rc;
+    YB_CUDA(cudaEventRecord(c->ev[2], c->st));
+    c->last_ms[4] = tensor ? 1.f : 0.f;
+    return YAMS_OK;
+}
+
+yams_status_t yams_b200_merge_partials_device(yams_b200_corpus* c, const int64_t* d_rowids, const float* d_scores,
+                                              uint32_t nranks, uint32_t nq, uint32_t k, int64_t* d_out_rowids,
+                                              float* d_out_scores, uint32_t* d_out_counts) {
+    YB_ARG(c && d_rowids && d_scores && d_out_rowids && d_out_scores, "null argument");
+    YB_ARG(nranks >= 1 && k >= 1, "bad shape");
+    uint32_t total = nranks * k, np2 = 1;
+    while (np2 < total) np2 <<= 1;
+    YB_ARG(np2 <= 4096, "nranks * k too large to merge in one CTA");
+    size_t smem = (((size_t)np2 * 4 + 7) & ~(size_t)7) + (size_t)np2 * 8;
+    merge_partials_kernel<<<nq, SEL_THREADS, smem, c->st>>>(d_rowids, d_scores, nranks, nq, k, c->metric == YAMS_B200_L2,
+                                                            d_out_rowids, d_out_scores, d_out_counts);
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
+yams_status_t yams_b200_search_last_timings(yams_b200_corpus* c, float out_ms[8]) {
+    YB_ARG(c && out_ms, "null argument");
+    if (cudaEventQuery(c->ev[2]) == cudaSuccess) {
+        cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
+        cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]);
+        cudaEventElapsedTime(&c->last_ms[2], c->ev[0], c->ev[2]);
+        c->last_ms[5] = 0.f;
+        if (c->scan_timed) cudaEventElapsedTime(&c->last_ms[5], c->ev_scan[0], c->ev_scan[1]);
+    }
+    for (int i = 0; i < 8; ++i) out_ms[i] = c->last_ms[i];
+    return YAMS_OK;
+}
+
+yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim, const float* rows, const int64_t* rowids,
+                                   uint64_t n, uint64_t k, int use_range, int64_t rowid_lo, int64_t rowid_hi,
+                                   int64_t* out_rowids, float* out_dist, uint64_t* out_count) {
+    (void)self;
+    YB_ARG(out_count, "out_count is null");
+    *out_count = 0;
+    YB_ARG(query && dim > 0, "bad query");
+    if (n == 0) return YAMS_OK;
+    YB_ARG(rows && out_rowids && out_dist, "null argument");
+    YB_ARG(n < 0xFFFFFFFFull, "too many rows");
+    DeviceCtx* dev = nullptr;
+    yams_status_t rc = ensure_device(&dev);
+    if (rc != YAMS_OK) return rc;
+    // rowid range filter (vec0_module.hpp:399-401) is applied on the host side of the copy: only rows in
+    // range are uploaded (pure data movement, no arithmetic)
+    std::vector<uint32_t> keep;
+    if (use_range) {
+        keep.reserve((size_t)n);
+        for (uint64_t i = 0; i < n; ++i) {
+            int64_t rid = rowids ? rowids[i] : (int64_t)i;
+            if (rid >= rowid_lo && rid <= rowid_hi) keep.push_back((uint32_t)i);
+        }
+        if (keep.empty()) return YAMS_OK;
+    }
+    uint64_t m = use_range ? keep.size() : n;
+    cudaStream_t st;
+    YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint64_t np2 = 1;
+    while (np2 < m) np2 <<= 1;
+    DevBuf d_rows, d_q, d_dist, d_keys, d_rid, d_or, d_od;
+    rc = d_rows.reserve((size_t)m * dim * 4);
+    if (rc == YAMS_OK) rc = d_q.reserve((size_t)dim * 4);
+    if (rc == YAMS_OK) rc = d_dist.reserve((size_t)m * 4);
+    if (rc == YAMS_OK) rc = d_keys.reserve((size_t)np2 * 8);
+    if (rc == YAMS_OK) rc = d_rid.reserve((size_t)m * 8);
+    if (rc == YAMS_OK) rc = d_or.reserve((size_t)m * 8);
+    if (rc == YAMS_OK) rc = d_od.reserve((size_t)m * 4);
+    if (rc == YAMS_OK) {
+        std::vector<int64_t> rid_h((size_t)m);
+        if (use_range) {
+            for (uint64_t j = 0; j < m; ++j) {
+                cudaMemcpyAsync(d_rows.as<float>() + (size_t)j * dim, rows + (size_t)keep[j] * dim, (size_t)dim * 4,
+                                cudaMemcpyHostToDevice, st);
+                rid_h[j] = rowids ? rowids[keep[j]] : (int64_t)keep[j];
+            }
+        } else {
+            cudaMemcpyAsync(d_rows.p, rows, (size_t)m * dim * 4, cudaMemcpyHostToDevice, st);
+            for (uint64_t j = 0; j < m; ++j) rid_h[j] = rowids ? rowids[j] : (int64_t)j;
+        }
+        cudaMemcpyAsync(d_rid.p, rid_h.data(), (size_t)m * 8, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(d_q.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, st);
+        dim3 grid((unsigned)((m * 32 + 255) / 256), 1);
+        l2_dense_kernel<<<grid, 256, 0, st>>>(d_rows.p, YAMS_B200_F32, dim, m, d_q.as<float>(), 1, d_dist.as<float>());
+        unsigned g = (unsigned)std::min<uint64_t>((np2 + 255) / 256, 65535);
+        make_keys_kernel<<<g, 256, 0, st>>>(d_dist.as<float>(), m, np2, d_keys.as<uint64_t>());
+        for (uint64_t size = 2; size <= np2; size <<= 1)
+            for (uint64_t stride = size >> 1; stride > 0; stride >>= 1)
+                bitonic_step_kernel<<<g, 256, 0, st>>>(d_keys.as<uint64_t>(), np2, size, stride);
+        uint64_t outn = (k && k < m) ? k : m;
+        unpack_keys_kernel<<<g, 256, 0, st>>>(d_keys.as<uint64_t>(), outn, d_rid.as<int64_t>(), d_or.as<int64_t>(), d_od.as<float>());
+        cudaError_t e = cudaMemcpyAsync(out_rowids, d_or.p, (size_t)outn * 8, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, d_od.p, (size_t)outn * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_last_error("vec0_exact failed: %s", cudaGetErrorString(e));
+            rc = YAMS_ERR_INTERNAL;
+        } else {
+            *out_count = outn;
+        }
+    }
+    for (DevBuf* b : {&d_rows, &d_q, &d_dist, &d_keys, &d_rid, &d_or, &d_od}) b->release();
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+}  // extern "C"
