@@ -298,6 +298,13 @@ YAMS_B200_API int sqlite3_vec_distance_cosine(const void* vec1, size_t size1, co
 YAMS_B200_API yams_status_t yams_b200_synth_bytes_device(uint64_t seed, uint64_t start, uint64_t n,
                                                          uint8_t* d_out);
 
+/* diagnostics: dense stage-1 (approximate) scores of rows row_start + i*row_stride, i < nrows, with the
+ * chosen engine (0 = CUDA-core, 1 = tcgen05); out[q * nrows + i] on the HOST. YAMS_ERR_UNSUPPORTED when the
+ * engine cannot take the shape. */
+YAMS_B200_API yams_status_t yams_b200_debug_stage1_scores(yams_b200_corpus* c, const float* queries, uint32_t nq,
+                                                          int engine, uint64_t row_start, uint64_t row_stride,
+                                                          uint64_t nrows, float* out);
+
 /* ---- misc ------------------------------------------------------------------------------------ */
 YAMS_B200_API int yams_b200_device_count(void);
 /* last error text of the calling thread (static storage) */

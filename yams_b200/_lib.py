@@ -85,6 +85,7 @@ SYMBOLS = {
     "sqlite3_vec_distance_l2": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, f32p]),
     "sqlite3_vec_distance_cosine": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, f32p]),
     "yams_b200_synth_bytes_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "yams_b200_debug_stage1_scores": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
     "yams_b200_device_count": (C.c_int, []),
     "yams_b200_last_error": (C.c_char_p, []),
 }
@@ -186,7 +187,8 @@ def chunk_and_hash_device(dev_ptr: int, length: int, cfg: Optional[CdcConfig] = 
 def ingest_last_timings() -> dict:
     ms = (C.c_float * 8)()
     lib().yams_b200_ingest_last_timings(None, ms)
-    return {"scan_ms": ms[0], "select_ms": ms[1], "sha256_ms": ms[2], "total_ms": ms[3]}
+    return {"scan_ms": ms[0], "select_ms": ms[1], "sha256_ms": ms[2], "total_ms": ms[3],
+            "host_sync1_ms": ms[4], "host_sync2_ms": ms[5], "host_alloc_ms": ms[6], "host_process_ms": ms[7]}
 
 
 class IngestSession:
@@ -320,6 +322,14 @@ class Corpus:
                               d_out_scores: int, d_out_counts: int = 0):
         _check(lib().yams_b200_merge_partials_device(self._h, d_rowids, d_scores, nranks, nq, k, d_out_rowids, d_out_scores,
                                                      d_out_counts or None), "merge_partials_device")
+
+    def debug_stage1_scores(self, queries, engine: int, row_start: int = 0, row_stride: int = 1, nrows: int = 0):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        nrows = nrows or len(self)
+        out = np.empty((q.shape[0], nrows), dtype=np.float32)
+        _check(lib().yams_b200_debug_stage1_scores(self._h, q.ctypes.data_as(f32p), q.shape[0], engine, row_start, row_stride,
+                                                   nrows, out.ctypes.data_as(f32p)), "debug_stage1_scores")
+        return out
 
     def sync(self):
         _check(lib().yams_b200_corpus_sync(self._h), "corpus_sync")

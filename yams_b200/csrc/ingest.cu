@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <chrono>
 #include <mutex>
 #include <new>
 #include <vector>
@@ -18,7 +19,16 @@
 namespace yb {
 
 constexpr uint32_t kTileBytesHost = kTileBytes;
-constexpr uint64_t kSegmentBytes = 1ull << 30;     // device-resident data is processed 1 GiB at a time
+static uint64_t segment_bytes() {   // device-resident data is processed in segments (default 1 GiB)
+    const char* e = getenv("YAMS_B200_SEGMENT_MIB");
+    uint64_t mib = e ? strtoull(e, nullptr, 10) : 1024;
+    if (mib < 1) mib = 1;
+    if (mib > 16384) mib = 16384;
+    return mib << 20;
+}
+static inline double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 constexpr uint64_t kFeedSlice = 256ull << 20;      // host feeds are staged 256 MiB at a time
 
 // All device-side working state of one chunking stream.
@@ -34,6 +44,7 @@ struct CdcStream {
     uint64_t chunk_start = 0;    // stream position where the open chunk starts
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     float ms_scan = 0, ms_select = 0;
+    double host_sync1 = 0, host_sync2 = 0, host_alloc = 0, host_total = 0;  // wall-clock ms (diagnostics)
 
     yams_status_t init(const yams_cdc_config* cfg) {
         yams_status_t rc = ensure_device(&dev);
@@ -68,6 +79,7 @@ struct CdcStream {
     yams_status_t process(const uint8_t* data, uint64_t base_pos, uint64_t lowest, uint64_t scan_lo,
                           uint64_t scan_hi, bool final) {
         yams_status_t rc;
+        const double t_begin = now_ms();
         uint64_t* d_sc = scalars.as<uint64_t>();
         volatile uint64_t* h_sc = h_scalars.as<uint64_t>();
         uint32_t ncand = 0;
@@ -90,7 +102,7 @@ struct CdcStream {
                                          d_sc + 0, scan_scratch, st)) != YAMS_OK)
                 return rc;
             YB_CUDA(cudaMemcpyAsync((void*)h_sc, d_sc, 8, cudaMemcpyDeviceToHost, st));
-            YB_CUDA(cudaStreamSynchronize(st));
+            { const double t0 = now_ms(); YB_CUDA(cudaStreamSynchronize(st)); host_sync1 += now_ms() - t0; }
             uint64_t nc = h_sc[0];
             YB_ARG(nc < 0xFFFFFFF0ull, "too many boundary candidates in one segment");
             ncand = (uint32_t)nc;
@@ -126,10 +138,12 @@ struct CdcStream {
                                      scan_scratch, st)) != YAMS_OK)
             return rc;
         YB_CUDA(cudaMemcpyAsync((void*)h_sc, d_sc, 8, cudaMemcpyDeviceToHost, st));
-        YB_CUDA(cudaStreamSynchronize(st));
+        { const double t0 = now_ms(); YB_CUDA(cudaStreamSynchronize(st)); host_sync2 += now_ms() - t0; }
         uint64_t nnew = h_sc[0];
-        if ((rc = descs.reserve((size_t)(ndescs + nnew + 1) * sizeof(yams_chunk_desc), true, st)) != YAMS_OK)
+        { const double t0 = now_ms();
+          if ((rc = descs.reserve((size_t)(ndescs + nnew + 1) * sizeof(yams_chunk_desc), true, st)) != YAMS_OK)
             return rc;
+          host_alloc += now_ms() - t0; }
         cdc_emit_kernel<<<tgrid, 256, 0, st>>>(S, next.as<uint32_t>(), forced.as<uint32_t>(),
                                                onchain.as<uint8_t>(), emit_offsets.as<uint32_t>(),
                                                descs.as<yams_chunk_desc>(), ndescs, d_sc + 1);
@@ -144,6 +158,7 @@ struct CdcStream {
         cudaEventElapsedTime(&b, ev[1], ev[2]);
         ms_scan += a;
         ms_select += b;
+        host_total += now_ms() - t_begin;
         return YAMS_OK;
     }
 };
@@ -181,8 +196,9 @@ static yams_status_t run_device(const uint8_t* d_data, size_t len, const yams_cd
         cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
         cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
         cudaEventRecord(e0, cs.st);
-        for (uint64_t lo = 0; lo < len && rc == YAMS_OK; lo += kSegmentBytes) {
-            uint64_t hi = std::min<uint64_t>(len, lo + kSegmentBytes);
+        const uint64_t seg = segment_bytes();
+        for (uint64_t lo = 0; lo < len && rc == YAMS_OK; lo += seg) {
+            uint64_t hi = std::min<uint64_t>(len, lo + seg);
             rc = cs.process(d_data, 0, 0, lo, hi, hi == len);
         }
         cudaEventRecord(e1, cs.st);
@@ -202,7 +218,8 @@ static yams_status_t run_device(const uint8_t* d_data, size_t len, const yams_cd
         cudaEventElapsedTime(&t_sha, e1, e2);
         cudaEventElapsedTime(&t_all, e0, e2);
         g_last_ms[0] = cs.ms_scan; g_last_ms[1] = cs.ms_select; g_last_ms[2] = t_sha; g_last_ms[3] = t_all;
-        g_last_ms[4] = 0;
+        g_last_ms[4] = (float)cs.host_sync1; g_last_ms[5] = (float)cs.host_sync2; g_last_ms[6] = (float)cs.host_alloc;
+        g_last_ms[7] = (float)cs.host_total;
         cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     }
     cs.destroy();

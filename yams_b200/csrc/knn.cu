@@ -1183,6 +1183,32 @@ yams_status_t yams_b200_search_last_timings(yams_b200_corpus* c, float out_ms[8]
     return YAMS_OK;
 }
 
+// diagnostics: dense stage-1 scores of rows [row_start + i*row_stride, i < nrows) against the queries with the
+// chosen engine (0 cuda-core, 1 tcgen05) -> out[q * nrows + i] (HOST). Used by the tests to compare engines.
+yams_status_t yams_b200_debug_stage1_scores(yams_b200_corpus* c, const float* queries, uint32_t nq, int engine,
+                                            uint64_t row_start, uint64_t row_stride, uint64_t nrows, float* out) {
+    YB_ARG(c && queries && out && nq > 0 && nrows > 0 && row_stride > 0, "bad argument");
+    YB_ARG(row_start + (nrows - 1) * row_stride < c->n, "rows out of range");
+    yams_status_t rc;
+    if ((rc = prepare_queries(c, queries, false, nq)) != YAMS_OK) return rc;
+    if ((rc = c->dense.reserve((size_t)nq * nrows * 4)) != YAMS_OK) return rc;
+    YB_CUDA(cudaMemsetAsync(c->dense.p, 0xFF, (size_t)nq * nrows * 4, c->st));
+    Stage1Args a{};
+    a.rows = c->rows.p; a.inv_norm = c->inv_norm.as<float>(); a.dim = c->dim; a.dtype = c->dtype;
+    a.q32 = c->q32.as<float>(); a.qinv = c->qinv.as<float>(); a.nq = nq;
+    a.row_start = row_start; a.row_stride = row_stride; a.nrows = nrows;
+    a.out_scores = c->dense.as<float>(); a.ld = nrows;
+    if (engine == 1) {
+        rc = stage1_tcgen05(c, a, false, c->st);
+    } else {
+        rc = stage1_cuda_core(a, false, c->st);
+    }
+    if (rc != YAMS_OK) return rc;
+    YB_CUDA(cudaMemcpyAsync(out, c->dense.p, (size_t)nq * nrows * 4, cudaMemcpyDeviceToHost, c->st));
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    return YAMS_OK;
+}
+
 yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim, const float* rows, const int64_t* rowids,
                                    uint64_t n, uint64_t k, int use_range, int64_t rowid_lo, int64_t rowid_hi,
                                    int64_t* out_rowids, float* out_dist, uint64_t* out_count) {

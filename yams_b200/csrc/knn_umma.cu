@@ -1,7 +1,355 @@
-// knn_umma.cu -- tcgen05 (5th-gen tensor core) stage-1 engine. Placeholder until the UMMA kernel lands:
-// reports "unsupported" so the CUDA-core engine runs.
+// knn_umma.cu -- stage-1 scan engine on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Same contract as the CUDA-core engine in knn.cu (Stage1Args): approximate cosine scores of corpus rows
+// against a query batch with a fused epilogue (store, or per-query threshold filter -> candidate lists).
+// The scan of `rows x dim` fp16 against `nq x dim` queries IS a dense GEMM (tensor-bound above
+// ~Q=281, HBM-bound below), so it runs as:
+//
+//   warp 0      TMA producer : cp.async.bulk.tensor 2D loads of a 128-row corpus tile (A, K-major, 128B swizzle)
+//                               and an N-query tile (B) per 64-element K block into a multi-stage smem ring
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=256,
+//                               K=16 per instruction) accumulating fp32 in TMEM; tcgen05.commit releases smem
+//                               stages and publishes finished accumulators
+//   warps 2..5  epilogue     : tcgen05.ld the accumulator (lane = corpus row, column = query), scale by
+//                               1/|row|, compare with the per-query threshold, append survivors
+//   two TMEM accumulator buffers (2 x 256 columns) let the epilogue of tile i overlap the MMAs of tile i+1.
+//
+// Queries are pre-scaled by 1/|q| and rounded to fp16; the resulting ~1e-5 score error only affects which
+// rows reach stage 2, where the survivors are re-scored exactly in fp64 (knn.cu).
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <stdlib.h>
+
+#include <algorithm>
+
 #include "knn.cuh"
+
 namespace yb {
-bool tcgen05_supported(const Corpus*, uint32_t) { return false; }
-yams_status_t stage1_tcgen05(Corpus*, const Stage1Args&, bool, cudaStream_t) { return YAMS_ERR_UNSUPPORTED; }
+
+constexpr int UM_BLOCK_M = 128;
+constexpr int UM_BLOCK_K = 64;           // fp16 elements = 128 bytes = one swizzle row
+constexpr int UM_UMMA_K = 16;
+constexpr int UM_MAX_N = 256;
+constexpr int UM_THREADS = 192;          // 6 warps
+constexpr uint32_t UM_A_STAGE = UM_BLOCK_M * UM_BLOCK_K * 2;   // 16 KiB
+constexpr uint32_t UM_TMEM_COLS = 512;
+constexpr uint32_t UM_SPIN_LIMIT = 1u << 28;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t addr = smem_u32(bar);
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (!done && ++spins > UM_SPIN_LIMIT) __trap();  // never hang the GPU: abort the kernel instead
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 columns of fp32 accumulator -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO); version 1 (sm_100)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFFu);   // start address, 16-byte units
+    d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset between 8-row core groups
+    d |= (uint64_t)1 << 46;                        // descriptor version
+    d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+    return d;
+}
+
+struct UmmaArgs {
+    Stage1Args a;
+    uint32_t n_tile;      // queries per tile (multiple of 16, <= 256)
+    uint32_t nqt;         // query tiles
+    uint32_t nrt;         // corpus row tiles
+    uint32_t kblocks;     // ceil(dim / 64)
+    uint32_t stages;
+    uint32_t b_stage;     // bytes of one B stage = n_tile * 128
+    uint32_t idesc;
+};
+
+template <bool FILTER>
+__global__ void __launch_bounds__(UM_THREADS, 1)
+stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, UmmaArgs u) {
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128B-swizzled tiles
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t stage_bytes = UM_A_STAGE + u.b_stage;
+    uint8_t* tiles = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)u.stages * stage_bytes);
+    uint64_t* full = bars;                      // [stages]
+    uint64_t* empty = bars + u.stages;          // [stages]
+    uint64_t* tfull = bars + 2 * u.stages;      // [2]
+    uint64_t* tempty = tfull + 2;               // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint64_t n_units = (uint64_t)u.nrt * u.nqt;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        for (uint32_t s = 0; s < u.stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(&tfull[0], 1);
+        mbar_init(&tfull[1], 1);
+        mbar_init(&tempty[0], 4);
+        mbar_init(&tempty[1], 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(UM_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0;
+            for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+                const uint32_t rt = (uint32_t)(unit / u.nqt), qt = (uint32_t)(unit % u.nqt);
+                for (uint32_t kb = 0; kb < u.kblocks; ++kb) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    uint8_t* sa = tiles + (size_t)s * stage_bytes;
+                    uint8_t* sb = sa + UM_A_STAGE;
+                    mbar_expect_tx(&full[s], stage_bytes);
+                    tma_load_2d(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), (int)(rt * UM_BLOCK_M));
+                    tma_load_2d(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), (int)(qt * u.n_tile));
+                    if (++s == u.stages) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t s = 0, ph = 0, it = 0;
+            for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+                const uint32_t as = it & 1, aph = (it >> 1) & 1;
+                mbar_wait(&tempty[as], aph ^ 1);
+                tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + as * UM_MAX_N;
+                for (uint32_t kb = 0; kb < u.kblocks; ++kb) {
+                    mbar_wait(&full[s], ph);
+                    tcgen05_fence_after();
+                    const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
+                    const uint64_t adesc = make_smem_desc(sa);
+                    const uint64_t bdesc = make_smem_desc(sa + UM_A_STAGE);
+#pragma unroll
+                    for (uint32_t k = 0; k < UM_BLOCK_K / UM_UMMA_K; ++k) {
+                        // advance 32 bytes (16 fp16) along K inside the swizzle row: +2 in 16-byte units
+                        umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty[s]);          // smem stage reusable once these MMAs have read it
+                    if (++s == u.stages) { s = 0; ph ^= 1; }
+                }
+                umma_commit(&tfull[as]);             // accumulator complete
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const uint32_t quad = warp & 3;              // TMEM lane quadrant this warp may access
+        uint32_t it = 0;
+        for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+            const uint32_t rt = (uint32_t)(unit / u.nqt), qt = (uint32_t)(unit % u.nqt);
+            const uint32_t as = it & 1, aph = (it >> 1) & 1;
+            const uint64_t li = (uint64_t)rt * UM_BLOCK_M + quad * 32 + lane;   // row index within this launch
+            const bool rvalid = li < u.a.nrows;
+            const uint64_t grow = u.a.row_start + li * u.a.row_stride;
+            const float inr = rvalid ? u.a.inv_norm[grow] : 0.f;
+            mbar_wait(&tfull[as], aph);
+            tcgen05_fence_after();
+            const uint32_t q0 = qt * u.n_tile;
+            for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + ((quad * 32u) << 16) + as * UM_MAX_N + c0, v);
+                if (q0 + c0 >= u.a.nq) continue;     // warp-uniform
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const uint32_t q = q0 + c0 + c;
+                    if (q >= u.a.nq) break;
+                    const float s = inr > 0.f ? __uint_as_float(v[c]) * inr : -INFINITY;
+                    if (FILTER) {
+                        bool pass = rvalid && s > __ldg(&u.a.tau[q]);
+                        if (u.a.mask) {
+                            // rows of a warp are consecutive: one word per (query, warp) when aligned
+                            uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
+                            pass = pass && ((w >> (grow & 31)) & 1u);
+                        }
+                        if (pass) {
+                            uint32_t pos = atomicAdd(&u.a.counts[q], 1u);
+                            if (pos < u.a.cap) {
+                                Cand cd;
+                                cd.score = s;
+                                cd.row = (uint32_t)grow;
+                                u.a.cands[(uint64_t)q * u.a.cap + pos] = cd;
+                            }
+                        }
+                    } else {
+                        if (rvalid) u.a.out_scores[(uint64_t)q * u.a.ld + li] = s;
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(UM_TMEM_COLS) : "memory");
+    }
+}
+
+// queries -> fp16, pre-scaled by 1/|q|
+__global__ void queries_to_f16_kernel(const float* __restrict__ q32, const float* __restrict__ qinv, uint32_t nq, uint32_t d,
+                                      __half* __restrict__ out) {
+    uint64_t total = (uint64_t)nq * d;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t q = (uint32_t)(i / d);
+        out[i] = __float2half_rn(q32[i] * qinv[q]);
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
+                        uint32_t box_inner, uint32_t box_outer) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {outer_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+bool tcgen05_supported(const Corpus* c, uint32_t nq) {
+    (void)nq;
+    if (getenv("YAMS_B200_DISABLE_TCGEN05")) return false;
+    return c->dtype == YAMS_B200_F16 && c->metric == YAMS_B200_COSINE && (c->dim % 8 == 0) && get_encode_fn() != nullptr;
+}
+
+yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaStream_t st) {
+    if (a.dtype != YAMS_B200_F16 || (a.dim % 8) != 0 || a.nrows == 0 || a.nq == 0) return YAMS_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(a.rows) & 15) != 0) return YAMS_ERR_UNSUPPORTED;
+    if (a.nrows >= (1ull << 32)) return YAMS_ERR_UNSUPPORTED;
+    yams_status_t rc;
+    // fp16 queries pre-scaled by 1/|q| (so the epilogue only multiplies by 1/|row|)
+    size_t qb = (size_t)a.nq * a.dim * 2;
+    if ((rc = c->q16.reserve(qb + 256)) != YAMS_OK) return rc;
+    __half* d_q16 = c->q16.as<__half>();
+    queries_to_f16_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)a.nq * a.dim + 255) / 256, 4096), 256, 0, st>>>(
+        a.q32, a.qinv, a.nq, a.dim, d_q16);
+
+    UmmaArgs u{};
+    u.a = a;
+    u.n_tile = a.nq >= UM_MAX_N ? UM_MAX_N : ((a.nq + 15) / 16) * 16;
+    u.nqt = (a.nq + u.n_tile - 1) / u.n_tile;
+    u.nrt = (uint32_t)((a.nrows + UM_BLOCK_M - 1) / UM_BLOCK_M);
+    u.kblocks = (a.dim + UM_BLOCK_K - 1) / UM_BLOCK_K;
+    u.b_stage = u.n_tile * 128;
+    uint32_t stage_bytes = UM_A_STAGE + u.b_stage;
+    const uint32_t budget = 200 * 1024;
+    u.stages = std::min<uint32_t>(8, budget / stage_bytes);
+    if (u.stages < 2) return YAMS_ERR_UNSUPPORTED;
+    // instruction descriptor: D=f32, A=B=f16, both K-major, N, M=128
+    u.idesc = (1u << 4) | ((u.n_tile >> 3) << 17) | ((UM_BLOCK_M >> 4) << 24);
+
+    CUtensorMap tmA, tmB;
+    const uint8_t* a_base = reinterpret_cast<const uint8_t*>(a.rows) + (size_t)a.row_start * a.dim * 2;
+    if (!make_map_2d(&tmA, a_base, a.dim, a.nrows, (uint64_t)a.row_stride * a.dim * 2, UM_BLOCK_K, UM_BLOCK_M))
+        return YAMS_ERR_UNSUPPORTED;
+    if (!make_map_2d(&tmB, d_q16, a.dim, a.nq, (uint64_t)a.dim * 2, UM_BLOCK_K, u.n_tile)) return YAMS_ERR_UNSUPPORTED;
+
+    size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16;
+    uint64_t n_units = (uint64_t)u.nrt * u.nqt;
+    unsigned grid = (unsigned)std::min<uint64_t>(n_units, (uint64_t)c->dev->sm_count);
+    if (filter) {
+        YB_CUDA(cudaFuncSetAttribute(stage1_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stage1_umma_kernel<true><<<grid, UM_THREADS, smem, st>>>(tmA, tmB, u);
+    } else {
+        YB_CUDA(cudaFuncSetAttribute(stage1_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        stage1_umma_kernel<false><<<grid, UM_THREADS, smem, st>>>(tmA, tmB, u);
+    }
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
 }  // namespace yb
