@@ -1,3 +1,5 @@
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import os, time, numpy as np, torch, json
 import yams_b200 as Y
 assert Y.plugin_init()==0

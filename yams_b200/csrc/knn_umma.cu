@@ -130,6 +130,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint64_t* tfull = bars + 2 * u.stages;      // [2]
     uint64_t* tempty = tfull + 2;               // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    float* tau_s = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][UM_MAX_N]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -204,6 +205,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const uint32_t quad = warp & 3;              // TMEM lane quadrant this warp may access
+        float* my_tau = tau_s + quad * UM_MAX_N;
         uint32_t it = 0;
         for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
             const uint32_t rt = (uint32_t)(unit / u.nqt), qt = (uint32_t)(unit % u.nqt);
@@ -212,36 +214,52 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const bool rvalid = li < u.a.nrows;
             const uint64_t grow = u.a.row_start + li * u.a.row_stride;
             const float inr = rvalid ? u.a.inv_norm[grow] : 0.f;
+            const uint32_t q0 = qt * u.n_tile;
+            if (FILTER) {
+                // this warp's private copy of the tile's thresholds (+inf for queries past the end)
+                __syncwarp();
+                for (uint32_t c = lane; c < u.n_tile; c += 32) my_tau[c] = (q0 + c < u.a.nq) ? __ldg(&u.a.tau[q0 + c]) : INFINITY;
+                __syncwarp();
+            }
             mbar_wait(&tfull[as], aph);
             tcgen05_fence_after();
-            const uint32_t q0 = qt * u.n_tile;
             for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + ((quad * 32u) << 16) + as * UM_MAX_N + c0, v);
                 if (q0 + c0 >= u.a.nq) continue;     // warp-uniform
+                if (FILTER) {
+                    // branch-free pass over the 32 columns; survivors are rare (~1e-4 of the scores)
+                    bool any = false;
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const uint32_t q = q0 + c0 + c;
-                    if (q >= u.a.nq) break;
-                    const float s = inr > 0.f ? __uint_as_float(v[c]) * inr : -INFINITY;
-                    if (FILTER) {
-                        bool pass = rvalid && s > __ldg(&u.a.tau[q]);
-                        if (u.a.mask) {
-                            // rows of a warp are consecutive: one word per (query, warp) when aligned
-                            uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
-                            pass = pass && ((w >> (grow & 31)) & 1u);
-                        }
-                        if (pass) {
-                            uint32_t pos = atomicAdd(&u.a.counts[q], 1u);
-                            if (pos < u.a.cap) {
-                                Cand cd;
-                                cd.score = s;
-                                cd.row = (uint32_t)grow;
-                                u.a.cands[(uint64_t)q * u.a.cap + pos] = cd;
+                    for (int c = 0; c < 32; ++c) any |= (__uint_as_float(v[c]) * inr > my_tau[c0 + c]);
+                    if (any && inr > 0.f) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) {
+                            const uint32_t q = q0 + c0 + c;
+                            if (q >= u.a.nq) break;
+                            const float s = __uint_as_float(v[c]) * inr;
+                            bool pass = s > my_tau[c0 + c];
+                            if (pass && u.a.mask) {
+                                uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
+                                pass = (w >> (grow & 31)) & 1u;
+                            }
+                            if (pass) {
+                                uint32_t pos = atomicAdd(&u.a.counts[q], 1u);
+                                if (pos < u.a.cap) {
+                                    Cand cd;
+                                    cd.score = s;
+                                    cd.row = (uint32_t)grow;
+                                    u.a.cands[(uint64_t)q * u.a.cap + pos] = cd;
+                                }
                             }
                         }
-                    } else {
-                        if (rvalid) u.a.out_scores[(uint64_t)q * u.a.ld + li] = s;
+                    }
+                } else if (rvalid) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const uint32_t q = q0 + c0 + c;
+                        if (q < u.a.nq)
+                            u.a.out_scores[(uint64_t)q * u.a.ld + li] = inr > 0.f ? __uint_as_float(v[c]) * inr : -INFINITY;
                     }
                 }
             }
@@ -326,7 +344,7 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     u.kblocks = (a.dim + UM_BLOCK_K - 1) / UM_BLOCK_K;
     u.b_stage = u.n_tile * 128;
     uint32_t stage_bytes = UM_A_STAGE + u.b_stage;
-    const uint32_t budget = 200 * 1024;
+    const uint32_t budget = 196 * 1024;
     u.stages = std::min<uint32_t>(8, budget / stage_bytes);
     if (u.stages < 2) return YAMS_ERR_UNSUPPORTED;
     // instruction descriptor: D=f32, A=B=f16, both K-major, N, M=128
@@ -338,7 +356,7 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
         return YAMS_ERR_UNSUPPORTED;
     if (!make_map_2d(&tmB, d_q16, a.dim, a.nq, (uint64_t)a.dim * 2, UM_BLOCK_K, u.n_tile)) return YAMS_ERR_UNSUPPORTED;
 
-    size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16;
+    size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16 + 4 * UM_MAX_N * 4;
     uint64_t n_units = (uint64_t)u.nrt * u.nqt;
     unsigned grid = (unsigned)std::min<uint64_t>(n_units, (uint64_t)c->dev->sm_count);
     if (filter) {
