@@ -167,6 +167,219 @@ __global__ void __launch_bounds__(kScanThreads) cdc_write_kernel(ScanArgs A, uin
     }
 }
 
+// ---- single-pass scan: contiguous range per CTA, tiles staged in shared memory by bulk async copies ----
+//
+// Each CTA owns a contiguous range of the segment and walks it in 16 KiB tiles.  One thread issues
+// cp.async.bulk (TMA 1-D) copies of [64-byte look-behind | tile] into a 3-stage shared-memory ring
+// (mbarrier complete_tx), all threads test 16-byte units from shared memory (prefilter) and confirm the
+// rare prefilter hits against the bytes already in shared memory.  Candidates are rare (~1 / 8 KiB), so
+// a tile's hits are appended to a small shared list and written in rank order to the CTA's private slice
+// of a global buffer; a second tiny kernel concatenates the slices.  The input is read from HBM exactly
+// once.  Anything exceptional (slice or list overflow on adversarial data) raises a flag and the host
+// re-runs the segment through the exact two-pass kernels above.
+constexpr int SC_THREADS = 256;
+constexpr uint32_t SC_TILE = 16384;
+constexpr uint32_t SC_HALO = 64;     // >= kHistory (56), multiple of 16
+constexpr int SC_STAGES = 3;
+constexpr uint32_t SC_LIST = 512;
+
+struct SinglePassArgs {
+    ScanArgs A;
+    uint32_t ntiles;        // tiles in the segment (from A.origin)
+    uint32_t tiles_per_cta;
+    uint32_t slice_cap;     // candidate capacity of one CTA slice
+    uint32_t halo_ok;       // 1: the 64 bytes before A.origin are readable memory
+    uint64_t end16;         // A.origin + floor16(A.scan_hi - A.origin): bulk copies stop here
+    uint64_t* cand_tmp;     // [gridDim.x][slice_cap]
+    uint32_t* cta_counts;   // [gridDim.x]; 0xFFFFFFFF marks overflow
+};
+
+struct SmemView {
+    const uint8_t* s;   // s[0] is stream position pos0
+    uint64_t pos0;
+    uint64_t lowest;
+    __device__ __forceinline__ uint32_t at(int64_t pos) const {
+        if (pos < (int64_t)lowest) return 0;
+        return s[pos - (int64_t)pos0];
+    }
+};
+
+__device__ __forceinline__ uint32_t sc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(SinglePassArgs S) {
+    extern __shared__ __align__(128) uint8_t sc_smem[];
+    uint8_t* bufs = sc_smem;                                              // SC_STAGES x (SC_HALO + SC_TILE)
+    uint64_t* T_s = reinterpret_cast<uint64_t*>(bufs + SC_STAGES * (SC_HALO + SC_TILE));
+    uint64_t* full = T_s + 256;                                           // SC_STAGES mbarriers
+    uint32_t* list = reinterpret_cast<uint32_t*>(full + SC_STAGES);       // SC_LIST
+    uint32_t* list_cnt = list + SC_LIST;
+    uint8_t* pass_s = reinterpret_cast<uint8_t*>(list_cnt + 4);           // 256
+    const ScanArgs& A = S.A;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += SC_THREADS) {
+        uint64_t t = A.table[i];
+        T_s[i] = t;
+        uint64_t m0 = A.P.mask & 0xffull;
+        pass_s[i] = ((t & m0) == m0) ? 1 : 0;
+    }
+    const uint32_t t_begin = blockIdx.x * S.tiles_per_cta;
+    const uint32_t t_end = min(t_begin + S.tiles_per_cta, S.ntiles);
+    const uint32_t n_my = t_end > t_begin ? t_end - t_begin : 0;
+    if (tid == 0) {
+        for (int s = 0; s < SC_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sc_smem_u32(&full[s])), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        *list_cnt = 0;
+    }
+    __syncthreads();
+
+    auto issue = [&](uint32_t i) {   // thread 0: start the copy of my i-th tile into stage i % SC_STAGES
+        const uint32_t tile = t_begin + i;
+        const uint32_t s = i % SC_STAGES;
+        uint8_t* dst = bufs + (size_t)s * (SC_HALO + SC_TILE);
+        const uint64_t tile_pos = A.origin + (uint64_t)tile * SC_TILE;
+        uint64_t lo = (tile == 0 && !S.halo_ok) ? tile_pos : tile_pos - SC_HALO;
+        uint64_t hi = tile_pos + SC_TILE < S.end16 ? tile_pos + SC_TILE : S.end16;
+        uint32_t bytes = hi > lo ? (uint32_t)(hi - lo) : 0u;
+        const uint32_t bar = sc_smem_u32(&full[s]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (bytes) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(sc_smem_u32(dst + (lo - (tile_pos - SC_HALO)))), "l"(A.data + (lo - A.base_pos)), "r"(bytes), "r"(bar)
+                         : "memory");
+        } else {
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+        }
+    };
+    if (tid == 0)
+        for (uint32_t i = 0; i < n_my && i < (uint32_t)SC_STAGES; ++i) issue(i);
+
+    uint32_t my_total = 0;          // candidates written by this CTA so far (uniform across threads)
+    bool overflow = false;
+    uint64_t* my_out = S.cand_tmp + (size_t)blockIdx.x * S.slice_cap;
+    for (uint32_t i = 0; i < n_my; ++i) {
+        const uint32_t tile = t_begin + i;
+        const uint32_t s = i % SC_STAGES;
+        const uint32_t parity = (i / SC_STAGES) & 1;
+        uint8_t* buf = bufs + (size_t)s * (SC_HALO + SC_TILE);
+        const uint64_t tile_pos = A.origin + (uint64_t)tile * SC_TILE;
+        // bytes the bulk copy cannot bring in: look-behind of the very first tile, ragged tail (< 16 B)
+        if (tile == 0 && !S.halo_ok) {
+            if (tid < (int)SC_HALO) {
+                int64_t pos = (int64_t)tile_pos - SC_HALO + tid;
+                buf[tid] = (pos >= (int64_t)A.lowest && pos >= 0) ? A.data[pos - (int64_t)A.base_pos] : 0;
+            }
+        }
+        if (S.end16 < A.scan_hi && S.end16 >= tile_pos && S.end16 < tile_pos + SC_TILE) {
+            uint64_t q = S.end16 + tid;
+            if (q < A.scan_hi) buf[SC_HALO + (q - tile_pos)] = A.data[q - A.base_pos];
+        }
+        {   // wait for the bulk copy of this stage
+            const uint32_t bar = sc_smem_u32(&full[s]);
+            uint32_t done = 0, spins = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+                if (!done && ++spins > (1u << 28)) __trap();
+            }
+        }
+        __syncthreads();
+        SmemView view{buf, tile_pos - SC_HALO, A.lowest};
+#pragma unroll
+        for (int it = 0; it < (int)(SC_TILE / 16 / SC_THREADS); ++it) {
+            const uint32_t u = tid + it * SC_THREADS;
+            const uint64_t p0 = tile_pos + (uint64_t)u * 16;
+            uint64_t lo = p0 > A.scan_lo ? p0 : A.scan_lo;
+            uint64_t hi = p0 + 16 < A.scan_hi ? p0 + 16 : A.scan_hi;
+            if (lo >= hi) continue;
+            uint4 v = *reinterpret_cast<const uint4*>(buf + SC_HALO + u * 16);
+            uint32_t valid = 0xffffu;
+            if (lo != p0 || hi != p0 + 16) valid = ((1u << (uint32_t)(hi - p0)) - 1u) & ~((1u << (uint32_t)(lo - p0)) - 1u);
+            uint32_t pre = prefilter16(v, A.P, pass_s) & valid;
+            while (pre) {
+                int b = __ffs(pre) - 1;
+                pre &= pre - 1;
+                if (is_candidate(view, T_s, A.P, p0 + (uint64_t)b)) {
+                    uint32_t idx = atomicAdd(list_cnt, 1u);
+                    if (idx < SC_LIST) list[idx] = u * 16 + (uint32_t)b;
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t cnt = *list_cnt;
+        if (overflow || cnt > SC_LIST || my_total + cnt > S.slice_cap) {
+            overflow = true;   // keep draining the copy pipeline, stop recording
+        } else {
+            // rank order == position order (positions are unique)
+            for (uint32_t j = tid; j < cnt; j += SC_THREADS) {
+                uint32_t mine = list[j], rank = 0;
+                for (uint32_t k = 0; k < cnt; ++k) rank += list[k] < mine ? 1u : 0u;
+                my_out[my_total + rank] = tile_pos + mine;
+            }
+            my_total += cnt;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            *list_cnt = 0;
+            if (i + SC_STAGES < n_my) issue(i + SC_STAGES);
+        }
+    }
+    if (tid == 0) S.cta_counts[blockIdx.x] = overflow ? 0xFFFFFFFFu : my_total;
+}
+
+// concatenates the CTA slices in CTA order; scalars[0] = total candidates, scalars[2] = overflow flag
+__global__ void __launch_bounds__(1024) cdc_compact_kernel(const uint64_t* __restrict__ cand_tmp, const uint32_t* __restrict__ cta_counts,
+                                                           uint32_t nctas, uint32_t slice_cap, uint64_t* __restrict__ cand,
+                                                           uint64_t* __restrict__ scalars) {
+    __shared__ uint64_t offs[1025];
+    __shared__ uint32_t bad;
+    if (threadIdx.x == 0) {
+        uint64_t run = 0;
+        uint32_t b = 0;
+        for (uint32_t c = 0; c < nctas; ++c) {
+            offs[c] = run;
+            uint32_t n = cta_counts[c];
+            if (n == 0xFFFFFFFFu) { b = 1; n = 0; }
+            run += n;
+        }
+        offs[nctas] = run;
+        bad = b;
+        scalars[0] = run;
+        scalars[2] = b;
+    }
+    __syncthreads();
+    if (bad) return;
+    for (uint32_t c = 0; c < nctas; ++c) {
+        uint32_t n = (uint32_t)(offs[c + 1] - offs[c]);
+        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) cand[offs[c] + j] = cand_tmp[(size_t)c * slice_cap + j];
+    }
+}
+
+yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm_count, uint64_t* cand_tmp, uint32_t* cta_counts,
+                                      uint32_t slice_cap, uint32_t nctas, uint64_t* cand, uint64_t* scalars, cudaStream_t st) {
+    SinglePassArgs S{};
+    S.A = A;
+    S.ntiles = ntiles;
+    S.tiles_per_cta = (ntiles + nctas - 1) / nctas;
+    S.slice_cap = slice_cap;
+    S.halo_ok = (A.origin >= A.lowest + SC_HALO) ? 1u : 0u;
+    S.end16 = A.origin + ((A.scan_hi - A.origin) & ~15ull);
+    S.cand_tmp = cand_tmp;
+    S.cta_counts = cta_counts;
+    size_t smem = (size_t)SC_STAGES * (SC_HALO + SC_TILE) + 256 * 8 + SC_STAGES * 8 + SC_LIST * 4 + 16 + 256;
+    YB_CUDA(cudaFuncSetAttribute(cdc_scan_single_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cdc_scan_single_pass_kernel<<<nctas, SC_THREADS, smem, st>>>(S);
+    cdc_compact_kernel<<<1, 1024, 0, st>>>(cand_tmp, cta_counts, nctas, slice_cap, cand, scalars);
+    YB_CUDA(cudaGetLastError());
+    (void)sm_count;
+    return YAMS_OK;
+}
+
 // ---- cut selection ----------------------------------------------------------------------------
 
 __global__ void cdc_next_kernel(SelectArgs S, uint32_t* __restrict__ next, uint32_t* __restrict__ forced) {

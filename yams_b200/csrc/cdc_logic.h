@@ -67,8 +67,8 @@ struct ByteView {
 // Masked rolling-hash value at stream position p, rebuilt from `steps` local bytes.  Bits below
 // 8*steps equal the reference's full 64-bit state because '<<8' and '-' only carry information
 // upward.  T is the 256-entry table (shared/constant memory on device).
-template <typename TableT>
-YB_HD bool is_candidate(const ByteView& v, const TableT& T, const CdcParams& P, uint64_t p) {
+template <typename ViewT, typename TableT>
+YB_HD bool is_candidate(const ViewT& v, const TableT& T, const CdcParams& P, uint64_t p) {
     uint64_t h = 0;
     for (int j = (int)P.steps - 1; j >= 0; --j) {
         int64_t q = (int64_t)p - j;

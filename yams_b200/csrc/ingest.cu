@@ -37,7 +37,9 @@ struct CdcStream {
     cudaStream_t st = nullptr;
     CdcParams P{};
     bool no_candidates = false;  // lo >= force: no candidate can ever cut
-    DevBuf table, tile_counts, tile_offsets, cand, next, forced, exit_, entry, onchain, emit_counts,
+    bool two_pass_only = false;  // YAMS_B200_TWO_PASS=1: skip the single-pass scan (diagnostics)
+    uint32_t two_pass_fallbacks = 0;
+    DevBuf table, tile_counts, tile_offsets, cand, cand_tmp, next, forced, exit_, entry, onchain, emit_counts,
         emit_offsets, scan_scratch, descs, scalars;
     HostBuf h_scalars;           // pinned: [0] ncand/ntotal, [1] new chunk start
     uint64_t ndescs = 0;         // chunks accumulated in `descs`
@@ -46,24 +48,39 @@ struct CdcStream {
     float ms_scan = 0, ms_select = 0;
     double host_sync1 = 0, host_sync2 = 0, host_alloc = 0, host_total = 0;  // wall-clock ms (diagnostics)
 
-    yams_status_t init(const yams_cdc_config* cfg) {
+    bool created = false;
+    yams_status_t create() {
+        if (created) return YAMS_OK;
         yams_status_t rc = ensure_device(&dev);
         if (rc != YAMS_OK) return rc;
-        uint64_t tbl[256];
-        rc = resolve_params(cfg, &P, tbl);
-        if (rc != YAMS_OK) return rc;
-        no_candidates = P.lo >= P.force;
         YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto& e : ev) YB_CUDA(cudaEventCreate(&e));
         if ((rc = table.reserve(256 * 8)) != YAMS_OK) return rc;
         if ((rc = scalars.reserve(64)) != YAMS_OK) return rc;
-        if ((rc = h_scalars.reserve(64)) != YAMS_OK) return rc;
-        YB_CUDA(cudaMemcpyAsync(table.p, tbl, sizeof tbl, cudaMemcpyHostToDevice, st));
+        if ((rc = h_scalars.reserve(64 + 256 * 8)) != YAMS_OK) return rc;
+        created = true;
+        return YAMS_OK;
+    }
+    // (re)configure for a new stream: parameters, table, counters. Buffers are kept.
+    yams_status_t init(const yams_cdc_config* cfg) {
+        yams_status_t rc = create();
+        if (rc != YAMS_OK) return rc;
+        uint64_t* tbl = h_scalars.as<uint64_t>() + 8;   // pinned staging for the table
         YB_CUDA(cudaStreamSynchronize(st));
+        rc = resolve_params(cfg, &P, tbl);
+        if (rc != YAMS_OK) return rc;
+        no_candidates = P.lo >= P.force;
+        two_pass_only = getenv("YAMS_B200_TWO_PASS") != nullptr;
+        ndescs = 0;
+        chunk_start = 0;
+        ms_scan = ms_select = 0;
+        host_sync1 = host_sync2 = host_alloc = host_total = 0;
+        two_pass_fallbacks = 0;
+        YB_CUDA(cudaMemcpyAsync(table.p, tbl, 256 * 8, cudaMemcpyHostToDevice, st));
         return YAMS_OK;
     }
     void destroy() {
-        for (DevBuf* b : {&table, &tile_counts, &tile_offsets, &cand, &next, &forced, &exit_, &entry, &onchain,
+        for (DevBuf* b : {&table, &tile_counts, &tile_offsets, &cand, &cand_tmp, &next, &forced, &exit_, &entry, &onchain,
                           &emit_counts, &emit_offsets, &scan_scratch, &descs, &scalars})
             b->release();
         h_scalars.release();
@@ -71,6 +88,7 @@ struct CdcStream {
             if (e) cudaEventDestroy(e);
         if (st) cudaStreamDestroy(st);
         st = nullptr;
+        created = false;
     }
 
     // Scan stream positions [scan_lo, scan_hi) (bytes readable from `lowest`), select cuts from the
@@ -93,23 +111,48 @@ struct CdcStream {
             uint64_t ntiles64 = (span + kTileBytesHost - 1) / kTileBytesHost;
             YB_ARG(ntiles64 < (1ull << 31), "segment too large");
             uint32_t ntiles = (uint32_t)ntiles64;
-            if ((rc = tile_counts.reserve((size_t)ntiles * 4)) != YAMS_OK) return rc;
-            if ((rc = tile_offsets.reserve((size_t)ntiles * 4)) != YAMS_OK) return rc;
             ScanArgs A{data, base_pos, lowest, origin, scan_lo, scan_hi, table.as<uint64_t>(), P};
-            uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)dev->sm_count * 8u);
-            cdc_count_kernel<<<grid, 256, 0, st>>>(A, ntiles, tile_counts.as<uint32_t>());
-            if ((rc = exclusive_scan_u32(tile_counts.as<uint32_t>(), tile_offsets.as<uint32_t>(), ntiles,
-                                         d_sc + 0, scan_scratch, st)) != YAMS_OK)
-                return rc;
-            YB_CUDA(cudaMemcpyAsync((void*)h_sc, d_sc, 8, cudaMemcpyDeviceToHost, st));
-            { const double t0 = now_ms(); YB_CUDA(cudaStreamSynchronize(st)); host_sync1 += now_ms() - t0; }
-            uint64_t nc = h_sc[0];
-            YB_ARG(nc < 0xFFFFFFF0ull, "too many boundary candidates in one segment");
-            ncand = (uint32_t)nc;
-            if (ncand) {
-                if ((rc = cand.reserve((size_t)ncand * 8)) != YAMS_OK) return rc;
-                cdc_write_kernel<<<grid, 256, 0, st>>>(A, ntiles, tile_counts.as<uint32_t>(),
-                                                       tile_offsets.as<uint32_t>(), cand.as<uint64_t>());
+            bool need_two_pass = two_pass_only;
+            if (!two_pass_only) {
+                // single pass: every CTA scans a contiguous range and appends to its own slice
+                uint32_t nctas = std::min<uint32_t>(ntiles, (uint32_t)dev->sm_count * 2u);
+                uint32_t tpc = (ntiles + nctas - 1) / nctas;
+                uint32_t slice_cap = std::max<uint32_t>(256u, tpc * 64u);   // 32x the 1/8192 density of random data
+                size_t total_cap = (size_t)nctas * slice_cap;
+                if ((rc = cand_tmp.reserve(total_cap * 8)) != YAMS_OK) return rc;
+                if ((rc = cand.reserve(total_cap * 8)) != YAMS_OK) return rc;
+                if ((rc = tile_counts.reserve((size_t)std::max<uint32_t>(ntiles, nctas) * 4)) != YAMS_OK) return rc;
+                if ((rc = launch_scan_single_pass(A, ntiles, dev->sm_count, cand_tmp.as<uint64_t>(), tile_counts.as<uint32_t>(),
+                                                  slice_cap, nctas, cand.as<uint64_t>(), d_sc, st)) != YAMS_OK)
+                    return rc;
+                YB_CUDA(cudaMemcpyAsync((void*)h_sc, d_sc, 24, cudaMemcpyDeviceToHost, st));
+                { const double t0 = now_ms(); YB_CUDA(cudaStreamSynchronize(st)); host_sync1 += now_ms() - t0; }
+                if (h_sc[2] != 0) {
+                    need_two_pass = true;   // dense candidates: exact two-pass kernels take over
+                    ++two_pass_fallbacks;
+                } else {
+                    YB_ARG(h_sc[0] < 0xFFFFFFF0ull, "too many boundary candidates in one segment");
+                    ncand = (uint32_t)h_sc[0];
+                }
+            }
+            if (need_two_pass) {
+                if ((rc = tile_counts.reserve((size_t)ntiles * 4)) != YAMS_OK) return rc;
+                if ((rc = tile_offsets.reserve((size_t)ntiles * 4)) != YAMS_OK) return rc;
+                uint32_t grid = std::min<uint32_t>(ntiles, (uint32_t)dev->sm_count * 8u);
+                cdc_count_kernel<<<grid, 256, 0, st>>>(A, ntiles, tile_counts.as<uint32_t>());
+                if ((rc = exclusive_scan_u32(tile_counts.as<uint32_t>(), tile_offsets.as<uint32_t>(), ntiles,
+                                             d_sc + 0, scan_scratch, st)) != YAMS_OK)
+                    return rc;
+                YB_CUDA(cudaMemcpyAsync((void*)h_sc, d_sc, 8, cudaMemcpyDeviceToHost, st));
+                { const double t0 = now_ms(); YB_CUDA(cudaStreamSynchronize(st)); host_sync1 += now_ms() - t0; }
+                uint64_t nc = h_sc[0];
+                YB_ARG(nc < 0xFFFFFFF0ull, "too many boundary candidates in one segment");
+                ncand = (uint32_t)nc;
+                if (ncand) {
+                    if ((rc = cand.reserve((size_t)ncand * 8)) != YAMS_OK) return rc;
+                    cdc_write_kernel<<<grid, 256, 0, st>>>(A, ntiles, tile_counts.as<uint32_t>(),
+                                                           tile_offsets.as<uint32_t>(), cand.as<uint64_t>());
+                }
             }
         }
         YB_CUDA(cudaEventRecord(ev[1], st));
@@ -165,6 +208,91 @@ struct CdcStream {
 
 static thread_local float g_last_ms[8] = {0};
 
+// Device-side resources of one ingest stream (kernel workspace + the two staging buffers of the host
+// path). They are pooled: `yams add` calls chunk_and_hash once per file, and cudaMalloc / cudaFree of the
+// workspace would otherwise dominate small inputs.
+struct IngestRes {
+    CdcStream cs;
+    cudaStream_t copy_st = nullptr;
+    DevBuf stage[2];
+    cudaEvent_t copied[2] = {nullptr, nullptr};
+    cudaEvent_t freed[2] = {nullptr, nullptr};
+    cudaEvent_t t0 = nullptr, t1 = nullptr, e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    bool created = false;
+    yams_status_t create() {
+        if (created) return YAMS_OK;
+        yams_status_t rc = cs.create();
+        if (rc != YAMS_OK) return rc;
+        YB_CUDA(cudaStreamCreateWithFlags(&copy_st, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; ++b) {
+            YB_CUDA(cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+            YB_CUDA(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
+        }
+        for (cudaEvent_t* e : {&t0, &t1, &e0, &e1, &e2}) YB_CUDA(cudaEventCreate(e));
+        created = true;
+        return YAMS_OK;
+    }
+    void destroy() {
+        if (cs.st) cudaStreamSynchronize(cs.st);
+        if (copy_st) cudaStreamSynchronize(copy_st);
+        for (int b = 0; b < 2; ++b) {
+            stage[b].release();
+            if (copied[b]) cudaEventDestroy(copied[b]);
+            if (freed[b]) cudaEventDestroy(freed[b]);
+        }
+        for (cudaEvent_t e : {t0, t1, e0, e1, e2})
+            if (e) cudaEventDestroy(e);
+        if (copy_st) cudaStreamDestroy(copy_st);
+        cs.destroy();
+        created = false;
+    }
+};
+
+static std::mutex g_pool_mu;
+static std::vector<IngestRes*> g_pool;
+constexpr size_t kPoolMax = 4;
+
+static yams_status_t acquire_res(const yams_cdc_config* cfg, IngestRes** out) {
+    IngestRes* r = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (!g_pool.empty()) {
+            r = g_pool.back();
+            g_pool.pop_back();
+        }
+    }
+    if (!r) r = new (std::nothrow) IngestRes();
+    if (!r) return YAMS_ERR_INTERNAL;
+    yams_status_t rc = r->create();
+    if (rc == YAMS_OK) rc = r->cs.init(cfg);
+    if (rc != YAMS_OK) {
+        r->destroy();
+        delete r;
+        return rc;
+    }
+    *out = r;
+    return YAMS_OK;
+}
+
+static void release_res(IngestRes* r) {
+    if (!r) return;
+    if (r->cs.st) cudaStreamSynchronize(r->cs.st);
+    if (r->copy_st) cudaStreamSynchronize(r->copy_st);
+    // drop very large buffers instead of parking them in the pool
+    const size_t kKeep = 1ull << 30;
+    for (DevBuf* b : {&r->stage[0], &r->stage[1], &r->cs.descs, &r->cs.cand, &r->cs.cand_tmp})
+        if (b->cap > kKeep) b->release();
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < kPoolMax) {
+            g_pool.push_back(r);
+            return;
+        }
+    }
+    r->destroy();
+    delete r;
+}
+
 static yams_status_t copy_out(CdcStream& cs, uint64_t first, uint64_t n, yams_chunk_desc** out, size_t* out_n) {
     *out = nullptr;
     *out_n = 0;
@@ -190,39 +318,42 @@ static yams_status_t copy_out(CdcStream& cs, uint64_t first, uint64_t n, yams_ch
 // One-shot over device-resident data.
 static yams_status_t run_device(const uint8_t* d_data, size_t len, const yams_cdc_config* cfg, bool hash,
                                 yams_chunk_desc** out, size_t* out_n) {
-    CdcStream cs;
-    yams_status_t rc = cs.init(cfg);
+    IngestRes* r = nullptr;
+    yams_status_t rc = acquire_res(cfg, &r);
+    if (rc != YAMS_OK) return rc;
+    CdcStream& cs = r->cs;
+    // size the descriptor table once: every chunk but the last is at least max(min_chunk,1) bytes long
+    {
+        uint64_t per = std::max<uint64_t>(cs.P.lo + 1, 4096);
+        rc = cs.descs.reserve((size_t)(len / per + 16) * sizeof(yams_chunk_desc));
+    }
+    cudaEventRecord(r->e0, cs.st);
+    const uint64_t seg = segment_bytes();
+    for (uint64_t lo = 0; lo < len && rc == YAMS_OK; lo += seg) {
+        uint64_t hi = std::min<uint64_t>(len, lo + seg);
+        rc = cs.process(d_data, 0, 0, lo, hi, hi == len);
+    }
+    cudaEventRecord(r->e1, cs.st);
+    if (rc == YAMS_OK && hash && cs.ndescs) {
+        if (cs.ndescs >= 0xFFFFFFFFull) {
+            set_last_error("too many chunks");
+            rc = YAMS_ERR_INVALID_ARG;
+        } else {
+            rc = launch_sha256_chunks(d_data, 0, cs.descs.as<yams_chunk_desc>(), 0, (uint32_t)cs.ndescs,
+                                      reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4), cs.dev->sm_count, cs.st);
+        }
+    }
+    cudaEventRecord(r->e2, cs.st);
+    if (rc == YAMS_OK) rc = copy_out(cs, 0, cs.ndescs, out, out_n);
     if (rc == YAMS_OK) {
-        cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
-        cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventCreate(&e2);
-        cudaEventRecord(e0, cs.st);
-        const uint64_t seg = segment_bytes();
-        for (uint64_t lo = 0; lo < len && rc == YAMS_OK; lo += seg) {
-            uint64_t hi = std::min<uint64_t>(len, lo + seg);
-            rc = cs.process(d_data, 0, 0, lo, hi, hi == len);
-        }
-        cudaEventRecord(e1, cs.st);
-        if (rc == YAMS_OK && hash && cs.ndescs) {
-            if (cs.ndescs >= 0xFFFFFFFFull) {
-                set_last_error("too many chunks");
-                rc = YAMS_ERR_INVALID_ARG;
-            } else {
-                rc = launch_sha256_chunks(d_data, 0, cs.descs.as<yams_chunk_desc>(), 0, (uint32_t)cs.ndescs,
-                                          reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4),
-                                          cs.dev->sm_count, cs.st);
-            }
-        }
-        cudaEventRecord(e2, cs.st);
-        if (rc == YAMS_OK) rc = copy_out(cs, 0, cs.ndescs, out, out_n);
         float t_sha = 0, t_all = 0;
-        cudaEventElapsedTime(&t_sha, e1, e2);
-        cudaEventElapsedTime(&t_all, e0, e2);
+        cudaEventElapsedTime(&t_sha, r->e1, r->e2);
+        cudaEventElapsedTime(&t_all, r->e0, r->e2);
         g_last_ms[0] = cs.ms_scan; g_last_ms[1] = cs.ms_select; g_last_ms[2] = t_sha; g_last_ms[3] = t_all;
         g_last_ms[4] = (float)cs.host_sync1; g_last_ms[5] = (float)cs.host_sync2; g_last_ms[6] = (float)cs.host_alloc;
         g_last_ms[7] = (float)cs.host_total;
-        cudaEventDestroy(e0); cudaEventDestroy(e1); cudaEventDestroy(e2);
     }
-    cs.destroy();
+    release_res(r);
     return rc;
 }
 
@@ -233,11 +364,7 @@ using namespace yb;
 // Streaming session: host bytes are staged [carry | slice] into one of two device buffers; the H2D copy
 // of slice i+1 overlaps the kernels of slice i (when the host memory is pinned).
 struct yams_b200_ingest {
-    CdcStream cs;
-    cudaStream_t copy_st = nullptr;
-    DevBuf stage[2];
-    cudaEvent_t copied[2] = {nullptr, nullptr};  // H2D into stage[b] complete
-    cudaEvent_t freed[2] = {nullptr, nullptr};   // everything that reads stage[b] has been enqueued+ordered
+    IngestRes* r = nullptr;
     uint64_t head = 0;            // bytes reserved in front of a slice for the carry
     uint64_t stream_pos = 0;      // bytes fed so far
     uint64_t keep_from = 0;       // lowest stream position still resident on the device
@@ -246,63 +373,44 @@ struct yams_b200_ingest {
     bool hash = true;
     bool finished = false;
     float ms_sha = 0;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
 };
 
 static yams_status_t session_open(const yams_cdc_config* cfg, bool hash, yams_b200_ingest** out) {
     yams_b200_ingest* s = new (std::nothrow) yams_b200_ingest();
     if (!s) return YAMS_ERR_INTERNAL;
     s->hash = hash;
-    yams_status_t rc = s->cs.init(cfg);
+    yams_status_t rc = acquire_res(cfg, &s->r);
     if (rc != YAMS_OK) {
-        s->cs.destroy();
         delete s;
         return rc;
     }
     // the open chunk is always shorter than `force`, and a position needs <= kHistory bytes behind it
-    uint64_t need = std::max<uint64_t>(s->cs.P.force, (uint64_t)kHistory) + 16;
+    uint64_t need = std::max<uint64_t>(s->r->cs.P.force, (uint64_t)kHistory) + 16;
     s->head = (need + 255) & ~255ull;
-    cudaStreamCreateWithFlags(&s->copy_st, cudaStreamNonBlocking);
-    for (int b = 0; b < 2; ++b) {
-        cudaEventCreateWithFlags(&s->copied[b], cudaEventDisableTiming);
-        cudaEventCreateWithFlags(&s->freed[b], cudaEventDisableTiming);
-    }
-    cudaEventCreate(&s->t0);
-    cudaEventCreate(&s->t1);
     *out = s;
     return YAMS_OK;
 }
 
 static void session_close(yams_b200_ingest* s) {
     if (!s) return;
-    if (s->cs.st) cudaStreamSynchronize(s->cs.st);
-    if (s->copy_st) cudaStreamSynchronize(s->copy_st);
-    for (int b = 0; b < 2; ++b) {
-        s->stage[b].release();
-        if (s->copied[b]) cudaEventDestroy(s->copied[b]);
-        if (s->freed[b]) cudaEventDestroy(s->freed[b]);
-    }
-    if (s->t0) cudaEventDestroy(s->t0);
-    if (s->t1) cudaEventDestroy(s->t1);
-    if (s->copy_st) cudaStreamDestroy(s->copy_st);
-    s->cs.destroy();
+    release_res(s->r);
     delete s;
 }
 
 static yams_status_t session_sha(yams_b200_ingest* s, const uint8_t* data, uint64_t base_pos, uint64_t first) {
-    CdcStream& cs = s->cs;
+    CdcStream& cs = s->r->cs;
     if (!s->hash || cs.ndescs <= first) return YAMS_OK;
     YB_ARG(cs.ndescs - first < 0xFFFFFFFFull, "too many chunks in one slice");
-    YB_CUDA(cudaEventRecord(s->t0, cs.st));
+    YB_CUDA(cudaEventRecord(s->r->t0, cs.st));
     yams_status_t rc = launch_sha256_chunks(data, base_pos, cs.descs.as<yams_chunk_desc>(), (uint32_t)first,
                                             (uint32_t)(cs.ndescs - first),
                                             reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4),
                                             cs.dev->sm_count, cs.st);
     if (rc != YAMS_OK) return rc;
-    YB_CUDA(cudaEventRecord(s->t1, cs.st));
-    YB_CUDA(cudaEventSynchronize(s->t1));
+    YB_CUDA(cudaEventRecord(s->r->t1, cs.st));
+    YB_CUDA(cudaEventSynchronize(s->r->t1));
     float ms = 0;
-    cudaEventElapsedTime(&ms, s->t0, s->t1);
+    cudaEventElapsedTime(&ms, s->r->t0, s->r->t1);
     s->ms_sha += ms;
     return YAMS_OK;
 }
@@ -310,7 +418,8 @@ static yams_status_t session_sha(yams_b200_ingest* s, const uint8_t* data, uint6
 // Feed `len` host bytes; when `final`, also close the stream.  Newly completed chunks are appended to
 // cs.descs (digests included when hashing is on).
 static yams_status_t session_feed(yams_b200_ingest* s, const uint8_t* data, size_t len, bool final) {
-    CdcStream& cs = s->cs;
+    IngestRes* r = s->r;
+    CdcStream& cs = r->cs;
     yams_status_t rc;
     YB_ARG(!s->finished, "ingest session already finished");
     const size_t nslices = (size_t)((len + kFeedSlice - 1) / kFeedSlice);
@@ -327,12 +436,12 @@ static yams_status_t session_feed(yams_b200_ingest* s, const uint8_t* data, size
     auto slice_len = [&](size_t i) { return (size_t)std::min<uint64_t>(kFeedSlice, (uint64_t)len - i * kFeedSlice); };
     auto issue_copy = [&](size_t i, int b) -> yams_status_t {
         size_t sl = slice_len(i);
-        yams_status_t r = s->stage[b].reserve((size_t)s->head + sl + 64);
-        if (r != YAMS_OK) return r;
-        YB_CUDA(cudaStreamWaitEvent(s->copy_st, s->freed[b], 0));
-        YB_CUDA(cudaMemcpyAsync(s->stage[b].as<uint8_t>() + s->head, data + i * kFeedSlice, sl,
-                                cudaMemcpyHostToDevice, s->copy_st));
-        YB_CUDA(cudaEventRecord(s->copied[b], s->copy_st));
+        yams_status_t rr = r->stage[b].reserve((size_t)s->head + sl + 64);
+        if (rr != YAMS_OK) return rr;
+        YB_CUDA(cudaStreamWaitEvent(r->copy_st, r->freed[b], 0));
+        YB_CUDA(cudaMemcpyAsync(r->stage[b].as<uint8_t>() + s->head, data + i * kFeedSlice, sl,
+                                cudaMemcpyHostToDevice, r->copy_st));
+        YB_CUDA(cudaEventRecord(r->copied[b], r->copy_st));
         return YAMS_OK;
     };
     int b = s->cur < 0 ? 0 : (s->cur ^ 1);
@@ -340,15 +449,15 @@ static yams_status_t session_feed(yams_b200_ingest* s, const uint8_t* data, size
     for (size_t i = 0; i < nslices; ++i) {
         const size_t sl = slice_len(i);
         const uint64_t carry = s->stream_pos - s->keep_from;
-        uint8_t* dst0 = s->stage[b].as<uint8_t>() + s->head;  // device address of stream position stream_pos
+        uint8_t* dst0 = r->stage[b].as<uint8_t>() + s->head;  // device address of stream position stream_pos
         if (carry) {
             YB_CUDA(cudaMemcpyAsync(dst0 - carry, s->res_ptr, (size_t)carry, cudaMemcpyDeviceToDevice, cs.st));
         }
-        if (s->cur >= 0) YB_CUDA(cudaEventRecord(s->freed[s->cur], cs.st));
+        if (s->cur >= 0) YB_CUDA(cudaEventRecord(r->freed[s->cur], cs.st));
         if (i + 1 < nslices) {
             if ((rc = issue_copy(i + 1, b ^ 1)) != YAMS_OK) return rc;
         }
-        YB_CUDA(cudaStreamWaitEvent(cs.st, s->copied[b], 0));
+        YB_CUDA(cudaStreamWaitEvent(cs.st, r->copied[b], 0));
         const uint64_t new_pos = s->stream_pos + sl;
         const uint64_t first = cs.ndescs;
         const uint8_t* view = dst0 - carry;  // stream position keep_from
@@ -369,8 +478,8 @@ static yams_status_t session_feed(yams_b200_ingest* s, const uint8_t* data, size
 }
 
 static yams_status_t session_take(yams_b200_ingest* s, yams_chunk_desc** out, size_t* out_n) {
-    yams_status_t rc = copy_out(s->cs, 0, s->cs.ndescs, out, out_n);
-    if (rc == YAMS_OK) s->cs.ndescs = 0;  // descriptors handed over; reuse the device table
+    yams_status_t rc = copy_out(s->r->cs, 0, s->r->cs.ndescs, out, out_n);
+    if (rc == YAMS_OK) s->r->cs.ndescs = 0;  // descriptors handed over; reuse the device table
     return rc;
 }
 
@@ -379,19 +488,21 @@ static yams_status_t run_host(const uint8_t* data, size_t len, const yams_cdc_co
     yams_b200_ingest* s = nullptr;
     yams_status_t rc = session_open(cfg, hash, &s);
     if (rc != YAMS_OK) return rc;
-    cudaEvent_t e0 = nullptr, e1 = nullptr;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0, s->cs.st);
-    rc = session_feed(s, data, len, true);
+    CdcStream& cs = s->r->cs;
+    {
+        uint64_t per = std::max<uint64_t>(cs.P.lo + 1, 4096);
+        rc = cs.descs.reserve((size_t)(len / per + 16) * sizeof(yams_chunk_desc));
+    }
+    cudaEventRecord(s->r->e0, cs.st);
+    if (rc == YAMS_OK) rc = session_feed(s, data, len, true);
     if (rc == YAMS_OK) rc = session_take(s, out, out_n);
-    cudaEventRecord(e1, s->cs.st);
-    cudaEventSynchronize(e1);
+    cudaEventRecord(s->r->e1, cs.st);
+    cudaEventSynchronize(s->r->e1);
     float t = 0;
-    cudaEventElapsedTime(&t, e0, e1);
-    g_last_ms[0] = s->cs.ms_scan; g_last_ms[1] = s->cs.ms_select; g_last_ms[2] = s->ms_sha; g_last_ms[3] = t;
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    cudaEventElapsedTime(&t, s->r->e0, s->r->e1);
+    g_last_ms[0] = cs.ms_scan; g_last_ms[1] = cs.ms_select; g_last_ms[2] = s->ms_sha; g_last_ms[3] = t;
+    g_last_ms[4] = (float)cs.host_sync1; g_last_ms[5] = (float)cs.host_sync2; g_last_ms[6] = (float)cs.host_alloc;
+    g_last_ms[7] = (float)cs.host_total;
     session_close(s);
     return rc;
 }

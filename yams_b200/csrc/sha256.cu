@@ -15,6 +15,8 @@
 // spans.  Lanes then read their row word-by-word; the byte misalignment of the chunk start and the
 // big-endian word order are both absorbed by ONE prmt per message word.
 // The kernel is INT32-ALU bound (~22 instr/byte), not HBM bound.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace yb {
@@ -36,7 +38,16 @@ __device__ __constant__ uint32_t kSha256K[64] = {
 
 __device__ __forceinline__ uint32_t rotr(uint32_t x, int n) { return __funnelshift_r(x, x, n); }
 
-__device__ __forceinline__ void sha256_compress(uint32_t (&st)[8], uint32_t (&w)[16]) {
+// MADD: with `one` an opaque runtime 1, x * one + y compiles to IMAD, which runs on the FMA pipe and takes
+// the additions off the INT32 ALU pipe where the SHF/LOP3 of the round function already saturate issue
+// (ALU-pipe instructions per block drop from ~1330 to ~1030).
+template <bool MADD>
+__device__ __forceinline__ uint32_t add2(uint32_t x, uint32_t y, uint32_t one) {
+    return MADD ? x * one + y : x + y;
+}
+
+template <bool MADD>
+__device__ __forceinline__ void sha256_compress(uint32_t (&st)[8], uint32_t (&w)[16], uint32_t one) {
     uint32_t a = st[0], b = st[1], c = st[2], d = st[3], e = st[4], f = st[5], g = st[6], h = st[7];
 #pragma unroll
     for (int i = 0; i < 64; ++i) {
@@ -44,24 +55,26 @@ __device__ __forceinline__ void sha256_compress(uint32_t (&st)[8], uint32_t (&w)
             uint32_t w15 = w[(i - 15) & 15], w2 = w[(i - 2) & 15];
             uint32_t s0 = rotr(w15, 7) ^ rotr(w15, 18) ^ (w15 >> 3);
             uint32_t s1 = rotr(w2, 17) ^ rotr(w2, 19) ^ (w2 >> 10);
-            w[i & 15] = w[i & 15] + s0 + w[(i - 7) & 15] + s1;
+            w[i & 15] = add2<MADD>(add2<MADD>(add2<MADD>(w[i & 15], s0, one), w[(i - 7) & 15], one), s1, one);
         }
         uint32_t S1 = rotr(e, 6) ^ rotr(e, 11) ^ rotr(e, 25);
         uint32_t ch = (e & f) ^ (~e & g);
-        uint32_t t1 = h + S1 + ch + kSha256K[i] + w[i & 15];
+        uint32_t kw = add2<MADD>(w[i & 15], kSha256K[i], one);
+        uint32_t t1 = add2<MADD>(add2<MADD>(add2<MADD>(h, S1, one), ch, one), kw, one);
         uint32_t S0 = rotr(a, 2) ^ rotr(a, 13) ^ rotr(a, 22);
         uint32_t mj = (a & b) ^ (a & c) ^ (b & c);
-        uint32_t t2 = S0 + mj;
-        h = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        uint32_t t2 = add2<MADD>(S0, mj, one);
+        h = g; g = f; f = e; e = add2<MADD>(d, t1, one); d = c; c = b; b = a; a = add2<MADD>(t1, t2, one);
     }
     st[0] += a; st[1] += b; st[2] += c; st[3] += d; st[4] += e; st[5] += f; st[6] += g; st[7] += h;
 }
 
 // data[0] is stream position base_pos; desc.offset is a stream position.
+template <bool MADD>
 __global__ void __launch_bounds__(kShaWarpsPerCta * 32, 4)
 sha256_chunks_kernel(const uint8_t* __restrict__ data, uint64_t base_pos,
                      yams_chunk_desc* __restrict__ descs, uint32_t first, uint32_t n,
-                     unsigned int* __restrict__ counter) {
+                     unsigned int* __restrict__ counter, uint32_t one) {
     __shared__ __align__(16) uint32_t smem[kShaWarpsPerCta][32 * kRowWords];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -170,7 +183,7 @@ sha256_chunks_kernel(const uint8_t* __restrict__ data, uint64_t base_pos,
                         }
                     }
                 }
-                sha256_compress(st, w);
+                sha256_compress<MADD>(st, w, one);
                 if (done) {
                     uint4 lo, hi;
                     lo.x = __byte_perm(st[0], 0, 0x0123); lo.y = __byte_perm(st[1], 0, 0x0123);
@@ -199,8 +212,11 @@ yams_status_t launch_sha256_chunks(const uint8_t* d_data, uint64_t base_pos, yam
     uint32_t ctas = (warps_needed + kShaWarpsPerCta - 1) / kShaWarpsPerCta;
     uint32_t max_ctas = (uint32_t)sm_count * 4u;
     if (ctas > max_ctas) ctas = max_ctas;
-    sha256_chunks_kernel<<<ctas, kShaWarpsPerCta * 32, 0, st>>>(d_data, base_pos, d_descs, first, n,
-                                                                 d_counter);
+    static const int variant = [] { const char* e = getenv("YAMS_B200_SHA_MADD"); return e ? atoi(e) : 1; }();
+    if (variant)
+        sha256_chunks_kernel<true><<<ctas, kShaWarpsPerCta * 32, 0, st>>>(d_data, base_pos, d_descs, first, n, d_counter, 1u);
+    else
+        sha256_chunks_kernel<false><<<ctas, kShaWarpsPerCta * 32, 0, st>>>(d_data, base_pos, d_descs, first, n, d_counter, 1u);
     YB_CUDA(cudaGetLastError());
     return YAMS_OK;
 }
