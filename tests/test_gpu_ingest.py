@@ -157,10 +157,21 @@ def test_device_resident_matches_host_path_and_oracle(Y, oracle):
         want = O.cdc_chunk(host, O.default_config(variant=variant))
         assert np.array_equal(got["offset"], want[0]) and np.array_equal(got["size"], want[1])
         assert np.array_equal(got["digest"], want[2])
-    # unaligned device sub-range
-    got = Y.chunk_and_hash_device(t.data_ptr() + 7, 5_000_001, Y.default_config(min_chunk=1024, max_chunk=8192))
-    want = O.cdc_chunk(host[7:7 + 5_000_001], O.default_config(min_chunk=1024, max_chunk=8192))
-    assert np.array_equal(got["offset"], want[0]) and np.array_equal(got["digest"], want[2])
+    # unaligned device sub-ranges (misaligned stream head), incl. inputs shorter than one 16-byte unit
+    for off, ln in [(7, 5_000_001), (1, 100_000), (15, 33), (9, 5), (3, 16), (0, 1), (13, 70_000)]:
+        for kw in (dict(min_chunk=1024, max_chunk=8192), dict(min_chunk=1, max_chunk=64, mask=0x3)):
+            got = Y.chunk_and_hash_device(t.data_ptr() + off, ln, Y.default_config(**kw))
+            want = O.cdc_chunk(host[off:off + ln], O.default_config(**kw))
+            assert np.array_equal(got["offset"], want[0]) and np.array_equal(got["size"], want[1]), (off, ln, kw)
+            assert np.array_equal(got["digest"], want[2]), (off, ln, kw)
+    # a 0xC5 in the very first bytes of a misaligned stream (candidate inside the unaligned head)
+    t2 = t[:200_000].clone()
+    t2[3:12] = 0xC5
+    h2 = t2.cpu().numpy()
+    for off in (3, 5, 11):
+        got = Y.chunk_and_hash_device(t2.data_ptr() + off, 150_000, Y.default_config(min_chunk=1, max_chunk=4096, mask=0xFF))
+        want = O.cdc_chunk(h2[off:off + 150_000], O.default_config(min_chunk=1, max_chunk=4096, mask=0xFF))
+        assert np.array_equal(got["offset"], want[0]) and np.array_equal(got["digest"], want[2]), off
 
 
 def test_full_size_properties(Y, oracle):

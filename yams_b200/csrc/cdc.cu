@@ -92,6 +92,16 @@ __device__ __forceinline__ void load_tables(const ScanArgs& A, uint64_t* T_s, ui
     __syncthreads();
 }
 
+// Candidates among the (< 16) positions [scan_lo, origin) that precede the first aligned unit (only when the
+// buffer starts misaligned at the very beginning of a stream); returned as a bit mask, bit i = scan_lo + i.
+__device__ __forceinline__ uint32_t scan_head(const ScanArgs& A, const uint64_t* T_s) {
+    uint32_t hits = 0;
+    ByteView view{A.data, A.base_pos, A.lowest};
+    for (uint64_t p = A.scan_lo; p < A.origin && p < A.scan_hi; ++p)
+        if (is_candidate(view, T_s, A.P, p)) hits |= 1u << (uint32_t)(p - A.scan_lo);
+    return hits;
+}
+
 // pass 1: number of candidates per 16 KiB tile
 __global__ void __launch_bounds__(kScanThreads) cdc_count_kernel(ScanArgs A, uint32_t ntiles,
                                                                  uint32_t* __restrict__ tile_counts) {
@@ -107,6 +117,7 @@ __global__ void __launch_bounds__(kScanThreads) cdc_count_kernel(ScanArgs A, uin
             uint64_t p0 = tile_pos + ((uint64_t)it * kScanThreads + threadIdx.x) * 16;
             cnt += __popc(scan16(A, T_s, pass_s, p0));
         }
+        if (tile == 0 && threadIdx.x == 0 && A.origin > A.scan_lo) cnt += __popc(scan_head(A, T_s));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
         if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = cnt;
@@ -138,7 +149,9 @@ __global__ void __launch_bounds__(kScanThreads) cdc_write_kernel(ScanArgs A, uin
         for (int it = 0; it < kScanIters; ++it) {
             uint64_t p0 = tile_pos + ((uint64_t)it * kScanThreads + threadIdx.x) * 16;
             uint32_t hits = scan16(A, T_s, pass_s, p0);
-            uint32_t c = __popc(hits);
+            uint32_t head = 0;
+            if (tile == 0 && it == 0 && threadIdx.x == 0 && A.origin > A.scan_lo) head = scan_head(A, T_s);
+            uint32_t c = __popc(hits) + __popc(head);
             // block-wide exclusive prefix of c in thread order
             uint32_t incl = c;
 #pragma unroll
@@ -156,6 +169,11 @@ __global__ void __launch_bounds__(kScanThreads) cdc_write_kernel(ScanArgs A, uin
                 total += s;
             }
             uint32_t o = running + wbase + incl - c;
+            while (head) {
+                int b = __ffs(head) - 1;
+                head &= head - 1;
+                cand[o++] = A.scan_lo + (uint64_t)b;
+            }
             while (hits) {
                 int b = __ffs(hits) - 1;
                 hits &= hits - 1;
@@ -181,7 +199,8 @@ constexpr int SC_THREADS = 256;
 constexpr uint32_t SC_TILE = 16384;
 constexpr uint32_t SC_HALO = 64;     // >= kHistory (56), multiple of 16
 constexpr int SC_STAGES = 3;
-constexpr uint32_t SC_LIST = 512;
+constexpr uint32_t SC_LIST = 512;     // confirmed candidates per tile kept in shared memory
+constexpr uint32_t SC_PRE = 1024;     // prefilter hits per tile kept in shared memory (expected 64)
 
 struct SinglePassArgs {
     ScanArgs A;
@@ -211,9 +230,10 @@ __global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(Sin
     uint8_t* bufs = sc_smem;                                              // SC_STAGES x (SC_HALO + SC_TILE)
     uint64_t* T_s = reinterpret_cast<uint64_t*>(bufs + SC_STAGES * (SC_HALO + SC_TILE));
     uint64_t* full = T_s + 256;                                           // SC_STAGES mbarriers
-    uint32_t* list = reinterpret_cast<uint32_t*>(full + SC_STAGES);       // SC_LIST
-    uint32_t* list_cnt = list + SC_LIST;
-    uint8_t* pass_s = reinterpret_cast<uint8_t*>(list_cnt + 4);           // 256
+    uint32_t* list = reinterpret_cast<uint32_t*>(full + SC_STAGES);       // confirmed candidates, SC_LIST
+    uint32_t* pre_list = list + SC_LIST;                                  // prefilter hits, SC_PRE
+    uint32_t* cnts = pre_list + SC_PRE;                                   // [0] confirmed, [1] prefilter hits
+    uint8_t* pass_s = reinterpret_cast<uint8_t*>(cnts + 4);               // 256
     const ScanArgs& A = S.A;
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += SC_THREADS) {
@@ -230,7 +250,8 @@ __global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(Sin
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sc_smem_u32(&full[s])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        *list_cnt = 0;
+        cnts[0] = 0;
+        cnts[1] = 0;
     }
     __syncthreads();
 
@@ -266,13 +287,13 @@ __global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(Sin
         uint8_t* buf = bufs + (size_t)s * (SC_HALO + SC_TILE);
         const uint64_t tile_pos = A.origin + (uint64_t)tile * SC_TILE;
         // bytes the bulk copy cannot bring in: look-behind of the very first tile, ragged tail (< 16 B)
-        if (tile == 0 && !S.halo_ok) {
-            if (tid < (int)SC_HALO) {
-                int64_t pos = (int64_t)tile_pos - SC_HALO + tid;
-                buf[tid] = (pos >= (int64_t)A.lowest && pos >= 0) ? A.data[pos - (int64_t)A.base_pos] : 0;
-            }
+        const bool manual_halo = (tile == 0 && !S.halo_ok);
+        const bool manual_tail = S.end16 < A.scan_hi && S.end16 >= tile_pos && S.end16 < tile_pos + SC_TILE;
+        if (manual_halo && tid < (int)SC_HALO) {
+            int64_t pos = (int64_t)tile_pos - SC_HALO + tid;
+            buf[tid] = (pos >= (int64_t)A.lowest && pos >= 0) ? A.data[pos - (int64_t)A.base_pos] : 0;
         }
-        if (S.end16 < A.scan_hi && S.end16 >= tile_pos && S.end16 < tile_pos + SC_TILE) {
+        if (manual_tail) {
             uint64_t q = S.end16 + tid;
             if (q < A.scan_hi) buf[SC_HALO + (q - tile_pos)] = A.data[q - A.base_pos];
         }
@@ -288,8 +309,8 @@ __global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(Sin
                 if (!done && ++spins > (1u << 28)) __trap();
             }
         }
-        __syncthreads();
-        SmemView view{buf, tile_pos - SC_HALO, A.lowest};
+        if (manual_halo || manual_tail) __syncthreads();   // block-uniform
+        // ---- phase 1: prefilter every 16-byte unit; positions that pass go to pre_list ----
 #pragma unroll
         for (int it = 0; it < (int)(SC_TILE / 16 / SC_THREADS); ++it) {
             const uint32_t u = tid + it * SC_THREADS;
@@ -304,14 +325,38 @@ __global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(Sin
             while (pre) {
                 int b = __ffs(pre) - 1;
                 pre &= pre - 1;
-                if (is_candidate(view, T_s, A.P, p0 + (uint64_t)b)) {
-                    uint32_t idx = atomicAdd(list_cnt, 1u);
-                    if (idx < SC_LIST) list[idx] = u * 16 + (uint32_t)b;
+                uint32_t idx = atomicAdd(&cnts[1], 1u);
+                if (idx < SC_PRE) pre_list[idx] = u * 16 + (uint32_t)b;
+            }
+        }
+        // positions of a misaligned stream head that precede the first aligned unit (tile 0 only)
+        if (tile == 0 && A.origin > A.scan_lo) {
+            uint64_t p = A.scan_lo + tid;
+            if (p < A.origin && p < A.scan_hi) {
+                ByteView gview{A.data, A.base_pos, A.lowest};
+                if (is_candidate(gview, T_s, A.P, p)) {
+                    uint32_t idx = atomicAdd(&cnts[0], 1u);
+                    if (idx < SC_LIST) list[idx] = 16u - (uint32_t)(A.origin - p);   // biased by 16: < every in-tile entry
                 }
             }
         }
         __syncthreads();
-        const uint32_t cnt = *list_cnt;
+        // ---- phase 2: one thread per prefilter hit confirms it against the bytes in shared memory ----
+        const uint32_t npre = cnts[1];
+        if (npre > SC_PRE) {
+            overflow = true;
+        } else {
+            SmemView view{buf, tile_pos - SC_HALO, A.lowest};
+            for (uint32_t j = tid; j < npre; j += SC_THREADS) {
+                uint32_t off = pre_list[j];
+                if (is_candidate(view, T_s, A.P, tile_pos + off)) {
+                    uint32_t idx = atomicAdd(&cnts[0], 1u);
+                    if (idx < SC_LIST) list[idx] = off + 16u;   // bias 16 (see the head case above)
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t cnt = cnts[0];
         if (overflow || cnt > SC_LIST || my_total + cnt > S.slice_cap) {
             overflow = true;   // keep draining the copy pipeline, stop recording
         } else {
@@ -319,13 +364,14 @@ __global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(Sin
             for (uint32_t j = tid; j < cnt; j += SC_THREADS) {
                 uint32_t mine = list[j], rank = 0;
                 for (uint32_t k = 0; k < cnt; ++k) rank += list[k] < mine ? 1u : 0u;
-                my_out[my_total + rank] = tile_pos + mine;
+                my_out[my_total + rank] = tile_pos + mine - 16u;
             }
             my_total += cnt;
         }
         __syncthreads();
         if (tid == 0) {
-            *list_cnt = 0;
+            cnts[0] = 0;
+            cnts[1] = 0;
             if (i + SC_STAGES < n_my) issue(i + SC_STAGES);
         }
     }
@@ -368,10 +414,10 @@ yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm
     S.tiles_per_cta = (ntiles + nctas - 1) / nctas;
     S.slice_cap = slice_cap;
     S.halo_ok = (A.origin >= A.lowest + SC_HALO) ? 1u : 0u;
-    S.end16 = A.origin + ((A.scan_hi - A.origin) & ~15ull);
+    S.end16 = A.scan_hi > A.origin ? A.origin + ((A.scan_hi - A.origin) & ~15ull) : A.origin;
     S.cand_tmp = cand_tmp;
     S.cta_counts = cta_counts;
-    size_t smem = (size_t)SC_STAGES * (SC_HALO + SC_TILE) + 256 * 8 + SC_STAGES * 8 + SC_LIST * 4 + 16 + 256;
+    size_t smem = (size_t)SC_STAGES * (SC_HALO + SC_TILE) + 256 * 8 + SC_STAGES * 8 + (SC_LIST + SC_PRE) * 4 + 16 + 256;
     YB_CUDA(cudaFuncSetAttribute(cdc_scan_single_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cdc_scan_single_pass_kernel<<<nctas, SC_THREADS, smem, st>>>(S);
     cdc_compact_kernel<<<1, 1024, 0, st>>>(cand_tmp, cta_counts, nctas, slice_cap, cand, scalars);

@@ -103,11 +103,14 @@ struct CdcStream {
         uint32_t ncand = 0;
         YB_CUDA(cudaEventRecord(ev[0], st));
         if (!no_candidates && scan_hi > scan_lo) {
-            // tiles start at the 16-byte-aligned address at or below scan_lo; the positions in
-            // [origin, scan_lo) are masked and never dereferenced (ragged-unit path of scan16)
+            // tiles start at a 16-byte-aligned ADDRESS: normally at or below scan_lo (the positions in
+            // [origin, scan_lo) are masked and never dereferenced); when that would fall before stream position
+            // 0 (misaligned buffer at the very start of a stream) the tiles start at the next aligned address
+            // and the < 16 head positions [scan_lo, origin) are tested separately by the kernels.
             uintptr_t addr_lo = reinterpret_cast<uintptr_t>(data) + (scan_lo - base_pos);
-            uint64_t origin = scan_lo - (uint64_t)(addr_lo & 15);
-            uint64_t span = scan_hi - origin;
+            uint64_t mis = (uint64_t)(addr_lo & 15);
+            uint64_t origin = scan_lo >= mis ? scan_lo - mis : scan_lo + (16 - mis);
+            uint64_t span = scan_hi > origin ? scan_hi - origin : 1;
             uint64_t ntiles64 = (span + kTileBytesHost - 1) / kTileBytesHost;
             YB_ARG(ntiles64 < (1ull << 31), "segment too large");
             uint32_t ntiles = (uint32_t)ntiles64;

@@ -109,18 +109,57 @@ struct UmmaArgs {
     Stage1Args a;
     uint32_t n_tile;      // queries per tile (multiple of 16, <= 256)
     uint32_t nqt;         // query tiles
-    uint32_t nrt;         // corpus row tiles
+    uint32_t nrt;         // corpus row tiles (128 rows x CTAS)
     uint32_t kblocks;     // ceil(dim / 64)
     uint32_t stages;
-    uint32_t b_stage;     // bytes of one B stage = n_tile * 128
+    uint32_t b_stage;     // bytes of one B stage held by ONE CTA = (n_tile / CTAS) * 128
     uint32_t idesc;
 };
 
-template <bool FILTER>
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// 2-SM TMA load: bytes are credited to the barrier of the pair's leader CTA (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrive on this barrier in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// CTAS == 1: one CTA per 128-row tile (cta_group::1).  CTAS == 2: a CTA pair (cluster of 2) shares a 256-row x
+// n_tile unit: each CTA stages its own 128 corpus rows and HALF of the query tile, the leader issues
+// tcgen05.mma.cta_group::2 (M = 256), each CTA's TMEM receives the accumulator rows of its own corpus rows.
+// Halving the query bytes each SM pulls through L2 is what lifts the L2-bound 1-CTA version.
+template <bool FILTER, int CTAS>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, UmmaArgs u) {
     extern __shared__ uint8_t smem_raw[];
-    // 1024-byte alignment for the 128B-swizzled tiles
+    // 1024-byte alignment for the 128B-swizzled tiles (identical offsets in both CTAs of a pair)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const uint32_t stage_bytes = UM_A_STAGE + u.b_stage;
     uint8_t* tiles = smem;
@@ -134,53 +173,70 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const uint32_t group = blockIdx.x / CTAS, ngroups = gridDim.x / CTAS;
     const uint64_t n_units = (uint64_t)u.nrt * u.nqt;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         for (uint32_t s = 0; s < u.stages; ++s) {
-            mbar_init(&full[s], 1);
+            mbar_init(&full[s], CTAS);          // leader's expect_tx arrive (+ the peer's remote arrive)
             mbar_init(&empty[s], 1);
         }
         mbar_init(&tfull[0], 1);
         mbar_init(&tfull[1], 1);
-        mbar_init(&tempty[0], 4);
-        mbar_init(&tempty[1], 4);
+        mbar_init(&tempty[0], 4 * CTAS);        // 4 epilogue warps per CTA
+        mbar_init(&tempty[1], 4 * CTAS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(UM_TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CTAS == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(UM_TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(UM_TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer (every CTA loads its own rows and its share of the queries) =====
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
+            for (uint64_t unit = group; unit < n_units; unit += ngroups) {
                 const uint32_t rt = (uint32_t)(unit / u.nqt), qt = (uint32_t)(unit % u.nqt);
+                const int a_row = (int)((rt * CTAS + rank) * UM_BLOCK_M);
+                const int b_row = (int)(qt * u.n_tile + rank * (u.n_tile / CTAS));
                 for (uint32_t kb = 0; kb < u.kblocks; ++kb) {
                     mbar_wait(&empty[s], ph ^ 1);
                     uint8_t* sa = tiles + (size_t)s * stage_bytes;
                     uint8_t* sb = sa + UM_A_STAGE;
-                    mbar_expect_tx(&full[s], stage_bytes);
-                    tma_load_2d(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), (int)(rt * UM_BLOCK_M));
-                    tma_load_2d(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), (int)(qt * u.n_tile));
+                    if (CTAS == 2) {
+                        if (leader) mbar_expect_tx(&full[s], stage_bytes * 2);
+                        else mbar_arrive_remote(&full[s], 0);
+                        tma_load_2d_2sm(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), a_row);
+                        tma_load_2d_2sm(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), b_row);
+                    } else {
+                        mbar_expect_tx(&full[s], stage_bytes);
+                        tma_load_2d(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), a_row);
+                        tma_load_2d(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), b_row);
+                    }
                     if (++s == u.stages) { s = 0; ph ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && leader) {
             uint32_t s = 0, ph = 0, it = 0;
-            for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+            for (uint64_t unit = group; unit < n_units; unit += ngroups, ++it) {
                 const uint32_t as = it & 1, aph = (it >> 1) & 1;
                 mbar_wait(&tempty[as], aph ^ 1);
                 tcgen05_fence_after();
@@ -194,12 +250,14 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                     for (uint32_t k = 0; k < UM_BLOCK_K / UM_UMMA_K; ++k) {
                         // advance 32 bytes (16 fp16) along K inside the swizzle row: +2 in 16-byte units
-                        umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (CTAS == 2) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, (kb | k) != 0 ? 1u : 0u);
                     }
-                    umma_commit(&empty[s]);          // smem stage reusable once these MMAs have read it
+                    // smem stage reusable (in both CTAs) once these MMAs have read it
+                    if (CTAS == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
                     if (++s == u.stages) { s = 0; ph ^= 1; }
                 }
-                umma_commit(&tfull[as]);             // accumulator complete
+                if (CTAS == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);   // accumulator complete
             }
         }
     } else {
@@ -207,10 +265,10 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const uint32_t quad = warp & 3;              // TMEM lane quadrant this warp may access
         float* my_tau = tau_s + quad * UM_MAX_N;
         uint32_t it = 0;
-        for (uint64_t unit = blockIdx.x; unit < n_units; unit += gridDim.x, ++it) {
+        for (uint64_t unit = group; unit < n_units; unit += ngroups, ++it) {
             const uint32_t rt = (uint32_t)(unit / u.nqt), qt = (uint32_t)(unit % u.nqt);
             const uint32_t as = it & 1, aph = (it >> 1) & 1;
-            const uint64_t li = (uint64_t)rt * UM_BLOCK_M + quad * 32 + lane;   // row index within this launch
+            const uint64_t li = ((uint64_t)rt * CTAS + rank) * UM_BLOCK_M + quad * 32 + lane;   // row within this launch
             const bool rvalid = li < u.a.nrows;
             const uint64_t grow = u.a.row_start + li * u.a.row_stride;
             const float inr = rvalid ? u.a.inv_norm[grow] : 0.f;
@@ -265,14 +323,19 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty[as]);
+            if (lane == 0) {
+                if (CTAS == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+            }
         }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (CTAS == 2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(UM_TMEM_COLS) : "memory");
+        if (CTAS == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(UM_TMEM_COLS) : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(UM_TMEM_COLS) : "memory");
     }
 }
 
@@ -336,36 +399,56 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     queries_to_f16_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)a.nq * a.dim + 255) / 256, 4096), 256, 0, st>>>(
         a.q32, a.qinv, a.nq, a.dim, d_q16);
 
+    static const int ctas_env = [] { const char* e = getenv("YAMS_B200_UMMA_CTAS"); return e ? atoi(e) : 2; }();
+    const int ctas = (ctas_env == 1 || c->dev->sm_count < 2) ? 1 : 2;
     UmmaArgs u{};
     u.a = a;
-    u.n_tile = a.nq >= UM_MAX_N ? UM_MAX_N : ((a.nq + 15) / 16) * 16;
+    const uint32_t nmult = 16 * ctas;   // each CTA's share of the query tile must be a multiple of 8 rows (16 for M=128)
+    u.n_tile = a.nq >= UM_MAX_N ? UM_MAX_N : ((a.nq + nmult - 1) / nmult) * nmult;
     u.nqt = (a.nq + u.n_tile - 1) / u.n_tile;
-    u.nrt = (uint32_t)((a.nrows + UM_BLOCK_M - 1) / UM_BLOCK_M);
+    const uint32_t rows_per_unit = UM_BLOCK_M * ctas;
+    u.nrt = (uint32_t)((a.nrows + rows_per_unit - 1) / rows_per_unit);
     u.kblocks = (a.dim + UM_BLOCK_K - 1) / UM_BLOCK_K;
-    u.b_stage = u.n_tile * 128;
+    u.b_stage = (u.n_tile / ctas) * 128;
     uint32_t stage_bytes = UM_A_STAGE + u.b_stage;
     const uint32_t budget = 196 * 1024;
     u.stages = std::min<uint32_t>(8, budget / stage_bytes);
     if (u.stages < 2) return YAMS_ERR_UNSUPPORTED;
-    // instruction descriptor: D=f32, A=B=f16, both K-major, N, M=128
-    u.idesc = (1u << 4) | ((u.n_tile >> 3) << 17) | ((UM_BLOCK_M >> 4) << 24);
+    // instruction descriptor: D=f32, A=B=f16, both K-major, N = n_tile, M = 128 per CTA
+    u.idesc = (1u << 4) | ((u.n_tile >> 3) << 17) | (((UM_BLOCK_M * ctas) >> 4) << 24);
 
     CUtensorMap tmA, tmB;
     const uint8_t* a_base = reinterpret_cast<const uint8_t*>(a.rows) + (size_t)a.row_start * a.dim * 2;
     if (!make_map_2d(&tmA, a_base, a.dim, a.nrows, (uint64_t)a.row_stride * a.dim * 2, UM_BLOCK_K, UM_BLOCK_M))
         return YAMS_ERR_UNSUPPORTED;
-    if (!make_map_2d(&tmB, d_q16, a.dim, a.nq, (uint64_t)a.dim * 2, UM_BLOCK_K, u.n_tile)) return YAMS_ERR_UNSUPPORTED;
+    if (!make_map_2d(&tmB, d_q16, a.dim, a.nq, (uint64_t)a.dim * 2, UM_BLOCK_K, u.n_tile / ctas)) return YAMS_ERR_UNSUPPORTED;
 
     size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16 + 4 * UM_MAX_N * 4;
     uint64_t n_units = (uint64_t)u.nrt * u.nqt;
-    unsigned grid = (unsigned)std::min<uint64_t>(n_units, (uint64_t)c->dev->sm_count);
-    if (filter) {
-        YB_CUDA(cudaFuncSetAttribute(stage1_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stage1_umma_kernel<true><<<grid, UM_THREADS, smem, st>>>(tmA, tmB, u);
+    unsigned groups = (unsigned)std::min<uint64_t>(n_units, (uint64_t)(c->dev->sm_count / ctas));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(groups * ctas);
+    cfg.blockDim = dim3(UM_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ctas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+#define YB_LAUNCH_UMMA(F, C)                                                                                          \
+    do {                                                                                                              \
+        YB_CUDA(cudaFuncSetAttribute(stage1_umma_kernel<F, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        YB_CUDA(cudaLaunchKernelEx(&cfg, stage1_umma_kernel<F, C>, tmA, tmB, u));                                     \
+    } while (0)
+    if (ctas == 2) {
+        if (filter) YB_LAUNCH_UMMA(true, 2); else YB_LAUNCH_UMMA(false, 2);
     } else {
-        YB_CUDA(cudaFuncSetAttribute(stage1_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        stage1_umma_kernel<false><<<grid, UM_THREADS, smem, st>>>(tmA, tmB, u);
+        if (filter) YB_LAUNCH_UMMA(true, 1); else YB_LAUNCH_UMMA(false, 1);
     }
+#undef YB_LAUNCH_UMMA
     YB_CUDA(cudaGetLastError());
     return YAMS_OK;
 }
