@@ -33,7 +33,7 @@ constexpr int UM_MAX_N = 256;
 constexpr int UM_THREADS = 192;          // 6 warps
 constexpr uint32_t UM_A_STAGE = UM_BLOCK_M * UM_BLOCK_K * 2;   // 16 KiB
 constexpr uint32_t UM_TMEM_COLS = 512;
-constexpr uint32_t UM_SPIN_LIMIT = 1u << 28;
+constexpr uint32_t UM_SPIN_LIMIT = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
