@@ -1,0 +1,87 @@
+// GPU test of the C++ host adapters (yams_b200/host/b200_host.hpp) through the C ABI.  The expectations mirror the
+// reference's own unit tests: chunk invariants + per-chunk hash of the pattern stream
+// (/root/reference/tests/unit/chunking/chunking_test.cpp:55-62,146-216), lazy == full (:588-609), SHA-256 KATs
+// (/root/reference/tests/unit/crypto/crypto_test.cpp:92-99), exact-scan contract incl. chunk_id tie-break
+// (/root/reference/tests/unit/vector/vector_smoke_catch2_test.cpp:188-340).  Prints "ALL OK" on success.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../yams_b200/host/b200_host.hpp"
+
+using namespace yams_b200::host;
+
+#define CHECK(cond)                                                                  \
+    do {                                                                             \
+        if (!(cond)) {                                                               \
+            std::fprintf(stderr, "CHECK failed %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            std::exit(1);                                                            \
+        }                                                                            \
+    } while (0)
+
+int main() {
+    if (yams_plugin_init("{}", nullptr) != YAMS_PLUGIN_OK) {
+        std::fprintf(stderr, "plugin init failed: %s\n", yams_b200_last_error());
+        return 2;
+    }
+    // ---- hasher KATs ----
+    auto bytes = [](const char* s) { return std::span<const std::byte>(reinterpret_cast<const std::byte*>(s), std::strlen(s)); };
+    CHECK(B200ContentHasher::hash(bytes("")) == "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855");
+    CHECK(B200ContentHasher::hash(bytes("abc")) == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad");
+    B200ContentHasher h;
+    h.init();
+    h.update(bytes("Hello "));
+    h.update(bytes("World"));
+    CHECK(h.finalize() == "a591a6d40bf420404a011733cfb7b190d62c65bf0bcda32b57b277d9ad9f146e");
+    // ---- chunker: pattern data, chunk invariants, per-chunk hash, lazy == full ----
+    std::vector<std::byte> data(3 * 1024 * 1024 + 123);
+    for (size_t i = 0; i < data.size(); ++i) data[i] = (std::byte)((i * 1315423911u + 0x9E3779B9u) & 0xFF);
+    ChunkingConfig cfg;
+    cfg.minChunkSize = 4096;
+    cfg.maxChunkSize = 65536;
+    B200Chunker chunker(cfg);
+    auto full = chunker.chunkData(data);
+    auto lazy = chunker.chunkDataLazy(data);
+    CHECK(!full.empty() && full.size() == lazy.size());
+    size_t pos = 0;
+    for (size_t i = 0; i < full.size(); ++i) {
+        CHECK(full[i].offset == pos && lazy[i].offset == pos && full[i].size == lazy[i].size && full[i].hash == lazy[i].hash);
+        CHECK(lazy[i].data.empty() && full[i].data.size() == full[i].size);
+        if (i + 1 < full.size()) CHECK(full[i].size >= cfg.minChunkSize && full[i].size <= cfg.maxChunkSize);
+        CHECK(full[i].hash == B200ContentHasher::hash(std::span<const std::byte>(data.data() + pos, full[i].size)));
+        CHECK(std::memcmp(full[i].data.data(), data.data() + pos, full[i].size) == 0);
+        pos += full[i].size;
+    }
+    CHECK(pos == data.size());
+    // chunkFile == chunkData (streamed in 4 MiB reads)
+    auto path = std::filesystem::temp_directory_path() / "yams_b200_host_test.bin";
+    {
+        std::ofstream f(path, std::ios::binary);
+        f.write(reinterpret_cast<const char*>(data.data()), (std::streamsize)data.size());
+    }
+    auto filed = chunker.chunkFile(path);
+    CHECK(filed.size() == full.size());
+    for (size_t i = 0; i < full.size(); ++i) CHECK(filed[i].offset == full[i].offset && filed[i].hash == full[i].hash && filed[i].data == full[i].data);
+    std::filesystem::remove(path);
+    bool threw = false;
+    try { chunker.chunkFile("/nonexistent/yams_b200"); } catch (const std::runtime_error&) { threw = true; }
+    CHECK(threw);
+    // ---- vector store: top-1, threshold, invalid query, deterministic chunk_id tie-break ----
+    B200VectorStore vs(4);
+    std::vector<float> rows = {1, 0, 0, 0, /**/ 0.9f, 0.1f, 0, 0, /**/ 2, 0, 0, 0, /**/ -1, 0, 0, 0};
+    vs.insertVectorsBatch(rows, {1, 2, 3, 4}, {"zz", "mm", "aa", "bb"});   // rows 1 and 3 tie at similarity 1.0
+    auto hits = vs.searchSimilar({1, 0, 0, 0}, 1, -1.0f);
+    CHECK(hits.size() == 1 && hits[0].chunk_id == "aa" && hits[0].relevance_score == 1.0f);   // chunk_id order, not rowid
+    hits = vs.searchSimilar({1, 0, 0, 0}, 10, 0.5f);
+    CHECK(hits.size() == 3 && hits[0].chunk_id == "aa" && hits[1].chunk_id == "zz" && hits[2].chunk_id == "mm");
+    CHECK(vs.searchSimilar({1, 0, 0, 0}, 0).empty());
+    threw = false;
+    try { vs.searchSimilar({0, 0, 0, 0}, 3); } catch (const std::invalid_argument&) { threw = true; }
+    CHECK(threw);
+    threw = false;
+    try { vs.searchSimilar({NAN, 0, 0, 0}, 3); } catch (const std::invalid_argument&) { threw = true; }
+    CHECK(threw);
+    CHECK(vs.size() == 4);
+    std::puts("ALL OK");
+    return 0;
+}

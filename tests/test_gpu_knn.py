@@ -274,3 +274,16 @@ def test_large_k_and_many_queries_through_tensor_engine(Y, oracle):
     sub = list(range(0, nq, 37))
     check_against_oracle(O, rows, queries[sub], tuple(x[sub] for x in got), 10)
     c.close()
+
+
+def test_cpp_host_adapters(Y, tmp_path):
+    """yams_b200/host/b200_host.hpp (IChunker / IContentHasher / IVectorStore shaped C++ adapters) over the C ABI."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_host_adapters")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++20", "-O1", os.path.join(root, "tests", "host_cpp", "test_host_adapters.cpp"),
+                           "-o", exe, "-L" + os.path.join(root, "yams_b200"), "-lyams_b200",
+                           "-Wl,-rpath," + os.path.join(root, "yams_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
