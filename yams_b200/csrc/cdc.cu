@@ -299,14 +299,19 @@ __global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(Sin
         }
         {   // wait for the bulk copy of this stage
             const uint32_t bar = sc_smem_u32(&full[s]);
-            uint32_t done = 0, spins = 0;
+            uint32_t done = 0;
+            long long t0 = 0;
             while (!done) {
                 asm volatile(
                     "{\n\t.reg .pred p;\n\t"
                     "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
                     "selp.u32 %0, 1, 0, p;\n\t}"
                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-                if (!done && ++spins > (1u << 28)) __trap();
+                if (!done) {   // a wait longer than ~2 s of SM clocks aborts the kernel instead of hanging the GPU
+                    long long now = clock64();
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > 4000000000ll) __trap();
+                }
             }
         }
         if (manual_halo || manual_tail) __syncthreads();   // block-uniform

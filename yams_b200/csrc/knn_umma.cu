@@ -33,7 +33,7 @@ constexpr int UM_MAX_N = 256;
 constexpr int UM_THREADS = 192;          // 6 warps
 constexpr uint32_t UM_A_STAGE = UM_BLOCK_M * UM_BLOCK_K * 2;   // 16 KiB
 constexpr uint32_t UM_TMEM_COLS = 512;
-constexpr uint32_t UM_SPIN_LIMIT = 1u << 26;
+constexpr long long UM_WAIT_LIMIT_CYCLES = 4000000000ll;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -48,7 +48,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t addr = smem_u32(bar);
-    uint32_t done = 0, spins = 0;
+    uint32_t done = 0;
+    long long t0 = 0;
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -57,7 +58,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (!done && ++spins > UM_SPIN_LIMIT) __trap();  // never hang the GPU: abort the kernel instead
+        if (!done) {   // never hang the GPU: a wait longer than ~2 s of SM clocks aborts the kernel
+            long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > UM_WAIT_LIMIT_CYCLES) __trap();
+        }
     }
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
