@@ -185,32 +185,32 @@ __global__ void __launch_bounds__(kScanThreads) cdc_write_kernel(ScanArgs A, uin
     }
 }
 
-// ---- single-pass scan: contiguous range per CTA, tiles staged in shared memory by bulk async copies ----
+// ---- single-pass scan: one contiguous byte range per WARP, tiles staged in shared memory by bulk async copies ----
 //
-// Each CTA owns a contiguous range of the segment and walks it in 16 KiB tiles.  One thread issues
-// cp.async.bulk (TMA 1-D) copies of [64-byte look-behind | tile] into a 3-stage shared-memory ring
-// (mbarrier complete_tx), all threads test 16-byte units from shared memory (prefilter) and confirm the
-// rare prefilter hits against the bytes already in shared memory.  Candidates are rare (~1 / 8 KiB), so
-// a tile's hits are appended to a small shared list and written in rank order to the CTA's private slice
-// of a global buffer; a second tiny kernel concatenates the slices.  The input is read from HBM exactly
-// once.  Anything exceptional (slice or list overflow on adversarial data) raises a flag and the host
-// re-runs the segment through the exact two-pass kernels above.
-constexpr int SC_THREADS = 256;
-constexpr uint32_t SC_TILE = 16384;
-constexpr uint32_t SC_HALO = 64;     // >= kHistory (56), multiple of 16
-constexpr int SC_STAGES = 3;
-constexpr uint32_t SC_LIST = 512;     // confirmed candidates per tile kept in shared memory
-constexpr uint32_t SC_PRE = 1024;     // prefilter hits per tile kept in shared memory (expected 64)
+// Every warp owns a contiguous range of the segment and walks it in 4 KiB tiles.  Lane 0 issues cp.async.bulk
+// (TMA 1-D) copies of [64-byte look-behind | tile] into the warp's private 3-stage shared-memory ring (mbarrier
+// complete_tx); the 32 lanes then read 16-byte units from shared memory (conflict-free LDS.128), run the SIMD
+// low-byte prefilter and confirm the rare prefilter hits against bytes that are already in shared memory.
+// Hits are written in position order (ballot + popc) to the warp's private slice of a global buffer; a second
+// tiny kernel concatenates the slices.  No block-level synchronisation, no atomics; the input is read from HBM
+// exactly once (+1.6% look-behind).  Anything exceptional (slice overflow on adversarial data) raises a flag
+// and the host re-runs the segment through the exact two-pass kernels above.
+constexpr int WS_WARPS = 16;
+constexpr int WS_THREADS = WS_WARPS * 32;
+constexpr uint32_t WS_TILE = 4096;
+constexpr uint32_t WS_HALO = 64;      // >= kHistory (56), multiple of 16
+constexpr int WS_STAGES = 3;
+constexpr uint32_t WS_BUF = WS_HALO + WS_TILE;
 
 struct SinglePassArgs {
     ScanArgs A;
-    uint32_t ntiles;        // tiles in the segment (from A.origin)
-    uint32_t tiles_per_cta;
-    uint32_t slice_cap;     // candidate capacity of one CTA slice
+    uint32_t ntiles;        // 4 KiB tiles in the segment (from A.origin)
+    uint32_t tiles_per_warp;
+    uint32_t slice_cap;     // candidate capacity of one warp slice
     uint32_t halo_ok;       // 1: the 64 bytes before A.origin are readable memory
     uint64_t end16;         // A.origin + floor16(A.scan_hi - A.origin): bulk copies stop here
-    uint64_t* cand_tmp;     // [gridDim.x][slice_cap]
-    uint32_t* cta_counts;   // [gridDim.x]; 0xFFFFFFFF marks overflow
+    uint64_t* cand_tmp;     // [nwarps][slice_cap]
+    uint32_t* slice_counts; // [nwarps]; 0xFFFFFFFF marks overflow
 };
 
 struct SmemView {
@@ -225,80 +225,117 @@ struct SmemView {
 
 __device__ __forceinline__ uint32_t sc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(SinglePassArgs S) {
+// per-word "some byte equals one of the fast values" flags (bit 7 of each matching byte)
+__device__ __forceinline__ uint32_t fast_flags(uint32_t w, const CdcParams& P) {
+    uint32_t z = 0;
+    for (uint32_t f = 0; f < P.nfast; ++f) {
+        uint32_t m = w ^ (0x01010101u * P.fast[f]);
+        uint32_t t = (m & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+        z |= ~(t | m | 0x7f7f7f7fu);
+    }
+    return z;
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(SinglePassArgs S) {
     extern __shared__ __align__(128) uint8_t sc_smem[];
-    uint8_t* bufs = sc_smem;                                              // SC_STAGES x (SC_HALO + SC_TILE)
-    uint64_t* T_s = reinterpret_cast<uint64_t*>(bufs + SC_STAGES * (SC_HALO + SC_TILE));
-    uint64_t* full = T_s + 256;                                           // SC_STAGES mbarriers
-    uint32_t* list = reinterpret_cast<uint32_t*>(full + SC_STAGES);       // confirmed candidates, SC_LIST
-    uint32_t* pre_list = list + SC_LIST;                                  // prefilter hits, SC_PRE
-    uint32_t* cnts = pre_list + SC_PRE;                                   // [0] confirmed, [1] prefilter hits
-    uint8_t* pass_s = reinterpret_cast<uint8_t*>(cnts + 4);               // 256
+    uint8_t* bufs = sc_smem;                                                        // WS_WARPS x WS_STAGES x WS_BUF
+    uint64_t* T_s = reinterpret_cast<uint64_t*>(bufs + (size_t)WS_WARPS * WS_STAGES * WS_BUF);
+    uint64_t* bars = T_s + 256;                                                     // WS_WARPS x WS_STAGES
+    uint8_t* pass_s = reinterpret_cast<uint8_t*>(bars + WS_WARPS * WS_STAGES);      // 256
     const ScanArgs& A = S.A;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 256; i += SC_THREADS) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 256; i += WS_THREADS) {
         uint64_t t = A.table[i];
         T_s[i] = t;
         uint64_t m0 = A.P.mask & 0xffull;
         pass_s[i] = ((t & m0) == m0) ? 1 : 0;
     }
-    const uint32_t t_begin = blockIdx.x * S.tiles_per_cta;
-    const uint32_t t_end = min(t_begin + S.tiles_per_cta, S.ntiles);
-    const uint32_t n_my = t_end > t_begin ? t_end - t_begin : 0;
-    if (tid == 0) {
-        for (int s = 0; s < SC_STAGES; ++s)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sc_smem_u32(&full[s])), "r"(1));
+    uint8_t* my_bufs = bufs + (size_t)warp * WS_STAGES * WS_BUF;
+    uint64_t* my_bars = bars + warp * WS_STAGES;
+    if (lane == 0) {
+        for (int s = 0; s < WS_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sc_smem_u32(&my_bars[s])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        cnts[0] = 0;
-        cnts[1] = 0;
     }
     __syncthreads();
 
-    auto issue = [&](uint32_t i) {   // thread 0: start the copy of my i-th tile into stage i % SC_STAGES
+    const uint32_t gw = blockIdx.x * WS_WARPS + warp;
+    const uint64_t t_begin64 = (uint64_t)gw * S.tiles_per_warp;
+    const uint32_t t_begin = (uint32_t)(t_begin64 < S.ntiles ? t_begin64 : S.ntiles);
+    const uint32_t t_end = (uint32_t)(t_begin64 + S.tiles_per_warp < S.ntiles ? t_begin64 + S.tiles_per_warp : S.ntiles);
+    const uint32_t n_my = t_end > t_begin ? t_end - t_begin : 0;
+
+    auto issue = [&](uint32_t i) {   // lane 0: start the copy of my i-th tile into stage i % WS_STAGES
         const uint32_t tile = t_begin + i;
-        const uint32_t s = i % SC_STAGES;
-        uint8_t* dst = bufs + (size_t)s * (SC_HALO + SC_TILE);
-        const uint64_t tile_pos = A.origin + (uint64_t)tile * SC_TILE;
-        uint64_t lo = (tile == 0 && !S.halo_ok) ? tile_pos : tile_pos - SC_HALO;
-        uint64_t hi = tile_pos + SC_TILE < S.end16 ? tile_pos + SC_TILE : S.end16;
+        const uint32_t s = i % WS_STAGES;
+        uint8_t* dst = my_bufs + (size_t)s * WS_BUF;
+        const uint64_t tile_pos = A.origin + (uint64_t)tile * WS_TILE;
+        uint64_t lo = (tile == 0 && !S.halo_ok) ? tile_pos : tile_pos - WS_HALO;
+        uint64_t hi = tile_pos + WS_TILE < S.end16 ? tile_pos + WS_TILE : S.end16;
         uint32_t bytes = hi > lo ? (uint32_t)(hi - lo) : 0u;
-        const uint32_t bar = sc_smem_u32(&full[s]);
+        const uint32_t bar = sc_smem_u32(&my_bars[s]);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (bytes) {
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(sc_smem_u32(dst + (lo - (tile_pos - SC_HALO)))), "l"(A.data + (lo - A.base_pos)), "r"(bytes), "r"(bar)
+                         ::"r"(sc_smem_u32(dst + (lo - (tile_pos - WS_HALO)))), "l"(A.data + (lo - A.base_pos)), "r"(bytes), "r"(bar)
                          : "memory");
         } else {
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
         }
     };
-    if (tid == 0)
-        for (uint32_t i = 0; i < n_my && i < (uint32_t)SC_STAGES; ++i) issue(i);
+    if (lane == 0)
+        for (uint32_t i = 0; i < n_my && i < (uint32_t)WS_STAGES; ++i) issue(i);
 
-    uint32_t my_total = 0;          // candidates written by this CTA so far (uniform across threads)
+    uint32_t my_total = 0;          // candidates written by this warp so far (uniform across lanes)
     bool overflow = false;
-    uint64_t* my_out = S.cand_tmp + (size_t)blockIdx.x * S.slice_cap;
+    uint64_t* my_out = S.cand_tmp + (size_t)gw * S.slice_cap;
+    const uint32_t lane_lt = (1u << lane) - 1u;
+
+    // ordered append of a lane's hit mask (bit b = position p0 + b); lanes are in position order
+    auto emit = [&](uint32_t hits, uint64_t p0) {
+        uint32_t c = __popc(hits);
+        // exclusive prefix over lanes
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+        if (overflow || my_total + total > S.slice_cap) {
+            overflow = true;
+        } else {
+            uint32_t o = my_total + incl - c;
+            while (hits) {
+                int b = __ffs(hits) - 1;
+                hits &= hits - 1;
+                my_out[o++] = p0 + (uint64_t)b;
+            }
+            my_total += total;
+        }
+    };
+
     for (uint32_t i = 0; i < n_my; ++i) {
         const uint32_t tile = t_begin + i;
-        const uint32_t s = i % SC_STAGES;
-        const uint32_t parity = (i / SC_STAGES) & 1;
-        uint8_t* buf = bufs + (size_t)s * (SC_HALO + SC_TILE);
-        const uint64_t tile_pos = A.origin + (uint64_t)tile * SC_TILE;
+        const uint32_t s = i % WS_STAGES;
+        const uint32_t parity = (i / WS_STAGES) & 1;
+        uint8_t* buf = my_bufs + (size_t)s * WS_BUF;
+        const uint64_t tile_pos = A.origin + (uint64_t)tile * WS_TILE;
         // bytes the bulk copy cannot bring in: look-behind of the very first tile, ragged tail (< 16 B)
-        const bool manual_halo = (tile == 0 && !S.halo_ok);
-        const bool manual_tail = S.end16 < A.scan_hi && S.end16 >= tile_pos && S.end16 < tile_pos + SC_TILE;
-        if (manual_halo && tid < (int)SC_HALO) {
-            int64_t pos = (int64_t)tile_pos - SC_HALO + tid;
-            buf[tid] = (pos >= (int64_t)A.lowest && pos >= 0) ? A.data[pos - (int64_t)A.base_pos] : 0;
+        if (tile == 0 && !S.halo_ok) {
+            for (uint32_t j = lane; j < WS_HALO; j += 32) {
+                int64_t pos = (int64_t)tile_pos - WS_HALO + j;
+                buf[j] = (pos >= (int64_t)A.lowest && pos >= 0) ? A.data[pos - (int64_t)A.base_pos] : 0;
+            }
         }
-        if (manual_tail) {
-            uint64_t q = S.end16 + tid;
-            if (q < A.scan_hi) buf[SC_HALO + (q - tile_pos)] = A.data[q - A.base_pos];
+        if (S.end16 < A.scan_hi && S.end16 >= tile_pos && S.end16 < tile_pos + WS_TILE) {
+            uint64_t q = S.end16 + lane;
+            if (q < A.scan_hi) buf[WS_HALO + (q - tile_pos)] = A.data[q - A.base_pos];
         }
         {   // wait for the bulk copy of this stage
-            const uint32_t bar = sc_smem_u32(&full[s]);
+            const uint32_t bar = sc_smem_u32(&my_bars[s]);
             uint32_t done = 0;
             long long t0 = 0;
             while (!done) {
@@ -314,118 +351,104 @@ __global__ void __launch_bounds__(SC_THREADS, 2) cdc_scan_single_pass_kernel(Sin
                 }
             }
         }
-        if (manual_halo || manual_tail) __syncthreads();   // block-uniform
-        // ---- phase 1: prefilter every 16-byte unit; positions that pass go to pre_list ----
-#pragma unroll
-        for (int it = 0; it < (int)(SC_TILE / 16 / SC_THREADS); ++it) {
-            const uint32_t u = tid + it * SC_THREADS;
+        __syncwarp();
+        // positions of a misaligned stream head that precede the first aligned unit (global tile 0 only)
+        if (tile == 0 && A.origin > A.scan_lo) {
+            uint64_t p = A.scan_lo + lane;
+            uint32_t hit = 0;
+            if (p < A.origin && p < A.scan_hi) {
+                ByteView gview{A.data, A.base_pos, A.lowest};
+                hit = is_candidate(gview, T_s, A.P, p) ? 1u : 0u;
+            }
+            emit(hit, p);   // one position per lane: bit 0 = position p
+        }
+        SmemView view{buf, tile_pos - WS_HALO, A.lowest};
+        const bool inside = tile_pos >= A.scan_lo && tile_pos + WS_TILE <= A.scan_hi;   // warp-uniform
+#pragma unroll 2
+        for (int j = 0; j < (int)(WS_TILE / 16 / 32); ++j) {
+            const uint32_t u = j * 32 + lane;
             const uint64_t p0 = tile_pos + (uint64_t)u * 16;
-            uint64_t lo = p0 > A.scan_lo ? p0 : A.scan_lo;
-            uint64_t hi = p0 + 16 < A.scan_hi ? p0 + 16 : A.scan_hi;
-            if (lo >= hi) continue;
-            uint4 v = *reinterpret_cast<const uint4*>(buf + SC_HALO + u * 16);
-            uint32_t valid = 0xffffu;
-            if (lo != p0 || hi != p0 + 16) valid = ((1u << (uint32_t)(hi - p0)) - 1u) & ~((1u << (uint32_t)(lo - p0)) - 1u);
-            uint32_t pre = prefilter16(v, A.P, pass_s) & valid;
+            uint4 v = *reinterpret_cast<const uint4*>(buf + WS_HALO + u * 16);
+            uint32_t pre;
+            if (A.P.nfast) {
+                uint32_t z0 = fast_flags(v.x, A.P), z1 = fast_flags(v.y, A.P), z2 = fast_flags(v.z, A.P), z3 = fast_flags(v.w, A.P);
+                pre = 0;
+                if (z0 | z1 | z2 | z3) {   // rare: compress the per-byte flags into a 16-bit mask
+                    uint32_t zz[4] = {z0, z1, z2, z3};
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        pre |= (((zz[w] >> 7) & 1u) | ((zz[w] >> 14) & 2u) | ((zz[w] >> 21) & 4u) | ((zz[w] >> 28) & 8u)) << (4 * w);
+                }
+            } else {
+                pre = prefilter16(v, A.P, pass_s);
+            }
+            if (!inside) {
+                uint64_t lo = p0 > A.scan_lo ? p0 : A.scan_lo;
+                uint64_t hi = p0 + 16 < A.scan_hi ? p0 + 16 : A.scan_hi;
+                uint32_t valid = 0;
+                if (lo < hi) valid = ((hi - p0 >= 16) ? 0xffffu : ((1u << (uint32_t)(hi - p0)) - 1u)) & ~((1u << (uint32_t)(lo - p0)) - 1u);
+                pre &= valid;
+            }
+            uint32_t hits = 0;
             while (pre) {
                 int b = __ffs(pre) - 1;
                 pre &= pre - 1;
-                uint32_t idx = atomicAdd(&cnts[1], 1u);
-                if (idx < SC_PRE) pre_list[idx] = u * 16 + (uint32_t)b;
+                if (is_candidate(view, T_s, A.P, p0 + (uint64_t)b)) hits |= 1u << b;
             }
+            if (__ballot_sync(0xffffffffu, hits != 0)) emit(hits, p0);
         }
-        // positions of a misaligned stream head that precede the first aligned unit (tile 0 only)
-        if (tile == 0 && A.origin > A.scan_lo) {
-            uint64_t p = A.scan_lo + tid;
-            if (p < A.origin && p < A.scan_hi) {
-                ByteView gview{A.data, A.base_pos, A.lowest};
-                if (is_candidate(gview, T_s, A.P, p)) {
-                    uint32_t idx = atomicAdd(&cnts[0], 1u);
-                    if (idx < SC_LIST) list[idx] = 16u - (uint32_t)(A.origin - p);   // biased by 16: < every in-tile entry
-                }
-            }
-        }
-        __syncthreads();
-        // ---- phase 2: one thread per prefilter hit confirms it against the bytes in shared memory ----
-        const uint32_t npre = cnts[1];
-        if (npre > SC_PRE) {
-            overflow = true;
-        } else {
-            SmemView view{buf, tile_pos - SC_HALO, A.lowest};
-            for (uint32_t j = tid; j < npre; j += SC_THREADS) {
-                uint32_t off = pre_list[j];
-                if (is_candidate(view, T_s, A.P, tile_pos + off)) {
-                    uint32_t idx = atomicAdd(&cnts[0], 1u);
-                    if (idx < SC_LIST) list[idx] = off + 16u;   // bias 16 (see the head case above)
-                }
-            }
-        }
-        __syncthreads();
-        const uint32_t cnt = cnts[0];
-        if (overflow || cnt > SC_LIST || my_total + cnt > S.slice_cap) {
-            overflow = true;   // keep draining the copy pipeline, stop recording
-        } else {
-            // rank order == position order (positions are unique)
-            for (uint32_t j = tid; j < cnt; j += SC_THREADS) {
-                uint32_t mine = list[j], rank = 0;
-                for (uint32_t k = 0; k < cnt; ++k) rank += list[k] < mine ? 1u : 0u;
-                my_out[my_total + rank] = tile_pos + mine - 16u;
-            }
-            my_total += cnt;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            cnts[0] = 0;
-            cnts[1] = 0;
-            if (i + SC_STAGES < n_my) issue(i + SC_STAGES);
-        }
+        __syncwarp();
+        if (lane == 0 && i + WS_STAGES < n_my) issue(i + WS_STAGES);
     }
-    if (tid == 0) S.cta_counts[blockIdx.x] = overflow ? 0xFFFFFFFFu : my_total;
+    (void)lane_lt;
+    if (lane == 0) S.slice_counts[gw] = overflow ? 0xFFFFFFFFu : my_total;
 }
 
-// concatenates the CTA slices in CTA order; scalars[0] = total candidates, scalars[2] = overflow flag
-__global__ void __launch_bounds__(1024) cdc_compact_kernel(const uint64_t* __restrict__ cand_tmp, const uint32_t* __restrict__ cta_counts,
-                                                           uint32_t nctas, uint32_t slice_cap, uint64_t* __restrict__ cand,
+// concatenates the warp slices in warp order; scalars[0] = total candidates, scalars[2] = overflow flag
+__global__ void __launch_bounds__(1024) cdc_compact_kernel(const uint64_t* __restrict__ cand_tmp, const uint32_t* __restrict__ slice_counts,
+                                                           uint32_t nslices, uint32_t slice_cap, uint64_t* __restrict__ cand,
                                                            uint64_t* __restrict__ scalars) {
-    __shared__ uint64_t offs[1025];
+    extern __shared__ uint64_t offs[];   // nslices + 1
     __shared__ uint32_t bad;
     if (threadIdx.x == 0) {
         uint64_t run = 0;
         uint32_t b = 0;
-        for (uint32_t c = 0; c < nctas; ++c) {
+        for (uint32_t c = 0; c < nslices; ++c) {
             offs[c] = run;
-            uint32_t n = cta_counts[c];
+            uint32_t n = slice_counts[c];
             if (n == 0xFFFFFFFFu) { b = 1; n = 0; }
             run += n;
         }
-        offs[nctas] = run;
+        offs[nslices] = run;
         bad = b;
         scalars[0] = run;
         scalars[2] = b;
     }
     __syncthreads();
     if (bad) return;
-    for (uint32_t c = 0; c < nctas; ++c) {
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (uint32_t c = warp; c < nslices; c += nw) {
         uint32_t n = (uint32_t)(offs[c + 1] - offs[c]);
-        for (uint32_t j = threadIdx.x; j < n; j += blockDim.x) cand[offs[c] + j] = cand_tmp[(size_t)c * slice_cap + j];
+        for (uint32_t j = lane; j < n; j += 32) cand[offs[c] + j] = cand_tmp[(size_t)c * slice_cap + j];
     }
 }
 
-yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm_count, uint64_t* cand_tmp, uint32_t* cta_counts,
-                                      uint32_t slice_cap, uint32_t nctas, uint64_t* cand, uint64_t* scalars, cudaStream_t st) {
+yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm_count, uint64_t* cand_tmp, uint32_t* slice_counts,
+                                      uint32_t slice_cap, uint32_t nslices, uint64_t* cand, uint64_t* scalars, cudaStream_t st) {
     SinglePassArgs S{};
     S.A = A;
     S.ntiles = ntiles;
-    S.tiles_per_cta = (ntiles + nctas - 1) / nctas;
+    S.tiles_per_warp = (ntiles + nslices - 1) / nslices;
     S.slice_cap = slice_cap;
-    S.halo_ok = (A.origin >= A.lowest + SC_HALO) ? 1u : 0u;
+    S.halo_ok = (A.origin >= A.lowest + WS_HALO) ? 1u : 0u;
     S.end16 = A.scan_hi > A.origin ? A.origin + ((A.scan_hi - A.origin) & ~15ull) : A.origin;
     S.cand_tmp = cand_tmp;
-    S.cta_counts = cta_counts;
-    size_t smem = (size_t)SC_STAGES * (SC_HALO + SC_TILE) + 256 * 8 + SC_STAGES * 8 + (SC_LIST + SC_PRE) * 4 + 16 + 256;
+    S.slice_counts = slice_counts;
+    size_t smem = (size_t)WS_WARPS * WS_STAGES * WS_BUF + 256 * 8 + (size_t)WS_WARPS * WS_STAGES * 8 + 256 + 64;
     YB_CUDA(cudaFuncSetAttribute(cdc_scan_single_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cdc_scan_single_pass_kernel<<<nctas, SC_THREADS, smem, st>>>(S);
-    cdc_compact_kernel<<<1, 1024, 0, st>>>(cand_tmp, cta_counts, nctas, slice_cap, cand, scalars);
+    unsigned nctas = (nslices + WS_WARPS - 1) / WS_WARPS;
+    cdc_scan_single_pass_kernel<<<nctas, WS_THREADS, smem, st>>>(S);
+    cdc_compact_kernel<<<1, 1024, (size_t)(nslices + 1) * 8, st>>>(cand_tmp, slice_counts, nslices, slice_cap, cand, scalars);
     YB_CUDA(cudaGetLastError());
     (void)sm_count;
     return YAMS_OK;

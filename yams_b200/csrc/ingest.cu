@@ -117,16 +117,17 @@ struct CdcStream {
             ScanArgs A{data, base_pos, lowest, origin, scan_lo, scan_hi, table.as<uint64_t>(), P};
             bool need_two_pass = two_pass_only;
             if (!two_pass_only) {
-                // single pass: every CTA scans a contiguous range and appends to its own slice
-                uint32_t nctas = std::min<uint32_t>(ntiles, (uint32_t)dev->sm_count * 2u);
-                uint32_t tpc = (ntiles + nctas - 1) / nctas;
-                uint32_t slice_cap = std::max<uint32_t>(256u, tpc * 64u);   // 32x the 1/8192 density of random data
-                size_t total_cap = (size_t)nctas * slice_cap;
+                // single pass: every warp scans a contiguous range (4 KiB tiles) and appends to its own slice
+                uint32_t ntiles4 = (uint32_t)((span + kSinglePassTile - 1) / kSinglePassTile);
+                uint32_t nslices = std::min<uint32_t>(ntiles4, (uint32_t)dev->sm_count * kSinglePassWarpsPerCta);
+                uint32_t tpw = (ntiles4 + nslices - 1) / nslices;
+                uint32_t slice_cap = std::max<uint32_t>(64u, tpw * 16u);   // 32x the 1/8192 density of random data
+                size_t total_cap = (size_t)nslices * slice_cap;
                 if ((rc = cand_tmp.reserve(total_cap * 8)) != YAMS_OK) return rc;
                 if ((rc = cand.reserve(total_cap * 8)) != YAMS_OK) return rc;
-                if ((rc = tile_counts.reserve((size_t)std::max<uint32_t>(ntiles, nctas) * 4)) != YAMS_OK) return rc;
-                if ((rc = launch_scan_single_pass(A, ntiles, dev->sm_count, cand_tmp.as<uint64_t>(), tile_counts.as<uint32_t>(),
-                                                  slice_cap, nctas, cand.as<uint64_t>(), d_sc, st)) != YAMS_OK)
+                if ((rc = tile_counts.reserve((size_t)std::max<uint32_t>(ntiles, nslices) * 4)) != YAMS_OK) return rc;
+                if ((rc = launch_scan_single_pass(A, ntiles4, dev->sm_count, cand_tmp.as<uint64_t>(), tile_counts.as<uint32_t>(),
+                                                  slice_cap, nslices, cand.as<uint64_t>(), d_sc, st)) != YAMS_OK)
                     return rc;
                 YB_CUDA(cudaMemcpyAsync((void*)h_sc, d_sc, 24, cudaMemcpyDeviceToHost, st));
                 { const double t0 = now_ms(); YB_CUDA(cudaStreamSynchronize(st)); host_sync1 += now_ms() - t0; }

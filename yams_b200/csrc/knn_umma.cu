@@ -21,6 +21,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "knn.cuh"
 
@@ -46,7 +47,7 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, long long* waited = nullptr) {
     uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
     long long t0 = 0;
@@ -64,12 +65,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             else if (now - t0 > UM_WAIT_LIMIT_CYCLES) __trap();
         }
     }
+    if (waited && t0) *waited += clock64() - t0;
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
+}
+// pull a tile into L2 ahead of time (no shared-memory destination, no barrier)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -119,6 +126,7 @@ struct UmmaArgs {
     uint32_t stages;
     uint32_t b_stage;     // bytes of one B stage held by ONE CTA = (n_tile / CTAS) * 128
     uint32_t idesc;
+    unsigned long long* prof;   // nullable diagnostics: per CTA {producer wait, mma wait full, mma wait tempty, epi wait, epi work, total}
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -181,7 +189,8 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const uint32_t group = blockIdx.x / CTAS, ngroups = gridDim.x / CTAS;
-    const uint64_t n_units = (uint64_t)u.nrt * u.nqt;
+    // row tiles group, group+ngroups, ... belong to this CTA (pair); each is run against all nqt query tiles
+    const uint64_t my_units = group < u.nrt ? (uint64_t)((u.nrt - group + ngroups - 1) / ngroups) * u.nqt : 0;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
@@ -215,39 +224,49 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         // ===================== TMA producer (every CTA loads its own rows and its share of the queries) =====
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (uint64_t unit = group; unit < n_units; unit += ngroups) {
-                const uint32_t rt = (uint32_t)(unit / u.nqt), qt = (uint32_t)(unit % u.nqt);
+            long long w_prod = 0;
+            // A CTA (pair) owns whole row tiles and runs every query tile against each: the corpus tile is fetched
+            // from HBM once and re-read from L2 by the same SM; the next row tile is prefetched into L2 meanwhile.
+            for (uint32_t rt = group; rt < u.nrt; rt += ngroups) {
                 const int a_row = (int)((rt * CTAS + rank) * UM_BLOCK_M);
-                const int b_row = (int)(qt * u.n_tile + rank * (u.n_tile / CTAS));
-                for (uint32_t kb = 0; kb < u.kblocks; ++kb) {
-                    mbar_wait(&empty[s], ph ^ 1);
-                    uint8_t* sa = tiles + (size_t)s * stage_bytes;
-                    uint8_t* sb = sa + UM_A_STAGE;
-                    if (CTAS == 2) {
-                        if (leader) mbar_expect_tx(&full[s], stage_bytes * 2);
-                        else mbar_arrive_remote(&full[s], 0);
-                        tma_load_2d_2sm(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), a_row);
-                        tma_load_2d_2sm(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), b_row);
-                    } else {
-                        mbar_expect_tx(&full[s], stage_bytes);
-                        tma_load_2d(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), a_row);
-                        tma_load_2d(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), b_row);
+                const int a_next = (int)(((rt + ngroups) * CTAS + rank) * UM_BLOCK_M);
+                const bool have_next = rt + ngroups < u.nrt;
+                for (uint32_t qt = 0; qt < u.nqt; ++qt) {
+                    const int b_row = (int)(qt * u.n_tile + rank * (u.n_tile / CTAS));
+                    for (uint32_t kb = 0; kb < u.kblocks; ++kb) {
+                        mbar_wait(&empty[s], ph ^ 1, &w_prod);
+                        uint8_t* sa = tiles + (size_t)s * stage_bytes;
+                        uint8_t* sb = sa + UM_A_STAGE;
+                        if (CTAS == 2) {
+                            if (leader) mbar_expect_tx(&full[s], stage_bytes * 2);
+                            else mbar_arrive_remote(&full[s], 0);
+                            tma_load_2d_2sm(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), a_row);
+                            tma_load_2d_2sm(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), b_row);
+                        } else {
+                            mbar_expect_tx(&full[s], stage_bytes);
+                            tma_load_2d(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), a_row);
+                            tma_load_2d(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), b_row);
+                        }
+                        if (qt == 0 && have_next) tma_prefetch_2d(&tmA, (int)(kb * UM_BLOCK_K), a_next);
+                        if (++s == u.stages) { s = 0; ph ^= 1; }
                     }
-                    if (++s == u.stages) { s = 0; ph ^= 1; }
                 }
             }
+            if (u.prof) u.prof[blockIdx.x * 8 + 0] = (unsigned long long)w_prod;
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (lane == 0 && leader) {
             uint32_t s = 0, ph = 0, it = 0;
-            for (uint64_t unit = group; unit < n_units; unit += ngroups, ++it) {
+            long long w_full = 0, w_tempty = 0;
+            const long long t_start = clock64();
+            for (uint64_t unit = 0; unit < my_units; ++unit, ++it) {
                 const uint32_t as = it & 1, aph = (it >> 1) & 1;
-                mbar_wait(&tempty[as], aph ^ 1);
+                mbar_wait(&tempty[as], aph ^ 1, &w_tempty);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + as * UM_MAX_N;
                 for (uint32_t kb = 0; kb < u.kblocks; ++kb) {
-                    mbar_wait(&full[s], ph);
+                    mbar_wait(&full[s], ph, &w_full);
                     tcgen05_fence_after();
                     const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
                     const uint64_t adesc = make_smem_desc(sa);
@@ -264,14 +283,21 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 }
                 if (CTAS == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);   // accumulator complete
             }
+            if (u.prof) {
+                u.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
+                u.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tempty;
+                u.prof[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_start);
+            }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const uint32_t quad = warp & 3;              // TMEM lane quadrant this warp may access
         float* my_tau = tau_s + quad * UM_MAX_N;
         uint32_t it = 0;
-        for (uint64_t unit = group; unit < n_units; unit += ngroups, ++it) {
-            const uint32_t rt = (uint32_t)(unit / u.nqt), qt = (uint32_t)(unit % u.nqt);
+        long long w_epi = 0;
+        const long long e_start = clock64();
+        for (uint64_t unit = 0; unit < my_units; ++unit, ++it) {
+            const uint32_t rt = group + (uint32_t)(unit / u.nqt) * ngroups, qt = (uint32_t)(unit % u.nqt);
             const uint32_t as = it & 1, aph = (it >> 1) & 1;
             const uint64_t li = ((uint64_t)rt * CTAS + rank) * UM_BLOCK_M + quad * 32 + lane;   // row within this launch
             const bool rvalid = li < u.a.nrows;
@@ -284,7 +310,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 for (uint32_t c = lane; c < u.n_tile; c += 32) my_tau[c] = (q0 + c < u.a.nq) ? __ldg(&u.a.tau[q0 + c]) : INFINITY;
                 __syncwarp();
             }
-            mbar_wait(&tfull[as], aph);
+            mbar_wait(&tfull[as], aph, &w_epi);
             tcgen05_fence_after();
             for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 32) {
                 uint32_t v[32];
@@ -331,6 +357,10 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (lane == 0) {
                 if (CTAS == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
             }
+        }
+        if (u.prof && quad == 0 && lane == 0) {
+            u.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_epi;
+            u.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
         }
     }
     tcgen05_fence_before();
@@ -429,8 +459,11 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     if (!make_map_2d(&tmB, d_q16, a.dim, a.nq, (uint64_t)a.dim * 2, UM_BLOCK_K, u.n_tile / ctas)) return YAMS_ERR_UNSUPPORTED;
 
     size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16 + 4 * UM_MAX_N * 4;
-    uint64_t n_units = (uint64_t)u.nrt * u.nqt;
-    unsigned groups = (unsigned)std::min<uint64_t>(n_units, (uint64_t)(c->dev->sm_count / ctas));
+    unsigned groups = (unsigned)std::min<uint64_t>(u.nrt, (uint64_t)(c->dev->sm_count / ctas));
+    if (getenv("YAMS_B200_UMMA_PROF")) {
+        YB_CUDA(cudaMalloc(&u.prof, (size_t)groups * ctas * 8 * 8));
+        YB_CUDA(cudaMemsetAsync(u.prof, 0, (size_t)groups * ctas * 8 * 8, st));
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(groups * ctas);
     cfg.blockDim = dim3(UM_THREADS);
@@ -455,6 +488,25 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     }
 #undef YB_LAUNCH_UMMA
     YB_CUDA(cudaGetLastError());
+    if (u.prof) {
+        // diagnostics (YAMS_B200_UMMA_PROF=1): aggregate per-role wait cycles
+        YB_CUDA(cudaStreamSynchronize(st));
+        std::vector<unsigned long long> h((size_t)groups * ctas * 8);
+        YB_CUDA(cudaMemcpy(h.data(), u.prof, h.size() * 8, cudaMemcpyDeviceToHost));
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        int nlead = 0;
+        for (unsigned b = 0; b < groups * ctas; ++b) {
+            acc[0] += (double)h[b * 8 + 0];
+            acc[3] += (double)h[b * 8 + 3];
+            acc[4] += (double)h[b * 8 + 4];
+            if (h[b * 8 + 5]) { acc[1] += (double)h[b * 8 + 1]; acc[2] += (double)h[b * 8 + 2]; acc[5] += (double)h[b * 8 + 5]; ++nlead; }
+        }
+        unsigned nb = groups * ctas;
+        fprintf(stderr, "[umma prof] ctas=%d filter=%d units/group=%llu | per-CTA Mcycles: producer-wait-empty %.2f | mma total %.2f wait-full %.2f wait-tempty %.2f | epilogue total %.2f wait-tfull %.2f\n",
+                ctas, (int)filter, (unsigned long long)(((uint64_t)u.nrt + groups - 1) / groups * u.nqt), acc[0] / nb / 1e6, acc[5] / nlead / 1e6,
+                acc[1] / nlead / 1e6, acc[2] / nlead / 1e6, acc[4] / nb / 1e6, acc[3] / nb / 1e6);
+        cudaFree(u.prof);
+    }
     return YAMS_OK;
 }
 
