@@ -262,7 +262,7 @@ def main():
         def step_resident():
             corpus.search_device(q_dev.data_ptr(), nq, k, -1.0, part_r.data_ptr(), part_s.data_ptr())
             if dist:
-                with torch.cuda.stream(stream):
+                with torch.cuda.stream(stream):   # one NCCL all-gather of the per-shard partial top-k
                     dist.all_gather_into_tensor(all_r, part_r)
                     dist.all_gather_into_tensor(all_s, part_s)
                 corpus.merge_partials_device(all_r.data_ptr(), all_s.data_ptr(), world, nq, k, fin_r.data_ptr(), fin_s.data_ptr())
