@@ -225,17 +225,22 @@ struct SmemView {
 
 __device__ __forceinline__ uint32_t sc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// per-word "some byte equals one of the fast values" flags (bit 7 of each matching byte)
-__device__ __forceinline__ uint32_t fast_flags(uint32_t w, const CdcParams& P) {
+// per-word "some byte equals one of the NFAST prefilter values" flags (bit 7 of each matching byte);
+// pat[f] = 0x01010101 * value, held in registers
+template <int NFAST>
+__device__ __forceinline__ uint32_t fast_flags(uint32_t w, const uint32_t (&pat)[4]) {
     uint32_t z = 0;
-    for (uint32_t f = 0; f < P.nfast; ++f) {
-        uint32_t m = w ^ (0x01010101u * P.fast[f]);
+#pragma unroll
+    for (int f = 0; f < NFAST; ++f) {
+        uint32_t m = w ^ pat[f];
         uint32_t t = (m & 0x7f7f7f7fu) + 0x7f7f7f7fu;
         z |= ~(t | m | 0x7f7f7f7fu);
     }
     return z;
 }
 
+// NFAST = number of byte values that pass the low-byte prefilter (1..4), or 0 for the generic table path
+template <int NFAST>
 __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(SinglePassArgs S) {
     extern __shared__ __align__(128) uint8_t sc_smem[];
     uint8_t* bufs = sc_smem;                                                        // WS_WARPS x WS_STAGES x WS_BUF
@@ -291,7 +296,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
     uint32_t my_total = 0;          // candidates written by this warp so far (uniform across lanes)
     bool overflow = false;
     uint64_t* my_out = S.cand_tmp + (size_t)gw * S.slice_cap;
-    const uint32_t lane_lt = (1u << lane) - 1u;
+    uint32_t pat[4];
+#pragma unroll
+    for (int f = 0; f < 4; ++f) pat[f] = 0x01010101u * (uint32_t)A.P.fast[f];
 
     // ordered append of a lane's hit mask (bit b = position p0 + b); lanes are in position order
     auto emit = [&](uint32_t hits, uint64_t p0) {
@@ -370,8 +377,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
             const uint64_t p0 = tile_pos + (uint64_t)u * 16;
             uint4 v = *reinterpret_cast<const uint4*>(buf + WS_HALO + u * 16);
             uint32_t pre;
-            if (A.P.nfast) {
-                uint32_t z0 = fast_flags(v.x, A.P), z1 = fast_flags(v.y, A.P), z2 = fast_flags(v.z, A.P), z3 = fast_flags(v.w, A.P);
+            if (NFAST > 0) {
+                uint32_t z0 = fast_flags<NFAST>(v.x, pat), z1 = fast_flags<NFAST>(v.y, pat), z2 = fast_flags<NFAST>(v.z, pat),
+                         z3 = fast_flags<NFAST>(v.w, pat);
                 pre = 0;
                 if (z0 | z1 | z2 | z3) {   // rare: compress the per-byte flags into a 16-bit mask
                     uint32_t zz[4] = {z0, z1, z2, z3};
@@ -400,7 +408,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
         __syncwarp();
         if (lane == 0 && i + WS_STAGES < n_my) issue(i + WS_STAGES);
     }
-    (void)lane_lt;
     if (lane == 0) S.slice_counts[gw] = overflow ? 0xFFFFFFFFu : my_total;
 }
 
@@ -445,9 +452,20 @@ yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm
     S.cand_tmp = cand_tmp;
     S.slice_counts = slice_counts;
     size_t smem = (size_t)WS_WARPS * WS_STAGES * WS_BUF + 256 * 8 + (size_t)WS_WARPS * WS_STAGES * 8 + 256 + 64;
-    YB_CUDA(cudaFuncSetAttribute(cdc_scan_single_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     unsigned nctas = (nslices + WS_WARPS - 1) / WS_WARPS;
-    cdc_scan_single_pass_kernel<<<nctas, WS_THREADS, smem, st>>>(S);
+#define YB_LAUNCH_SCAN(NF)                                                                                                  \
+    do {                                                                                                                    \
+        YB_CUDA(cudaFuncSetAttribute(cdc_scan_single_pass_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        cdc_scan_single_pass_kernel<NF><<<nctas, WS_THREADS, smem, st>>>(S);                                                \
+    } while (0)
+    switch (A.P.nfast) {
+        case 1: YB_LAUNCH_SCAN(1); break;
+        case 2: YB_LAUNCH_SCAN(2); break;
+        case 3: YB_LAUNCH_SCAN(3); break;
+        case 4: YB_LAUNCH_SCAN(4); break;
+        default: YB_LAUNCH_SCAN(0); break;
+    }
+#undef YB_LAUNCH_SCAN
     cdc_compact_kernel<<<1, 1024, (size_t)(nslices + 1) * 8, st>>>(cand_tmp, slice_counts, nslices, slice_cap, cand, scalars);
     YB_CUDA(cudaGetLastError());
     (void)sm_count;

@@ -35,6 +35,13 @@ constexpr int UM_THREADS = 192;          // 6 warps
 constexpr uint32_t UM_A_STAGE = UM_BLOCK_M * UM_BLOCK_K * 2;   // 16 KiB
 constexpr uint32_t UM_TMEM_COLS = 512;
 constexpr long long UM_WAIT_LIMIT_CYCLES = 4000000000ll;
+constexpr uint32_t UM_EPI_CAP = 128;      // survivors staged per epilogue warp before a batched flush
+
+struct EpiEntry {
+    uint32_t q;
+    uint32_t row;
+    float score;
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -105,6 +112,20 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+__device__ __forceinline__ void tmem_ld_32x32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row groups 1024 B apart (SBO); version 1 (sm_100)
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
@@ -182,7 +203,10 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     uint64_t* tfull = bars + 2 * u.stages;      // [2]
     uint64_t* tempty = tfull + 2;               // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-    float* tau_s = reinterpret_cast<float*>(tmem_slot + 4);   // [4 epilogue warps][UM_MAX_N]
+    float* tmin_s = reinterpret_cast<float*>(tmem_slot + 4);             // [32] smallest threshold of each query tile
+    uint32_t* wcnt_s = reinterpret_cast<uint32_t*>(tmin_s + 32);           // [4] staged survivors per epilogue warp
+    float* tau_all = reinterpret_cast<float*>(wcnt_s + 4);                 // [nqt * n_tile] thresholds (+inf past nq)
+    EpiEntry* stage_s = reinterpret_cast<EpiEntry*>(tau_all + (size_t)u.nqt * u.n_tile);   // [4][UM_EPI_CAP]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -213,6 +237,17 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         } else {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(UM_TMEM_COLS) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
+    }
+    if (FILTER) {
+        const uint32_t nqpad = u.nqt * u.n_tile;
+        for (uint32_t i = threadIdx.x; i < nqpad; i += UM_THREADS) tau_all[i] = i < u.a.nq ? __ldg(&u.a.tau[i]) : INFINITY;
+        if (threadIdx.x < 4) wcnt_s[threadIdx.x] = 0;
+        __syncthreads();
+        for (uint32_t t = threadIdx.x; t < u.nqt; t += UM_THREADS) {
+            float m = INFINITY;
+            for (uint32_t c = 0; c < u.n_tile; ++c) m = fminf(m, tau_all[t * u.n_tile + c]);
+            tmin_s[t] = m;
         }
     }
     tcgen05_fence_before();
@@ -292,58 +327,117 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const uint32_t quad = warp & 3;              // TMEM lane quadrant this warp may access
-        float* my_tau = tau_s + quad * UM_MAX_N;
+        EpiEntry* my_stage = stage_s + quad * UM_EPI_CAP;
+        uint32_t* my_cnt = wcnt_s + quad;
+        const bool direct = u.a.mask != nullptr;     // candidate-set mode: most allowed rows survive, no staging
         uint32_t it = 0;
         long long w_epi = 0;
         const long long e_start = clock64();
+
+        auto append_global = [&](uint32_t q, uint32_t row, float sc) {
+            uint32_t pos = atomicAdd(&u.a.counts[q], 1u);
+            if (pos < u.a.cap) {
+                Cand cd;
+                cd.score = sc;
+                cd.row = row;
+                u.a.cands[(uint64_t)q * u.a.cap + pos] = cd;
+            }
+        };
+        auto flush = [&]() {   // warp-uniform: drain the staged survivors with the atomics in flight together
+            __syncwarp();
+            uint32_t n = min(*my_cnt, UM_EPI_CAP);
+            for (uint32_t i = lane; i < n; i += 32) {
+                EpiEntry e = my_stage[i];
+                append_global(e.q, e.row, e.score);
+            }
+            __syncwarp();
+            if (lane == 0) *my_cnt = 0;
+            __syncwarp();
+        };
+        // row-level data of the first unit
+        auto row_of = [&](uint64_t unit, uint64_t& li_out) {
+            const uint32_t rt_ = group + (uint32_t)(unit / u.nqt) * ngroups;
+            li_out = ((uint64_t)rt_ * CTAS + rank) * UM_BLOCK_M + quad * 32 + lane;
+        };
+        uint64_t li = 0;
+        float inr = 0.f;
+        if (my_units) {
+            row_of(0, li);
+            inr = li < u.a.nrows ? __ldg(&u.a.inv_norm[u.a.row_start + li * u.a.row_stride]) : 0.f;
+        }
         for (uint64_t unit = 0; unit < my_units; ++unit, ++it) {
-            const uint32_t rt = group + (uint32_t)(unit / u.nqt) * ngroups, qt = (uint32_t)(unit % u.nqt);
+            const uint32_t qt = (uint32_t)(unit % u.nqt);
             const uint32_t as = it & 1, aph = (it >> 1) & 1;
-            const uint64_t li = ((uint64_t)rt * CTAS + rank) * UM_BLOCK_M + quad * 32 + lane;   // row within this launch
             const bool rvalid = li < u.a.nrows;
             const uint64_t grow = u.a.row_start + li * u.a.row_stride;
-            const float inr = rvalid ? u.a.inv_norm[grow] : 0.f;
-            const uint32_t q0 = qt * u.n_tile;
-            if (FILTER) {
-                // this warp's private copy of the tile's thresholds (+inf for queries past the end)
-                __syncwarp();
-                for (uint32_t c = lane; c < u.n_tile; c += 32) my_tau[c] = (q0 + c < u.a.nq) ? __ldg(&u.a.tau[q0 + c]) : INFINITY;
-                __syncwarp();
+            // prefetch the next unit's row scale while this unit is processed
+            uint64_t li_next = li;
+            float inr_next = inr;
+            if (unit + 1 < my_units && qt + 1 == u.nqt) {
+                row_of(unit + 1, li_next);
+                inr_next = li_next < u.a.nrows ? __ldg(&u.a.inv_norm[u.a.row_start + li_next * u.a.row_stride]) : 0.f;
             }
+            const uint32_t q0 = qt * u.n_tile;
+            const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * UM_MAX_N;
             mbar_wait(&tfull[as], aph, &w_epi);
             tcgen05_fence_after();
-            for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32(tmem_base + ((quad * 32u) << 16) + as * UM_MAX_N + c0, v);
-                if (q0 + c0 >= u.a.nq) continue;     // warp-uniform
-                if (FILTER) {
-                    // branch-free pass over the 32 columns; survivors are rare (~1e-4 of the scores)
-                    bool any = false;
+            if (FILTER) {
+                const float* tau_t = tau_all + q0;
+                // conservative row-level bound: score > tau_q  =>  acc > tmin * |row| (slightly relaxed)
+                float bound = INFINITY;
+                if (rvalid && inr > 0.f) {
+                    float b0 = tmin_s[qt] * (1.0f / inr);
+                    bound = b0 - fabsf(b0) * 1e-6f - 1e-30f;
+                }
+                auto process = [&](const uint32_t (&v)[32], uint32_t c0) {
+                    float m = __uint_as_float(v[0]);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) any |= (__uint_as_float(v[c]) * inr > my_tau[c0 + c]);
-                    if (any && inr > 0.f) {
+                    for (int c = 1; c + 1 < 32; c += 2)
+                        asm("max.f32 %0, %0, %1, %2;" : "+f"(m) : "f"(__uint_as_float(v[c])), "f"(__uint_as_float(v[c + 1])));
+                    m = fmaxf(m, __uint_as_float(v[31]));
+                    if (m > bound) {   // rare: some column of this row may survive
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
-                            const uint32_t q = q0 + c0 + c;
-                            if (q >= u.a.nq) break;
-                            const float s = __uint_as_float(v[c]) * inr;
-                            bool pass = s > my_tau[c0 + c];
-                            if (pass && u.a.mask) {
-                                uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
-                                pass = (w >> (grow & 31)) & 1u;
-                            }
-                            if (pass) {
-                                uint32_t pos = atomicAdd(&u.a.counts[q], 1u);
-                                if (pos < u.a.cap) {
-                                    Cand cd;
-                                    cd.score = s;
-                                    cd.row = (uint32_t)grow;
-                                    u.a.cands[(uint64_t)q * u.a.cap + pos] = cd;
+                            const float sc = __uint_as_float(v[c]) * inr;
+                            if (sc > tau_t[c0 + c]) {
+                                const uint32_t q = q0 + c0 + c;
+                                bool pass = true;
+                                if (direct) {
+                                    uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
+                                    pass = (w >> (grow & 31)) & 1u;
+                                    if (pass) append_global(q, (uint32_t)grow, sc);
+                                } else {
+                                    uint32_t idx = atomicAdd(my_cnt, 1u);
+                                    if (idx < UM_EPI_CAP) {
+                                        EpiEntry e;
+                                        e.q = q; e.row = (uint32_t)grow; e.score = sc;
+                                        my_stage[idx] = e;
+                                    } else {
+                                        append_global(q, (uint32_t)grow, sc);
+                                    }
                                 }
                             }
                         }
                     }
-                } else if (rvalid) {
+                };
+                // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is tested
+                uint32_t va[32], vb[32];
+                tmem_ld_32x32_nowait(taddr, va);
+                tmem_ld_wait();
+                for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 64) {
+                    const bool has_b = c0 + 32 < u.n_tile;
+                    if (has_b) tmem_ld_32x32_nowait(taddr + c0 + 32, vb);
+                    process(va, c0);
+                    tmem_ld_wait();
+                    if (c0 + 64 < u.n_tile) tmem_ld_32x32_nowait(taddr + c0 + 64, va);
+                    if (has_b) process(vb, c0 + 32);
+                    tmem_ld_wait();
+                }
+            } else {
+                for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(taddr + c0, v);
+                    if (q0 + c0 >= u.a.nq || !rvalid) continue;
 #pragma unroll
                     for (int c = 0; c < 32; ++c) {
                         const uint32_t q = q0 + c0 + c;
@@ -357,7 +451,11 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (lane == 0) {
                 if (CTAS == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
             }
+            if (FILTER && !direct && *my_cnt >= (UM_EPI_CAP * 3) / 4) flush();   // warp-uniform (smem value)
+            li = li_next;
+            inr = inr_next;
         }
+        if (FILTER && !direct) flush();
         if (u.prof && quad == 0 && lane == 0) {
             u.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_epi;
             u.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
@@ -446,7 +544,8 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     u.kblocks = (a.dim + UM_BLOCK_K - 1) / UM_BLOCK_K;
     u.b_stage = (u.n_tile / ctas) * 128;
     uint32_t stage_bytes = UM_A_STAGE + u.b_stage;
-    const uint32_t budget = 196 * 1024;
+    if (u.nqt > 32 || (size_t)u.nqt * u.n_tile > 4096) return YAMS_ERR_UNSUPPORTED;   // thresholds live in shared memory
+    const uint32_t budget = 224 * 1024 - (uint32_t)(32 * 4 + 16 + (size_t)u.nqt * u.n_tile * 4 + 4 * UM_EPI_CAP * sizeof(EpiEntry)) - 2048;
     u.stages = std::min<uint32_t>(8, budget / stage_bytes);
     if (u.stages < 2) return YAMS_ERR_UNSUPPORTED;
     // instruction descriptor: D=f32, A=B=f16, both K-major, N = n_tile, M = 128 per CTA
@@ -458,7 +557,8 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
         return YAMS_ERR_UNSUPPORTED;
     if (!make_map_2d(&tmB, d_q16, a.dim, a.nq, (uint64_t)a.dim * 2, UM_BLOCK_K, u.n_tile / ctas)) return YAMS_ERR_UNSUPPORTED;
 
-    size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16 + 4 * UM_MAX_N * 4;
+    const size_t epi_bytes = 32 * 4 + 16 + (size_t)u.nqt * u.n_tile * 4 + 4 * UM_EPI_CAP * sizeof(EpiEntry);
+    size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16 + epi_bytes;
     unsigned groups = (unsigned)std::min<uint64_t>(u.nrt, (uint64_t)(c->dev->sm_count / ctas));
     if (getenv("YAMS_B200_UMMA_PROF")) {
         YB_CUDA(cudaMalloc(&u.prof, (size_t)groups * ctas * 8 * 8));
