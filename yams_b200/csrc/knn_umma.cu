@@ -331,8 +331,10 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t* my_cnt = wcnt_s + quad;
         const bool direct = u.a.mask != nullptr;     // candidate-set mode: most allowed rows survive, no staging
         uint32_t it = 0;
-        long long w_epi = 0;
+        long long w_epi = 0, w_ld = 0;
+        unsigned long long n_slow = 0;
         const long long e_start = clock64();
+        const bool profiling = u.prof != nullptr;
 
         auto append_global = [&](uint32_t q, uint32_t row, float sc) {
             uint32_t pos = atomicAdd(&u.a.counts[q], 1u);
@@ -396,6 +398,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         asm("max.f32 %0, %0, %1, %2;" : "+f"(m) : "f"(__uint_as_float(v[c])), "f"(__uint_as_float(v[c + 1])));
                     m = fmaxf(m, __uint_as_float(v[31]));
                     if (m > bound) {   // rare: some column of this row may survive
+                        ++n_slow;
 #pragma unroll
                         for (int c = 0; c < 32; ++c) {
                             const float sc = __uint_as_float(v[c]) * inr;
@@ -422,16 +425,25 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                 };
                 // software-pipelined TMEM reads: the load of chunk c+1 is in flight while chunk c is tested
                 uint32_t va[32], vb[32];
+                auto timed_wait = [&]() {
+                    if (profiling) {
+                        long long t0 = clock64();
+                        tmem_ld_wait();
+                        w_ld += clock64() - t0;
+                    } else {
+                        tmem_ld_wait();
+                    }
+                };
                 tmem_ld_32x32_nowait(taddr, va);
-                tmem_ld_wait();
+                timed_wait();
                 for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 64) {
                     const bool has_b = c0 + 32 < u.n_tile;
                     if (has_b) tmem_ld_32x32_nowait(taddr + c0 + 32, vb);
                     process(va, c0);
-                    tmem_ld_wait();
+                    timed_wait();
                     if (c0 + 64 < u.n_tile) tmem_ld_32x32_nowait(taddr + c0 + 64, va);
                     if (has_b) process(vb, c0 + 32);
-                    tmem_ld_wait();
+                    timed_wait();
                 }
             } else {
                 for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 32) {
@@ -459,6 +471,8 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         if (u.prof && quad == 0 && lane == 0) {
             u.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_epi;
             u.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
+            u.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_ld;
+            u.prof[blockIdx.x * 8 + 7] = n_slow;
         }
     }
     tcgen05_fence_before();
@@ -593,18 +607,20 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
         YB_CUDA(cudaStreamSynchronize(st));
         std::vector<unsigned long long> h((size_t)groups * ctas * 8);
         YB_CUDA(cudaMemcpy(h.data(), u.prof, h.size() * 8, cudaMemcpyDeviceToHost));
-        double acc[6] = {0, 0, 0, 0, 0, 0};
+        double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int nlead = 0;
         for (unsigned b = 0; b < groups * ctas; ++b) {
             acc[0] += (double)h[b * 8 + 0];
             acc[3] += (double)h[b * 8 + 3];
             acc[4] += (double)h[b * 8 + 4];
+            acc[6] += (double)h[b * 8 + 6];
+            acc[7] += (double)h[b * 8 + 7];
             if (h[b * 8 + 5]) { acc[1] += (double)h[b * 8 + 1]; acc[2] += (double)h[b * 8 + 2]; acc[5] += (double)h[b * 8 + 5]; ++nlead; }
         }
         unsigned nb = groups * ctas;
-        fprintf(stderr, "[umma prof] ctas=%d filter=%d units/group=%llu | per-CTA Mcycles: producer-wait-empty %.2f | mma total %.2f wait-full %.2f wait-tempty %.2f | epilogue total %.2f wait-tfull %.2f\n",
+        fprintf(stderr, "[umma prof] ctas=%d filter=%d units/group=%llu | per-CTA Mcycles: producer-wait-empty %.2f | mma total %.2f wait-full %.2f wait-tempty %.2f | epilogue total %.2f wait-tfull %.2f tmem-ld-wait %.2f slow-path entries/lane %.0f\n",
                 ctas, (int)filter, (unsigned long long)(((uint64_t)u.nrt + groups - 1) / groups * u.nqt), acc[0] / nb / 1e6, acc[5] / nlead / 1e6,
-                acc[1] / nlead / 1e6, acc[2] / nlead / 1e6, acc[4] / nb / 1e6, acc[3] / nb / 1e6);
+                acc[1] / nlead / 1e6, acc[2] / nlead / 1e6, acc[4] / nb / 1e6, acc[3] / nb / 1e6, acc[6] / nb / 1e6, acc[7] / nb);
         cudaFree(u.prof);
     }
     return YAMS_OK;
