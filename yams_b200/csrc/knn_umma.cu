@@ -194,7 +194,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1)
 stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, UmmaArgs u) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzled tiles (identical offsets in both CTAs of a pair)
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // (pointer arithmetic, not integer casts, so the compiler keeps these in the shared address space: LDS/STS/ATOMS)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t stage_bytes = UM_A_STAGE + u.b_stage;
     uint8_t* tiles = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tiles + (size_t)u.stages * stage_bytes);
@@ -397,26 +398,36 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     for (int c = 1; c + 1 < 32; c += 2)
                         asm("max.f32 %0, %0, %1, %2;" : "+f"(m) : "f"(__uint_as_float(v[c])), "f"(__uint_as_float(v[c + 1])));
                     m = fmaxf(m, __uint_as_float(v[31]));
-                    if (m > bound) {   // rare: some column of this row may survive
+                    if (m > bound) {   // rare (~1% of rows per chunk): some column of this row may survive
                         ++n_slow;
+                        // exact per-column test, branch-free: thresholds come in as 8 independent LDS.128
+                        uint32_t pm = 0;
 #pragma unroll
-                        for (int c = 0; c < 32; ++c) {
-                            const float sc = __uint_as_float(v[c]) * inr;
-                            if (sc > tau_t[c0 + c]) {
-                                const uint32_t q = q0 + c0 + c;
-                                bool pass = true;
-                                if (direct) {
-                                    uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
-                                    pass = (w >> (grow & 31)) & 1u;
-                                    if (pass) append_global(q, (uint32_t)grow, sc);
-                                } else {
-                                    uint32_t idx = atomicAdd(my_cnt, 1u);
-                                    if (idx < UM_EPI_CAP) {
-                                        EpiEntry e;
-                                        e.q = q; e.row = (uint32_t)grow; e.score = sc;
-                                        my_stage[idx] = e;
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 t4 = *reinterpret_cast<const float4*>(tau_t + c0 + c);
+                            pm |= (__uint_as_float(v[c + 0]) * inr > t4.x ? 1u : 0u) << (c + 0);
+                            pm |= (__uint_as_float(v[c + 1]) * inr > t4.y ? 1u : 0u) << (c + 1);
+                            pm |= (__uint_as_float(v[c + 2]) * inr > t4.z ? 1u : 0u) << (c + 2);
+                            pm |= (__uint_as_float(v[c + 3]) * inr > t4.w ? 1u : 0u) << (c + 3);
+                        }
+                        if (pm) {
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                if (pm & (1u << c)) {
+                                    const float sc = __uint_as_float(v[c]) * inr;
+                                    const uint32_t q = q0 + c0 + c;
+                                    if (direct) {
+                                        uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
+                                        if ((w >> (grow & 31)) & 1u) append_global(q, (uint32_t)grow, sc);
                                     } else {
-                                        append_global(q, (uint32_t)grow, sc);
+                                        uint32_t idx = atomicAdd(my_cnt, 1u);
+                                        if (idx < UM_EPI_CAP) {
+                                            EpiEntry e;
+                                            e.q = q; e.row = (uint32_t)grow; e.score = sc;
+                                            my_stage[idx] = e;
+                                        } else {
+                                            append_global(q, (uint32_t)grow, sc);
+                                        }
                                     }
                                 }
                             }
