@@ -57,7 +57,8 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, long long* waited = nullptr) {
     uint32_t addr = smem_u32(bar);
     uint32_t done = 0;
-    long long t0 = 0;
+    // try_wait may itself suspend the thread until the phase completes, so time from before the first attempt
+    const long long t_begin = clock64();
     while (!done) {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
@@ -66,13 +67,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, long l
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
-        if (!done) {   // never hang the GPU: a wait longer than ~2 s of SM clocks aborts the kernel
-            long long now = clock64();
-            if (t0 == 0) t0 = now;
-            else if (now - t0 > UM_WAIT_LIMIT_CYCLES) __trap();
-        }
+        // never hang the GPU: a wait longer than ~2 s of SM clocks aborts the kernel
+        if (!done && clock64() - t_begin > UM_WAIT_LIMIT_CYCLES) __trap();
     }
-    if (waited && t0) *waited += clock64() - t0;
+    if (waited) *waited += clock64() - t_begin;
 }
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
     asm volatile(
