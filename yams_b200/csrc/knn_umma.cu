@@ -330,7 +330,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t* my_cnt = wcnt_s + quad;
         const bool direct = u.a.mask != nullptr;     // candidate-set mode: most allowed rows survive, no staging
         uint32_t it = 0;
-        long long w_epi = 0, w_ld = 0;
+        long long w_epi = 0, w_ld = 0, t_ldissue = 0, t_proc = 0, t_tail = 0, t_head = 0;
         unsigned long long n_slow = 0;
         const long long e_start = clock64();
         const bool profiling = u.prof != nullptr;
@@ -367,6 +367,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             inr = li < u.a.nrows ? __ldg(&u.a.inv_norm[u.a.row_start + li * u.a.row_stride]) : 0.f;
         }
         for (uint64_t unit = 0; unit < my_units; ++unit, ++it) {
+            const long long t_h0 = profiling ? clock64() : 0;
             const uint32_t qt = (uint32_t)(unit % u.nqt);
             const uint32_t as = it & 1, aph = (it >> 1) & 1;
             const bool rvalid = li < u.a.nrows;
@@ -380,6 +381,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             }
             const uint32_t q0 = qt * u.n_tile;
             const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * UM_MAX_N;
+            if (profiling) t_head += clock64() - t_h0;
             mbar_wait(&tfull[as], aph, &w_epi);
             tcgen05_fence_after();
             if (FILTER) {
@@ -443,16 +445,32 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         tmem_ld_wait();
                     }
                 };
+                long long tq = profiling ? clock64() : 0;
+                auto lap = [&](long long& acc) {
+                    if (profiling) {
+                        long long now = clock64();
+                        acc += now - tq;
+                        tq = now;
+                    }
+                };
                 tmem_ld_32x32_nowait(taddr, va);
+                lap(t_ldissue);
                 timed_wait();
+                lap(w_ld);
                 for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 64) {
                     const bool has_b = c0 + 32 < u.n_tile;
                     if (has_b) tmem_ld_32x32_nowait(taddr + c0 + 32, vb);
+                    lap(t_ldissue);
                     process(va, c0);
-                    timed_wait();
+                    lap(t_proc);
+                    tmem_ld_wait();
+                    lap(w_ld);
                     if (c0 + 64 < u.n_tile) tmem_ld_32x32_nowait(taddr + c0 + 64, va);
+                    lap(t_ldissue);
                     if (has_b) process(vb, c0 + 32);
-                    timed_wait();
+                    lap(t_proc);
+                    tmem_ld_wait();
+                    lap(w_ld);
                 }
             } else {
                 for (uint32_t c0 = 0; c0 < u.n_tile; c0 += 32) {
@@ -467,6 +485,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     }
                 }
             }
+            const long long t_t0 = profiling ? clock64() : 0;
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -475,6 +494,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (FILTER && !direct && *my_cnt >= (UM_EPI_CAP * 3) / 4) flush();   // warp-uniform (smem value)
             li = li_next;
             inr = inr_next;
+            if (profiling) t_tail += clock64() - t_t0;
         }
         if (FILTER && !direct) flush();
         if (u.prof && quad == 0 && lane == 0) {
@@ -482,6 +502,9 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             u.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
             u.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_ld;
             u.prof[blockIdx.x * 8 + 7] = n_slow;
+            // detail slots live after the 8 per-CTA slots of all CTAs
+            unsigned long long* d = u.prof + (size_t)gridDim.x * 8 + (size_t)blockIdx.x * 4;
+            d[0] = (unsigned long long)t_ldissue; d[1] = (unsigned long long)t_proc; d[2] = (unsigned long long)t_tail; d[3] = (unsigned long long)t_head;
         }
     }
     tcgen05_fence_before();
@@ -584,8 +607,8 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16 + epi_bytes;
     unsigned groups = (unsigned)std::min<uint64_t>(u.nrt, (uint64_t)(c->dev->sm_count / ctas));
     if (getenv("YAMS_B200_UMMA_PROF")) {
-        YB_CUDA(cudaMalloc(&u.prof, (size_t)groups * ctas * 8 * 8));
-        YB_CUDA(cudaMemsetAsync(u.prof, 0, (size_t)groups * ctas * 8 * 8, st));
+        YB_CUDA(cudaMalloc(&u.prof, (size_t)groups * ctas * 12 * 8));
+        YB_CUDA(cudaMemsetAsync(u.prof, 0, (size_t)groups * ctas * 12 * 8, st));
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(groups * ctas);
@@ -614,7 +637,7 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     if (u.prof) {
         // diagnostics (YAMS_B200_UMMA_PROF=1): aggregate per-role wait cycles
         YB_CUDA(cudaStreamSynchronize(st));
-        std::vector<unsigned long long> h((size_t)groups * ctas * 8);
+        std::vector<unsigned long long> h((size_t)groups * ctas * 12);
         YB_CUDA(cudaMemcpy(h.data(), u.prof, h.size() * 8, cudaMemcpyDeviceToHost));
         double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         int nlead = 0;
@@ -627,6 +650,11 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
             if (h[b * 8 + 5]) { acc[1] += (double)h[b * 8 + 1]; acc[2] += (double)h[b * 8 + 2]; acc[5] += (double)h[b * 8 + 5]; ++nlead; }
         }
         unsigned nb = groups * ctas;
+        double det[4] = {0, 0, 0, 0};
+        for (unsigned b = 0; b < nb; ++b)
+            for (int j = 0; j < 4; ++j) det[j] += (double)h[(size_t)nb * 8 + (size_t)b * 4 + j];
+        fprintf(stderr, "[umma prof] epilogue detail per-CTA Mcycles: ld-issue %.2f process %.2f tail(arrive/flush) %.2f head %.2f\n", det[0] / nb / 1e6,
+                det[1] / nb / 1e6, det[2] / nb / 1e6, det[3] / nb / 1e6);
         fprintf(stderr, "[umma prof] ctas=%d filter=%d units/group=%llu | per-CTA Mcycles: producer-wait-empty %.2f | mma total %.2f wait-full %.2f wait-tempty %.2f | epilogue total %.2f wait-tfull %.2f tmem-ld-wait %.2f slow-path entries/lane %.0f\n",
                 ctas, (int)filter, (unsigned long long)(((uint64_t)u.nrt + groups - 1) / groups * u.nqt), acc[0] / nb / 1e6, acc[5] / nlead / 1e6,
                 acc[1] / nlead / 1e6, acc[2] / nlead / 1e6, acc[4] / nb / 1e6, acc[3] / nb / 1e6, acc[6] / nb / 1e6, acc[7] / nb);
