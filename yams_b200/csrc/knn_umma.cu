@@ -183,6 +183,16 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
         : "memory");
 }
 
+__device__ __noinline__ void append_candidate(uint32_t* counts, Cand* cands, uint32_t cap, uint32_t q, uint32_t row, float sc) {
+    uint32_t pos = atomicAdd(&counts[q], 1u);
+    if (pos < cap) {
+        Cand cd;
+        cd.score = sc;
+        cd.row = row;
+        cands[(uint64_t)q * cap + pos] = cd;
+    }
+}
+
 // CTAS == 1: one CTA per 128-row tile (cta_group::1).  CTAS == 2: a CTA pair (cluster of 2) shares a 256-row x
 // n_tile unit: each CTA stages its own 128 corpus rows and HALF of the query tile, the leader issues
 // tcgen05.mma.cta_group::2 (M = 256), each CTA's TMEM receives the accumulator rows of its own corpus rows.
@@ -335,15 +345,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         const long long e_start = clock64();
         const bool profiling = u.prof != nullptr;
 
-        auto append_global = [&](uint32_t q, uint32_t row, float sc) {
-            uint32_t pos = atomicAdd(&u.a.counts[q], 1u);
-            if (pos < u.a.cap) {
-                Cand cd;
-                cd.score = sc;
-                cd.row = row;
-                u.a.cands[(uint64_t)q * u.a.cap + pos] = cd;
-            }
-        };
+        auto append_global = [&](uint32_t q, uint32_t row, float sc) { append_candidate(u.a.counts, u.a.cands, u.a.cap, q, row, sc); };
         auto flush = [&]() {   // warp-uniform: drain the staged survivors with the atomics in flight together
             __syncwarp();
             uint32_t n = min(*my_cnt, UM_EPI_CAP);
@@ -410,25 +412,33 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             pm |= (__uint_as_float(v[c + 2]) * inr > t4.z ? 1u : 0u) << (c + 2);
                             pm |= (__uint_as_float(v[c + 3]) * inr > t4.w ? 1u : 0u) << (c + 3);
                         }
-                        if (pm) {
+                        // survivors (about one per entry): compact loop, the column is extracted with a select tree
+                        // so the code stays small (an unrolled per-column body thrashed the instruction cache)
+                        while (pm) {
+                            const int c = __ffs(pm) - 1;
+                            pm &= pm - 1;
+                            uint32_t x16[16], x8[8], x4[4], x2[2];
 #pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                if (pm & (1u << c)) {
-                                    const float sc = __uint_as_float(v[c]) * inr;
-                                    const uint32_t q = q0 + c0 + c;
-                                    if (direct) {
-                                        uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
-                                        if ((w >> (grow & 31)) & 1u) append_global(q, (uint32_t)grow, sc);
-                                    } else {
-                                        uint32_t idx = atomicAdd(my_cnt, 1u);
-                                        if (idx < UM_EPI_CAP) {
-                                            EpiEntry e;
-                                            e.q = q; e.row = (uint32_t)grow; e.score = sc;
-                                            my_stage[idx] = e;
-                                        } else {
-                                            append_global(q, (uint32_t)grow, sc);
-                                        }
-                                    }
+                            for (int i = 0; i < 16; ++i) x16[i] = (c & 16) ? v[i + 16] : v[i];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) x8[i] = (c & 8) ? x16[i + 8] : x16[i];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) x4[i] = (c & 4) ? x8[i + 4] : x8[i];
+#pragma unroll
+                            for (int i = 0; i < 2; ++i) x2[i] = (c & 2) ? x4[i + 2] : x4[i];
+                            const float sc = __uint_as_float((c & 1) ? x2[1] : x2[0]) * inr;
+                            const uint32_t q = q0 + c0 + (uint32_t)c;
+                            if (direct) {
+                                uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
+                                if ((w >> (grow & 31)) & 1u) append_global(q, (uint32_t)grow, sc);
+                            } else {
+                                uint32_t idx = atomicAdd(my_cnt, 1u);
+                                if (idx < UM_EPI_CAP) {
+                                    EpiEntry e;
+                                    e.q = q; e.row = (uint32_t)grow; e.score = sc;
+                                    my_stage[idx] = e;
+                                } else {
+                                    append_global(q, (uint32_t)grow, sc);
                                 }
                             }
                         }
