@@ -588,7 +588,7 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     queries_to_f16_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)a.nq * a.dim + 255) / 256, 4096), 256, 0, st>>>(
         a.q32, a.qinv, a.nq, a.dim, d_q16);
 
-    static const int ctas_env = [] { const char* e = getenv("YAMS_B200_UMMA_CTAS"); return e ? atoi(e) : 2; }();
+    static const int ctas_env = [] { const char* e = getenv("YAMS_B200_UMMA_CTAS"); return e ? atoi(e) : 1; }();
     const int ctas = (ctas_env == 1 || c->dev->sm_count < 2) ? 1 : 2;
     UmmaArgs u{};
     u.a = a;
