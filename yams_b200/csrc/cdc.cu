@@ -411,32 +411,64 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
     if (lane == 0) S.slice_counts[gw] = overflow ? 0xFFFFFFFFu : my_total;
 }
 
-// concatenates the warp slices in warp order; scalars[0] = total candidates, scalars[2] = overflow flag
+// concatenates the warp slices in warp order; scalars[0] = total candidates, scalars[2] = overflow flag.
+// One block: a parallel exclusive scan of the slice counts (4 per thread), then a warp-per-slice copy.
 __global__ void __launch_bounds__(1024) cdc_compact_kernel(const uint64_t* __restrict__ cand_tmp, const uint32_t* __restrict__ slice_counts,
                                                            uint32_t nslices, uint32_t slice_cap, uint64_t* __restrict__ cand,
                                                            uint64_t* __restrict__ scalars) {
-    extern __shared__ uint64_t offs[];   // nslices + 1
+    extern __shared__ uint64_t offs[];   // nslices + 1 (nslices <= 4096)
+    __shared__ uint64_t warp_tot[32];
     __shared__ uint32_t bad;
-    if (threadIdx.x == 0) {
-        uint64_t run = 0;
-        uint32_t b = 0;
-        for (uint32_t c = 0; c < nslices; ++c) {
-            offs[c] = run;
-            uint32_t n = slice_counts[c];
-            if (n == 0xFFFFFFFFu) { b = 1; n = 0; }
-            run += n;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) bad = 0;
+    __syncthreads();
+    uint32_t c[4];
+    uint64_t local = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t s = tid * 4 + j;
+        uint32_t n = s < nslices ? slice_counts[s] : 0u;
+        if (n == 0xFFFFFFFFu) { bad = 1; n = 0; }
+        c[j] = n;
+        local += n;
+    }
+    uint64_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint64_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += nb;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = warp_tot[lane];
+        uint64_t wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint64_t nb = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (uint32_t)o) wi += nb;
         }
-        offs[nslices] = run;
-        bad = b;
-        scalars[0] = run;
-        scalars[2] = b;
+        warp_tot[lane] = wi - w;   // exclusive
+        if (lane == 31) {
+            scalars[0] = wi;
+            offs[nslices] = wi;
+        }
     }
     __syncthreads();
+    uint64_t run = warp_tot[warp] + incl - local;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t s = tid * 4 + j;
+        if (s < nslices) offs[s] = run;
+        run += c[j];
+    }
+    __syncthreads();
+    if (tid == 0) scalars[2] = bad;
     if (bad) return;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (uint32_t c = warp; c < nslices; c += nw) {
-        uint32_t n = (uint32_t)(offs[c + 1] - offs[c]);
-        for (uint32_t j = lane; j < n; j += 32) cand[offs[c] + j] = cand_tmp[(size_t)c * slice_cap + j];
+    const uint32_t nw = blockDim.x >> 5;
+    for (uint32_t s = warp; s < nslices; s += nw) {
+        uint32_t n = (uint32_t)(offs[s + 1] - offs[s]);
+        for (uint32_t j = lane; j < n; j += 32) cand[offs[s] + j] = cand_tmp[(size_t)s * slice_cap + j];
     }
 }
 

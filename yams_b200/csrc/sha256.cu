@@ -70,8 +70,8 @@ __device__ __forceinline__ void sha256_compress(uint32_t (&st)[8], uint32_t (&w)
 }
 
 // data[0] is stream position base_pos; desc.offset is a stream position.
-template <bool MADD>
-__global__ void __launch_bounds__(kShaWarpsPerCta * 32, 4)
+template <bool MADD, int MINB>
+__global__ void __launch_bounds__(kShaWarpsPerCta * 32, MINB)
 sha256_chunks_kernel(const uint8_t* __restrict__ data, uint64_t base_pos,
                      yams_chunk_desc* __restrict__ descs, uint32_t first, uint32_t n,
                      unsigned int* __restrict__ counter, uint32_t one) {
@@ -213,10 +213,17 @@ yams_status_t launch_sha256_chunks(const uint8_t* d_data, uint64_t base_pos, yam
     uint32_t max_ctas = (uint32_t)sm_count * 4u;
     if (ctas > max_ctas) ctas = max_ctas;
     static const int variant = [] { const char* e = getenv("YAMS_B200_SHA_MADD"); return e ? atoi(e) : 1; }();
-    if (variant)
-        sha256_chunks_kernel<true><<<ctas, kShaWarpsPerCta * 32, 0, st>>>(d_data, base_pos, d_descs, first, n, d_counter, 1u);
-    else
-        sha256_chunks_kernel<false><<<ctas, kShaWarpsPerCta * 32, 0, st>>>(d_data, base_pos, d_descs, first, n, d_counter, 1u);
+    static const int per_sm = [] { const char* e = getenv("YAMS_B200_SHA_CTAS"); int v = e ? atoi(e) : 4; return v < 3 ? 3 : (v > 6 ? 6 : v); }();
+    max_ctas = (uint32_t)sm_count * (uint32_t)per_sm;
+    ctas = (warps_needed + kShaWarpsPerCta - 1) / kShaWarpsPerCta;
+    if (ctas > max_ctas) ctas = max_ctas;
+#define YB_SHA(M, B) sha256_chunks_kernel<M, B><<<ctas, kShaWarpsPerCta * 32, 0, st>>>(d_data, base_pos, d_descs, first, n, d_counter, 1u)
+    if (variant) {
+        switch (per_sm) { case 3: YB_SHA(true, 3); break; case 4: YB_SHA(true, 4); break; case 5: YB_SHA(true, 5); break; default: YB_SHA(true, 6); break; }
+    } else {
+        YB_SHA(false, 4);
+    }
+#undef YB_SHA
     YB_CUDA(cudaGetLastError());
     return YAMS_OK;
 }
