@@ -285,21 +285,23 @@ def main():
         ms_step = ms_total / K
         qps = nq / (ms_step / 1e3) * world      # every rank answers the batch against its own 10M-row shard
         # ---- e2e through the public host API: pinned host queries in, host results out, every step ----
-        out_r = np.empty((nq, k), dtype=np.int64)
-        out_s = np.empty((nq, k), dtype=np.float32)
+        q_dev2 = torch.empty_like(q_dev)
 
         def step_e2e():
             if not dist:
                 r = corpus.search(q_host.numpy(), k, threshold=-1.0)
                 return r
-            q_dev2 = q_host.to("cuda", non_blocking=True)
+            with torch.cuda.stream(stream):   # H2D of the step's queries on the stream the scan runs on
+                q_dev2.copy_(q_host, non_blocking=True)
             corpus.search_device(q_dev2.data_ptr(), nq, k, -1.0, part_r.data_ptr(), part_s.data_ptr())
             with torch.cuda.stream(stream):
                 dist.all_gather_into_tensor(all_r, part_r)
                 dist.all_gather_into_tensor(all_s, part_s)
             corpus.merge_partials_device(all_r.data_ptr(), all_s.data_ptr(), world, nq, k, fin_r.data_ptr(), fin_s.data_ptr())
+            with torch.cuda.stream(stream):
+                r_host, s_host = fin_r.to("cpu", non_blocking=True), fin_s.to("cpu", non_blocking=True)
             corpus.sync()
-            return fin_r.cpu(), fin_s.cpu()
+            return r_host, s_host
 
         step_e2e()
         barrier_sync()
