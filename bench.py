@@ -417,10 +417,15 @@ def main():
         del buf
 
     if rank == 0:
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if dist:
+        # all ranks are done; leave without running NCCL / CUDA teardown (the external-stream communicator
+        # segfaults in destroy_process_group on this torch build after the line above is already out)
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
