@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
     uint64_t* T_s = reinterpret_cast<uint64_t*>(bufs + (size_t)WS_WARPS * WS_STAGES * WS_BUF);
     uint64_t* bars = T_s + 256;                                                     // WS_WARPS x WS_STAGES
     uint8_t* pass_s = reinterpret_cast<uint8_t*>(bars + WS_WARPS * WS_STAGES);      // 256
+    uint16_t* T16_s = reinterpret_cast<uint16_t*>(pass_s + 256);                    // 256: low 16 bits of the table
     const ScanArgs& A = S.A;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 256; i += WS_THREADS) {
@@ -254,7 +255,12 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
         T_s[i] = t;
         uint64_t m0 = A.P.mask & 0xffull;
         pass_s[i] = ((t & m0) == m0) ? 1 : 0;
+        T16_s[i] = (uint16_t)(t & 0xffffu);
     }
+    // masks of <= 16 bits (every YAMS configuration) depend on exactly three bytes: b[p], b[p-1], b[p-W]
+    const bool three_byte = A.P.steps <= 2;
+    const uint32_t mask16 = (uint32_t)(A.P.mask & 0xffffu);
+    const uint32_t W = A.P.window;
     uint8_t* my_bufs = bufs + (size_t)warp * WS_STAGES * WS_BUF;
     uint64_t* my_bars = bars + warp * WS_STAGES;
     if (lane == 0) {
@@ -398,10 +404,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
                 pre &= valid;
             }
             uint32_t hits = 0;
-            while (pre) {
-                int b = __ffs(pre) - 1;
-                pre &= pre - 1;
-                if (is_candidate(view, T_s, A.P, p0 + (uint64_t)b)) hits |= 1u << b;
+            if (three_byte) {
+                // h_p & 0xffff = ((T[b[p-1]] - T[b[p-W]]) & 0xff) << 8  ^  (T[b[p]] & 0xffff); the look-behind bytes are
+                // already in this tile's shared-memory buffer (the 64-byte halo holds zeros before the stream start)
+                const uint8_t* ub = buf + WS_HALO + u * 16;
+                while (pre) {
+                    int b = __ffs(pre) - 1;
+                    pre &= pre - 1;
+                    uint32_t t0 = T16_s[ub[b]], t1 = T16_s[ub[b - 1]], tw = T16_s[ub[b - (int)W]];
+                    uint32_t h = (((t1 - tw) & 0xffu) << 8) ^ t0;
+                    if ((h & mask16) == mask16) hits |= 1u << b;
+                }
+            } else {
+                while (pre) {
+                    int b = __ffs(pre) - 1;
+                    pre &= pre - 1;
+                    if (is_candidate(view, T_s, A.P, p0 + (uint64_t)b)) hits |= 1u << b;
+                }
             }
             if (__ballot_sync(0xffffffffu, hits != 0)) emit(hits, p0);
         }
@@ -483,7 +502,7 @@ yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm
     S.end16 = A.scan_hi > A.origin ? A.origin + ((A.scan_hi - A.origin) & ~15ull) : A.origin;
     S.cand_tmp = cand_tmp;
     S.slice_counts = slice_counts;
-    size_t smem = (size_t)WS_WARPS * WS_STAGES * WS_BUF + 256 * 8 + (size_t)WS_WARPS * WS_STAGES * 8 + 256 + 64;
+    size_t smem = (size_t)WS_WARPS * WS_STAGES * WS_BUF + 256 * 8 + (size_t)WS_WARPS * WS_STAGES * 8 + 256 + 512 + 64;
     unsigned nctas = (nslices + WS_WARPS - 1) / WS_WARPS;
 #define YB_LAUNCH_SCAN(NF)                                                                                                  \
     do {                                                                                                                    \
