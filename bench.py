@@ -420,7 +420,7 @@ def main():
                                             "note": "single pass over the input (cdc_scan_single_pass_kernel) incl. per-segment host syncs"}},
             "e2e": {"value": e2e_bytes / (e2e_ms / 1e3) / 1e9 * world, "unit": "GB/s", "h2d_bytes_per_step": e2e_bytes,
                     "d2h_bytes_per_step": int(len(che)) * 48, "sample": f"{args.e2e_ingest_gib:g} GiB pinned host buffer"},
-            "gpu_launches": (int((nbytes + (1 << 30) - 1) // (1 << 30)) * 11 + 1) * Ki,
+            "gpu_launches": (int((nbytes + (1 << 32) - 1) // (1 << 32)) * 11 + 1) * Ki,
         }
         if rank == 0 and not args.no_cpu_baseline:
             kind = "reference" if O.ref_available() else "port"

@@ -19,9 +19,9 @@
 namespace yb {
 
 constexpr uint32_t kTileBytesHost = kTileBytes;
-static uint64_t segment_bytes() {   // device-resident data is processed in segments (default 1 GiB)
+static uint64_t segment_bytes() {   // device-resident data is processed in segments (default 4 GiB)
     const char* e = getenv("YAMS_B200_SEGMENT_MIB");
-    uint64_t mib = e ? strtoull(e, nullptr, 10) : 1024;
+    uint64_t mib = e ? strtoull(e, nullptr, 10) : 4096;
     if (mib < 1) mib = 1;
     if (mib > 16384) mib = 16384;
     return mib << 20;
