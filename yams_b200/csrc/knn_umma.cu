@@ -215,7 +215,8 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     float* tmin_s = reinterpret_cast<float*>(tmem_slot + 4);             // [32] smallest threshold of each query tile
     uint32_t* wcnt_s = reinterpret_cast<uint32_t*>(tmin_s + 32);           // [4] staged survivors per epilogue warp
     float* tau_all = reinterpret_cast<float*>(wcnt_s + 4);                 // [nqt * n_tile] thresholds (+inf past nq)
-    EpiEntry* stage_s = reinterpret_cast<EpiEntry*>(tau_all + (size_t)u.nqt * u.n_tile);   // [4][UM_EPI_CAP]
+    // (padded to a whole 32-column TMEM chunk: columns past the tile hold stale accumulators and must never pass)
+    EpiEntry* stage_s = reinterpret_cast<EpiEntry*>(tau_all + (((size_t)u.nqt * u.n_tile + 31) & ~(size_t)31));   // [4][UM_EPI_CAP]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -249,7 +250,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         }
     }
     if (FILTER) {
-        const uint32_t nqpad = u.nqt * u.n_tile;
+        const uint32_t nqpad = (u.nqt * u.n_tile + 31u) & ~31u;
         for (uint32_t i = threadIdx.x; i < nqpad; i += UM_THREADS) tau_all[i] = i < u.a.nq ? __ldg(&u.a.tau[i]) : INFINITY;
         if (threadIdx.x < 4) wcnt_s[threadIdx.x] = 0;
         __syncthreads();
@@ -601,7 +602,7 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     u.b_stage = (u.n_tile / ctas) * 128;
     uint32_t stage_bytes = UM_A_STAGE + u.b_stage;
     if (u.nqt > 32 || (size_t)u.nqt * u.n_tile > 4096) return YAMS_ERR_UNSUPPORTED;   // thresholds live in shared memory
-    const uint32_t budget = 224 * 1024 - (uint32_t)(32 * 4 + 16 + (size_t)u.nqt * u.n_tile * 4 + 4 * UM_EPI_CAP * sizeof(EpiEntry)) - 2048;
+    const uint32_t budget = 224 * 1024 - (uint32_t)(32 * 4 + 16 + (((size_t)u.nqt * u.n_tile + 31) & ~(size_t)31) * 4 + 4 * UM_EPI_CAP * sizeof(EpiEntry)) - 2048;
     u.stages = std::min<uint32_t>(8, budget / stage_bytes);
     if (u.stages < 2) return YAMS_ERR_UNSUPPORTED;
     // instruction descriptor: D=f32, A=B=f16, both K-major, N = n_tile, M = 128 per CTA
@@ -613,7 +614,7 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
         return YAMS_ERR_UNSUPPORTED;
     if (!make_map_2d(&tmB, d_q16, a.dim, a.nq, (uint64_t)a.dim * 2, UM_BLOCK_K, u.n_tile / ctas)) return YAMS_ERR_UNSUPPORTED;
 
-    const size_t epi_bytes = 32 * 4 + 16 + (size_t)u.nqt * u.n_tile * 4 + 4 * UM_EPI_CAP * sizeof(EpiEntry);
+    const size_t epi_bytes = 32 * 4 + 16 + (((size_t)u.nqt * u.n_tile + 31) & ~(size_t)31) * 4 + 4 * UM_EPI_CAP * sizeof(EpiEntry);
     size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16 + epi_bytes;
     unsigned groups = (unsigned)std::min<uint64_t>(u.nrt, (uint64_t)(c->dev->sm_count / ctas));
     if (getenv("YAMS_B200_UMMA_PROF")) {
