@@ -262,6 +262,23 @@ def test_tcgen05_engine_matches_cuda_core_engine(Y, oracle, shape):
     c.close()
 
 
+@pytest.mark.parametrize("nq", [1, 3, 17, 40, 100])
+def test_small_query_batches_through_tensor_engine(Y, oracle, nq):
+    """Query tiles that are not a multiple of the 32-column TMEM chunk: stale accumulator columns must never
+    reach the candidate lists (Q=1 once wrote past the per-query counters)."""
+    O = oracle
+    n, d = 100_000, 64
+    rows = O.f16_from_float(O.gen_rows_f32(42, 0, n, d)).reshape(n, d)
+    c = Y.Corpus(d, Y.F16, Y.COSINE)
+    c.append_synthetic(42, 0, n)
+    queries = O.gen_rows_f32(43, 0, nq, d)
+    for _ in range(3):      # repeated searches reuse TMEM columns with stale contents
+        got = c.search(queries, 10, threshold=-1.0)
+    assert c.last_timings()["engine"] == "tcgen05"
+    check_against_oracle(O, rows, queries, got, 10)
+    c.close()
+
+
 def test_large_k_and_many_queries_through_tensor_engine(Y, oracle):
     O = oracle
     n, d, nq = 120_000, 128, 300
