@@ -201,6 +201,7 @@ constexpr uint32_t WS_TILE = 4096;
 constexpr uint32_t WS_HALO = 64;      // >= kHistory (56), multiple of 16
 constexpr int WS_STAGES = 3;
 constexpr uint32_t WS_BUF = WS_HALO + WS_TILE;
+constexpr uint32_t WS_LIST = 64;      // confirmed candidates of one tile kept in shared memory (expected 0.5)
 
 struct SinglePassArgs {
     ScanArgs A;
@@ -248,6 +249,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
     uint64_t* bars = T_s + 256;                                                     // WS_WARPS x WS_STAGES
     uint8_t* pass_s = reinterpret_cast<uint8_t*>(bars + WS_WARPS * WS_STAGES);      // 256
     uint16_t* T16_s = reinterpret_cast<uint16_t*>(pass_s + 256);                    // 256: low 16 bits of the table
+    uint32_t* wlist_s = reinterpret_cast<uint32_t*>(T16_s + 256);                   // WS_WARPS x WS_LIST confirmed candidates
+    uint32_t* wcnt_s = wlist_s + WS_WARPS * WS_LIST;                                // WS_WARPS counters
+    uint8_t* wqueue_s = reinterpret_cast<uint8_t*>(wcnt_s + WS_WARPS);              // WS_WARPS x 256 flagged units
     const ScanArgs& A = S.A;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < 256; i += WS_THREADS) {
@@ -264,6 +268,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
     uint8_t* my_bufs = bufs + (size_t)warp * WS_STAGES * WS_BUF;
     uint64_t* my_bars = bars + warp * WS_STAGES;
     if (lane == 0) {
+        wcnt_s[warp] = 0;
         for (int s = 0; s < WS_STAGES; ++s)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sc_smem_u32(&my_bars[s])), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -306,30 +311,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
 #pragma unroll
     for (int f = 0; f < 4; ++f) pat[f] = 0x01010101u * (uint32_t)A.P.fast[f];
 
-    // ordered append of a lane's hit mask (bit b = position p0 + b); lanes are in position order
-    auto emit = [&](uint32_t hits, uint64_t p0) {
-        uint32_t c = __popc(hits);
-        // exclusive prefix over lanes
-        uint32_t incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += nb;
-        }
-        uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-        if (overflow || my_total + total > S.slice_cap) {
-            overflow = true;
-        } else {
-            uint32_t o = my_total + incl - c;
-            while (hits) {
-                int b = __ffs(hits) - 1;
-                hits &= hits - 1;
-                my_out[o++] = p0 + (uint64_t)b;
-            }
-            my_total += total;
-        }
-    };
-
     for (uint32_t i = 0; i < n_my; ++i) {
         const uint32_t tile = t_begin + i;
         const uint32_t s = i % WS_STAGES;
@@ -365,64 +346,112 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
             }
         }
         __syncwarp();
-        // positions of a misaligned stream head that precede the first aligned unit (global tile 0 only)
+        uint32_t* my_list = wlist_s + warp * WS_LIST;
+        uint32_t* my_cnt = wcnt_s + warp;
+        uint8_t* my_queue = wqueue_s + warp * 256;
+        // positions of a misaligned stream head that precede the first aligned unit (global tile 0 only);
+        // list entries are offsets from tile_pos biased by 16, so the head sorts before every in-tile entry
         if (tile == 0 && A.origin > A.scan_lo) {
             uint64_t p = A.scan_lo + lane;
-            uint32_t hit = 0;
             if (p < A.origin && p < A.scan_hi) {
                 ByteView gview{A.data, A.base_pos, A.lowest};
-                hit = is_candidate(gview, T_s, A.P, p) ? 1u : 0u;
+                if (is_candidate(gview, T_s, A.P, p)) {
+                    uint32_t idx = atomicAdd(my_cnt, 1u);
+                    if (idx < WS_LIST) my_list[idx] = 16u - (uint32_t)(A.origin - p);
+                }
             }
-            emit(hit, p);   // one position per lane: bit 0 = position p
         }
         SmemView view{buf, tile_pos - WS_HALO, A.lowest};
         const bool inside = tile_pos >= A.scan_lo && tile_pos + WS_TILE <= A.scan_hi;   // warp-uniform
-#pragma unroll 2
+        // ---- phase 1: which of my 8 units contain a byte that passes the low-byte prefilter? (~6% of units) ----
+        uint32_t fm = 0;
+#pragma unroll
         for (int j = 0; j < (int)(WS_TILE / 16 / 32); ++j) {
-            const uint32_t u = j * 32 + lane;
-            const uint64_t p0 = tile_pos + (uint64_t)u * 16;
-            uint4 v = *reinterpret_cast<const uint4*>(buf + WS_HALO + u * 16);
-            uint32_t pre;
-            if (NFAST > 0) {
-                uint32_t z0 = fast_flags<NFAST>(v.x, pat), z1 = fast_flags<NFAST>(v.y, pat), z2 = fast_flags<NFAST>(v.z, pat),
-                         z3 = fast_flags<NFAST>(v.w, pat);
-                pre = 0;
-                if (z0 | z1 | z2 | z3) {   // rare: compress the per-byte flags into a 16-bit mask
-                    uint32_t zz[4] = {z0, z1, z2, z3};
+            const uint4 v = *reinterpret_cast<const uint4*>(buf + WS_HALO + (j * 32 + lane) * 16);
+            uint32_t any;
+            if (NFAST > 0) any = fast_flags<NFAST>(v.x, pat) | fast_flags<NFAST>(v.y, pat) | fast_flags<NFAST>(v.z, pat) | fast_flags<NFAST>(v.w, pat);
+            else any = prefilter16(v, A.P, pass_s);
+            fm |= (any != 0 ? 1u : 0u) << j;
+        }
+        // ---- compaction: flagged (lane, unit) pairs -> a dense queue, so phase 2 runs once per 32 flagged units ----
+        const uint32_t c = __popc(fm);
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += nb;
+        }
+        const uint32_t nflag = __shfl_sync(0xffffffffu, incl, 31);
+        {
+            uint32_t o = incl - c;
+            while (fm) {
+                int j = __ffs(fm) - 1;
+                fm &= fm - 1;
+                my_queue[o++] = (uint8_t)(j * 32 + lane);   // unit index 0..255
+            }
+        }
+        __syncwarp();
+        // ---- phase 2: one lane per flagged unit: exact byte positions, 3-byte (or generic) confirm ----
+        for (uint32_t qi = lane; qi < ((nflag + 31u) & ~31u); qi += 32) {
+            if (qi < nflag) {
+                const uint32_t u = my_queue[qi];
+                const uint64_t p0 = tile_pos + (uint64_t)u * 16;
+                const uint4 v = *reinterpret_cast<const uint4*>(buf + WS_HALO + u * 16);
+                uint32_t pre;
+                if (NFAST > 0) {
+                    uint32_t zz[4] = {fast_flags<NFAST>(v.x, pat), fast_flags<NFAST>(v.y, pat), fast_flags<NFAST>(v.z, pat),
+                                      fast_flags<NFAST>(v.w, pat)};
+                    pre = 0;
 #pragma unroll
                     for (int w = 0; w < 4; ++w)
                         pre |= (((zz[w] >> 7) & 1u) | ((zz[w] >> 14) & 2u) | ((zz[w] >> 21) & 4u) | ((zz[w] >> 28) & 8u)) << (4 * w);
+                } else {
+                    pre = prefilter16(v, A.P, pass_s);
                 }
-            } else {
-                pre = prefilter16(v, A.P, pass_s);
-            }
-            if (!inside) {
-                uint64_t lo = p0 > A.scan_lo ? p0 : A.scan_lo;
-                uint64_t hi = p0 + 16 < A.scan_hi ? p0 + 16 : A.scan_hi;
-                uint32_t valid = 0;
-                if (lo < hi) valid = ((hi - p0 >= 16) ? 0xffffu : ((1u << (uint32_t)(hi - p0)) - 1u)) & ~((1u << (uint32_t)(lo - p0)) - 1u);
-                pre &= valid;
-            }
-            uint32_t hits = 0;
-            if (three_byte) {
-                // h_p & 0xffff = ((T[b[p-1]] - T[b[p-W]]) & 0xff) << 8  ^  (T[b[p]] & 0xffff); the look-behind bytes are
-                // already in this tile's shared-memory buffer (the 64-byte halo holds zeros before the stream start)
+                if (!inside) {
+                    uint64_t lo = p0 > A.scan_lo ? p0 : A.scan_lo;
+                    uint64_t hi = p0 + 16 < A.scan_hi ? p0 + 16 : A.scan_hi;
+                    uint32_t valid = 0;
+                    if (lo < hi) valid = ((hi - p0 >= 16) ? 0xffffu : ((1u << (uint32_t)(hi - p0)) - 1u)) & ~((1u << (uint32_t)(lo - p0)) - 1u);
+                    pre &= valid;
+                }
                 const uint8_t* ub = buf + WS_HALO + u * 16;
                 while (pre) {
                     int b = __ffs(pre) - 1;
                     pre &= pre - 1;
-                    uint32_t t0 = T16_s[ub[b]], t1 = T16_s[ub[b - 1]], tw = T16_s[ub[b - (int)W]];
-                    uint32_t h = (((t1 - tw) & 0xffu) << 8) ^ t0;
-                    if ((h & mask16) == mask16) hits |= 1u << b;
-                }
-            } else {
-                while (pre) {
-                    int b = __ffs(pre) - 1;
-                    pre &= pre - 1;
-                    if (is_candidate(view, T_s, A.P, p0 + (uint64_t)b)) hits |= 1u << b;
+                    bool hit;
+                    if (three_byte) {
+                        // h_p & 0xffff = ((T[b[p-1]] - T[b[p-W]]) & 0xff) << 8  ^  (T[b[p]] & 0xffff); the look-behind bytes
+                        // are in this tile's buffer (the 64-byte halo holds zeros before the stream start)
+                        uint32_t t0 = T16_s[ub[b]], t1 = T16_s[ub[b - 1]], tw = T16_s[ub[b - (int)W]];
+                        uint32_t h = (((t1 - tw) & 0xffu) << 8) ^ t0;
+                        hit = (h & mask16) == mask16;
+                    } else {
+                        hit = is_candidate(view, T_s, A.P, p0 + (uint64_t)b);
+                    }
+                    if (hit) {
+                        uint32_t idx = atomicAdd(my_cnt, 1u);
+                        if (idx < WS_LIST) my_list[idx] = u * 16 + (uint32_t)b + 16u;
+                    }
                 }
             }
-            if (__ballot_sync(0xffffffffu, hits != 0)) emit(hits, p0);
+        }
+        __syncwarp();
+        // ---- ordered write-out: rank order == position order (entries are unique) ----
+        const uint32_t ncand = *my_cnt;
+        if (ncand) {
+            if (overflow || ncand > WS_LIST || my_total + ncand > S.slice_cap) {
+                overflow = true;
+            } else {
+                for (uint32_t j = lane; j < ncand; j += 32) {
+                    uint32_t mine = my_list[j], rank = 0;
+                    for (uint32_t t = 0; t < ncand; ++t) rank += my_list[t] < mine ? 1u : 0u;
+                    my_out[my_total + rank] = tile_pos + mine - 16u;
+                }
+                my_total += ncand;
+            }
+            __syncwarp();
+            if (lane == 0) *my_cnt = 0;
         }
         __syncwarp();
         if (lane == 0 && i + WS_STAGES < n_my) issue(i + WS_STAGES);
@@ -502,7 +531,8 @@ yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm
     S.end16 = A.scan_hi > A.origin ? A.origin + ((A.scan_hi - A.origin) & ~15ull) : A.origin;
     S.cand_tmp = cand_tmp;
     S.slice_counts = slice_counts;
-    size_t smem = (size_t)WS_WARPS * WS_STAGES * WS_BUF + 256 * 8 + (size_t)WS_WARPS * WS_STAGES * 8 + 256 + 512 + 64;
+    size_t smem = (size_t)WS_WARPS * WS_STAGES * WS_BUF + 256 * 8 + (size_t)WS_WARPS * WS_STAGES * 8 + 256 + 512 +
+                  (size_t)WS_WARPS * (WS_LIST * 4 + 4 + 256) + 64;
     unsigned nctas = (nslices + WS_WARPS - 1) / WS_WARPS;
 #define YB_LAUNCH_SCAN(NF)                                                                                                  \
     do {                                                                                                                    \
