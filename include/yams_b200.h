@@ -148,6 +148,17 @@ YAMS_B200_API yams_status_t yams_b200_chunk_boundaries(void* self, const uint8_t
                                                        const yams_cdc_config* cfg,
                                                        yams_chunk_desc** out, size_t* out_n);
 
+/* calculateDeduplication (src/chunking/rabin_chunker.cpp:224-239): unique-hash accounting over a chunk table.
+ * A chunk is "unique" the first time its digest appears.  chunks: HOST array (as returned by chunk_and_hash). */
+typedef struct yams_dedup_stats {
+    uint64_t total_size;     /* DeduplicationStats::totalSize   (chunker.h:204-209) */
+    uint64_t unique_size;    /* uniqueSize   */
+    uint64_t chunk_count;    /* chunkCount   */
+    uint64_t unique_chunks;  /* uniqueChunks */
+} yams_dedup_stats;
+YAMS_B200_API yams_status_t yams_b200_dedup_stats(void* self, const yams_chunk_desc* chunks, size_t n,
+                                                  yams_dedup_stats* out);
+
 /* Per-stage device timings (ms) of the last chunk_and_hash* call on this thread's context:
  * [0] candidate scan, [1] cut selection, [2] sha256, [3] total device, [4] h2d (0 for _device) */
 YAMS_B200_API yams_status_t yams_b200_ingest_last_timings(void* self, float out_ms[8]);
@@ -226,6 +237,15 @@ YAMS_B200_API yams_status_t yams_b200_search(yams_b200_corpus* c, const float* q
                                              const uint64_t* allowed_offsets, int64_t* out_rowids,
                                              float* out_scores, uint32_t* out_counts,
                                              uint64_t* out_flags);
+
+/* ExactRowSelection::AllMatching (sqlite_vec_backend.cpp:4283-4288,4315-4316; IAllExactCandidateVectorStore,
+ * vector_store.h:131-138): EVERY row of the candidate set that passes the skip rules and the threshold, ordered
+ * (sim desc, rowid asc), scored exactly (double accumulation). One query. out arrays hold n_allowed entries.
+ * allowed_rowids == NULL means the whole corpus (out arrays then hold corpus_size entries). */
+YAMS_B200_API yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, const float* query, float threshold,
+                                                          const int64_t* allowed_rowids, uint64_t n_allowed,
+                                                          int64_t* out_rowids, float* out_scores,
+                                                          uint64_t* out_count);
 
 /* Device-pointer form for multi-GPU sharding: queries and outputs are DEVICE pointers, the call
  * is enqueued on the corpus stream and returns after enqueueing; outputs are the rank-local partial

@@ -205,3 +205,22 @@ def test_full_size_properties(Y, oracle):
     got_cuts = offs[j + 1:][offs[j + 1:] <= start + span] - 1
     cand_abs = want.astype(np.int64) + (start - hist)
     assert np.isin(got_cuts[sizes[j:j + len(got_cuts)] < (1 << 20)], cand_abs).all()
+
+
+def test_dedup_stats_matches_reference_accounting(Y, oracle):
+    """calculateDeduplication (/root/reference/src/chunking/rabin_chunker.cpp:224-239): unique-hash accounting."""
+    O = oracle
+    block = O.gen_bytes(21, 0, 1 << 20)
+    data = np.concatenate([block, block, O.gen_bytes(22, 0, 300_000), block[:500_000], np.zeros(0, dtype=np.uint8)])
+    ch = Y.chunk_and_hash(data, Y.default_config(min_chunk=2048, max_chunk=32768))
+    got = Y.dedup_stats(ch)
+    seen, usz = set(), 0
+    for c in ch:
+        key = bytes(c["digest"])
+        if key not in seen:
+            seen.add(key)
+            usz += int(c["size"])
+    assert got["chunkCount"] == len(ch) and got["totalSize"] == data.size
+    assert got["uniqueChunks"] == len(seen) and got["uniqueSize"] == usz
+    assert got["uniqueChunks"] < got["chunkCount"]          # the repeated megabyte dedups
+    assert Y.dedup_stats(ch[:0])["chunkCount"] == 0

@@ -304,3 +304,30 @@ def test_cpp_host_adapters(Y, tmp_path):
                            "-Wl,-rpath," + os.path.join(root, "yams_b200")])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_all_matching_candidate_rows(Y, oracle):
+    """ExactRowSelection::AllMatching (sqlite_vec_backend.cpp:4283-4288,4315-4316): every passing candidate row."""
+    O = oracle
+    n, d = 20_000, 48
+    rows = O.gen_rows_f32(42, 0, n, d)
+    rows[123] = 0                      # zero norm -> skipped
+    rows[77] = rows[5]                 # tie
+    rowids = np.arange(n, dtype=np.int64) * 2 + 7
+    c = Y.Corpus(d, Y.F32, Y.COSINE)
+    c.append(rows, rowids=rowids)
+    q = O.gen_rows_f32(43, 0, 1, d)[0]
+    rng = np.random.default_rng(3)
+    sel = np.sort(rng.choice(n, size=3000, replace=False))
+    sel = np.unique(np.concatenate([sel, [5, 77, 123]]))
+    allowed = np.concatenate([rowids[sel], [10**9]])           # one rowid that does not exist
+    for thr in (-1.0, 0.05):
+        rid, sc = c.search_all_matching(q, threshold=thr, allowed=np.concatenate([allowed[::-1], allowed[:5]]))
+        rc, wr, ws = O.exact_scan_cosine(rows, q, 1, threshold=thr, rowids=rowids, allowed=np.sort(allowed), all_matching=True)
+        assert rc == 0 and list(rid) == list(wr) and np.array_equal(sc, ws), thr
+    rid, sc = c.search_all_matching(q, threshold=0.2)           # whole corpus
+    rc, wr, ws = O.exact_scan_cosine(rows, q, 1, threshold=0.2, rowids=rowids, all_matching=True)
+    assert list(rid) == list(wr) and np.array_equal(sc, ws)
+    with pytest.raises(Y.YamsB200Error):
+        c.search_all_matching(np.zeros(d, dtype=np.float32))
+    c.close()

@@ -66,6 +66,7 @@ SYMBOLS = {
     "yams_b200_sha256_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p, C.c_size_t, u8p]),
     "yams_b200_chunk_boundaries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CdcConfig), _descpp, _szp]),
     "yams_b200_ingest_last_timings": (C.c_int, [C.c_void_p, f32p]),
+    "yams_b200_dedup_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "yams_b200_corpus_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
     "yams_b200_corpus_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, i64p]),
     "yams_b200_corpus_append_f32_as_f16": (C.c_int, [C.c_void_p, f32p, C.c_uint64, i64p]),
@@ -74,6 +75,7 @@ SYMBOLS = {
     "yams_b200_corpus_size": (C.c_int, [C.c_void_p, u64p]),
     "yams_b200_corpus_destroy": (None, [C.c_void_p]),
     "yams_b200_search": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_float, i64p, u64p, i64p, f32p, u32p, u64p]),
+    "yams_b200_search_all_matching": (C.c_int, [C.c_void_p, f32p, C.c_float, i64p, C.c_uint64, i64p, f32p, u64p]),
     "yams_b200_search_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]),
     "yams_b200_merge_partials_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                                   C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -182,6 +184,16 @@ def chunk_boundaries(data, cfg: Optional[CdcConfig] = None) -> np.ndarray:
 def chunk_and_hash_device(dev_ptr: int, length: int, cfg: Optional[CdcConfig] = None) -> np.ndarray:
     """Input already resident in HBM (e.g. ``tensor.data_ptr()``)."""
     return _chunks("yams_b200_chunk_and_hash_device", dev_ptr, length, cfg or default_config())
+
+
+def dedup_stats(chunks: np.ndarray) -> dict:
+    """calculateDeduplication over a chunk table (structured array from chunk_and_hash)."""
+    arr = np.ascontiguousarray(chunks, dtype=CHUNK_DTYPE)
+    out = (C.c_uint64 * 4)()
+    _check(lib().yams_b200_dedup_stats(None, arr.ctypes.data if len(arr) else None, len(arr), out), "dedup_stats")
+    total, unique, count, ucount = (int(x) for x in out)
+    return {"totalSize": total, "uniqueSize": unique, "chunkCount": count, "uniqueChunks": ucount,
+            "ratio": (1.0 - unique / total) if total else 0.0}
 
 
 def ingest_last_timings() -> dict:
@@ -314,6 +326,21 @@ class Corpus:
                                     out_f.ctypes.data_as(u64p))
         _check(rc, "search")
         return out_r[:, :k], out_s[:, :k], out_c, out_f
+
+    def search_all_matching(self, query, threshold: float = -1.0, allowed=None):
+        """ExactRowSelection::AllMatching: every passing row of the candidate set, sorted (sim desc, rowid asc)."""
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        al = np.ascontiguousarray(allowed, dtype=np.int64) if allowed is not None else None
+        m = len(al) if al is not None else len(self)
+        out_r = np.empty(max(m, 1), dtype=np.int64)
+        out_s = np.empty(max(m, 1), dtype=np.float32)
+        cnt = C.c_uint64(0)
+        rc = lib().yams_b200_search_all_matching(self._h, q.ctypes.data_as(f32p), threshold,
+                                                 al.ctypes.data_as(i64p) if al is not None and len(al) else None,
+                                                 len(al) if al is not None else 0, out_r.ctypes.data_as(i64p),
+                                                 out_s.ctypes.data_as(f32p), C.byref(cnt))
+        _check(rc, "search_all_matching")
+        return out_r[:cnt.value].copy(), out_s[:cnt.value].copy()
 
     def search_device(self, d_queries: int, nq: int, k: int, threshold: float, d_out_rowids: int, d_out_scores: int):
         _check(lib().yams_b200_search_device(self._h, d_queries, nq, k, threshold, d_out_rowids, d_out_scores), "search_device")

@@ -760,6 +760,53 @@ yams_status_t exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n
     return YAMS_OK;
 }
 
+// ---- calculateDeduplication (/root/reference/src/chunking/rabin_chunker.cpp:224-239) ----------------------
+// Open-addressing set of chunk indices keyed by the digest: the thread that claims a slot owns the first
+// occurrence of that digest; later chunks with an identical 32-byte digest are duplicates.
+__global__ void dedup_stats_kernel(const yams_chunk_desc* __restrict__ descs, uint32_t n, uint32_t* __restrict__ table,
+                                   uint64_t slots, unsigned long long* __restrict__ out /* total, unique, count, uniq */) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long tot = 0, usz = 0, ucnt = 0, cnt = 0;
+    if (i < n) {
+        const uint64_t* dg = reinterpret_cast<const uint64_t*>(descs[i].digest);
+        const uint64_t d0 = dg[0], d1 = dg[1], d2 = dg[2], d3 = dg[3];
+        const uint64_t size = descs[i].size;
+        uint64_t slot = splitmix64(d0 ^ (d1 << 1)) & (slots - 1);
+        bool unique = false;
+        for (;;) {
+            uint32_t cur = atomicCAS(&table[slot], 0xFFFFFFFFu, i);
+            if (cur == 0xFFFFFFFFu) { unique = true; break; }   // claimed: first occurrence
+            const uint64_t* og = reinterpret_cast<const uint64_t*>(descs[cur].digest);
+            if (og[0] == d0 && og[1] == d1 && og[2] == d2 && og[3] == d3) break;   // duplicate of chunk `cur`
+            slot = (slot + 1) & (slots - 1);
+        }
+        tot = size;
+        cnt = 1;
+        if (unique) { usz = size; ucnt = 1; }
+    }
+    // warp-level reduction, one atomic per warp and counter
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        usz += __shfl_xor_sync(0xffffffffu, usz, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        ucnt += __shfl_xor_sync(0xffffffffu, ucnt, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], tot);
+        atomicAdd(&out[1], usz);
+        atomicAdd(&out[2], cnt);
+        atomicAdd(&out[3], ucnt);
+    }
+}
+
+yams_status_t launch_dedup_stats(const yams_chunk_desc* d_descs, uint32_t n, uint32_t* d_table, uint64_t slots,
+                                 unsigned long long* d_out, cudaStream_t st) {
+    dedup_stats_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_descs, n, d_table, slots, d_out);
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
 // ---- synthetic byte stream: byte[i] = (splitmix64(seed ^ (i>>3)) >> (8*(i&7))) ----
 __global__ void synth_bytes_kernel(uint64_t seed, uint64_t start, uint64_t n, uint8_t* __restrict__ out) {
     // one thread per aligned 8-byte group of the STREAM

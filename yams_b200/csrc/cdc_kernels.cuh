@@ -53,6 +53,8 @@ yams_status_t resolve_params(const yams_cdc_config* cfg, CdcParams* P, uint64_t 
 yams_status_t launch_sha256_chunks(const uint8_t* d_data, uint64_t base_pos, yams_chunk_desc* d_descs,
                                    uint32_t first, uint32_t n, unsigned int* d_counter, int sm_count,
                                    cudaStream_t st);
+yams_status_t launch_dedup_stats(const yams_chunk_desc* d_descs, uint32_t n, uint32_t* d_table, uint64_t slots,
+                                 unsigned long long* d_out, cudaStream_t st);
 yams_status_t launch_synth_bytes(uint64_t seed, uint64_t start, uint64_t n, uint8_t* d_out, int sm_count,
                                  cudaStream_t st);
 

@@ -670,6 +670,44 @@ yams_status_t yams_b200_sha256_batch(void* self, const uint8_t* base, size_t bas
     return rc;
 }
 
+yams_status_t yams_b200_dedup_stats(void* self, const yams_chunk_desc* chunks, size_t n, yams_dedup_stats* out) {
+    (void)self;
+    YB_ARG(out, "out is null");
+    memset(out, 0, sizeof(*out));
+    if (n == 0) return YAMS_OK;
+    YB_ARG(chunks, "chunks is null");
+    YB_ARG(n < (1ull << 31), "too many chunks");
+    DeviceCtx* dev = nullptr;
+    yams_status_t rc = ensure_device(&dev);
+    if (rc != YAMS_OK) return rc;
+    cudaStream_t st;
+    YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint64_t slots = 1;
+    while (slots < 2 * (uint64_t)n) slots <<= 1;   // load factor <= 0.5
+    DevBuf d_descs, d_table, d_out;
+    rc = d_descs.reserve(n * sizeof(yams_chunk_desc));
+    if (rc == YAMS_OK) rc = d_table.reserve(slots * 4);
+    if (rc == YAMS_OK) rc = d_out.reserve(sizeof(yams_dedup_stats));
+    if (rc == YAMS_OK) {
+        cudaMemcpyAsync(d_descs.p, chunks, n * sizeof(yams_chunk_desc), cudaMemcpyHostToDevice, st);
+        cudaMemsetAsync(d_table.p, 0xFF, slots * 4, st);
+        cudaMemsetAsync(d_out.p, 0, sizeof(yams_dedup_stats), st);
+        rc = launch_dedup_stats(d_descs.as<yams_chunk_desc>(), (uint32_t)n, d_table.as<uint32_t>(), slots,
+                                reinterpret_cast<unsigned long long*>(d_out.p), st);
+        if (rc == YAMS_OK) {
+            cudaError_t e = cudaMemcpyAsync(out, d_out.p, sizeof(yams_dedup_stats), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) {
+                set_last_error("dedup_stats failed: %s", cudaGetErrorString(e));
+                rc = YAMS_ERR_INTERNAL;
+            }
+        }
+    }
+    for (DevBuf* b : {&d_descs, &d_table, &d_out}) b->release();
+    cudaStreamDestroy(st);
+    return rc;
+}
+
 yams_status_t yams_b200_ingest_last_timings(void* self, float out_ms[8]) {
     (void)self;
     YB_ARG(out_ms, "out_ms is null");

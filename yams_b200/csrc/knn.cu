@@ -432,7 +432,7 @@ __global__ void rescore_kernel(const void* __restrict__ rows, int dtype, uint32_
     Exact e;
     e.sim = __int_as_float(0x7FC00000);
     e.row = 0xFFFFFFFFu;
-    if (j < sel_n[q]) {
+    if (j < sel_n[q] && sel[(uint64_t)q * Kp + j].row != 0xFFFFFFFFu) {
         uint32_t row = sel[(uint64_t)q * Kp + j].row;
         uint64_t base = (uint64_t)row * d;
         const float* qv = q32 + (uint64_t)q * d;
@@ -652,6 +652,57 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_partials_kernel(const int64
         }
     }
     if (threadIdx.x == 0 && out_counts) out_counts[q] = nout;
+}
+
+// candidate rowids -> row indices (binary search in the ascending device rowid table); misses get 0xFFFFFFFF
+__global__ void map_rowids_kernel(const int64_t* __restrict__ allowed, uint64_t na, const int64_t* __restrict__ rowids, uint64_t n,
+                                  Cand* __restrict__ sel) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na; i += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t want = allowed[i];
+        uint64_t a = 0, b = n;
+        while (a < b) {
+            uint64_t m = a + ((b - a) >> 1);
+            if (rowids[m] < want) a = m + 1; else b = m;
+        }
+        Cand c;
+        c.score = 0.f;
+        c.row = (a < n && rowids[a] == want) ? (uint32_t)a : 0xFFFFFFFFu;
+        sel[i] = c;
+    }
+}
+__global__ void iota_sel_kernel(Cand* sel, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        Cand c;
+        c.score = 0.f;
+        c.row = (uint32_t)i;
+        sel[i] = c;
+    }
+}
+// Exact results -> sortable keys (skipped entries sort last as 0)
+__global__ void exact_keys_kernel(const Exact* __restrict__ ex, uint64_t n, uint64_t np2, uint64_t* __restrict__ keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np2; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t key = 0;
+        if (i < n) {
+            Exact e = ex[i];
+            if (e.sim == e.sim) key = ((uint64_t)fkey(e.sim) << 32) | (uint64_t)(0xFFFFFFFFu - e.row);
+        }
+        keys[i] = key;
+    }
+}
+__global__ void count_nonzero_kernel(const uint64_t* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) c += keys[i] != 0;
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+__global__ void unpack_sim_keys_kernel(const uint64_t* __restrict__ keys, uint64_t m, const int64_t* __restrict__ rowids,
+                                       int64_t* __restrict__ out_rowids, float* __restrict__ out_scores) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t key = keys[i];
+        uint32_t row = 0xFFFFFFFFu - (uint32_t)key;
+        out_rowids[i] = rowids[row];
+        out_scores[i] = fkey_inv((uint32_t)(key >> 32));
+    }
 }
 
 __global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
@@ -1132,6 +1183,77 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
         }
     }
     return rc;
+}
+
+yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, const float* query, float threshold,
+                                            const int64_t* allowed_rowids, uint64_t n_allowed, int64_t* out_rowids,
+                                            float* out_scores, uint64_t* out_count) {
+    YB_ARG(c && query && out_count, "null argument");
+    *out_count = 0;
+    YB_ARG(c->metric == YAMS_B200_COSINE, "all-matching selection is defined for the cosine scan");
+    // the reference gathers the candidate rowids into a set (:4412-4448): duplicates count once
+    std::vector<int64_t> uniq;
+    if (allowed_rowids) {
+        bool ascending = true;
+        for (uint64_t i = 1; i < n_allowed && ascending; ++i) ascending = allowed_rowids[i - 1] < allowed_rowids[i];
+        if (!ascending) {
+            uniq.assign(allowed_rowids, allowed_rowids + n_allowed);
+            std::sort(uniq.begin(), uniq.end());
+            uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end());
+            allowed_rowids = uniq.data();
+            n_allowed = uniq.size();
+        }
+    }
+    const uint64_t m = allowed_rowids ? n_allowed : c->n;
+    yams_status_t rc;
+    if ((rc = prepare_queries(c, query, false, 1)) != YAMS_OK) return rc;   // InvalidArgument for a bad query (:4127)
+    if (m == 0 || c->n == 0) return YAMS_OK;
+    YB_ARG(out_rowids && out_scores, "null output");
+    YB_ARG(m < (1ull << 31), "candidate set too large");
+    cudaStream_t st = c->st;
+    uint64_t np2 = 1;
+    while (np2 < m) np2 <<= 1;
+    if ((rc = c->sel.reserve((size_t)m * sizeof(Cand) + 16)) != YAMS_OK) return rc;
+    if ((rc = c->outbuf.reserve((size_t)m * sizeof(Exact))) != YAMS_OK) return rc;
+    if ((rc = c->dense.reserve((size_t)np2 * 8 + (size_t)m * 12 + 64)) != YAMS_OK) return rc;
+    if ((rc = c->mask.reserve((size_t)m * 8 + 64)) != YAMS_OK) return rc;
+    Cand* d_sel = c->sel.as<Cand>();
+    uint64_t* d_keys = c->dense.as<uint64_t>();
+    int64_t* d_or = reinterpret_cast<int64_t*>(d_keys + np2);
+    float* d_os = reinterpret_cast<float*>(d_or + m);
+    unsigned g = (unsigned)std::min<uint64_t>((np2 + 255) / 256, 65535);
+    if (allowed_rowids) {
+        int64_t* d_allowed = c->mask.as<int64_t>();
+        YB_CUDA(cudaMemcpyAsync(d_allowed, allowed_rowids, (size_t)m * 8, cudaMemcpyHostToDevice, st));
+        map_rowids_kernel<<<g, 256, 0, st>>>(d_allowed, m, c->rowids.as<int64_t>(), c->n, d_sel);
+    } else {
+        iota_sel_kernel<<<g, 256, 0, st>>>(d_sel, m);
+    }
+    // one "query" with Kp = m survivors: exact re-scoring of every candidate
+    uint32_t* d_seln = c->counts.as<uint32_t>();
+    uint32_t mm = (uint32_t)m;
+    YB_CUDA(cudaMemcpyAsync(d_seln, &mm, 4, cudaMemcpyHostToDevice, st));
+    double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());
+    rescore_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(c->rows.p, c->dtype, c->dim, c->q32.as<float>(), d_qnorm, d_sel, d_seln,
+                                                               (uint32_t)m, 1, threshold, c->outbuf.as<Exact>());
+    exact_keys_kernel<<<g, 256, 0, st>>>(c->outbuf.as<Exact>(), m, np2, d_keys);
+    for (uint64_t size = 2; size <= np2; size <<= 1)
+        for (uint64_t stride = size >> 1; stride > 0; stride >>= 1) bitonic_step_kernel<<<g, 256, 0, st>>>(d_keys, np2, size, stride);
+    if ((rc = c->tau.reserve(8)) != YAMS_OK) return rc;
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(c->tau.p);
+    YB_CUDA(cudaMemsetAsync(d_cnt, 0, 8, st));
+    count_nonzero_kernel<<<g, 256, 0, st>>>(d_keys, np2, d_cnt);
+    unsigned long long h_cnt = 0;
+    YB_CUDA(cudaMemcpyAsync(&h_cnt, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    if (h_cnt) {
+        unpack_sim_keys_kernel<<<g, 256, 0, st>>>(d_keys, h_cnt, c->rowids.as<int64_t>(), d_or, d_os);
+        YB_CUDA(cudaMemcpyAsync(out_rowids, d_or, (size_t)h_cnt * 8, cudaMemcpyDeviceToHost, st));
+        YB_CUDA(cudaMemcpyAsync(out_scores, d_os, (size_t)h_cnt * 4, cudaMemcpyDeviceToHost, st));
+        YB_CUDA(cudaStreamSynchronize(st));
+    }
+    *out_count = h_cnt;
+    return YAMS_OK;
 }
 
 yams_status_t yams_b200_search_device(yams_b200_corpus* c, const float* d_queries, uint32_t nq, uint32_t k, float threshold,
