@@ -178,6 +178,8 @@ typedef struct yams_content_ingest_v1 {
     yams_status_t (*sha256_batch)(void* self, const uint8_t* base, size_t base_len,
                                   const uint64_t* offsets, const uint64_t* sizes, size_t n,
                                   uint8_t* digests);
+    yams_status_t (*dedup_stats)(void* self, const yams_chunk_desc* chunks, size_t n,
+                                 yams_dedup_stats* out);
 } yams_content_ingest_v1;
 
 /* =============================================================================================
@@ -210,6 +212,12 @@ YAMS_B200_API yams_status_t yams_b200_corpus_append_f32_as_f16(yams_b200_corpus*
  * oracle yo_gen_rows_f32 [+ truncating fp16]); rowid = first_row + i */
 YAMS_B200_API yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t seed,
                                                               uint64_t first_row, uint64_t n);
+/* Remove rows by rowid (IVectorStore::deleteVector / deleteVectorsByDocument after the SQLite delete,
+ * vector_store.h; the scan then no longer sees them, exactly as `SELECT ... FROM vectors` would not).
+ * Unknown rowids are ignored; the remaining rows keep their order (ORDER BY rowid). Stable on-device compaction.
+ * out_removed (nullable) receives the number of rows actually removed. */
+YAMS_B200_API yams_status_t yams_b200_corpus_remove(yams_b200_corpus* c, const int64_t* rowids, uint64_t n,
+                                                    uint64_t* out_removed);
 YAMS_B200_API yams_status_t yams_b200_corpus_clear(yams_b200_corpus* c);
 YAMS_B200_API yams_status_t yams_b200_corpus_size(const yams_b200_corpus* c, uint64_t* out_n);
 YAMS_B200_API void yams_b200_corpus_destroy(yams_b200_corpus* c);
@@ -276,6 +284,26 @@ YAMS_B200_API yams_status_t yams_b200_vec0_exact(void* self, const float* query,
                                                  int64_t* out_rowids, float* out_dist,
                                                  uint64_t* out_count);
 
+/* sqlite-vec-cpp batch surface (distances/batch.hpp:24-146): ONE query against n contiguous fp32 rows, float
+ * accumulation like distances/{cosine,l2}.hpp (cosine DISTANCE = 1 - cos, 1.0 when the norm product < 1e-8).
+ *   mode ALL      batch_distance / batch_distance_contiguous / batch_distance_parallel: out_dist[n] in row order
+ *   mode TOP_K    batch_top_k: indices of the k smallest distances, ascending (ties by index -- a legal refinement
+ *                 of the reference's unstable partial_sort); out_idx[min(k,n)], out_dist optional
+ *   mode FILTERED batch_distance_filtered: every (index, dist) with dist < threshold, ascending; out arrays hold n
+ * database is a HOST pointer (n x dim, row-major). */
+#define YAMS_B200_BATCH_ALL 0
+#define YAMS_B200_BATCH_TOP_K 1
+#define YAMS_B200_BATCH_FILTERED 2
+YAMS_B200_API yams_status_t yams_b200_batch_distance(void* self, int metric, const float* query, uint32_t dim,
+                                                     const float* database, uint64_t n, int mode, uint64_t k,
+                                                     float threshold, uint64_t* out_idx, float* out_dist,
+                                                     uint64_t* out_count);
+
+/* VectorDatabase::computeCosineSimilarity (vector_database.cpp:1786-1810): double dot / (sqrt(na) * sqrt(nb)),
+ * 0 on a size mismatch, an empty vector or a zero norm. Sequential double accumulation -> bit-identical. */
+YAMS_B200_API yams_status_t yams_b200_compute_cosine_similarity(void* self, const float* a, size_t na,
+                                                                const float* b, size_t nb, double* out);
+
 /* [0] stage-1 scan ms, [1] rescoring+select ms, [2] total device ms, [3] h2d+d2h ms of the last
  * yams_b200_search on this corpus; [4] = which stage-1 kernel ran (0 cuda-core, 1 tcgen05);
  * [5] = duration of the full-corpus filtered scan launch alone (the dominant kernel) */
@@ -299,6 +327,17 @@ typedef struct yams_vector_scan_v1 {
                                 const int64_t* rowids, uint64_t n, uint64_t k, int use_range,
                                 int64_t rowid_lo, int64_t rowid_hi, int64_t* out_rowids,
                                 float* out_dist, uint64_t* out_count);
+    yams_status_t (*corpus_remove)(yams_b200_corpus* c, const int64_t* rowids, uint64_t n,
+                                   uint64_t* out_removed);
+    yams_status_t (*search_all_matching)(yams_b200_corpus* c, const float* query, float threshold,
+                                         const int64_t* allowed_rowids, uint64_t n_allowed,
+                                         int64_t* out_rowids, float* out_scores, uint64_t* out_count);
+    yams_status_t (*batch_distance)(void* self, int metric, const float* query, uint32_t dim,
+                                    const float* database, uint64_t n, int mode, uint64_t k,
+                                    float threshold, uint64_t* out_idx, float* out_dist,
+                                    uint64_t* out_count);
+    yams_status_t (*compute_cosine_similarity)(void* self, const float* a, size_t na, const float* b,
+                                               size_t nb, double* out);
 } yams_vector_scan_v1;
 
 /* ---- sqlite-vec-cpp C API kept bit-for-bit in signature and error behaviour ------------------

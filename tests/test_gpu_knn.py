@@ -331,3 +331,91 @@ def test_all_matching_candidate_rows(Y, oracle):
     with pytest.raises(Y.YamsB200Error):
         c.search_all_matching(np.zeros(d, dtype=np.float32))
     c.close()
+
+
+def test_batch_distance_surface(Y, oracle):
+    """distances/batch.hpp:24-146 (batch_distance, batch_top_k, batch_distance_filtered), both metrics; the reference
+    tests' epsilon 1e-4 (test_batch_distance.cpp:19-104)."""
+    import ctypes as C
+    O = oracle
+    n, d = 5000, 96
+    rows = O.gen_rows_f32(7, 0, n, d)
+    rows[17] = 0                                            # zero norm: cosine distance 1.0 (cosine.hpp:64-68)
+    rows[40] = rows[3]
+    q = O.gen_rows_f32(8, 0, 1, d)[0]
+    f32p = C.POINTER(C.c_float)
+    for metric, om, fn in ((Y.COSINE, O.METRIC_COSINE, O.lib().yo_cosine_distance_f32), (Y.L2, O.METRIC_L2, O.lib().yo_l2_distance_f32)):
+        want = np.array([fn(q.ctypes.data_as(f32p), rows[i].ctypes.data_as(f32p), d) for i in range(n)], dtype=np.float32)
+        got = Y.batch_distance(q, rows, metric=metric, mode=Y.BATCH_ALL)
+        assert got.shape == (n,) and np.max(np.abs(got - want)) <= 1e-4
+        if metric == Y.COSINE:
+            assert got[17] == 1.0
+        # top-k: ascending, ids equal up to near-ties
+        for k in (1, 10, 257, n + 5):
+            idx, dist = Y.batch_distance(q, rows, metric=metric, mode=Y.BATCH_TOP_K, k=k)
+            wi, wd = O.batch_top_k(q, rows, k, metric=om)
+            m = min(k, n)
+            assert len(idx) == m == len(wi)
+            assert np.all(np.diff(dist) >= 0)
+            assert np.max(np.abs(dist - wd)) <= 1e-4
+            assert np.max(np.abs(want[idx.astype(np.int64)] - dist)) <= 1e-4
+            differ = idx != wi
+            assert np.all(np.abs(want[idx[differ].astype(np.int64)] - want[wi[differ].astype(np.int64)]) <= 1e-4)
+        # filtered: strictly below the threshold, sorted
+        thr = float(np.sort(want)[300]) + 1e-3
+        idx, dist = Y.batch_distance(q, rows, metric=metric, mode=Y.BATCH_FILTERED, threshold=thr)
+        sure = np.nonzero(want < thr - 1e-4)[0]
+        maybe = np.nonzero(want < thr + 1e-4)[0]
+        assert set(sure) <= set(idx.astype(np.int64)) <= set(maybe)
+        assert np.all(np.diff(dist) >= 0) and np.all(dist < thr)
+    assert len(Y.batch_distance(q, np.zeros((0, d), np.float32))) == 0
+    idx, _ = Y.batch_distance(q, rows, mode=Y.BATCH_TOP_K, k=0)
+    assert len(idx) == 0
+
+
+def test_compute_cosine_similarity_is_bit_identical(Y, oracle):
+    """VectorDatabase::computeCosineSimilarity (vector_database.cpp:1786-1810)."""
+    import ctypes as C
+    O = oracle
+    f32p = C.POINTER(C.c_float)
+    for d in (1, 3, 128, 769, 4096):
+        ab = O.gen_rows_f32(100 + d, 0, 2, d) * np.float32(3.7)
+        want = O.lib().yo_cosine_similarity_f64(ab[0].ctypes.data_as(f32p), ab[1].ctypes.data_as(f32p), d)
+        assert Y.compute_cosine_similarity(ab[0], ab[1]) == want
+    assert Y.compute_cosine_similarity(np.ones(4), np.ones(5)) == 0.0          # size mismatch
+    assert Y.compute_cosine_similarity(np.zeros(8), np.ones(8)) == 0.0         # zero norm
+    assert Y.compute_cosine_similarity(np.ones(8), np.ones(8)) == pytest.approx(1.0, abs=1e-15)
+
+
+def test_corpus_remove_keeps_scan_order(Y, oracle):
+    """deleteVector / deleteVectorsByDocument mirror: after removing rows the scan equals a scan of the remaining table."""
+    O = oracle
+    for dtype, d in ((Y.F32, 40), (Y.F16, 64), (Y.F32, 33)):
+        n = 30_000
+        rows = O.gen_rows_f32(11, 0, n, d)
+        rowids = np.arange(n, dtype=np.int64) * 3 + 1
+        c = Y.Corpus(d, dtype, Y.COSINE)
+        c.append(rows, rowids=rowids)                        # F16 corpora convert with the truncating from_float
+        stored = O.f16_from_float(rows) if dtype == Y.F16 else rows
+        rng = np.random.default_rng(5)
+        gone = np.sort(rng.choice(n, size=7000, replace=False))
+        gone = np.unique(np.concatenate([gone, [0, n - 1]]))
+        ask = np.concatenate([rowids[gone][::-1], [2, 10**12], rowids[gone][:10]])   # unknown ids and duplicates are ignored
+        assert c.remove(ask) == len(gone)
+        keep = np.setdiff1d(np.arange(n), gone)
+        assert len(c) == len(keep)
+        qs = O.gen_rows_f32(12, 0, 4, d)
+        rid, sc, cnt, _ = c.search(qs, k=10)
+        rc, wr, ws, wc = O.exact_scan_cosine_batch(stored[keep], qs, 10)
+        assert rc == 0
+        assert np.array_equal(rid, rowids[keep][wr]) and np.array_equal(sc, ws)
+        # appending after a removal continues above the last remaining rowid
+        extra = O.gen_rows_f32(13, 0, 5, d)
+        with pytest.raises(Y.YamsB200Error):
+            c.append(extra, rowids=np.arange(5, dtype=np.int64))
+        new_ids = rowids[keep][-1] + 1 + np.arange(5, dtype=np.int64)
+        c.append(extra, rowids=new_ids)
+        assert len(c) == len(keep) + 5
+        assert c.remove(rowids[keep]) == len(keep) and len(c) == 5
+        assert c.remove(new_ids) == 5 and len(c) == 0
+        c.close()

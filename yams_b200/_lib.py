@@ -71,7 +71,12 @@ SYMBOLS = {
     "yams_b200_corpus_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, i64p]),
     "yams_b200_corpus_append_f32_as_f16": (C.c_int, [C.c_void_p, f32p, C.c_uint64, i64p]),
     "yams_b200_corpus_append_synthetic": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "yams_b200_corpus_remove": (C.c_int, [C.c_void_p, i64p, C.c_uint64, u64p]),
     "yams_b200_corpus_clear": (C.c_int, [C.c_void_p]),
+    "yams_b200_batch_distance": (C.c_int, [C.c_void_p, C.c_int, f32p, C.c_uint32, f32p, C.c_uint64, C.c_int, C.c_uint64,
+                                           C.c_float, u64p, f32p, u64p]),
+    "yams_b200_compute_cosine_similarity": (C.c_int, [C.c_void_p, f32p, C.c_size_t, f32p, C.c_size_t,
+                                                      C.POINTER(C.c_double)]),
     "yams_b200_corpus_size": (C.c_int, [C.c_void_p, u64p]),
     "yams_b200_corpus_destroy": (None, [C.c_void_p]),
     "yams_b200_search": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_float, i64p, u64p, i64p, f32p, u32p, u64p]),
@@ -298,6 +303,14 @@ class Corpus:
     def clear(self):
         _check(lib().yams_b200_corpus_clear(self._h), "corpus_clear")
 
+    def remove(self, rowids) -> int:
+        """deleteVector / deleteVectorsByDocument mirror: drop rows by rowid, keep the rest in rowid order."""
+        r = np.ascontiguousarray(rowids, dtype=np.int64).reshape(-1)
+        out = C.c_uint64(0)
+        _check(lib().yams_b200_corpus_remove(self._h, r.ctypes.data_as(i64p) if len(r) else None, len(r), C.byref(out)),
+               "corpus_remove")
+        return out.value
+
     def __len__(self):
         n = C.c_uint64(0)
         _check(lib().yams_b200_corpus_size(self._h, C.byref(n)), "corpus_size")
@@ -399,6 +412,36 @@ def vec0_exact(query, rows, k: int = 0, rowids=None, rowid_range=None):
                                     out_d.ctypes.data_as(f32p), C.byref(cnt))
     _check(rc, "vec0_exact")
     return out_r[:cnt.value].copy(), out_d[:cnt.value].copy()
+
+
+BATCH_ALL, BATCH_TOP_K, BATCH_FILTERED = 0, 1, 2
+
+
+def batch_distance(query, database, metric: int = COSINE, mode: int = BATCH_ALL, k: int = 0, threshold: float = 0.0):
+    """distances/batch.hpp: ALL -> dist[n]; TOP_K -> (idx[k], dist[k]); FILTERED -> (idx[m], dist[m])."""
+    q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+    db = np.ascontiguousarray(database, dtype=np.float32)
+    n = db.shape[0] if db.ndim == 2 else 0
+    out_i = np.zeros(max(n, 1), dtype=np.uint64)
+    out_d = np.zeros(max(n, 1), dtype=np.float32)
+    cnt = C.c_uint64(0)
+    rc = lib().yams_b200_batch_distance(None, metric, q.ctypes.data_as(f32p), q.size, db.ctypes.data_as(f32p) if n else None,
+                                        n, mode, k, threshold, out_i.ctypes.data_as(u64p), out_d.ctypes.data_as(f32p),
+                                        C.byref(cnt))
+    _check(rc, "batch_distance")
+    if mode == BATCH_ALL:
+        return out_d[:cnt.value].copy()
+    return out_i[:cnt.value].copy(), out_d[:cnt.value].copy()
+
+
+def compute_cosine_similarity(a, b) -> float:
+    """VectorDatabase::computeCosineSimilarity (double)."""
+    a = np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+    b = np.ascontiguousarray(b, dtype=np.float32).reshape(-1)
+    out = C.c_double(0)
+    _check(lib().yams_b200_compute_cosine_similarity(None, a.ctypes.data_as(f32p), a.size, b.ctypes.data_as(f32p), b.size,
+                                                     C.byref(out)), "compute_cosine_similarity")
+    return out.value
 
 
 def _pair(fn, a, b):

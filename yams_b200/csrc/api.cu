@@ -158,6 +158,7 @@ int yams_plugin_init(const char* config_json, const void* host_context) {
     g_ingest_vt.ingest_finish = yams_b200_ingest_finish;
     g_ingest_vt.ingest_close = yams_b200_ingest_close;
     g_ingest_vt.sha256_batch = yams_b200_sha256_batch;
+    g_ingest_vt.dedup_stats = yams_b200_dedup_stats;
     g_scan_vt.abi_version = YAMS_IFACE_VECTOR_SCAN_V1_VERSION;
     g_scan_vt.self = nullptr;
     g_scan_vt.corpus_create = yams_b200_corpus_create;
@@ -167,6 +168,10 @@ int yams_plugin_init(const char* config_json, const void* host_context) {
     g_scan_vt.corpus_destroy = yams_b200_corpus_destroy;
     g_scan_vt.search = yams_b200_search;
     g_scan_vt.vec0_exact = yams_b200_vec0_exact;
+    g_scan_vt.corpus_remove = yams_b200_corpus_remove;
+    g_scan_vt.search_all_matching = yams_b200_search_all_matching;
+    g_scan_vt.batch_distance = yams_b200_batch_distance;
+    g_scan_vt.compute_cosine_similarity = yams_b200_compute_cosine_similarity;
     DeviceCtx* dev = nullptr;
     if (ensure_device(&dev) != YAMS_OK) return YAMS_PLUGIN_ERR_INIT_FAILED;  // no CPU fallback
     g_inited = true;

@@ -566,6 +566,77 @@ __global__ void l2_dense_kernel(const void* __restrict__ rows, int dtype, uint32
     if (lane == 0) out[(uint64_t)q * n + warp] = -sqrtf(s);
 }
 
+// batch.hpp surface: one warp per row, float accumulation (cosine.hpp:48-69, l2.hpp:108-118); NEGATED distance out
+// so that the descending key sort used everywhere else yields ascending distances
+__global__ void batch_dist_kernel(const float* __restrict__ rows, uint32_t d, uint64_t n, const float* __restrict__ q, int metric,
+                                  float* __restrict__ out_neg) {
+    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    uint32_t lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const float* r = rows + warp * d;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+    for (uint32_t c = lane; c < d; c += 32) {
+        float x = q[c], y = r[c];
+        if (metric == YAMS_B200_L2) {
+            float df = x - y;
+            s0 = fmaf(df, df, s0);
+        } else {
+            s0 = fmaf(x, y, s0);
+            s1 = fmaf(x, x, s1);
+            s2 = fmaf(y, y, s2);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+        float dist;
+        if (metric == YAMS_B200_L2) {
+            dist = sqrtf(s0);
+        } else {
+            float denom = sqrtf(s1) * sqrtf(s2);
+            dist = denom < 1e-8f ? 1.0f : 1.0f - (s0 / denom);
+        }
+        out_neg[warp] = -dist;
+    }
+}
+// keys for the FILTERED mode: rows failing dist < threshold get key 0 (sort last)
+__global__ void make_keys_filtered_kernel(const float* __restrict__ neg_dist, uint64_t n, uint64_t np2, float threshold,
+                                          uint64_t* __restrict__ keys) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < np2; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t key = 0;
+        if (i < n && (-neg_dist[i]) < threshold) key = ((uint64_t)fkey(neg_dist[i]) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)i);
+        keys[i] = key;
+    }
+}
+__global__ void unpack_idx_keys_kernel(const uint64_t* __restrict__ keys, uint64_t m, uint64_t* __restrict__ out_idx,
+                                       float* __restrict__ out_dist) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t key = keys[i];
+        out_idx[i] = 0xFFFFFFFFu - (uint32_t)key;
+        out_dist[i] = -fkey_inv((uint32_t)(key >> 32));
+    }
+}
+__global__ void negate_kernel(float* p, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = -p[i];
+}
+// computeCosineSimilarity (vector_database.cpp:1786-1810): one thread, the reference's accumulation order
+__global__ void cosine_similarity_f64_kernel(const float* __restrict__ a, const float* __restrict__ b, uint64_t d, double* out) {
+    double dp = 0.0, na = 0.0, nb = 0.0;
+    for (uint64_t i = 0; i < d; ++i) {
+        double x = (double)a[i], y = (double)b[i];
+        dp += x * y;
+        na += x * x;
+        nb += y * y;
+    }
+    na = sqrt(na);
+    nb = sqrt(nb);
+    *out = (na == 0.0 || nb == 0.0) ? 0.0 : dp / (na * nb);
+}
+
 // global-memory bitonic sort (descending) of 64-bit keys, n a power of two
 __global__ void bitonic_step_kernel(uint64_t* __restrict__ keys, uint64_t n, uint64_t size, uint64_t stride) {
     for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n / 2; t += (uint64_t)gridDim.x * blockDim.x) {
@@ -703,6 +774,44 @@ __global__ void unpack_sim_keys_kernel(const uint64_t* __restrict__ keys, uint64
         out_rowids[i] = rowids[row];
         out_scores[i] = fkey_inv((uint32_t)(key >> 32));
     }
+}
+
+// ---- corpus_remove: stable compaction ------------------------------------------------------------------
+__global__ void fill_u32_kernel(uint32_t* p, uint64_t n, uint32_t v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void mark_removed_kernel(const int64_t* __restrict__ gone, uint64_t ng, const int64_t* __restrict__ rowids, uint64_t n,
+                                    uint32_t* __restrict__ keep) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < ng; i += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t want = gone[i];
+        uint64_t a = 0, b = n;
+        while (a < b) {
+            uint64_t m = a + ((b - a) >> 1);
+            if (rowids[m] < want) a = m + 1; else b = m;
+        }
+        if (a < n && rowids[a] == want) keep[a] = 0u;
+    }
+}
+// kept rows of [b0, b1) -> tmp[dst[row] - dst[b0]]; one warp per row, UNIT-byte elements
+template <typename UNIT>
+__global__ void compact_gather_kernel(const UNIT* __restrict__ src, uint64_t units_per_row, uint64_t b0, uint64_t b1,
+                                      const uint32_t* __restrict__ keep, const uint32_t* __restrict__ dst, UNIT* __restrict__ tmp) {
+    uint64_t row = b0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    uint32_t lane = threadIdx.x & 31;
+    if (row >= b1 || !keep[row] || dst[row] == row) return;
+    const UNIT* s = src + row * units_per_row;
+    UNIT* t = tmp + (uint64_t)(dst[row] - dst[b0]) * units_per_row;
+    for (uint64_t u = lane; u < units_per_row; u += 32) t[u] = s[u];
+}
+template <typename UNIT>
+__global__ void compact_scatter_kernel(UNIT* __restrict__ rows, uint64_t units_per_row, uint64_t b0, uint64_t b1,
+                                       const uint32_t* __restrict__ keep, const uint32_t* __restrict__ dst, const UNIT* __restrict__ tmp) {
+    uint64_t row = b0 + (((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    uint32_t lane = threadIdx.x & 31;
+    if (row >= b1 || !keep[row] || dst[row] == row) return;
+    UNIT* d = rows + (uint64_t)dst[row] * units_per_row;
+    const UNIT* t = tmp + (uint64_t)(dst[row] - dst[b0]) * units_per_row;
+    for (uint64_t u = lane; u < units_per_row; u += 32) d[u] = t[u];
 }
 
 __global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
@@ -949,6 +1058,25 @@ static yams_status_t search_l2_device(Corpus* c, uint32_t nq, uint32_t k, int64_
 
 using namespace yb;
 
+template <typename UNIT>
+static yams_status_t compact_array(Corpus* c, void* base, uint64_t row_bytes, const uint32_t* d_keep, const uint32_t* d_dst,
+                                   DevBuf& tmp) {
+    const uint64_t units = row_bytes / sizeof(UNIT);
+    // batches of <= 256 MiB: destinations never pass sources, so batch i only overwrites rows that batches <= i
+    // have already moved (or staged in tmp)
+    uint64_t batch = std::max<uint64_t>(1, (256ull << 20) / row_bytes);
+    yams_status_t rc = tmp.reserve((size_t)std::min<uint64_t>(batch, c->n) * row_bytes);
+    if (rc != YAMS_OK) return rc;
+    for (uint64_t b0 = 0; b0 < c->n; b0 += batch) {
+        uint64_t b1 = std::min<uint64_t>(c->n, b0 + batch);
+        unsigned grid = (unsigned)(((b1 - b0) * 32 + 255) / 256);
+        compact_gather_kernel<UNIT><<<grid, 256, 0, c->st>>>(static_cast<const UNIT*>(base), units, b0, b1, d_keep, d_dst, tmp.as<UNIT>());
+        compact_scatter_kernel<UNIT><<<grid, 256, 0, c->st>>>(static_cast<UNIT*>(base), units, b0, b1, d_keep, d_dst, tmp.as<UNIT>());
+    }
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
 extern "C" {
 
 yams_status_t yams_b200_corpus_create(void* self, uint32_t dim, int dtype, int metric, uint64_t capacity_hint,
@@ -1053,6 +1181,47 @@ yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t se
     YB_CUDA(cudaGetLastError());
     YB_CUDA(cudaStreamSynchronize(c->st));
     c->n += n;
+    return YAMS_OK;
+}
+
+yams_status_t yams_b200_corpus_remove(yams_b200_corpus* c, const int64_t* rowids, uint64_t n, uint64_t* out_removed) {
+    YB_ARG(c, "corpus is null");
+    if (out_removed) *out_removed = 0;
+    if (n == 0 || c->n == 0) return YAMS_OK;
+    YB_ARG(rowids, "rowids is null");
+    yams_status_t rc;
+    cudaStream_t st = c->st;
+    if ((rc = c->mask.reserve((size_t)n * 8)) != YAMS_OK) return rc;
+    if ((rc = c->sel.reserve((size_t)c->n * 4 + 16)) != YAMS_OK) return rc;
+    if ((rc = c->outbuf.reserve((size_t)c->n * 4 + 16)) != YAMS_OK) return rc;
+    if ((rc = c->tau.reserve(8)) != YAMS_OK) return rc;
+    uint32_t* d_keep = c->sel.as<uint32_t>();
+    uint32_t* d_dst = c->outbuf.as<uint32_t>();
+    uint64_t* d_total = reinterpret_cast<uint64_t*>(c->tau.p);
+    YB_CUDA(cudaMemcpyAsync(c->mask.p, rowids, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    unsigned g = (unsigned)std::min<uint64_t>((c->n + 255) / 256, 65535);
+    fill_u32_kernel<<<g, 256, 0, st>>>(d_keep, c->n, 1u);
+    mark_removed_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 65535), 256, 0, st>>>(c->mask.as<int64_t>(), n, c->rowids.as<int64_t>(),
+                                                                                              c->n, d_keep);
+    if ((rc = exclusive_scan_u32(d_keep, d_dst, c->n, d_total, c->misc, st)) != YAMS_OK) return rc;
+    uint64_t kept = 0;
+    YB_CUDA(cudaMemcpyAsync(&kept, d_total, 8, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    if (kept == c->n) return YAMS_OK;
+    const uint64_t row_bytes = (uint64_t)c->dim * c->elem();
+    if (row_bytes % 16 == 0) rc = compact_array<uint4>(c, c->rows.p, row_bytes, d_keep, d_dst, c->dense);
+    else if (row_bytes % 4 == 0) rc = compact_array<uint32_t>(c, c->rows.p, row_bytes, d_keep, d_dst, c->dense);
+    else rc = compact_array<uint16_t>(c, c->rows.p, row_bytes, d_keep, d_dst, c->dense);
+    if (rc == YAMS_OK) rc = compact_array<uint64_t>(c, c->rowids.p, 8, d_keep, d_dst, c->dense);
+    if (rc == YAMS_OK) rc = compact_array<uint32_t>(c, c->inv_norm.p, 4, d_keep, d_dst, c->dense);
+    if (rc != YAMS_OK) return rc;
+    int64_t last = INT64_MIN;
+    if (kept) YB_CUDA(cudaMemcpyAsync(&last, c->rowids.as<int64_t>() + (kept - 1), 8, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    if (out_removed) *out_removed = c->n - kept;
+    c->n = kept;
+    c->last_rowid = last;
+    c->rowids_dense = false;
     return YAMS_OK;
 }
 
@@ -1403,6 +1572,113 @@ yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim,
     }
     for (DevBuf* b : {&d_rows, &d_q, &d_dist, &d_keys, &d_rid, &d_or, &d_od}) b->release();
     cudaStreamDestroy(st);
+    return rc;
+}
+
+yams_status_t yams_b200_batch_distance(void* self, int metric, const float* query, uint32_t dim, const float* database,
+                                       uint64_t n, int mode, uint64_t k, float threshold, uint64_t* out_idx, float* out_dist,
+                                       uint64_t* out_count) {
+    (void)self;
+    YB_ARG(out_count, "out_count is null");
+    *out_count = 0;
+    YB_ARG(metric == YAMS_B200_COSINE || metric == YAMS_B200_L2, "unknown metric");
+    YB_ARG(mode >= YAMS_B200_BATCH_ALL && mode <= YAMS_B200_BATCH_FILTERED, "unknown mode");
+    YB_ARG(query && dim > 0, "bad query");
+    if (n == 0 || (mode == YAMS_B200_BATCH_TOP_K && k == 0)) return YAMS_OK;
+    YB_ARG(database, "database is null");
+    YB_ARG(n < 0xFFFFFFFFull, "too many rows");
+    YB_ARG(mode == YAMS_B200_BATCH_ALL ? out_dist != nullptr : out_idx != nullptr, "null output");
+    YB_ARG(mode != YAMS_B200_BATCH_FILTERED || out_dist, "null output");
+    DeviceCtx* dev = nullptr;
+    yams_status_t rc = ensure_device(&dev);
+    if (rc != YAMS_OK) return rc;
+    cudaStream_t st;
+    YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint64_t np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    DevBuf d_rows, d_q, d_dist, d_keys, d_oi, d_od, d_cnt;
+    rc = d_rows.reserve((size_t)n * dim * 4);
+    if (rc == YAMS_OK) rc = d_q.reserve((size_t)dim * 4);
+    if (rc == YAMS_OK) rc = d_dist.reserve((size_t)n * 4);
+    if (rc == YAMS_OK && mode != YAMS_B200_BATCH_ALL) {
+        rc = d_keys.reserve((size_t)np2 * 8);
+        if (rc == YAMS_OK) rc = d_oi.reserve((size_t)n * 8);
+        if (rc == YAMS_OK) rc = d_od.reserve((size_t)n * 4);
+        if (rc == YAMS_OK) rc = d_cnt.reserve(8);
+    }
+    if (rc == YAMS_OK) {
+        cudaError_t e = cudaMemcpyAsync(d_rows.p, database, (size_t)n * dim * 4, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_q.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, st);
+        batch_dist_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_rows.as<float>(), dim, n, d_q.as<float>(), metric,
+                                                                           d_dist.as<float>());
+        unsigned g = (unsigned)std::min<uint64_t>((np2 + 255) / 256, 65535);
+        uint64_t outn = n;
+        if (mode == YAMS_B200_BATCH_ALL) {
+            negate_kernel<<<g, 256, 0, st>>>(d_dist.as<float>(), n);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out_dist, d_dist.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        } else {
+            if (mode == YAMS_B200_BATCH_TOP_K)
+                make_keys_kernel<<<g, 256, 0, st>>>(d_dist.as<float>(), n, np2, d_keys.as<uint64_t>());
+            else
+                make_keys_filtered_kernel<<<g, 256, 0, st>>>(d_dist.as<float>(), n, np2, threshold, d_keys.as<uint64_t>());
+            for (uint64_t size = 2; size <= np2; size <<= 1)
+                for (uint64_t stride = size >> 1; stride > 0; stride >>= 1)
+                    bitonic_step_kernel<<<g, 256, 0, st>>>(d_keys.as<uint64_t>(), np2, size, stride);
+            if (mode == YAMS_B200_BATCH_TOP_K) {
+                outn = std::min<uint64_t>(k, n);
+            } else {
+                unsigned long long h_cnt = 0;
+                if (e == cudaSuccess) e = cudaMemsetAsync(d_cnt.p, 0, 8, st);
+                count_nonzero_kernel<<<g, 256, 0, st>>>(d_keys.as<uint64_t>(), np2, d_cnt.as<unsigned long long>());
+                if (e == cudaSuccess) e = cudaMemcpyAsync(&h_cnt, d_cnt.p, 8, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                outn = h_cnt;
+            }
+            if (outn && e == cudaSuccess) {
+                unpack_idx_keys_kernel<<<g, 256, 0, st>>>(d_keys.as<uint64_t>(), outn, d_oi.as<uint64_t>(), d_od.as<float>());
+                e = cudaMemcpyAsync(out_idx, d_oi.p, (size_t)outn * 8, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess && out_dist) e = cudaMemcpyAsync(out_dist, d_od.p, (size_t)outn * 4, cudaMemcpyDeviceToHost, st);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            }
+        }
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_last_error("batch_distance failed: %s", cudaGetErrorString(e));
+            rc = YAMS_ERR_INTERNAL;
+        } else {
+            *out_count = outn;
+        }
+    }
+    for (DevBuf* b : {&d_rows, &d_q, &d_dist, &d_keys, &d_oi, &d_od, &d_cnt}) b->release();
+    cudaStreamDestroy(st);
+    return rc;
+}
+
+yams_status_t yams_b200_compute_cosine_similarity(void* self, const float* a, size_t na, const float* b, size_t nb, double* out) {
+    (void)self;
+    YB_ARG(out, "out is null");
+    *out = 0.0;
+    if (na != nb || na == 0) return YAMS_OK;   // vector_database.cpp:1788-1790
+    YB_ARG(a && b, "null vector");
+    DeviceCtx* dev = nullptr;
+    yams_status_t rc = ensure_device(&dev);
+    if (rc != YAMS_OK) return rc;
+    DevBuf d_ab, d_o;
+    rc = d_ab.reserve(na * 8);
+    if (rc == YAMS_OK) rc = d_o.reserve(8);
+    if (rc == YAMS_OK) {
+        cudaError_t e = cudaMemcpy(d_ab.p, a, na * 4, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(d_ab.as<float>() + na, b, na * 4, cudaMemcpyHostToDevice);
+        cosine_similarity_f64_kernel<<<1, 1>>>(d_ab.as<float>(), d_ab.as<float>() + na, na, d_o.as<double>());
+        if (e == cudaSuccess) e = cudaMemcpy(out, d_o.p, 8, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            set_last_error("compute_cosine_similarity failed: %s", cudaGetErrorString(e));
+            rc = YAMS_ERR_INTERNAL;
+        }
+    }
+    d_ab.release();
+    d_o.release();
     return rc;
 }
 
