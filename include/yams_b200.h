@@ -159,6 +159,28 @@ typedef struct yams_dedup_stats {
 YAMS_B200_API yams_status_t yams_b200_dedup_stats(void* self, const yams_chunk_desc* chunks, size_t n,
                                                   yams_dedup_stats* out);
 
+/* ---- device-resident digest set --------------------------------------------------------
+ * Batched form of the per-chunk `storage_->exists(hash)` / `storage_->store(hash, data)` loop that follows
+ * chunking (src/api/content_store_impl.cpp:245-288, src/storage/storage_engine.cpp:281-305): one call answers
+ * the existence question for every chunk of a file. digests are HOST pointers, `stride` bytes apart (32 for a
+ * packed array; sizeof(yams_chunk_desc) with digests = chunks[0].digest for a chunk table). */
+typedef struct yams_b200_digest_set yams_b200_digest_set;
+YAMS_B200_API yams_status_t yams_b200_digest_set_create(void* self, uint64_t capacity_hint,
+                                                        yams_b200_digest_set** out);
+/* exists-then-store: out_existed[i] = 1 iff digest i was in the set before the call or equals an EARLIER
+ * digest of this batch (exactly what the sequential loop observes); afterwards every digest is in the set.
+ * out_existed and out_new (number of digests that were new) are nullable. */
+YAMS_B200_API yams_status_t yams_b200_digest_set_insert(yams_b200_digest_set* s, const uint8_t* digests,
+                                                        size_t stride, size_t n, uint8_t* out_existed,
+                                                        uint64_t* out_new);
+/* read-only membership (storage_->exists) */
+YAMS_B200_API yams_status_t yams_b200_digest_set_contains(yams_b200_digest_set* s, const uint8_t* digests,
+                                                          size_t stride, size_t n, uint8_t* out_exists);
+YAMS_B200_API yams_status_t yams_b200_digest_set_size(yams_b200_digest_set* s, uint64_t* out);
+/* device time (ms) of the kernels of the last insert/contains call */
+YAMS_B200_API yams_status_t yams_b200_digest_set_last_ms(yams_b200_digest_set* s, float* out_ms);
+YAMS_B200_API void yams_b200_digest_set_destroy(yams_b200_digest_set* s);
+
 /* Per-stage device timings (ms) of the last chunk_and_hash* call on this thread's context:
  * [0] candidate scan, [1] cut selection, [2] sha256, [3] total device, [4] h2d (0 for _device) */
 YAMS_B200_API yams_status_t yams_b200_ingest_last_timings(void* self, float out_ms[8]);
@@ -180,6 +202,13 @@ typedef struct yams_content_ingest_v1 {
                                   uint8_t* digests);
     yams_status_t (*dedup_stats)(void* self, const yams_chunk_desc* chunks, size_t n,
                                  yams_dedup_stats* out);
+    yams_status_t (*digest_set_create)(void* self, uint64_t capacity_hint, yams_b200_digest_set** out);
+    yams_status_t (*digest_set_insert)(yams_b200_digest_set* s, const uint8_t* digests, size_t stride,
+                                       size_t n, uint8_t* out_existed, uint64_t* out_new);
+    yams_status_t (*digest_set_contains)(yams_b200_digest_set* s, const uint8_t* digests, size_t stride,
+                                         size_t n, uint8_t* out_exists);
+    yams_status_t (*digest_set_size)(yams_b200_digest_set* s, uint64_t* out);
+    void (*digest_set_destroy)(yams_b200_digest_set* s);
 } yams_content_ingest_v1;
 
 /* =============================================================================================

@@ -224,3 +224,40 @@ def test_dedup_stats_matches_reference_accounting(Y, oracle):
     assert got["uniqueChunks"] == len(seen) and got["uniqueSize"] == usz
     assert got["uniqueChunks"] < got["chunkCount"]          # the repeated megabyte dedups
     assert Y.dedup_stats(ch[:0])["chunkCount"] == 0
+
+
+def test_digest_set_matches_sequential_exists_store_loop(Y, oracle):
+    """content_store_impl.cpp:245-288: per chunk `exists(hash)` then store -- replayed on a Python set."""
+    rng = np.random.default_rng(9)
+    pool = rng.integers(0, 256, size=(5000, 32), dtype=np.uint8)
+    pool[1, :16] = pool[0, :16]                       # same hash-slot key, different digest
+    s = Y.DigestSet()
+    model = set()
+    assert len(s.contains(pool[:0])) == 0
+    for rnd, n in enumerate((1, 7, 1000, 20000, 3, 60000)):
+        batch = pool[rng.integers(0, min(len(pool), 50 + 2000 * rnd), size=n)]
+        before = s.contains(batch)
+        assert list(before) == [bytes(d) in model for d in batch]
+        existed, new = s.insert(batch)
+        want = []
+        for d in batch:
+            b = bytes(d)
+            want.append(b in model)
+            model.add(b)
+        assert list(existed) == want
+        assert new == want.count(False) and len(s) == len(model)
+        assert np.all(s.contains(batch) == 1)
+    assert np.all(s.contains(rng.integers(0, 256, size=(1000, 32), dtype=np.uint8)) == 0)
+    s.close()
+    # chunk tables go in directly (stride = sizeof(yams_chunk_desc)); agrees with calculateDeduplication
+    block = oracle.gen_bytes(5, 0, 1 << 20)
+    data = np.concatenate([block, block, oracle.gen_bytes(6, 0, 1 << 19), block])
+    ch = Y.chunk_and_hash(data, Y.default_config(min_chunk_size=2048, max_chunk_size=32768, chunk_mask=0x3FF))
+    s = Y.DigestSet(capacity_hint=16)
+    existed, new = s.insert(ch)
+    st = Y.dedup_stats(ch)
+    assert new == st["uniqueChunks"] == len(s)
+    assert int(ch["size"][existed == 0].sum()) == st["uniqueSize"]
+    existed2, new2 = s.insert(ch)
+    assert new2 == 0 and np.all(existed2 == 1)
+    s.close()

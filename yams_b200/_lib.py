@@ -65,6 +65,12 @@ SYMBOLS = {
     "yams_b200_sha256_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p, C.c_size_t, u8p]),
     "yams_b200_sha256_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p, C.c_size_t, u8p]),
     "yams_b200_chunk_boundaries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CdcConfig), _descpp, _szp]),
+    "yams_b200_digest_set_create": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "yams_b200_digest_set_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, u64p]),
+    "yams_b200_digest_set_contains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
+    "yams_b200_digest_set_size": (C.c_int, [C.c_void_p, u64p]),
+    "yams_b200_digest_set_last_ms": (C.c_int, [C.c_void_p, f32p]),
+    "yams_b200_digest_set_destroy": (None, [C.c_void_p]),
     "yams_b200_ingest_last_timings": (C.c_int, [C.c_void_p, f32p]),
     "yams_b200_dedup_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "yams_b200_corpus_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
@@ -412,6 +418,63 @@ def vec0_exact(query, rows, k: int = 0, rowids=None, rowid_range=None):
                                     out_d.ctypes.data_as(f32p), C.byref(cnt))
     _check(rc, "vec0_exact")
     return out_r[:cnt.value].copy(), out_d[:cnt.value].copy()
+
+
+class DigestSet:
+    """Device-resident set of chunk digests: the batched `storage_->exists` / `store` loop
+    (content_store_impl.cpp:245-288)."""
+
+    def __init__(self, capacity_hint: int = 0):
+        h = C.c_void_p()
+        _check(lib().yams_b200_digest_set_create(None, capacity_hint, C.byref(h)), "digest_set_create")
+        self._h = h
+
+    @staticmethod
+    def _digests(x):
+        """chunk table (structured, field 'digest') or [n,32] uint8 -> (base pointer, stride, n, keepalive)"""
+        a = np.asarray(x)
+        if a.dtype.names and "digest" in a.dtype.names:
+            a = np.ascontiguousarray(a)
+            off = a.dtype.fields["digest"][1]
+            return a.ctypes.data + off, a.dtype.itemsize, len(a), a
+        a = np.ascontiguousarray(a, dtype=np.uint8).reshape(-1, 32)
+        return a.ctypes.data, 32, len(a), a
+
+    def insert(self, digests):
+        """-> (existed uint8[n], n_new)"""
+        ptr, stride, n, keep = self._digests(digests)
+        existed = np.zeros(max(n, 1), dtype=np.uint8)
+        new = C.c_uint64(0)
+        _check(lib().yams_b200_digest_set_insert(self._h, ptr if n else None, stride, n, existed.ctypes.data, C.byref(new)),
+               "digest_set_insert")
+        return existed[:n], new.value
+
+    def contains(self, digests) -> np.ndarray:
+        ptr, stride, n, keep = self._digests(digests)
+        out = np.zeros(max(n, 1), dtype=np.uint8)
+        _check(lib().yams_b200_digest_set_contains(self._h, ptr if n else None, stride, n, out.ctypes.data), "digest_set_contains")
+        return out[:n]
+
+    def __len__(self):
+        n = C.c_uint64(0)
+        _check(lib().yams_b200_digest_set_size(self._h, C.byref(n)), "digest_set_size")
+        return n.value
+
+    def last_ms(self) -> float:
+        v = C.c_float(0)
+        _check(lib().yams_b200_digest_set_last_ms(self._h, C.byref(v)), "digest_set_last_ms")
+        return v.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().yams_b200_digest_set_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 BATCH_ALL, BATCH_TOP_K, BATCH_FILTERED = 0, 1, 2

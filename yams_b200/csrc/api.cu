@@ -159,6 +159,11 @@ int yams_plugin_init(const char* config_json, const void* host_context) {
     g_ingest_vt.ingest_close = yams_b200_ingest_close;
     g_ingest_vt.sha256_batch = yams_b200_sha256_batch;
     g_ingest_vt.dedup_stats = yams_b200_dedup_stats;
+    g_ingest_vt.digest_set_create = yams_b200_digest_set_create;
+    g_ingest_vt.digest_set_insert = yams_b200_digest_set_insert;
+    g_ingest_vt.digest_set_contains = yams_b200_digest_set_contains;
+    g_ingest_vt.digest_set_size = yams_b200_digest_set_size;
+    g_ingest_vt.digest_set_destroy = yams_b200_digest_set_destroy;
     g_scan_vt.abi_version = YAMS_IFACE_VECTOR_SCAN_V1_VERSION;
     g_scan_vt.self = nullptr;
     g_scan_vt.corpus_create = yams_b200_corpus_create;
