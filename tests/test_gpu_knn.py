@@ -419,3 +419,47 @@ def test_corpus_remove_keeps_scan_order(Y, oracle):
         assert c.remove(rowids[keep]) == len(keep) and len(c) == 5
         assert c.remove(new_ids) == 5 and len(c) == 0
         c.close()
+
+
+@pytest.mark.parametrize("dtype_name,d", [("f16", 64), ("f32", 36), ("f32", 30), ("f16", 20)])
+def test_candidate_sets_direct_and_masked_paths(Y, oracle, dtype_name, d):
+    """Candidate sets take one of two device paths: small ascending lists are scored row by row
+    (gather_score_kernel), everything else by a masked corpus pass with thresholds calibrated on the allowed sample
+    rows.  Both must equal the reference scan restricted to the candidate set (sqlite_vec_backend.cpp:4138-4175)."""
+    O = oracle
+    n, nq, k = 150_000, 6, 10
+    rows32 = O.gen_rows_f32(21, 0, n, d)
+    rows32[500] = 0
+    if dtype_name == "f16":
+        stored = O.f16_from_float(rows32).reshape(n, d)
+        c = Y.Corpus(d, Y.F16, Y.COSINE)
+        c.append(stored.view(np.float16), rowids=None)
+    else:
+        stored = rows32
+        c = Y.Corpus(d, Y.F32, Y.COSINE)
+        c.append(stored)
+    rowids = np.arange(n, dtype=np.int64)
+    queries = O.gen_rows_f32(22, 0, nq, d)
+    rng = np.random.default_rng(17)
+
+    def check(allowed, what):
+        rid, sc, cnt, flags = c.search(queries, k, threshold=-1.0, allowed=allowed)
+        for qi in range(nq):
+            al = np.unique(np.asarray(allowed[qi], dtype=np.int64))
+            rc, wr, ws = O.exact_scan_cosine(stored, queries[qi], k, threshold=-1.0, rowids=rowids, allowed=al)
+            assert cnt[qi] == len(wr) and list(rid[qi, :len(wr)]) == list(wr), (what, qi)
+            assert np.array_equal(sc[qi, :len(wr)], ws), (what, qi)
+
+    # direct: ascending lists with repeats, ids that do not exist, a list shorter than k, an empty list, the zero row
+    small = []
+    for qi in range(nq):
+        sel = np.sort(rng.choice(n, size=[3, 40, 700, 5000, 1, 2500][qi], replace=False))
+        small.append(np.sort(np.concatenate([sel, sel[:2], [500], [n + 5, n + 9]])).astype(np.int64))
+    small[4] = np.zeros(0, dtype=np.int64)
+    check(small, "direct")
+    # masked pass, few allowed rows (unsorted lists cannot take the direct path): thresholds fall back to -inf
+    check([a[::-1].copy() for a in small], "masked-small")
+    # masked pass, large lists: thresholds come from the allowed rows of the sample
+    big = [np.sort(rng.choice(n, size=int(n * f), replace=False)).astype(np.int64) for f in (0.6, 0.3, 0.9, 0.05, 0.5, 0.7)]
+    check(big, "masked-big")
+    c.close()

@@ -425,14 +425,20 @@ struct Exact {
 // one thread per (query, survivor): sqlite_vec_backend.cpp:4253-4279 evaluated in the same order
 __global__ void rescore_kernel(const void* __restrict__ rows, int dtype, uint32_t d, const float* __restrict__ q32,
                                const double* __restrict__ qnorm, const Cand* __restrict__ sel, const uint32_t* __restrict__ sel_n,
-                               uint32_t Kp, uint32_t nq, float threshold, Exact* __restrict__ out) {
+                               uint32_t Kp, uint32_t nq, float threshold, Exact* __restrict__ out,
+                               const uint32_t* __restrict__ mask = nullptr, uint64_t mask_ld = 0) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= nq * Kp) return;
     uint32_t q = t / Kp, j = t % Kp;
     Exact e;
     e.sim = __int_as_float(0x7FC00000);
     e.row = 0xFFFFFFFFu;
-    if (j < sel_n[q] && sel[(uint64_t)q * Kp + j].row != 0xFFFFFFFFu) {
+    bool take = j < sel_n[q] && sel[(uint64_t)q * Kp + j].row != 0xFFFFFFFFu;
+    if (take && mask) {   // candidate-set mode: a row outside the allowed set is never a result
+        uint32_t row = sel[(uint64_t)q * Kp + j].row;
+        take = (mask[(uint64_t)q * mask_ld + (row >> 5)] >> (row & 31)) & 1u;
+    }
+    if (take) {
         uint32_t row = sel[(uint64_t)q * Kp + j].row;
         uint64_t base = (uint64_t)row * d;
         const float* qv = q32 + (uint64_t)q * d;
@@ -544,6 +550,83 @@ __global__ void build_mask_kernel(const int64_t* __restrict__ allowed, const uin
             if (!((old >> (a & 31)) & 1u)) atomicAdd(&per_query[q], 1u);
         }
     }
+}
+
+// scores of rows outside query q's allowed set become -inf (threshold calibration sample / exhaustive fallback).
+// scores[b * ld + i] belongs to query (qmap ? qmap[b] : b) and row row_start + i * row_stride.
+__global__ void mask_scores_kernel(float* __restrict__ scores, uint64_t ld, uint64_t len, uint64_t row_stride,
+                                   const uint32_t* __restrict__ mask, uint64_t mask_ld, const uint32_t* __restrict__ qmap) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t q = qmap ? qmap[b] : b;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t row = i * row_stride;
+        if (!((mask[(uint64_t)q * mask_ld + (row >> 5)] >> (row & 31)) & 1u)) scores[(uint64_t)b * ld + i] = -INFINITY;
+    }
+}
+
+// Small candidate sets: no corpus pass at all.  One warp per (query, allowed rowid) pair: rowid -> row by binary
+// search, stage-1 score by a coalesced fp32 dot product of that one row, Cand written at the pair's list position
+// (unknown or repeated rowids become (-inf, 0xFFFFFFFF) and are skipped downstream).  Lists must be ascending.
+template <int VEC>   // 8: fp16 rows, dim % 8 == 0; 4: fp32 rows, dim % 4 == 0; 0: scalar
+__global__ void gather_score_kernel(const void* __restrict__ rows, int dtype, uint32_t d, const float* __restrict__ inv_norm,
+                                    const int64_t* __restrict__ rowids, uint64_t n, const float* __restrict__ q32,
+                                    const float* __restrict__ qinv, const int64_t* __restrict__ allowed,
+                                    const uint64_t* __restrict__ offsets, uint32_t nq, uint64_t total, Cand* __restrict__ cands,
+                                    uint32_t cap) {
+    const uint64_t pair = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (pair >= total) return;
+    uint32_t qa = 0, qb = nq;   // last q with offsets[q] <= pair
+    while (qb - qa > 1) {
+        uint32_t m = (qa + qb) >> 1;
+        if (offsets[m] <= pair) qa = m; else qb = m;
+    }
+    const uint32_t q = qa;
+    const uint64_t j = pair - offsets[q];
+    const int64_t want = allowed[pair];
+    bool valid = !(j > 0 && allowed[pair - 1] == want);
+    uint64_t a = 0, b = n;
+    while (a < b) {
+        uint64_t m = a + ((b - a) >> 1);
+        if (rowids[m] < want) a = m + 1; else b = m;
+    }
+    valid = valid && a < n && rowids[a] == want;
+    Cand out;
+    out.score = -INFINITY;
+    out.row = 0xFFFFFFFFu;
+    if (valid) {
+        const float* qv = q32 + (uint64_t)q * d;
+        float s = 0.f;
+        if (VEC == 8) {
+            const uint4* r = reinterpret_cast<const uint4*>(static_cast<const __half*>(rows) + a * d);
+            for (uint32_t u = lane; u < d / 8; u += 32) {
+                uint4 v = __ldg(r + u);
+                const __half2* h = reinterpret_cast<const __half2*>(&v);
+                const float4 q0 = *reinterpret_cast<const float4*>(qv + u * 8), q1 = *reinterpret_cast<const float4*>(qv + u * 8 + 4);
+                float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+                s = fmaf(f0.x, q0.x, s); s = fmaf(f0.y, q0.y, s); s = fmaf(f1.x, q0.z, s); s = fmaf(f1.y, q0.w, s);
+                s = fmaf(f2.x, q1.x, s); s = fmaf(f2.y, q1.y, s); s = fmaf(f3.x, q1.z, s); s = fmaf(f3.y, q1.w, s);
+            }
+        } else if (VEC == 4) {
+            const float4* r = reinterpret_cast<const float4*>(static_cast<const float*>(rows) + a * d);
+            for (uint32_t u = lane; u < d / 4; u += 32) {
+                float4 v = __ldg(r + u);
+                const float4 qq = *reinterpret_cast<const float4*>(qv + u * 4);
+                s = fmaf(v.x, qq.x, s); s = fmaf(v.y, qq.y, s); s = fmaf(v.z, qq.z, s); s = fmaf(v.w, qq.w, s);
+            }
+        } else {
+            for (uint32_t cidx = lane; cidx < d; cidx += 32) s = fmaf(load_elem(rows, dtype, a * d + cidx), qv[cidx], s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        out.score = s * inv_norm[a] * qinv[q];
+        out.row = (uint32_t)a;
+    }
+    if (lane == 0) cands[(uint64_t)q * cap + j] = out;
+}
+__global__ void list_lengths_kernel(const uint64_t* __restrict__ offsets, uint32_t nq, uint32_t* __restrict__ counts) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) counts[q] = (uint32_t)(offsets[q + 1] - offsets[q]);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -887,9 +970,20 @@ static yams_status_t corpus_finish_append(Corpus* c, uint64_t n_new, const int64
 
 // Runs the whole cosine pipeline for nq queries already resident at c->q32 (device) and writes the
 // padded [nq][k] result into device buffers.
+// Candidate sets (CandidateFilterMode::Exact) come in one of two forms:
+//   d_mask  : bit matrix [nq][mask_ld*32] of allowed rows + h_allowed[q] = allowed rows of query q  -> masked corpus pass
+//   direct  : device lists (ascending rowids, d_offsets[nq+1]) small enough that scoring the listed rows one by one is
+//             cheaper than a corpus pass                                                             -> gather_score_kernel
+struct DirectLists {
+    const int64_t* d_allowed = nullptr;
+    const uint64_t* d_offsets = nullptr;
+    uint64_t total = 0;
+    uint32_t max_len = 0;
+};
 static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, float threshold, const uint32_t* d_mask,
-                                          uint64_t mask_ld, uint32_t mask_max, int64_t* d_out_rowids, float* d_out_scores,
-                                          uint32_t* d_out_counts, uint64_t* d_out_flags, bool use_tensor) {
+                                          uint64_t mask_ld, const uint32_t* h_allowed, int64_t* d_out_rowids, float* d_out_scores,
+                                          uint32_t* d_out_counts, uint64_t* d_out_flags, bool use_tensor,
+                                          const DirectLists* direct = nullptr) {
     yams_status_t rc;
     cudaStream_t st = c->st;
     const uint32_t Kp = survivors_for(k);
@@ -922,6 +1016,27 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
     std::vector<uint32_t> bad;  // queries that need the exhaustive path
     if (n == 0) {
         // nothing to score
+    } else if (direct) {
+        // ---- small candidate sets: score the listed rows only ----
+        const uint32_t cap = std::max<uint32_t>(direct->max_len, 1);
+        if ((rc = c->cands.reserve((size_t)nq * cap * sizeof(Cand))) != YAMS_OK) return rc;
+        list_lengths_kernel<<<(nq + 255) / 256, 256, 0, st>>>(direct->d_offsets, nq, d_counts);
+        if (direct->total) {
+            const unsigned grid = (unsigned)((direct->total * 32 + 255) / 256);
+            const bool v8 = c->dtype == YAMS_B200_F16 && c->dim % 8 == 0, v4 = c->dtype == YAMS_B200_F32 && c->dim % 4 == 0;
+#define YB_GATHER(V)                                                                                                              \
+    gather_score_kernel<V><<<grid, 256, 0, st>>>(c->rows.p, c->dtype, c->dim, c->inv_norm.as<float>(), c->rowids.as<int64_t>(), n, \
+                                                 a.q32, d_qinv, direct->d_allowed, direct->d_offsets, nq, direct->total,           \
+                                                 c->cands.as<Cand>(), cap)
+            YB_CUDA(cudaEventRecord(c->ev_scan[0], st));
+            if (v8) YB_GATHER(8); else if (v4) YB_GATHER(4); else YB_GATHER(0);
+#undef YB_GATHER
+            YB_CUDA(cudaEventRecord(c->ev_scan[1], st));
+            c->scan_timed = true;
+        }
+        SelectIn in{};
+        in.cands = c->cands.as<Cand>(); in.counts = d_counts; in.cap = cap;
+        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
     } else if (!d_mask && n <= kDenseLimit) {
         // ---- dense: every score materialised, exact top-K' straight from the matrix ----
         if ((rc = c->dense.reserve((size_t)nq * n * 4)) != YAMS_OK) return rc;
@@ -935,12 +1050,9 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
         uint32_t cap;
         if ((rc = c->tau.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
         float* d_tau = c->tau.as<float>();
-        if (d_mask) {
-            // ---- candidate-set mode: every allowed row is a candidate ----
-            cap = std::max<uint32_t>(mask_max, 1);
-            fill_f32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_tau, nq, -INFINITY);
-        } else {
-            // ---- thresholds from a strided sample ----
+        {
+            // ---- thresholds from a strided sample (candidate-set mode: of the ALLOWED sample rows, so that ~4*K'
+            //      allowed rows are expected above it; -inf when the sample holds fewer than m allowed rows) ----
             uint64_t S = std::min<uint64_t>(n, kSampleRows);
             uint64_t stride = n / S;
             // the sample rank is chosen so that ~4*K' rows are expected above the threshold
@@ -952,6 +1064,9 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
             s1.row_start = 0; s1.row_stride = stride; s1.nrows = S;
             s1.out_scores = c->sample_scores.as<float>(); s1.ld = S;
             if ((rc = run_stage1(s1, false)) != YAMS_OK) return rc;
+            if (d_mask)
+                mask_scores_kernel<<<dim3((unsigned)((S + 255) / 256), nq), 256, 0, st>>>(c->sample_scores.as<float>(), S, S, stride, d_mask,
+                                                                                         mask_ld, nullptr);
             SelectIn in{};
             in.dense = c->sample_scores.as<float>(); in.ld = S; in.row_start = 0; in.row_stride = stride; in.dense_len = S;
             topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, m, 1, d_tau, nullptr, nullptr);
@@ -971,14 +1086,15 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
         SelectIn in{};
         in.cands = c->cands.as<Cand>(); in.counts = d_counts; in.cap = cap;
         topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
-        if (!d_mask) {
+        {
             // verify every list: overflow or too few survivors -> exhaustive path for that query
-            uint32_t* h_counts = c->h_pin.as<uint32_t>();
+            uint32_t* h_counts = c->h_pin.as<uint32_t>() + nq;   // [0, nq) may hold the caller's h_allowed
             YB_CUDA(cudaMemcpyAsync(h_counts, d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
             YB_CUDA(cudaStreamSynchronize(st));
-            uint64_t need = std::min<uint64_t>(Kp, n);
-            for (uint32_t q = 0; q < nq; ++q)
+            for (uint32_t q = 0; q < nq; ++q) {
+                uint64_t need = std::min<uint64_t>(Kp, d_mask ? (uint64_t)h_allowed[q] : n);
                 if (h_counts[q] > cap || h_counts[q] < need) bad.push_back(q);
+            }
         }
     }
     // ---- exhaustive path for the (rare) queries whose threshold was off ----
@@ -1001,6 +1117,9 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
             e.q32 = d_qg; e.qinv = d_qinv_g; e.nq = g;
             e.row_start = 0; e.row_stride = 1; e.nrows = n; e.out_scores = d_scores; e.ld = n;
             if ((rc = stage1_cuda_core(e, false, st)) != YAMS_OK) return rc;
+            if (d_mask)
+                mask_scores_kernel<<<dim3((unsigned)std::min<uint64_t>((n + 255) / 256, 65535), g), 256, 0, st>>>(d_scores, n, n, 1, d_mask,
+                                                                                                                 mask_ld, d_qmap);
             SelectIn in{};
             in.dense = d_scores; in.ld = n; in.row_start = 0; in.row_stride = 1; in.dense_len = n; in.qmap = d_qmap;
             topk_select_kernel<<<g, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
@@ -1019,7 +1138,7 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
     Exact* d_ex = c->outbuf.as<Exact>();
     uint32_t tot = nq * Kp;
     rescore_kernel<<<(tot + 127) / 128, 128, 0, st>>>(c->rows.p, c->dtype, c->dim, a.q32, d_qnorm, d_sel, d_sel_n, Kp, nq,
-                                                      threshold, d_ex);
+                                                      threshold, d_ex, d_mask, mask_ld);
     final_kernel<<<nq, SEL_THREADS, 0, st>>>(d_ex, nullptr, Kp, k, c->rowids.as<int64_t>(), 0, d_out_rowids, d_out_scores,
                                              d_out_counts, d_out_flags, -INFINITY);
     YB_CUDA(cudaGetLastError());
@@ -1300,8 +1419,32 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
     if (c->metric == YAMS_B200_COSINE) {
         const uint32_t* d_mask = nullptr;
         uint64_t mask_ld = 0;
-        uint32_t mask_max = 0;
+        const uint32_t* h_allowed = nullptr;
+        DirectLists lists;
+        bool direct = false;
         if (allowed_offsets && c->n) {
+            // small ascending lists: score the listed rows directly instead of passing over the corpus.  Break-even
+            // (DESIGN.md §4.4): a corpus pass costs ~max(1, nq/400) row reads per row, a gathered row about two.
+            const uint64_t total = allowed_offsets[nq];
+            direct = total <= std::max<uint64_t>(c->n / 2, c->n / 400 * nq) && total < (1ull << 31);
+            for (uint32_t q = 0; q < nq && direct; ++q) {
+                uint64_t lo = allowed_offsets[q], hi = allowed_offsets[q + 1];
+                direct = hi >= lo && hi - lo < 0xFFFFFFFFull;
+                for (uint64_t i = lo + 1; i < hi && direct; ++i) direct = allowed_rowids[i - 1] <= allowed_rowids[i];
+                if (direct) lists.max_len = std::max<uint32_t>(lists.max_len, (uint32_t)(hi - lo));
+            }
+        }
+        if (direct) {
+            const uint64_t total = allowed_offsets[nq];
+            if ((rc = c->mask.reserve((size_t)total * 8 + (size_t)(nq + 1) * 8 + 64)) != YAMS_OK) return rc;
+            int64_t* d_allowed = c->mask.as<int64_t>();
+            uint64_t* d_offs = reinterpret_cast<uint64_t*>(d_allowed + total);
+            if (total) YB_CUDA(cudaMemcpyAsync(d_allowed, allowed_rowids, (size_t)total * 8, cudaMemcpyHostToDevice, c->st));
+            YB_CUDA(cudaMemcpyAsync(d_offs, allowed_offsets, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->st));
+            lists.d_allowed = d_allowed;
+            lists.d_offsets = d_offs;
+            lists.total = total;
+        } else if (allowed_offsets && c->n) {
             uint64_t total = allowed_offsets[nq];
             mask_ld = (c->n + 31) / 32;
             size_t mb = (size_t)nq * mask_ld * 4;
@@ -1324,10 +1467,11 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
                 set_last_error("mask build failed");
                 return YAMS_ERR_INTERNAL;
             }
-            for (uint32_t q = 0; q < nq; ++q) mask_max = std::max(mask_max, h_pq[q]);
+            h_allowed = h_pq;
             d_mask = dm;
         }
-        rc = search_cosine_device(c, nq, k, threshold, d_mask, mask_ld, mask_max, d_or, d_os, d_oc, d_of, tensor);
+        rc = search_cosine_device(c, nq, k, threshold, d_mask, mask_ld, h_allowed, d_or, d_os, d_oc, d_of, tensor,
+                                  direct ? &lists : nullptr);
     } else {
         YB_ARG(!allowed_offsets, "candidate sets are only supported for the cosine metric");
         cudaMemsetAsync(d_of, 0, (size_t)nq * 8, c->st);
