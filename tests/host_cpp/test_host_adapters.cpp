@@ -82,6 +82,37 @@ int main() {
     try { vs.searchSimilar({NAN, 0, 0, 0}, 3); } catch (const std::invalid_argument&) { threw = true; }
     CHECK(threw);
     CHECK(vs.size() == 4);
+    // ---- candidate documents, all-matching, deletes (vector_store.h:39-40,121-138) ----
+    B200VectorStore cs(4);
+    std::vector<float> crow = {1, 0, 0, 0, /**/ 0.9f, 0.1f, 0, 0, /**/ 0.5f, 0.5f, 0, 0, /**/ 0, 1, 0, 0, /**/ 0.8f, 0.2f, 0, 0};
+    cs.insertVectorsBatch(crow, {10, 11, 12, 13, 14}, {"c0", "c1", "c2", "c3", "c4"}, {"docA", "docB", "docB", "docC", "docA"});
+    auto ch = cs.searchExactCandidates({1, 0, 0, 0}, 2, -1.0f, {"docB", "docC"});
+    CHECK(ch.size() == 2 && ch[0].chunk_id == "c1" && ch[1].chunk_id == "c2");
+    CHECK(cs.searchExactCandidates({1, 0, 0, 0}, 3, -1.0f, {"nope"}).empty());
+    auto am = cs.searchAllExactCandidateRows({1, 0, 0, 0}, 0.5f, {"docA", "docB", "docC"});
+    CHECK(am.size() == 4 && am[0].chunk_id == "c0" && am[1].chunk_id == "c1" && am[2].chunk_id == "c4" && am[3].chunk_id == "c2");
+    cs.deleteVectorsByDocument("docB");
+    CHECK(cs.size() == 3);
+    hits = cs.searchSimilar({1, 0, 0, 0}, 10, -1.0f);
+    CHECK(hits.size() == 3 && hits[0].chunk_id == "c0" && hits[1].chunk_id == "c4" && hits[2].chunk_id == "c3");
+    cs.deleteVector("c0");
+    hits = cs.searchSimilar({1, 0, 0, 0}, 1, -1.0f);
+    CHECK(cs.size() == 2 && hits.size() == 1 && hits[0].chunk_id == "c4");
+    CHECK(computeCosineSimilarity({1, 2, 3}, {1, 2, 3, 4}) == 0.0);
+    CHECK(std::fabs(computeCosineSimilarity({1, 0}, {1, 1}) - 0.70710678118654757) < 1e-15);
+    // ---- dedup accounting + the exists/store loop over repeated content ----
+    {
+        std::vector<std::byte> twice(data.begin(), data.end());
+        twice.insert(twice.end(), data.begin(), data.end());
+        auto cc = chunker.chunkDataLazy(twice);
+        auto ds = calculateDeduplication(cc);
+        CHECK(ds.chunkCount == cc.size() && ds.totalSize == twice.size() && ds.uniqueChunks < ds.chunkCount && ds.getRatio() > 0.3);
+        B200ChunkIndex index;
+        auto acc = index.addChunks(cc);
+        CHECK(acc.bytesStored == ds.uniqueSize && acc.bytesStored + acc.bytesDeduped == twice.size() && index.size() == ds.uniqueChunks);
+        auto again = index.addChunks(cc);
+        CHECK(again.bytesStored == 0 && again.bytesDeduped == twice.size());
+    }
     std::puts("ALL OK");
     return 0;
 }

@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/yams_b200.h"
@@ -147,6 +148,24 @@ private:
     int variant_;
 };
 
+// DeduplicationStats / calculateDeduplication (chunker.h:204-218, rabin_chunker.cpp:224-239)
+struct DeduplicationStats {
+    size_t totalSize = 0, uniqueSize = 0, chunkCount = 0, uniqueChunks = 0;
+    double getRatio() const { return totalSize == 0 ? 0.0 : 1.0 - static_cast<double>(uniqueSize) / static_cast<double>(totalSize); }
+};
+inline DeduplicationStats calculateDeduplication(const std::vector<Chunk>& chunks) {
+    std::vector<yams_chunk_desc> d(chunks.size());
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        d[i].offset = chunks[i].offset;
+        d[i].size = chunks[i].size;
+        for (int b = 0; b < 32; ++b) d[i].digest[b] = (uint8_t)std::stoi(chunks[i].hash.substr(2 * b, 2), nullptr, 16);
+    }
+    yams_dedup_stats st{};
+    yams_status_t rc = yams_b200_dedup_stats(nullptr, d.data(), d.size(), &st);
+    if (rc != YAMS_OK) throw_status("dedup_stats", rc);
+    return DeduplicationStats{(size_t)st.total_size, (size_t)st.unique_size, (size_t)st.chunk_count, (size_t)st.unique_chunks};
+}
+
 // IContentHasher: init / update / finalize accumulate on the host side (the digest of ONE message is a serial
 // chain; the GPU earns its keep when many messages are hashed at once -> hashMany).
 class B200ContentHasher {
@@ -200,10 +219,80 @@ public:
     B200VectorStore& operator=(const B200VectorStore&) = delete;
 
     // insertVectorsBatch: rows are fp32 (the reference BLOB layout); rowids ascending
-    void insertVectorsBatch(const std::vector<float>& rows, const std::vector<int64_t>& rowids, const std::vector<std::string>& chunk_ids) {
+    void insertVectorsBatch(const std::vector<float>& rows, const std::vector<int64_t>& rowids, const std::vector<std::string>& chunk_ids,
+                            const std::vector<std::string>& document_hashes = {}) {
         yams_status_t st = yams_b200_corpus_append(c_, rows.data(), rowids.size(), rowids.data());
         if (st != YAMS_OK) throw_status("corpus_append", st);
-        for (size_t i = 0; i < rowids.size(); ++i) chunk_of_[rowids[i]] = chunk_ids[i];
+        for (size_t i = 0; i < rowids.size(); ++i) {
+            chunk_of_[rowids[i]] = chunk_ids[i];
+            if (i < document_hashes.size()) {
+                doc_of_[rowids[i]] = document_hashes[i];
+                rows_of_doc_[document_hashes[i]].push_back(rowids[i]);
+            }
+        }
+    }
+
+    // deleteVector(chunk_id) / deleteVectorsByDocument(document_hash) (vector_store.h:39-40): the device mirror drops
+    // the rows; the remaining rows keep their rowid order
+    void deleteVector(const std::string& chunk_id) {
+        std::vector<int64_t> gone;
+        for (const auto& [rid, cid] : chunk_of_)
+            if (cid == chunk_id) gone.push_back(rid);
+        removeRows(gone);
+    }
+    void deleteVectorsByDocument(const std::string& document_hash) {
+        auto it = rows_of_doc_.find(document_hash);
+        if (it == rows_of_doc_.end()) return;
+        std::vector<int64_t> gone = it->second;
+        removeRows(gone);
+    }
+
+    // lookupCandidateRowidsUnlocked (sqlite_vec_backend.cpp:4412-4448): document hashes -> ascending rowids
+    std::vector<int64_t> lookupCandidateRowids(const std::unordered_set<std::string>& candidate_hashes) const {
+        std::vector<int64_t> out;
+        for (const auto& h : candidate_hashes) {
+            auto it = rows_of_doc_.find(h);
+            if (it != rows_of_doc_.end()) out.insert(out.end(), it->second.begin(), it->second.end());
+        }
+        std::sort(out.begin(), out.end());
+        out.erase(std::unique(out.begin(), out.end()), out.end());
+        return out;
+    }
+
+    // searchExactCandidatesWithDiagnostics (vector_store.h:121-129): exact top-k within the candidate documents
+    std::vector<VectorHit> searchExactCandidates(const std::vector<float>& query, size_t k, float similarity_threshold,
+                                                 const std::unordered_set<std::string>& candidate_hashes) {
+        if (query.size() != dim_) throw std::invalid_argument("query dimension mismatch");
+        if (k == 0) return {};
+        std::vector<int64_t> allowed = lookupCandidateRowids(candidate_hashes);
+        uint64_t offs[2] = {0, allowed.size()};
+        size_t kk = std::min<size_t>(768, k + 8);
+        std::vector<int64_t> rid(kk);
+        std::vector<float> sc(kk);
+        uint32_t cnt = 0;
+        uint64_t flg = 0;
+        int64_t none = 0;
+        yams_status_t st = yams_b200_search(c_, query.data(), 1, (uint32_t)kk, similarity_threshold, allowed.empty() ? &none : allowed.data(),
+                                            offs, rid.data(), sc.data(), &cnt, &flg);
+        if (st == YAMS_ERR_INVALID_ARG) throw std::invalid_argument("Exact vector search requires a finite, non-zero query embedding");
+        if (st != YAMS_OK) throw_status("search", st);
+        return materialise(rid.data(), sc.data(), cnt, k);
+    }
+
+    // searchAllExactCandidateRowsWithDiagnostics (vector_store.h:131-138): every passing row of the candidate documents
+    std::vector<VectorHit> searchAllExactCandidateRows(const std::vector<float>& query, float similarity_threshold,
+                                                       const std::unordered_set<std::string>& candidate_hashes) {
+        if (query.size() != dim_) throw std::invalid_argument("query dimension mismatch");
+        std::vector<int64_t> allowed = lookupCandidateRowids(candidate_hashes);
+        if (allowed.empty()) return {};
+        std::vector<int64_t> rid(allowed.size());
+        std::vector<float> sc(allowed.size());
+        uint64_t cnt = 0;
+        yams_status_t st = yams_b200_search_all_matching(c_, query.data(), similarity_threshold, allowed.data(), allowed.size(), rid.data(),
+                                                         sc.data(), &cnt);
+        if (st == YAMS_ERR_INVALID_ARG) throw std::invalid_argument("Exact vector search requires a finite, non-zero query embedding");
+        if (st != YAMS_OK) throw_status("search_all_matching", st);
+        return materialise(rid.data(), sc.data(), (uint32_t)cnt, (size_t)cnt);
     }
 
     // searchSimilar (vector_store.h:44-49): InvalidArgument (std::invalid_argument here) for a non-finite or
@@ -265,9 +354,98 @@ public:
     }
 
 private:
+    // records for the winners + the chunk_id tie-break of sqlite_vec_backend.cpp:4218-4223
+    std::vector<VectorHit> materialise(const int64_t* rid, const float* sc, uint32_t cnt, size_t k) const {
+        std::vector<VectorHit> hits(cnt);
+        for (uint32_t i = 0; i < cnt; ++i) {
+            hits[i].rowid = rid[i];
+            hits[i].relevance_score = sc[i];
+            auto it = chunk_of_.find(rid[i]);
+            hits[i].chunk_id = it == chunk_of_.end() ? std::string() : it->second;
+        }
+        std::stable_sort(hits.begin(), hits.end(), [](const VectorHit& a, const VectorHit& b) {
+            if (a.relevance_score != b.relevance_score) return a.relevance_score > b.relevance_score;
+            return a.chunk_id < b.chunk_id;
+        });
+        if (hits.size() > k) hits.resize(k);
+        return hits;
+    }
+    void removeRows(const std::vector<int64_t>& gone) {
+        if (gone.empty()) return;
+        yams_status_t st = yams_b200_corpus_remove(c_, gone.data(), gone.size(), nullptr);
+        if (st != YAMS_OK) throw_status("corpus_remove", st);
+        for (int64_t r : gone) {
+            chunk_of_.erase(r);
+            auto d = doc_of_.find(r);
+            if (d != doc_of_.end()) {
+                auto& v = rows_of_doc_[d->second];
+                v.erase(std::remove(v.begin(), v.end(), r), v.end());
+                if (v.empty()) rows_of_doc_.erase(d->second);
+                doc_of_.erase(d);
+            }
+        }
+    }
     yams_b200_corpus* c_ = nullptr;
     uint32_t dim_;
     std::unordered_map<int64_t, std::string> chunk_of_;
+    std::unordered_map<int64_t, std::string> doc_of_;
+    std::unordered_map<std::string, std::vector<int64_t>> rows_of_doc_;
+};
+
+// VectorDatabase::computeCosineSimilarity (vector_database.cpp:1786-1810)
+inline double computeCosineSimilarity(const std::vector<float>& a, const std::vector<float>& b) {
+    double out = 0.0;
+    yams_status_t st = yams_b200_compute_cosine_similarity(nullptr, a.data(), a.size(), b.data(), b.size(), &out);
+    if (st != YAMS_OK) throw_status("compute_cosine_similarity", st);
+    return out;
+}
+
+// The exists / store loop of ContentStore::store (content_store_impl.cpp:245-288) over one file's chunk table.
+class B200ChunkIndex {
+public:
+    B200ChunkIndex() {
+        yams_status_t st = yams_b200_digest_set_create(nullptr, 0, &s_);
+        if (st != YAMS_OK) throw_status("digest_set_create", st);
+    }
+    ~B200ChunkIndex() { yams_b200_digest_set_destroy(s_); }
+    B200ChunkIndex(const B200ChunkIndex&) = delete;
+    B200ChunkIndex& operator=(const B200ChunkIndex&) = delete;
+    struct StoreAccounting {
+        uint64_t bytesStored = 0, bytesDeduped = 0;   // StoreResult fields, content_store_impl.cpp:255,277
+        std::vector<bool> existed;
+    };
+    // hashes are the 64-char lowercase hex strings of Chunk::hash
+    StoreAccounting addChunks(const std::vector<Chunk>& chunks) {
+        std::vector<uint8_t> dg(chunks.size() * 32);
+        for (size_t i = 0; i < chunks.size(); ++i) hexToBytes(chunks[i].hash, dg.data() + 32 * i);
+        std::vector<uint8_t> ex(chunks.size());
+        yams_status_t st = yams_b200_digest_set_insert(s_, dg.data(), 32, chunks.size(), ex.data(), nullptr);
+        if (st != YAMS_OK) throw_status("digest_set_insert", st);
+        StoreAccounting a;
+        a.existed.resize(chunks.size());
+        for (size_t i = 0; i < chunks.size(); ++i) {
+            a.existed[i] = ex[i] != 0;
+            (ex[i] ? a.bytesDeduped : a.bytesStored) += chunks[i].size;
+        }
+        return a;
+    }
+    size_t size() const {
+        uint64_t n = 0;
+        yams_b200_digest_set_size(s_, &n);
+        return (size_t)n;
+    }
+
+private:
+    static void hexToBytes(const std::string& hex, uint8_t* out) {
+        if (hex.size() != 64) throw std::invalid_argument("chunk hash must be 64 hex characters");
+        auto nib = [](char c) -> int { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; };
+        for (int i = 0; i < 32; ++i) {
+            int hi = nib(hex[2 * i]), lo = nib(hex[2 * i + 1]);
+            if (hi < 0 || lo < 0) throw std::invalid_argument("chunk hash is not hex");
+            out[i] = (uint8_t)(hi * 16 + lo);
+        }
+    }
+    yams_b200_digest_set* s_ = nullptr;
 };
 
 }  // namespace yams_b200::host
