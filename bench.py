@@ -193,10 +193,12 @@ METRIC = "queries/sec @10M x 768 brute-force kNN (cosine top-10)"
 
 
 def knn_config(args, world):
-    return {"workload": f"C2: {args.rows} x {args.dim} fp16 rows per GPU, {args.queries}-query batch, cosine top-{args.k}",
+    return {"workload": f"C2: {args.rows} x {args.dim} {'fp32' if args.corpus_dtype == 'f32' else 'fp16'} rows per GPU, "
+                        f"{args.queries}-query batch, cosine top-{args.k}",
             "rows_per_gpu": args.rows, "dim": args.dim, "queries": args.queries, "k": args.k,
             "parallelism": f"row-shard x{world}" if world > 1 else "single GPU",
-            "l2_policy": "corpus (15.4 GB) >> 126 MB L2: every step re-streams it from HBM"}
+            "l2_policy": f"corpus ({args.rows * args.dim * (4 if args.corpus_dtype == 'f32' else 2) / 1e9:.1f} GB) >> 126 MB L2: "
+                         "every step re-streams it from HBM"}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -213,6 +215,8 @@ def main():
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--queries", type=int, default=1024)
     ap.add_argument("--k", type=int, default=10)
+    ap.add_argument("--corpus-dtype", default="f16", choices=["f16", "f32"],
+                    help="f16 = BASELINE config C2 (default); f32 = the reference's BLOB layout (tf32 tensor-core engine)")
     ap.add_argument("--ingest-gib", type=float, default=64.0)
     ap.add_argument("--e2e-ingest-gib", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -255,7 +259,9 @@ def main():
     # ------------------------------------------------------------------ knn -------------------------
     if args.workload in ("both", "knn"):
         n, d, nq, k = args.rows, args.dim, args.queries, args.k
-        corpus = Y.Corpus(d, Y.F16, Y.COSINE, capacity_hint=n)
+        f32 = args.corpus_dtype == "f32"
+        esz = 4 if f32 else 2
+        corpus = Y.Corpus(d, Y.F32 if f32 else Y.F16, Y.COSINE, capacity_hint=n)
         step_rows = 1_000_000
         for r0 in range(0, n, step_rows):
             corpus.append_synthetic(42, rank * n + r0, min(step_rows, n - r0))
@@ -330,7 +336,9 @@ def main():
             sc = res[1]
             qi = 0
             top_rows = rid[qi]
-            rows = O.f16_from_float(np.concatenate([O.gen_rows_f32(42, int(r), 1, d) for r in top_rows])).reshape(len(top_rows), d)
+            rows = np.concatenate([O.gen_rows_f32(42, int(r), 1, d) for r in top_rows]).reshape(len(top_rows), d)
+            if not f32:
+                rows = O.f16_from_float(rows).reshape(len(top_rows), d)
             want = []
             for j in range(len(top_rows)):
                 _, _, ws = O.exact_scan_cosine(rows[j:j + 1], q_host.numpy()[qi], 1, threshold=-2.0)
@@ -339,22 +347,24 @@ def main():
         flops = 2.0 * nq * n * d
         scan_s = (tm["scan_kernel_ms"] or tm["stage1_ms"]) / 1e3
         ach_tf = flops / scan_s / 1e12
-        hbm_ach = n * d * 2 / scan_s / 1e9
+        hbm_ach = n * d * esz / scan_s / 1e9
         traffic = load_traffic().get("stage1_umma_kernel")
         # which roof binds this batch size (tensor above Q ~ 250, HBM below)
-        t_tensor = flops / (peaks["bf16_tflops"] * 1e12)
-        t_hbm = n * d * 2 / (peaks["hbm_gbs"] * 1e9)
-        tensor_view = {"achieved": ach_tf, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach_tf / peaks["bf16_tflops"]}
+        # tf32 MMAs run at half the fp16/bf16 rate: the measured bf16 peak is halved for an fp32 corpus
+        tensor_peak = peaks["bf16_tflops"] * (0.5 if f32 else 1.0)
+        t_tensor = flops / (tensor_peak * 1e12)
+        t_hbm = n * d * esz / (peaks["hbm_gbs"] * 1e9)
+        tensor_view = {"achieved": ach_tf, "peak": tensor_peak, "unit": "TFLOP/s", "frac": ach_tf / tensor_peak}
         hbm_view = {"achieved": hbm_ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": hbm_ach / peaks["hbm_gbs"]}
         roof = dict(bound="tensor", **tensor_view) if t_tensor >= t_hbm else dict(bound="hbm", **hbm_view)
         roof.update({"traffic": traffic, "peak_source": peaks["source"] + " (burst bf16 cuBLAS / copy bandwidth, MEASURED_PEAKS.json)",
                      "kernel": f"stage-1 filtered scan ({tm['engine']})", "kernel_ms": scan_s * 1e3,
-                     "algorithmic_flops": flops, "algorithmic_bytes": n * d * 2,
+                     "algorithmic_flops": flops, "algorithmic_bytes": n * d * esz,
                      "tensor_view": tensor_view, "hbm_view": hbm_view})
         out.update({
             "metric": METRIC, "value": qps, "unit": "queries/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic", "config": knn_config(args, world),
+            "dtype": "tf32" if f32 else "f16", "data": "synthetic", "config": knn_config(args, world),
             "roofline": roof,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
                     "d2h_bytes_per_step": nq * k * 12 + nq * 12, "ms_per_step": e2e_ms},
@@ -363,7 +373,7 @@ def main():
         })
         if clocks is not None:
             out["clocks"] = clocks
-        if rank == 0 and not args.no_cpu_baseline:
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:   # cpu_baseline: rank 0 at N=1 only
             kind = "reference" if O.ref_available() else "port"
             rs, qs = cpu_knn_sample(kind)
             v, dt, cores, sample = cpu_knn(O, d, qs, rs, k, n, kind)
@@ -422,7 +432,7 @@ def main():
                     "d2h_bytes_per_step": int(len(che)) * 48, "sample": f"{args.e2e_ingest_gib:g} GiB pinned host buffer"},
             "gpu_launches": (int((nbytes + (1 << 32) - 1) // (1 << 32)) * 11 + 1) * Ki,
         }
-        if rank == 0 and not args.no_cpu_baseline:
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:   # cpu_baseline: rank 0 at N=1 only
             kind = "reference" if O.ref_available() else "port"
             v, dt, cores, sample = cpu_ingest(O, cpu_ingest_sample(), kind)
             ing["cpu_baseline"] = {"value": v, "unit": "GB/s", "cores": cores, "kind": kind, "sample": sample}

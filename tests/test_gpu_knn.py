@@ -463,3 +463,36 @@ def test_candidate_sets_direct_and_masked_paths(Y, oracle, dtype_name, d):
     big = [np.sort(rng.choice(n, size=int(n * f), replace=False)).astype(np.int64) for f in (0.6, 0.3, 0.9, 0.05, 0.5, 0.7)]
     check(big, "masked-big")
     c.close()
+
+
+def test_fp32_corpus_tf32_engine_vs_oracle(Y, oracle):
+    """fp32 rows (the reference's BLOB layout, sqlite_vec_backend.cpp:343-363) take the kind::tf32 tensor-core engine for
+    stage 1; the returned ids and scores must still equal the reference's double-precision scan."""
+    O = oracle
+    n, d, nq, k = 300_000, 128, 40, 10
+    rows = O.gen_rows_f32(42, 0, n, d)
+    rows[1234] = 0
+    rows[777] = rows[5]
+    c = Y.Corpus(d, Y.F32, Y.COSINE)
+    c.append(rows)
+    queries = O.gen_rows_f32(43, 0, nq, d)
+    queries[3] = rows[5] * np.float32(2.5)                      # exact duplicates score 1.0 and tie
+    got = c.search(queries, k, threshold=-1.0)
+    assert c.last_timings()["engine"] == "tcgen05"
+    rc, wr, ws, wc = O.exact_scan_cosine_batch(rows, queries, k)
+    assert rc == 0 and np.array_equal(got[2], wc)
+    assert np.array_equal(got[0], wr) and np.array_equal(got[1], ws)
+    assert not np.any(got[3] & 2)                               # no query needed the exhaustive fallback
+    # a dimension that is not a multiple of the 32-element K block (TMA zero-fills the tail), small batch
+    d2 = 100
+    rows2 = O.gen_rows_f32(44, 0, 120_000, d2)
+    c2 = Y.Corpus(d2, Y.F32, Y.COSINE)
+    c2.append(rows2)
+    q2 = O.gen_rows_f32(45, 0, 3, d2)
+    got2 = c2.search(q2, 7, threshold=0.1)
+    rc, wr, ws, wc = O.exact_scan_cosine_batch(rows2, q2, 7, threshold=0.1)
+    assert np.array_equal(got2[2], wc)
+    for qi in range(3):
+        assert list(got2[0][qi][:wc[qi]]) == list(wr[qi][:wc[qi]]) and np.array_equal(got2[1][qi][:wc[qi]], ws[qi][:wc[qi]])
+    c.close()
+    c2.close()

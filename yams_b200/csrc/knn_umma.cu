@@ -28,11 +28,11 @@
 namespace yb {
 
 constexpr int UM_BLOCK_M = 128;
-constexpr int UM_BLOCK_K = 64;           // fp16 elements = 128 bytes = one swizzle row
-constexpr int UM_UMMA_K = 16;
+constexpr int UM_BLOCK_K_BYTES = 128;    // one swizzle row of K per stage: 64 fp16 or 32 fp32 (tf32) elements
+constexpr int UM_MMAS_PER_KBLOCK = 4;    // 4 x 32 bytes of K: 4 x (K=16 fp16) or 4 x (K=8 tf32)
 constexpr int UM_MAX_N = 256;
 constexpr int UM_THREADS = 192;          // 6 warps
-constexpr uint32_t UM_A_STAGE = UM_BLOCK_M * UM_BLOCK_K * 2;   // 16 KiB
+constexpr uint32_t UM_A_STAGE = UM_BLOCK_M * UM_BLOCK_K_BYTES;   // 16 KiB
 constexpr uint32_t UM_TMEM_COLS = 512;
 constexpr long long UM_WAIT_LIMIT_CYCLES = 4000000000ll;
 constexpr uint32_t UM_EPI_CAP = 128;      // survivors staged per epilogue warp before a batched flush
@@ -96,6 +96,15 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// fp32 operands read as tf32 (the tensor core uses sign, 8 exponent and the top 10 mantissa bits), K = 8 per instruction
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // 32 lanes x 32 columns of fp32 accumulator -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -141,7 +150,9 @@ struct UmmaArgs {
     uint32_t n_tile;      // queries per tile (multiple of 16, <= 256)
     uint32_t nqt;         // query tiles
     uint32_t nrt;         // corpus row tiles (128 rows x CTAS)
-    uint32_t kblocks;     // ceil(dim / 64)
+    uint32_t kblocks;     // ceil(dim / block_k)
+    uint32_t block_k;     // K elements per stage: 64 (fp16) or 32 (fp32 rows read as tf32)
+    uint32_t tf32;        // 1: kind::tf32 (fp32 corpus), 0: kind::f16
     uint32_t stages;
     uint32_t b_stage;     // bytes of one B stage held by ONE CTA = (n_tile / CTAS) * 128
     uint32_t idesc;
@@ -179,6 +190,14 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -285,14 +304,14 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         if (CTAS == 2) {
                             if (leader) mbar_expect_tx(&full[s], stage_bytes * 2);
                             else mbar_arrive_remote(&full[s], 0);
-                            tma_load_2d_2sm(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), a_row);
-                            tma_load_2d_2sm(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), b_row);
+                            tma_load_2d_2sm(sa, &tmA, &full[s], (int)(kb * u.block_k), a_row);
+                            tma_load_2d_2sm(sb, &tmB, &full[s], (int)(kb * u.block_k), b_row);
                         } else {
                             mbar_expect_tx(&full[s], stage_bytes);
-                            tma_load_2d(sa, &tmA, &full[s], (int)(kb * UM_BLOCK_K), a_row);
-                            tma_load_2d(sb, &tmB, &full[s], (int)(kb * UM_BLOCK_K), b_row);
+                            tma_load_2d(sa, &tmA, &full[s], (int)(kb * u.block_k), a_row);
+                            tma_load_2d(sb, &tmB, &full[s], (int)(kb * u.block_k), b_row);
                         }
-                        if (qt == 0 && have_next) tma_prefetch_2d(&tmA, (int)(kb * UM_BLOCK_K), a_next);
+                        if (qt == 0 && have_next) tma_prefetch_2d(&tmA, (int)(kb * u.block_k), a_next);
                         if (++s == u.stages) { s = 0; ph ^= 1; }
                     }
                 }
@@ -317,10 +336,16 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint64_t adesc = make_smem_desc(sa);
                     const uint64_t bdesc = make_smem_desc(sa + UM_A_STAGE);
 #pragma unroll
-                    for (uint32_t k = 0; k < UM_BLOCK_K / UM_UMMA_K; ++k) {
-                        // advance 32 bytes (16 fp16) along K inside the swizzle row: +2 in 16-byte units
-                        if (CTAS == 2) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, (kb | k) != 0 ? 1u : 0u);
-                        else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (uint32_t k = 0; k < UM_MMAS_PER_KBLOCK; ++k) {
+                        // advance 32 bytes (16 fp16 / 8 tf32) along K inside the swizzle row: +2 in 16-byte units
+                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
+                        if (u.tf32) {
+                            if (CTAS == 2) umma_tf32_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, acc);
+                            else umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, acc);
+                        } else {
+                            if (CTAS == 2) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, acc);
+                            else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, acc);
+                        }
                     }
                     // smem stage reusable (in both CTAs) once these MMAs have read it
                     if (CTAS == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
@@ -557,15 +582,23 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
+// queries pre-scaled by 1/|q|, kept in fp32 (tf32 engine)
+__global__ void queries_scale_f32_kernel(const float* __restrict__ q32, const float* __restrict__ qinv, uint32_t nq, uint32_t d,
+                                         float* __restrict__ out) {
+    uint64_t total = (uint64_t)nq * d;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = q32[i] * qinv[(uint32_t)(i / d)];
+}
+
 static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
-                        uint32_t box_inner, uint32_t box_outer) {
+                        uint32_t box_inner, uint32_t box_outer, bool f32 = false) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) return false;
     cuuint64_t dims[2] = {inner, outer};
     cuuint64_t strides[1] = {outer_stride_bytes};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+    CUresult r = fn(m, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
@@ -574,20 +607,26 @@ static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64
 bool tcgen05_supported(const Corpus* c, uint32_t nq) {
     (void)nq;
     if (getenv("YAMS_B200_DISABLE_TCGEN05")) return false;
-    return c->dtype == YAMS_B200_F16 && c->metric == YAMS_B200_COSINE && (c->dim % 8 == 0) && get_encode_fn() != nullptr;
+    if (c->metric != YAMS_B200_COSINE || get_encode_fn() == nullptr) return false;
+    // fp16 rows: kind::f16; fp32 rows (the reference's BLOB layout): kind::tf32.  TMA needs 16-byte row pitches.
+    return c->dtype == YAMS_B200_F16 ? (c->dim % 8 == 0) : (c->dim % 4 == 0 && !getenv("YAMS_B200_DISABLE_TF32"));
 }
 
 yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaStream_t st) {
-    if (a.dtype != YAMS_B200_F16 || (a.dim % 8) != 0 || a.nrows == 0 || a.nq == 0) return YAMS_ERR_UNSUPPORTED;
+    const bool tf32 = a.dtype == YAMS_B200_F32;
+    const uint32_t esz = tf32 ? 4 : 2;
+    if ((a.dim * esz) % 16 != 0 || a.nrows == 0 || a.nq == 0) return YAMS_ERR_UNSUPPORTED;
+    if (tf32 && getenv("YAMS_B200_DISABLE_TF32")) return YAMS_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(a.rows) & 15) != 0) return YAMS_ERR_UNSUPPORTED;
     if (a.nrows >= (1ull << 32)) return YAMS_ERR_UNSUPPORTED;
     yams_status_t rc;
-    // fp16 queries pre-scaled by 1/|q| (so the epilogue only multiplies by 1/|row|)
-    size_t qb = (size_t)a.nq * a.dim * 2;
+    // queries pre-scaled by 1/|q| (so the epilogue only multiplies by 1/|row|), in the operand type of the engine
+    size_t qb = (size_t)a.nq * a.dim * esz;
     if ((rc = c->q16.reserve(qb + 256)) != YAMS_OK) return rc;
-    __half* d_q16 = c->q16.as<__half>();
-    queries_to_f16_kernel<<<(unsigned)std::min<uint64_t>(((uint64_t)a.nq * a.dim + 255) / 256, 4096), 256, 0, st>>>(
-        a.q32, a.qinv, a.nq, a.dim, d_q16);
+    void* d_q16 = c->q16.p;
+    const unsigned qgrid = (unsigned)std::min<uint64_t>(((uint64_t)a.nq * a.dim + 255) / 256, 4096);
+    if (tf32) queries_scale_f32_kernel<<<qgrid, 256, 0, st>>>(a.q32, a.qinv, a.nq, a.dim, c->q16.as<float>());
+    else queries_to_f16_kernel<<<qgrid, 256, 0, st>>>(a.q32, a.qinv, a.nq, a.dim, c->q16.as<__half>());
 
     static const int ctas_env = [] { const char* e = getenv("YAMS_B200_UMMA_CTAS"); return e ? atoi(e) : 1; }();
     const int ctas = (ctas_env == 1 || c->dev->sm_count < 2) ? 1 : 2;
@@ -598,21 +637,24 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     u.nqt = (a.nq + u.n_tile - 1) / u.n_tile;
     const uint32_t rows_per_unit = UM_BLOCK_M * ctas;
     u.nrt = (uint32_t)((a.nrows + rows_per_unit - 1) / rows_per_unit);
-    u.kblocks = (a.dim + UM_BLOCK_K - 1) / UM_BLOCK_K;
+    u.tf32 = tf32 ? 1u : 0u;
+    u.block_k = UM_BLOCK_K_BYTES / esz;
+    u.kblocks = (a.dim + u.block_k - 1) / u.block_k;
     u.b_stage = (u.n_tile / ctas) * 128;
     uint32_t stage_bytes = UM_A_STAGE + u.b_stage;
     if (u.nqt > 32 || (size_t)u.nqt * u.n_tile > 4096) return YAMS_ERR_UNSUPPORTED;   // thresholds live in shared memory
     const uint32_t budget = 224 * 1024 - (uint32_t)(32 * 4 + 16 + (((size_t)u.nqt * u.n_tile + 31) & ~(size_t)31) * 4 + 4 * UM_EPI_CAP * sizeof(EpiEntry)) - 2048;
     u.stages = std::min<uint32_t>(8, budget / stage_bytes);
     if (u.stages < 2) return YAMS_ERR_UNSUPPORTED;
-    // instruction descriptor: D=f32, A=B=f16, both K-major, N = n_tile, M = 128 per CTA
-    u.idesc = (1u << 4) | ((u.n_tile >> 3) << 17) | (((UM_BLOCK_M * ctas) >> 4) << 24);
+    // instruction descriptor: D=f32 (bits 4-5), A/B format (bits 7-9 / 10-12: 0 = f16, 2 = tf32), both K-major,
+    // N = n_tile (bits 17-22, /8), M = 128 per CTA (bits 24-28, /16)
+    u.idesc = (1u << 4) | (tf32 ? ((2u << 7) | (2u << 10)) : 0u) | ((u.n_tile >> 3) << 17) | (((UM_BLOCK_M * ctas) >> 4) << 24);
 
     CUtensorMap tmA, tmB;
-    const uint8_t* a_base = reinterpret_cast<const uint8_t*>(a.rows) + (size_t)a.row_start * a.dim * 2;
-    if (!make_map_2d(&tmA, a_base, a.dim, a.nrows, (uint64_t)a.row_stride * a.dim * 2, UM_BLOCK_K, UM_BLOCK_M))
+    const uint8_t* a_base = reinterpret_cast<const uint8_t*>(a.rows) + (size_t)a.row_start * a.dim * esz;
+    if (!make_map_2d(&tmA, a_base, a.dim, a.nrows, (uint64_t)a.row_stride * a.dim * esz, u.block_k, UM_BLOCK_M, tf32))
         return YAMS_ERR_UNSUPPORTED;
-    if (!make_map_2d(&tmB, d_q16, a.dim, a.nq, (uint64_t)a.dim * 2, UM_BLOCK_K, u.n_tile / ctas)) return YAMS_ERR_UNSUPPORTED;
+    if (!make_map_2d(&tmB, d_q16, a.dim, a.nq, (uint64_t)a.dim * esz, u.block_k, u.n_tile / ctas, tf32)) return YAMS_ERR_UNSUPPORTED;
 
     const size_t epi_bytes = 32 * 4 + 16 + (((size_t)u.nqt * u.n_tile + 31) & ~(size_t)31) * 4 + 4 * UM_EPI_CAP * sizeof(EpiEntry);
     size_t smem = (size_t)u.stages * stage_bytes + 1024 /*align slack*/ + (2 * u.stages + 4) * 8 + 16 + epi_bytes;
