@@ -348,7 +348,7 @@ def main():
         scan_s = (tm["scan_kernel_ms"] or tm["stage1_ms"]) / 1e3
         ach_tf = flops / scan_s / 1e12
         hbm_ach = n * d * esz / scan_s / 1e9
-        traffic = load_traffic().get("stage1_umma_kernel")
+        traffic = None if f32 else load_traffic().get("stage1_umma_kernel")   # the ncu capture is of the fp16 C2 launch
         # which roof binds this batch size (tensor above Q ~ 250, HBM below)
         # tf32 MMAs run at half the fp16/bf16 rate: the measured bf16 peak is halved for an fp32 corpus
         tensor_peak = peaks["bf16_tflops"] * (0.5 if f32 else 1.0)
