@@ -112,6 +112,17 @@ YAMS_B200_API void yams_b200_cdc_default_config(yams_cdc_config* cfg);
 YAMS_B200_API yams_status_t yams_b200_chunk_and_hash(void* self, const uint8_t* data, size_t len,
                                                      const yams_cdc_config* cfg,
                                                      yams_chunk_desc** out, size_t* out_n);
+/* Many files per call -- the shape of `yams add -r` (one StreamingChunker run per file; the reference spreads files
+ * over ingest workers, src/app/services/indexing_service.cpp, src/api/content_store_impl.cpp:199-220).  Every file is
+ * an independent stream (rolling hash and cut positions restart at its first byte), but the whole batch shares ONE
+ * candidate scan, ONE cut-selection pass and ONE SHA-256 launch, so small files reach the throughput of one large
+ * stream.  files[i] / lens[i]: HOST buffers.  out: plugin-allocated table (free_chunks) with offsets relative to the
+ * owning file; chunks of file i are out[out_first[i] .. out_first[i+1]); out_first holds n_files + 1 entries. */
+YAMS_B200_API yams_status_t yams_b200_chunk_and_hash_batch(void* self, const uint8_t* const* files,
+                                                           const size_t* lens, size_t n_files,
+                                                           const yams_cdc_config* cfg, yams_chunk_desc** out,
+                                                           size_t* out_n, uint64_t* out_first);
+
 YAMS_B200_API void yams_b200_free_chunks(void* self, yams_chunk_desc* chunks, size_t n);
 
 /* Same with the input already resident in HBM (device pointer). Results come back on the host. */
@@ -202,6 +213,9 @@ typedef struct yams_content_ingest_v1 {
                                   uint8_t* digests);
     yams_status_t (*dedup_stats)(void* self, const yams_chunk_desc* chunks, size_t n,
                                  yams_dedup_stats* out);
+    yams_status_t (*chunk_and_hash_batch)(void* self, const uint8_t* const* files, const size_t* lens,
+                                          size_t n_files, const yams_cdc_config* cfg, yams_chunk_desc** out,
+                                          size_t* out_n, uint64_t* out_first);
     yams_status_t (*digest_set_create)(void* self, uint64_t capacity_hint, yams_b200_digest_set** out);
     yams_status_t (*digest_set_insert)(yams_b200_digest_set* s, const uint8_t* digests, size_t stride,
                                        size_t n, uint8_t* out_existed, uint64_t* out_new);

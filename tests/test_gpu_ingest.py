@@ -252,7 +252,7 @@ def test_digest_set_matches_sequential_exists_store_loop(Y, oracle):
     # chunk tables go in directly (stride = sizeof(yams_chunk_desc)); agrees with calculateDeduplication
     block = oracle.gen_bytes(5, 0, 1 << 20)
     data = np.concatenate([block, block, oracle.gen_bytes(6, 0, 1 << 19), block])
-    ch = Y.chunk_and_hash(data, Y.default_config(min_chunk_size=2048, max_chunk_size=32768, chunk_mask=0x3FF))
+    ch = Y.chunk_and_hash(data, Y.default_config(min_chunk=2048, max_chunk=32768, mask=0x3FF))
     s = Y.DigestSet(capacity_hint=16)
     existed, new = s.insert(ch)
     st = Y.dedup_stats(ch)
@@ -261,3 +261,67 @@ def test_digest_set_matches_sequential_exists_store_loop(Y, oracle):
     existed2, new2 = s.insert(ch)
     assert new2 == 0 and np.all(existed2 == 1)
     s.close()
+
+
+def _batch_files(O):
+    rng = np.random.default_rng(23)
+    sizes = [0, 1, 47, 48, 49, 100, 4095, 4096, 16383, 16384, 16385, 65536, (1 << 20) + 3, 0, 5 << 20, 333_333]
+    files = []
+    for i, n in enumerate(sizes):
+        kind = i % 4
+        if kind == 0:
+            files.append(O.gen_bytes(100 + i, 0, n))
+        elif kind == 1:
+            files.append(np.full(n, 0x42, dtype=np.uint8))                                   # no candidates at all
+        elif kind == 2:
+            files.append(((np.arange(n, dtype=np.uint64) * 1315423911 + 0x9E3779B9) & 0xFF).astype(np.uint8))   # reference pattern
+        else:
+            files.append(rng.integers(0, 256, size=n, dtype=np.uint8))
+    files.append(files[12].copy())                                                           # a repeated file
+    return files
+
+
+def _check_batch(Y, O, files, cfg):
+    got = Y.chunk_and_hash_batch(files, cfg)
+    assert len(got) == len(files)
+    for i, f in enumerate(files):
+        off, size, dig = O.cdc_chunk(f, cfg)
+        g = got[i]
+        assert len(g) == len(off), (i, len(f), len(g), len(off))
+        assert np.array_equal(g["offset"], off) and np.array_equal(g["size"], size), (i, len(f))
+        assert np.array_equal(g["digest"], dig), (i, len(f))
+
+
+def test_chunk_and_hash_batch_equals_per_file_reference(Y, oracle):
+    """Every file of a batch is an independent stream: identical to chunking + hashing the files one by one
+    (rabin_chunker.cpp:120-152 / streaming_chunker.h:146-204 per file)."""
+    O = oracle
+    files = _batch_files(O)
+    for variant in (Y.STREAMING, Y.RABIN):
+        _check_batch(Y, O, files, Y.default_config(variant))
+        _check_batch(Y, O, files, Y.default_config(variant, min_chunk=64, max_chunk=1024, mask=0x3F))
+        _check_batch(Y, O, files, Y.default_config(variant, min_chunk=4096, max_chunk=65536))
+    _check_batch(Y, O, files, Y.default_config(Y.STREAMING, min_chunk=2048, max_chunk=512))      # min >= max: forced cuts only
+    _check_batch(Y, O, files, Y.default_config(Y.STREAMING, min_chunk=0, max_chunk=4096, mask=0xFF))
+    assert Y.chunk_and_hash_batch([], Y.default_config()) == []
+    one = Y.chunk_and_hash_batch([files[12]], Y.default_config())
+    assert np.array_equal(one[0], Y.chunk_and_hash(files[12], Y.default_config()))
+
+
+def test_chunk_and_hash_batch_group_splitting(oracle):
+    """A 1 MiB staging budget forces several groups and sends the larger files through the streaming path."""
+    import subprocess, sys, os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys; sys.path.insert(0, %r)\n"
+        "import numpy as np, yams_b200 as Y\n"
+        "from oracle import oracle as O\n"
+        "from tests.test_gpu_ingest import _batch_files, _check_batch\n"
+        "assert Y.plugin_init() == 0\n"
+        "files = _batch_files(O) * 2\n"
+        "_check_batch(Y, O, files, Y.default_config())\n"
+        "_check_batch(Y, O, files, Y.default_config(Y.RABIN, min_chunk=256, max_chunk=8192, mask=0xFF))\n"
+        "print('BATCH OK')\n" % root)
+    env = dict(os.environ, YAMS_B200_BATCH_MIB="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert "BATCH OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

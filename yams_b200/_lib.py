@@ -65,6 +65,8 @@ SYMBOLS = {
     "yams_b200_sha256_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p, C.c_size_t, u8p]),
     "yams_b200_sha256_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p, C.c_size_t, u8p]),
     "yams_b200_chunk_boundaries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CdcConfig), _descpp, _szp]),
+    "yams_b200_chunk_and_hash_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t,
+                                                 C.POINTER(CdcConfig), C.POINTER(C.POINTER(ChunkDesc)), C.POINTER(C.c_size_t), u64p]),
     "yams_b200_digest_set_create": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "yams_b200_digest_set_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, u64p]),
     "yams_b200_digest_set_contains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
@@ -153,6 +155,8 @@ def default_config(variant: int = STREAMING, **kw) -> CdcConfig:
     lib().yams_b200_cdc_default_config(C.byref(cfg))
     cfg.variant = variant
     for k, v in kw.items():
+        if k not in {f[0] for f in CdcConfig._fields_}:
+            raise TypeError(f"unknown CdcConfig field {k!r}")
         setattr(cfg, k, v)
     return cfg
 
@@ -185,6 +189,23 @@ def chunk_and_hash(data, cfg: Optional[CdcConfig] = None) -> np.ndarray:
     """IChunker::chunkDataLazy over a host buffer -> structured array (offset, size, digest[32])."""
     a = _as_u8(data)
     return _chunks("yams_b200_chunk_and_hash", a.ctypes.data if a.size else None, a.size, cfg or default_config())
+
+
+def chunk_and_hash_batch(files, cfg: Optional[CdcConfig] = None):
+    """Many files in one call (`yams add -r`): -> list of per-file chunk tables (offsets relative to each file)."""
+    arrs = [_as_u8(f) for f in files]
+    n = len(arrs)
+    ptrs = (C.c_void_p * max(n, 1))(*[a.ctypes.data if a.size else None for a in arrs])
+    lens = (C.c_size_t * max(n, 1))(*[a.size for a in arrs])
+    first = np.zeros(n + 1, dtype=np.uint64)
+    out_p = C.POINTER(ChunkDesc)()
+    out_n = C.c_size_t(0)
+    c = cfg or default_config()
+    rc = lib().yams_b200_chunk_and_hash_batch(None, ptrs, lens, n, C.byref(c), C.byref(out_p), C.byref(out_n),
+                                              first.ctypes.data_as(u64p))
+    _check(rc, "chunk_and_hash_batch")
+    table = _take(out_p, out_n)
+    return [table[int(first[i]):int(first[i + 1])] for i in range(n)]
 
 
 def chunk_boundaries(data, cfg: Optional[CdcConfig] = None) -> np.ndarray:

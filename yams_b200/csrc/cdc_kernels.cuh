@@ -26,6 +26,29 @@ struct SelectArgs {
 };
 
 
+// Many independent streams ("files") laid out in ONE device buffer: file f occupies buffer positions
+// [starts[f], ends[f]); every file start is preceded by >= 64 zero bytes, so the rolling hash of the buffer equals the
+// hash of the file alone (the reference's ring buffer starts zeroed, chunker.h:150-154).
+struct BatchArgs {
+    const uint64_t* cand;     // ascending candidate positions of the whole buffer
+    uint32_t ncand;
+    const uint64_t* starts;   // ascending
+    const uint64_t* ends;
+    uint32_t nfiles;
+    CdcParams P;
+};
+constexpr uint32_t kBatchTail = 0x80000000u;   // forced[] flag: the node's chunks run to the end of its file
+
+__global__ void batch_nodes_kernel(BatchArgs B, uint64_t* npos, uint32_t* nref, uint32_t* root_node);
+__global__ void batch_next_kernel(BatchArgs B, const uint64_t* npos, const uint32_t* nref, const uint32_t* root_node, uint32_t nnodes,
+                                  uint32_t* next, uint32_t* forced, uint32_t* cnt);
+__global__ void batch_mask_counts_kernel(const uint8_t* onchain, uint32_t* cnt, uint32_t nnodes);
+__global__ void batch_emit_kernel(BatchArgs B, const uint64_t* npos, const uint32_t* next, const uint32_t* forced,
+                                  const uint8_t* onchain, const uint32_t* offsets, uint32_t nnodes, yams_chunk_desc* out);
+__global__ void batch_first_kernel(const uint32_t* root_node, const uint32_t* offsets, uint32_t nfiles, const uint64_t* total,
+                                   uint64_t* first);
+__global__ void batch_rebase_kernel(yams_chunk_desc* descs, uint64_t n, const uint64_t* starts, uint32_t nfiles);
+
 __global__ void cdc_count_kernel(ScanArgs A, uint32_t ntiles, uint32_t* tile_counts);
 __global__ void cdc_write_kernel(ScanArgs A, uint32_t ntiles, const uint32_t* tile_counts,
                                  const uint32_t* tile_offsets, uint64_t* cand);

@@ -41,6 +41,7 @@ struct CdcStream {
     uint32_t two_pass_fallbacks = 0;
     DevBuf table, tile_counts, tile_offsets, cand, cand_tmp, next, forced, exit_, entry, onchain, emit_counts,
         emit_offsets, scan_scratch, descs, scalars;
+    DevBuf npos, nref, roots, fileinfo, first;   // chunk_and_hash_batch: merged node table, file layout, per-file chunk ranges
     HostBuf h_scalars;           // pinned: [0] ncand/ntotal, [1] new chunk start
     uint64_t ndescs = 0;         // chunks accumulated in `descs`
     uint64_t chunk_start = 0;    // stream position where the open chunk starts
@@ -81,7 +82,7 @@ struct CdcStream {
     }
     void destroy() {
         for (DevBuf* b : {&table, &tile_counts, &tile_offsets, &cand, &cand_tmp, &next, &forced, &exit_, &entry, &onchain,
-                          &emit_counts, &emit_offsets, &scan_scratch, &descs, &scalars})
+                          &emit_counts, &emit_offsets, &scan_scratch, &descs, &scalars, &npos, &nref, &roots, &fileinfo, &first})
             b->release();
         h_scalars.release();
         for (auto& e : ev)
@@ -91,17 +92,14 @@ struct CdcStream {
         created = false;
     }
 
-    // Scan stream positions [scan_lo, scan_hi) (bytes readable from `lowest`), select cuts from the
-    // open chunk at chunk_start, append the completed chunks to descs. `data[0]` is stream position
-    // base_pos.  When final, the trailing partial chunk is emitted too.
-    yams_status_t process(const uint8_t* data, uint64_t base_pos, uint64_t lowest, uint64_t scan_lo,
-                          uint64_t scan_hi, bool final) {
+    // Candidate scan of stream positions [scan_lo, scan_hi): the ascending candidate positions land in `cand`,
+    // their number in *ncand_out.  Single pass; dense (adversarial) data falls back to the exact two-pass kernels.
+    yams_status_t scan(const uint8_t* data, uint64_t base_pos, uint64_t lowest, uint64_t scan_lo, uint64_t scan_hi,
+                       uint32_t* ncand_out) {
         yams_status_t rc;
-        const double t_begin = now_ms();
         uint64_t* d_sc = scalars.as<uint64_t>();
         volatile uint64_t* h_sc = h_scalars.as<uint64_t>();
         uint32_t ncand = 0;
-        YB_CUDA(cudaEventRecord(ev[0], st));
         if (!no_candidates && scan_hi > scan_lo) {
             // tiles start at a 16-byte-aligned ADDRESS: normally at or below scan_lo (the positions in
             // [origin, scan_lo) are masked and never dereferenced); when that would fall before stream position
@@ -159,6 +157,22 @@ struct CdcStream {
                 }
             }
         }
+        *ncand_out = ncand;
+        return YAMS_OK;
+    }
+
+    // Scan stream positions [scan_lo, scan_hi) (bytes readable from `lowest`), select cuts from the
+    // open chunk at chunk_start, append the completed chunks to descs. `data[0]` is stream position
+    // base_pos.  When final, the trailing partial chunk is emitted too.
+    yams_status_t process(const uint8_t* data, uint64_t base_pos, uint64_t lowest, uint64_t scan_lo,
+                          uint64_t scan_hi, bool final) {
+        yams_status_t rc;
+        const double t_begin = now_ms();
+        uint64_t* d_sc = scalars.as<uint64_t>();
+        volatile uint64_t* h_sc = h_scalars.as<uint64_t>();
+        uint32_t ncand = 0;
+        YB_CUDA(cudaEventRecord(ev[0], st));
+        if ((rc = scan(data, base_pos, lowest, scan_lo, scan_hi, &ncand)) != YAMS_OK) return rc;
         YB_CUDA(cudaEventRecord(ev[1], st));
         // ---- selection ------------------------------------------------------------------------
         uint32_t nnodes = ncand + 1;
@@ -254,7 +268,12 @@ struct IngestRes {
 
 static std::mutex g_pool_mu;
 static std::vector<IngestRes*> g_pool;
-constexpr size_t kPoolMax = 4;
+// one parked resource set per concurrently ingesting host thread (`yams add` workers); creating/destroying one costs
+// cudaMalloc/cudaFree/cudaMallocHost calls that serialise the whole device
+static size_t pool_max() {
+    static const size_t v = [] { const char* e = getenv("YAMS_B200_POOL_MAX"); long x = e ? atol(e) : 64; return (size_t)(x < 1 ? 1 : x); }();
+    return v;
+}
 
 static yams_status_t acquire_res(const yams_cdc_config* cfg, IngestRes** out) {
     IngestRes* r = nullptr;
@@ -288,7 +307,7 @@ static void release_res(IngestRes* r) {
         if (b->cap > kKeep) b->release();
     {
         std::lock_guard<std::mutex> lk(g_pool_mu);
-        if (g_pool.size() < kPoolMax) {
+        if (g_pool.size() < pool_max()) {
             g_pool.push_back(r);
             return;
         }
@@ -359,6 +378,113 @@ static yams_status_t run_device(const uint8_t* d_data, size_t len, const yams_cd
     }
     release_res(r);
     return rc;
+}
+
+// ---- many files per call ----------------------------------------------------------------------------------------
+// One group = consecutive files whose padded total fits the staging budget.  Layout: every file starts at a
+// 256-byte-aligned buffer position preceded by >= 64 zero bytes (the whole buffer is zeroed first), so ONE candidate
+// scan, ONE selection pass and ONE SHA-256 launch serve every file of the group.
+constexpr uint64_t kBatchGap = 64;
+static uint64_t batch_group_bytes() {
+    static const uint64_t v = [] { const char* e = getenv("YAMS_B200_BATCH_MIB"); long x = e ? atol(e) : 1024; return (uint64_t)(x < 1 ? 1 : x) << 20; }();
+    return v;
+}
+static inline uint64_t batch_padded(uint64_t len) { return (len + kBatchGap + 255) & ~255ull; }
+
+static yams_status_t run_batch_group(IngestRes* r, const uint8_t* const* files, const size_t* lens, size_t f0, size_t f1, bool hash,
+                                     std::vector<yams_chunk_desc>& out, uint64_t* out_first, float* ms_acc) {
+    CdcStream& cs = r->cs;
+    cudaStream_t st = cs.st;
+    yams_status_t rc;
+    const uint32_t nf = (uint32_t)(f1 - f0);
+    std::vector<uint64_t> lay(2 * (size_t)nf);   // starts | ends
+    uint64_t pos = 256;
+    for (uint32_t f = 0; f < nf; ++f) {
+        lay[f] = pos;
+        lay[nf + f] = pos + lens[f0 + f];
+        pos += batch_padded(lens[f0 + f]);
+    }
+    const uint64_t L = pos;
+    if ((rc = r->stage[0].reserve((size_t)L + 256)) != YAMS_OK) return rc;
+    uint8_t* d_buf = r->stage[0].as<uint8_t>();
+    if ((rc = cs.fileinfo.reserve((size_t)nf * 16)) != YAMS_OK) return rc;
+    if ((rc = cs.roots.reserve((size_t)nf * 4)) != YAMS_OK) return rc;
+    if ((rc = cs.first.reserve(((size_t)nf + 1) * 8)) != YAMS_OK) return rc;
+    YB_CUDA(cudaEventRecord(r->e0, st));
+    YB_CUDA(cudaMemsetAsync(d_buf, 0, (size_t)L + 256, st));
+    for (uint32_t f = 0; f < nf; ++f)
+        if (lens[f0 + f]) YB_CUDA(cudaMemcpyAsync(d_buf + lay[f], files[f0 + f], lens[f0 + f], cudaMemcpyHostToDevice, st));
+    YB_CUDA(cudaMemcpyAsync(cs.fileinfo.p, lay.data(), (size_t)nf * 16, cudaMemcpyHostToDevice, st));
+    YB_CUDA(cudaEventRecord(cs.ev[0], st));
+    uint32_t ncand = 0;
+    if ((rc = cs.scan(d_buf, 0, 0, 0, L, &ncand)) != YAMS_OK) return rc;
+    YB_CUDA(cudaEventRecord(cs.ev[1], st));
+    // ---- selection over the merged node table ----
+    YB_ARG((uint64_t)ncand + nf < 0xFFFFFFF0ull, "too many nodes in one batch group");
+    const uint32_t nnodes = ncand + nf;
+    const uint32_t nblocks = (nnodes + kNodeBlock - 1) / kNodeBlock;
+    if ((rc = cs.npos.reserve((size_t)nnodes * 8)) != YAMS_OK) return rc;
+    if ((rc = cs.nref.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+    if ((rc = cs.next.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+    if ((rc = cs.forced.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+    if ((rc = cs.exit_.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+    if ((rc = cs.entry.reserve((size_t)nblocks * 4)) != YAMS_OK) return rc;
+    if ((rc = cs.onchain.reserve((size_t)nnodes)) != YAMS_OK) return rc;
+    if ((rc = cs.emit_counts.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+    if ((rc = cs.emit_offsets.reserve((size_t)nnodes * 4)) != YAMS_OK) return rc;
+    if (!cs.cand.p && (rc = cs.cand.reserve(8)) != YAMS_OK) return rc;
+    uint64_t* d_sc = cs.scalars.as<uint64_t>();
+    volatile uint64_t* h_sc = cs.h_scalars.as<uint64_t>();
+    BatchArgs B{cs.cand.as<uint64_t>(), ncand, cs.fileinfo.as<uint64_t>(), cs.fileinfo.as<uint64_t>() + nf, nf, cs.P};
+    const uint32_t tgrid = (nnodes + 255) / 256;
+    batch_nodes_kernel<<<tgrid, 256, 0, st>>>(B, cs.npos.as<uint64_t>(), cs.nref.as<uint32_t>(), cs.roots.as<uint32_t>());
+    batch_next_kernel<<<tgrid, 256, 0, st>>>(B, cs.npos.as<uint64_t>(), cs.nref.as<uint32_t>(), cs.roots.as<uint32_t>(), nnodes,
+                                             cs.next.as<uint32_t>(), cs.forced.as<uint32_t>(), cs.emit_counts.as<uint32_t>());
+    cdc_exit_kernel<<<nblocks, 32, 0, st>>>(cs.next.as<uint32_t>(), nnodes, cs.exit_.as<uint32_t>());
+    YB_CUDA(cudaMemsetAsync(cs.entry.p, 0xFF, (size_t)nblocks * 4, st));
+    YB_CUDA(cudaMemsetAsync(cs.onchain.p, 0, (size_t)nnodes, st));
+    cdc_walk_kernel<<<1, 32, 0, st>>>(cs.exit_.as<uint32_t>(), nnodes, cs.entry.as<uint32_t>());
+    cdc_mark_kernel<<<nblocks, 32, 0, st>>>(cs.next.as<uint32_t>(), nnodes, cs.entry.as<uint32_t>(), cs.onchain.as<uint8_t>());
+    batch_mask_counts_kernel<<<tgrid, 256, 0, st>>>(cs.onchain.as<uint8_t>(), cs.emit_counts.as<uint32_t>(), nnodes);
+    if ((rc = exclusive_scan_u32(cs.emit_counts.as<uint32_t>(), cs.emit_offsets.as<uint32_t>(), nnodes, d_sc + 0, cs.scan_scratch,
+                                 st)) != YAMS_OK)
+        return rc;
+    YB_CUDA(cudaMemcpyAsync((void*)h_sc, d_sc, 8, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    const uint64_t nnew = h_sc[0];
+    YB_ARG(nnew < 0xFFFFFFFFull, "too many chunks in one batch group");
+    if ((rc = cs.descs.reserve((size_t)(nnew + 1) * sizeof(yams_chunk_desc))) != YAMS_OK) return rc;
+    batch_emit_kernel<<<tgrid, 256, 0, st>>>(B, cs.npos.as<uint64_t>(), cs.next.as<uint32_t>(), cs.forced.as<uint32_t>(),
+                                             cs.onchain.as<uint8_t>(), cs.emit_offsets.as<uint32_t>(), nnodes,
+                                             cs.descs.as<yams_chunk_desc>());
+    batch_first_kernel<<<(nf + 1 + 255) / 256, 256, 0, st>>>(cs.roots.as<uint32_t>(), cs.emit_offsets.as<uint32_t>(), nf, d_sc + 0,
+                                                             cs.first.as<uint64_t>());
+    YB_CUDA(cudaEventRecord(cs.ev[2], st));
+    if (hash && nnew) {
+        if ((rc = launch_sha256_chunks(d_buf, 0, cs.descs.as<yams_chunk_desc>(), 0, (uint32_t)nnew,
+                                       reinterpret_cast<unsigned int*>(d_sc + 4), cs.dev->sm_count, st)) != YAMS_OK)
+            return rc;
+    }
+    YB_CUDA(cudaEventRecord(cs.ev[3], st));
+    if (nnew) batch_rebase_kernel<<<(unsigned)((nnew + 255) / 256), 256, 0, st>>>(cs.descs.as<yams_chunk_desc>(), nnew,
+                                                                               cs.fileinfo.as<uint64_t>(), nf);
+    YB_CUDA(cudaGetLastError());
+    const size_t base = out.size();
+    out.resize(base + (size_t)nnew);
+    std::vector<uint64_t> first((size_t)nf + 1);
+    if (nnew) YB_CUDA(cudaMemcpyAsync(out.data() + base, cs.descs.p, (size_t)nnew * sizeof(yams_chunk_desc), cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaMemcpyAsync(first.data(), cs.first.p, ((size_t)nf + 1) * 8, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaEventRecord(r->e1, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    if (out_first)
+        for (uint32_t f = 0; f <= nf; ++f) out_first[f0 + f] = base + first[f];
+    float a = 0, b = 0, c = 0, d = 0;
+    cudaEventElapsedTime(&a, cs.ev[0], cs.ev[1]);
+    cudaEventElapsedTime(&b, cs.ev[1], cs.ev[2]);
+    cudaEventElapsedTime(&c, cs.ev[2], cs.ev[3]);
+    cudaEventElapsedTime(&d, r->e0, r->e1);
+    ms_acc[0] += a; ms_acc[1] += b; ms_acc[2] += c; ms_acc[3] += d;
+    return YAMS_OK;
 }
 
 }  // namespace yb
@@ -560,6 +686,63 @@ yams_status_t yams_b200_chunk_and_hash_device(void* self, const uint8_t* d_data,
     YB_ARG(d_data || len == 0, "d_data is null");
     YB_ARG(cfg, "cfg is null");
     return run_device(d_data, len, cfg, true, out, out_n);
+}
+
+yams_status_t yams_b200_chunk_and_hash_batch(void* self, const uint8_t* const* files, const size_t* lens, size_t n_files,
+                                             const yams_cdc_config* cfg, yams_chunk_desc** out, size_t* out_n, uint64_t* out_first) {
+    (void)self;
+    YB_ARG(out && out_n, "out / out_n is null");
+    *out = nullptr;
+    *out_n = 0;
+    YB_ARG(cfg, "cfg is null");
+    if (out_first) out_first[0] = 0;
+    if (n_files == 0) return YAMS_OK;
+    YB_ARG(files && lens && out_first, "null argument");
+    for (size_t f = 0; f < n_files; ++f) YB_ARG(files[f] || lens[f] == 0, "a file pointer is null");
+    IngestRes* r = nullptr;
+    yams_status_t rc = acquire_res(cfg, &r);
+    if (rc != YAMS_OK) return rc;
+    std::vector<yams_chunk_desc> all;
+    float ms[4] = {0, 0, 0, 0};
+    const uint64_t budget = batch_group_bytes();
+    size_t f = 0;
+    while (f < n_files && rc == YAMS_OK) {
+        if (batch_padded(lens[f]) + 256 > budget) {
+            // a file larger than a whole group goes through the streaming path on its own
+            yams_chunk_desc* d = nullptr;
+            size_t n = 0;
+            rc = run_host(files[f], lens[f], cfg, true, &d, &n);
+            if (rc == YAMS_OK) {
+                out_first[f] = all.size();
+                all.insert(all.end(), d, d + n);
+                out_first[f + 1] = all.size();
+                free(d);
+                for (int i = 0; i < 4; ++i) ms[i] += g_last_ms[i];
+            }
+            ++f;
+            continue;
+        }
+        size_t g = f;
+        uint64_t tot = 256;
+        while (g < n_files && tot + batch_padded(lens[g]) <= budget) tot += batch_padded(lens[g++]);
+        rc = run_batch_group(r, files, lens, f, g, true, all, out_first, ms);
+        f = g;
+    }
+    release_res(r);
+    if (rc != YAMS_OK) return rc;
+    for (int i = 0; i < 4; ++i) g_last_ms[i] = ms[i];
+    g_last_ms[4] = g_last_ms[5] = g_last_ms[6] = g_last_ms[7] = 0;
+    if (!all.empty()) {
+        yams_chunk_desc* h = static_cast<yams_chunk_desc*>(malloc(all.size() * sizeof(yams_chunk_desc)));
+        if (!h) {
+            set_last_error("out of host memory for %llu chunk descriptors", (unsigned long long)all.size());
+            return YAMS_ERR_INTERNAL;
+        }
+        memcpy(h, all.data(), all.size() * sizeof(yams_chunk_desc));
+        *out = h;
+        *out_n = all.size();
+    }
+    return YAMS_OK;
 }
 
 void yams_b200_free_chunks(void* self, yams_chunk_desc* chunks, size_t n) {
