@@ -284,8 +284,9 @@ def _batch_files(O):
 def _check_batch(Y, O, files, cfg):
     got = Y.chunk_and_hash_batch(files, cfg)
     assert len(got) == len(files)
+    ocfg = O.CdcConfig(cfg.window_size, cfg.min_chunk, cfg.max_chunk, cfg.polynomial, cfg.mask, cfg.variant)
     for i, f in enumerate(files):
-        off, size, dig = O.cdc_chunk(f, cfg)
+        off, size, dig = O.cdc_chunk(f, ocfg)
         g = got[i]
         assert len(g) == len(off), (i, len(f), len(g), len(off))
         assert np.array_equal(g["offset"], off) and np.array_equal(g["size"], size), (i, len(f))
@@ -303,6 +304,9 @@ def test_chunk_and_hash_batch_equals_per_file_reference(Y, oracle):
         _check_batch(Y, O, files, Y.default_config(variant, min_chunk=4096, max_chunk=65536))
     _check_batch(Y, O, files, Y.default_config(Y.STREAMING, min_chunk=2048, max_chunk=512))      # min >= max: forced cuts only
     _check_batch(Y, O, files, Y.default_config(Y.STREAMING, min_chunk=0, max_chunk=4096, mask=0xFF))
+    small = [f[:3000] for f in files]
+    _check_batch(Y, O, small, Y.default_config(Y.STREAMING, min_chunk=0, max_chunk=700, mask=0x0))          # every position is a candidate
+    _check_batch(Y, O, small, Y.default_config(Y.RABIN, min_chunk=5, max_chunk=900, mask=0x0, window_size=7))
     assert Y.chunk_and_hash_batch([], Y.default_config()) == []
     one = Y.chunk_and_hash_batch([files[12]], Y.default_config())
     assert np.array_equal(one[0], Y.chunk_and_hash(files[12], Y.default_config()))
