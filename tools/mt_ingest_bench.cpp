@@ -29,6 +29,33 @@ int main(int argc, char** argv) {
         yams_chunk_desc* d = nullptr; size_t n = 0;
         for (int i = 0; i < 3; ++i) { yams_b200_chunk_and_hash(nullptr, bufs[0].data(), bytes, &cfg, &d, &n); yams_b200_free_chunks(nullptr, d, n); }
     }
+    if (argc > 4 && !strcmp(argv[4], "batch")) {
+        // one chunk_and_hash_batch call over threads * calls files (the same buffers reused as distinct files)
+        size_t nfiles = (size_t)threads * calls;
+        std::vector<const uint8_t*> ptrs(nfiles);
+        std::vector<size_t> lens(nfiles, bytes);
+        for (size_t i = 0; i < nfiles; ++i) ptrs[i] = bufs[i % threads].data();
+        std::vector<uint64_t> first(nfiles + 1);
+        double best = 1e30;
+        size_t nchunks = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            yams_chunk_desc* d = nullptr; size_t n = 0;
+            double a = now_ms();
+            if (yams_b200_chunk_and_hash_batch(nullptr, ptrs.data(), lens.data(), nfiles, &cfg, &d, &n, first.data()) != YAMS_OK) {
+                fprintf(stderr, "batch failed: %s\n", yams_b200_last_error());
+                return 3;
+            }
+            double dt = now_ms() - a;
+            if (dt < best) best = dt;
+            nchunks = n;
+            yams_b200_free_chunks(nullptr, d, n);
+        }
+        float ms[8];
+        yams_b200_ingest_last_timings(nullptr, ms);
+        printf("| %zu KiB | batch of %zu files | %.3f ms per call | %.0f files/s | %.2f GB/s | %zu chunks | scan %.3f select %.3f sha %.3f dev-total %.3f |\n",
+               bytes >> 10, nfiles, best, nfiles / (best / 1e3), (double)bytes * nfiles / best / 1e6, nchunks, ms[0], ms[1], ms[2], ms[3]);
+        return 0;
+    }
     std::vector<double> tmax(threads, 0), tsum(threads, 0);
     std::vector<std::vector<float>> last(threads, std::vector<float>(8, 0.f));
     std::atomic<int> errors{0};

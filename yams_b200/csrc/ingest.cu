@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <chrono>
 #include <mutex>
+#include <thread>
 #include <new>
 #include <vector>
 
@@ -236,6 +237,8 @@ struct IngestRes {
     cudaEvent_t copied[2] = {nullptr, nullptr};
     cudaEvent_t freed[2] = {nullptr, nullptr};
     cudaEvent_t t0 = nullptr, t1 = nullptr, e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    HostBuf pin[2];                                   // batch path: pinned images of two device-buffer slices
+    cudaEvent_t pin_done[2] = {nullptr, nullptr};     // H2D copy out of pin[b] finished
     bool created = false;
     yams_status_t create() {
         if (created) return YAMS_OK;
@@ -247,6 +250,7 @@ struct IngestRes {
             YB_CUDA(cudaEventCreateWithFlags(&freed[b], cudaEventDisableTiming));
         }
         for (cudaEvent_t* e : {&t0, &t1, &e0, &e1, &e2}) YB_CUDA(cudaEventCreate(e));
+        for (int b = 0; b < 2; ++b) YB_CUDA(cudaEventCreateWithFlags(&pin_done[b], cudaEventDisableTiming));
         created = true;
         return YAMS_OK;
     }
@@ -258,8 +262,10 @@ struct IngestRes {
             if (copied[b]) cudaEventDestroy(copied[b]);
             if (freed[b]) cudaEventDestroy(freed[b]);
         }
-        for (cudaEvent_t e : {t0, t1, e0, e1, e2})
+        for (cudaEvent_t e : {t0, t1, e0, e1, e2, pin_done[0], pin_done[1]})
             if (e) cudaEventDestroy(e);
+        pin[0].release();
+        pin[1].release();
         if (copy_st) cudaStreamDestroy(copy_st);
         cs.destroy();
         created = false;
@@ -380,6 +386,59 @@ static yams_status_t run_device(const uint8_t* d_data, size_t len, const yams_cd
     return rc;
 }
 
+// Upload from ordinary (pageable) host memory.  A plain cudaMemcpy moves pageable memory at ~10 GB/s through the
+// driver's single staging thread; here host threads assemble each slice of the destination in one of two pinned buffers
+// (fill(dst, lo, hi) writes the image of destination bytes [lo, hi)) while the previous slice is on the wire.
+static uint64_t stage_slice_bytes() {
+    static const uint64_t v = [] { const char* e = getenv("YAMS_B200_STAGE_MIB"); long x = e ? atol(e) : 32; return (uint64_t)(x < 1 ? 1 : x) << 20; }();
+    return v;
+}
+static unsigned stage_threads() {
+    static const unsigned v = [] {
+        const char* e = getenv("YAMS_B200_STAGE_THREADS");
+        long x = e ? atol(e) : (long)std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+        return (unsigned)(x < 1 ? 1 : (x > 64 ? 64 : x));
+    }();
+    return v;
+}
+template <typename Fill>
+static yams_status_t staged_upload(IngestRes* r, uint8_t* d_dst, uint64_t total, const Fill& fill, cudaStream_t st) {
+    if (total == 0) return YAMS_OK;
+    yams_status_t rc;
+    const uint64_t S = std::min<uint64_t>(stage_slice_bytes(), (total + 255) & ~255ull);
+    for (int b = 0; b < 2; ++b)
+        if ((rc = r->pin[b].reserve((size_t)S)) != YAMS_OK) return rc;
+    const unsigned T = total < (4u << 20) ? 1u : stage_threads();
+    int b = 0;
+    for (uint64_t lo = 0; lo < total; lo += S, b ^= 1) {
+        const uint64_t hi = std::min<uint64_t>(total, lo + S);
+        YB_CUDA(cudaEventSynchronize(r->pin_done[b]));   // the copy that last used this pinned buffer has finished
+        uint8_t* img = r->pin[b].as<uint8_t>();
+        if (T == 1) {
+            fill(img, lo, hi);
+        } else {
+            std::vector<std::thread> th;
+            const uint64_t part = (((hi - lo) + T - 1) / T + 4095) & ~4095ull;
+            for (unsigned t = 0; t < T; ++t) {
+                uint64_t a = lo + (uint64_t)t * part, e = std::min<uint64_t>(hi, a + part);
+                if (a < e) th.emplace_back([&fill, img, lo, a, e] { fill(img + (a - lo), a, e); });
+            }
+            for (auto& x : th) x.join();
+        }
+        YB_CUDA(cudaMemcpyAsync(d_dst + lo, img, (size_t)(hi - lo), cudaMemcpyHostToDevice, st));
+        YB_CUDA(cudaEventRecord(r->pin_done[b], st));
+    }
+    return YAMS_OK;
+}
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return a.type == cudaMemoryTypeUnregistered;
+}
+
 // ---- many files per call ----------------------------------------------------------------------------------------
 // One group = consecutive files whose padded total fits the staging budget.  Layout: every file starts at a
 // 256-byte-aligned buffer position preceded by >= 64 zero bytes (the whole buffer is zeroed first), so ONE candidate
@@ -411,9 +470,29 @@ static yams_status_t run_batch_group(IngestRes* r, const uint8_t* const* files, 
     if ((rc = cs.roots.reserve((size_t)nf * 4)) != YAMS_OK) return rc;
     if ((rc = cs.first.reserve(((size_t)nf + 1) * 8)) != YAMS_OK) return rc;
     YB_CUDA(cudaEventRecord(r->e0, st));
-    YB_CUDA(cudaMemsetAsync(d_buf, 0, (size_t)L + 256, st));
-    for (uint32_t f = 0; f < nf; ++f)
-        if (lens[f0 + f]) YB_CUDA(cudaMemcpyAsync(d_buf + lay[f], files[f0 + f], lens[f0 + f], cudaMemcpyHostToDevice, st));
+    // Upload: the files sit in ordinary (pageable) host memory, which a plain cudaMemcpy moves at ~10 GB/s through
+    // the driver's single staging thread.  Instead, host threads assemble an exact image of each 32 MiB slice of the
+    // device buffer (file bytes + zero gaps) in one of two pinned buffers while the previous slice is on the wire.
+    {
+        auto fill = [&](uint8_t* dst, uint64_t lo, uint64_t hi) {   // image of buffer positions [lo, hi)
+            // first file whose end lies beyond lo
+            uint32_t f = (uint32_t)(std::upper_bound(lay.begin() + nf, lay.begin() + 2 * (size_t)nf, lo) - (lay.begin() + nf));
+            uint64_t p = lo;
+            while (p < hi) {
+                if (f < nf && lay[f] <= p) {   // inside file f
+                    uint64_t e = std::min<uint64_t>(hi, lay[nf + f]);
+                    if (e > p) memcpy(dst + (p - lo), files[f0 + f] + (p - lay[f]), (size_t)(e - p));
+                    p = std::max(p, e);
+                    if (p >= lay[nf + f]) ++f;
+                } else {                       // gap up to the next file start (or the end of the buffer)
+                    uint64_t e = std::min<uint64_t>(hi, f < nf ? lay[f] : hi);
+                    memset(dst + (p - lo), 0, (size_t)(e - p));
+                    p = e;
+                }
+            }
+        };
+        if ((rc = staged_upload(r, d_buf, L + 256, fill, st)) != YAMS_OK) return rc;
+    }
     YB_CUDA(cudaMemcpyAsync(cs.fileinfo.p, lay.data(), (size_t)nf * 16, cudaMemcpyHostToDevice, st));
     YB_CUDA(cudaEventRecord(cs.ev[0], st));
     uint32_t ncand = 0;
@@ -564,13 +643,21 @@ static yams_status_t session_feed(yams_b200_ingest* s, const uint8_t* data, size
         return YAMS_OK;
     }
     auto slice_len = [&](size_t i) { return (size_t)std::min<uint64_t>(kFeedSlice, (uint64_t)len - i * kFeedSlice); };
+    const bool pageable = len >= (4u << 20) && is_pageable(data);
     auto issue_copy = [&](size_t i, int b) -> yams_status_t {
         size_t sl = slice_len(i);
         yams_status_t rr = r->stage[b].reserve((size_t)s->head + sl + 64);
         if (rr != YAMS_OK) return rr;
         YB_CUDA(cudaStreamWaitEvent(r->copy_st, r->freed[b], 0));
-        YB_CUDA(cudaMemcpyAsync(r->stage[b].as<uint8_t>() + s->head, data + i * kFeedSlice, sl,
-                                cudaMemcpyHostToDevice, r->copy_st));
+        const uint8_t* src = data + i * kFeedSlice;
+        if (pageable && sl >= (4u << 20)) {
+            // ordinary host memory: pinned double-buffered upload filled by host threads (see staged_upload)
+            auto fill = [src](uint8_t* dst, uint64_t lo, uint64_t hi) { memcpy(dst, src + lo, (size_t)(hi - lo)); };
+            yams_status_t ur = staged_upload(r, r->stage[b].as<uint8_t>() + s->head, sl, fill, r->copy_st);
+            if (ur != YAMS_OK) return ur;
+        } else {
+            YB_CUDA(cudaMemcpyAsync(r->stage[b].as<uint8_t>() + s->head, src, sl, cudaMemcpyHostToDevice, r->copy_st));
+        }
         YB_CUDA(cudaEventRecord(r->copied[b], r->copy_st));
         return YAMS_OK;
     };
