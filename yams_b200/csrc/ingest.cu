@@ -390,7 +390,7 @@ static yams_status_t run_device(const uint8_t* d_data, size_t len, const yams_cd
 // driver's single staging thread; here host threads assemble each slice of the destination in one of two pinned buffers
 // (fill(dst, lo, hi) writes the image of destination bytes [lo, hi)) while the previous slice is on the wire.
 static uint64_t stage_slice_bytes() {
-    static const uint64_t v = [] { const char* e = getenv("YAMS_B200_STAGE_MIB"); long x = e ? atol(e) : 32; return (uint64_t)(x < 1 ? 1 : x) << 20; }();
+    static const uint64_t v = [] { const char* e = getenv("YAMS_B200_STAGE_MIB"); long x = e ? atol(e) : 64; return (uint64_t)(x < 1 ? 1 : x) << 20; }();
     return v;
 }
 static unsigned stage_threads() {
