@@ -100,6 +100,19 @@ int main() {
     CHECK(cs.size() == 2 && hits.size() == 1 && hits[0].chunk_id == "c4");
     CHECK(computeCosineSimilarity({1, 2, 3}, {1, 2, 3, 4}) == 0.0);
     CHECK(std::fabs(computeCosineSimilarity({1, 0}, {1, 1}) - 0.70710678118654757) < 1e-15);
+    // ---- many buffers in one device pass == one chunkDataLazy per buffer ----
+    {
+        std::vector<std::span<const std::byte>> many;
+        const size_t cuts[] = {0, 1, 100000, 100000, 1500000, data.size()};
+        for (size_t i = 0; i + 1 < sizeof(cuts) / sizeof(cuts[0]); ++i) many.emplace_back(data.data() + cuts[i], cuts[i + 1] - cuts[i]);
+        auto res = chunker.chunkManyLazy(many);
+        CHECK(res.size() == many.size());
+        for (size_t i = 0; i < many.size(); ++i) {
+            auto want = chunker.chunkDataLazy(many[i]);
+            CHECK(res[i].size() == want.size());
+            for (size_t j = 0; j < want.size(); ++j) CHECK(res[i][j].offset == want[j].offset && res[i][j].size == want[j].size && res[i][j].hash == want[j].hash);
+        }
+    }
     // ---- dedup accounting + the exists/store loop over repeated content ----
     {
         std::vector<std::byte> twice(data.begin(), data.end());

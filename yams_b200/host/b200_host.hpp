@@ -65,6 +65,27 @@ public:
     std::vector<Chunk> chunkData(std::span<const std::byte> data) { return run(data, false); }
     std::vector<Chunk> chunkDataLazy(std::span<const std::byte> data) { return run(data, true); }
 
+    // Many buffers in one device pass (`yams add -r`): result[i] == chunkDataLazy(buffers[i]).
+    std::vector<std::vector<Chunk>> chunkManyLazy(const std::vector<std::span<const std::byte>>& buffers) {
+        std::vector<const uint8_t*> ptrs(buffers.size());
+        std::vector<size_t> lens(buffers.size());
+        for (size_t i = 0; i < buffers.size(); ++i) {
+            ptrs[i] = reinterpret_cast<const uint8_t*>(buffers[i].data());
+            lens[i] = buffers[i].size();
+        }
+        std::vector<uint64_t> first(buffers.size() + 1, 0);
+        yams_cdc_config c = cfg();
+        yams_chunk_desc* d = nullptr;
+        size_t n = 0;
+        yams_status_t st = yams_b200_chunk_and_hash_batch(nullptr, ptrs.data(), lens.data(), buffers.size(), &c, &d, &n, first.data());
+        if (st != YAMS_OK) throw_status("chunk_and_hash_batch", st);
+        std::vector<std::vector<Chunk>> out(buffers.size());
+        static const std::vector<std::byte> none;
+        for (size_t i = 0; i < buffers.size(); ++i) append(out[i], d + first[i], (size_t)(first[i + 1] - first[i]), none, true);
+        yams_b200_free_chunks(nullptr, d, n);
+        return out;
+    }
+
     // streaming_chunker.cpp:71-90 / streaming_chunker.h:78-121: 64 KiB reads fed to a session
     std::vector<Chunk> chunkFile(const std::filesystem::path& path) {
         std::ifstream file(path, std::ios::binary);
