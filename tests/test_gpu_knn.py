@@ -496,3 +496,34 @@ def test_fp32_corpus_tf32_engine_vs_oracle(Y, oracle):
         assert list(got2[0][qi][:wc[qi]]) == list(wr[qi][:wc[qi]]) and np.array_equal(got2[1][qi][:wc[qi]], ws[qi][:wc[qi]])
     c.close()
     c2.close()
+
+
+def test_concurrent_searches_on_one_corpus(Y, oracle):
+    """The reference backend is shared by daemon worker threads (shared_mutex around the scan,
+    sqlite_vec_backend.cpp:1433-1568): concurrent callers on one corpus must each get their own answer."""
+    import threading
+    O = oracle
+    n, d = 120_000, 64
+    c = Y.Corpus(d, Y.F16, Y.COSINE)
+    c.append_synthetic(42, 0, n)
+    batches = [O.gen_rows_f32(50 + t, 0, 5 + t, d) for t in range(6)]
+    want = [c.search(b, 10) for b in batches]
+    got = [None] * len(batches)
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(20):
+                got[i] = c.search(batches[i], 10)
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(len(batches))]
+    for th in ts:
+        th.start()
+    for th in ts:
+        th.join()
+    assert not errs
+    for i in range(len(batches)):
+        assert np.array_equal(got[i][0], want[i][0]) and np.array_equal(got[i][1], want[i][1])
+    c.close()

@@ -1250,6 +1250,7 @@ void yams_b200_corpus_destroy(yams_b200_corpus* c) {
 
 yams_status_t yams_b200_corpus_append(yams_b200_corpus* c, const void* rows, uint64_t n, const int64_t* rowids) {
     YB_ARG(c, "corpus is null");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     if (n == 0) return YAMS_OK;
     YB_ARG(rows, "rows is null");
     YB_ARG(c->n + n < 0xFFFFFFFFull, "corpus is limited to 2^32-1 rows per GPU");
@@ -1262,6 +1263,7 @@ yams_status_t yams_b200_corpus_append(yams_b200_corpus* c, const void* rows, uin
 
 yams_status_t yams_b200_corpus_append_f32_as_f16(yams_b200_corpus* c, const float* rows, uint64_t n, const int64_t* rowids) {
     YB_ARG(c, "corpus is null");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_ARG(c->dtype == YAMS_B200_F16, "corpus is not fp16");
     if (n == 0) return YAMS_OK;
     YB_ARG(rows, "rows is null");
@@ -1278,6 +1280,7 @@ yams_status_t yams_b200_corpus_append_f32_as_f16(yams_b200_corpus* c, const floa
 
 yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t seed, uint64_t first_row, uint64_t n) {
     YB_ARG(c, "corpus is null");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     if (n == 0) return YAMS_OK;
     YB_ARG(c->n + n < 0xFFFFFFFFull, "corpus is limited to 2^32-1 rows per GPU");
     yams_status_t rc = corpus_reserve(c, c->n + n);
@@ -1305,6 +1308,7 @@ yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t se
 
 yams_status_t yams_b200_corpus_remove(yams_b200_corpus* c, const int64_t* rowids, uint64_t n, uint64_t* out_removed) {
     YB_ARG(c, "corpus is null");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     if (out_removed) *out_removed = 0;
     if (n == 0 || c->n == 0) return YAMS_OK;
     YB_ARG(rowids, "rowids is null");
@@ -1346,6 +1350,7 @@ yams_status_t yams_b200_corpus_remove(yams_b200_corpus* c, const int64_t* rowids
 
 yams_status_t yams_b200_corpus_clear(yams_b200_corpus* c) {
     YB_ARG(c, "corpus is null");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     c->n = 0;
     c->last_rowid = INT64_MIN;
     c->rowids_dense = true;
@@ -1360,6 +1365,7 @@ yams_status_t yams_b200_corpus_size(const yams_b200_corpus* c, uint64_t* out_n) 
 
 yams_status_t yams_b200_corpus_sync(yams_b200_corpus* c) {
     YB_ARG(c, "corpus is null");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_CUDA(cudaStreamSynchronize(c->st));
     return YAMS_OK;
 }
@@ -1391,6 +1397,7 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
                                const int64_t* allowed_rowids, const uint64_t* allowed_offsets, int64_t* out_rowids,
                                float* out_scores, uint32_t* out_counts, uint64_t* out_flags) {
     YB_ARG(c, "corpus is null");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     if (nq == 0) return YAMS_OK;
     YB_ARG(queries && out_counts, "null argument");
     YB_ARG(!allowed_rowids || allowed_offsets, "allowed_offsets missing");
@@ -1502,6 +1509,7 @@ yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, const float* qu
                                             const int64_t* allowed_rowids, uint64_t n_allowed, int64_t* out_rowids,
                                             float* out_scores, uint64_t* out_count) {
     YB_ARG(c && query && out_count, "null argument");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     *out_count = 0;
     YB_ARG(c->metric == YAMS_B200_COSINE, "all-matching selection is defined for the cosine scan");
     // the reference gathers the candidate rowids into a set (:4412-4448): duplicates count once
@@ -1572,6 +1580,7 @@ yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, const float* qu
 yams_status_t yams_b200_search_device(yams_b200_corpus* c, const float* d_queries, uint32_t nq, uint32_t k, float threshold,
                                       int64_t* d_out_rowids, float* d_out_scores) {
     YB_ARG(c && d_queries && d_out_rowids && d_out_scores, "null argument");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_ARG(k > 0 && k <= 768, "k must be in 1..768");
     if (nq == 0) return YAMS_OK;
     yams_status_t rc;
@@ -1594,6 +1603,7 @@ yams_status_t yams_b200_merge_partials_device(yams_b200_corpus* c, const int64_t
                                               uint32_t nranks, uint32_t nq, uint32_t k, int64_t* d_out_rowids,
                                               float* d_out_scores, uint32_t* d_out_counts) {
     YB_ARG(c && d_rowids && d_scores && d_out_rowids && d_out_scores, "null argument");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_ARG(nranks >= 1 && k >= 1, "bad shape");
     uint32_t total = nranks * k, np2 = 1;
     while (np2 < total) np2 <<= 1;
@@ -1623,6 +1633,7 @@ yams_status_t yams_b200_search_last_timings(yams_b200_corpus* c, float out_ms[8]
 yams_status_t yams_b200_debug_stage1_scores(yams_b200_corpus* c, const float* queries, uint32_t nq, int engine,
                                             uint64_t row_start, uint64_t row_stride, uint64_t nrows, float* out) {
     YB_ARG(c && queries && out && nq > 0 && nrows > 0 && row_stride > 0, "bad argument");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_ARG(row_start + (nrows - 1) * row_stride < c->n, "rows out of range");
     yams_status_t rc;
     if ((rc = prepare_queries(c, queries, false, nq)) != YAMS_OK) return rc;

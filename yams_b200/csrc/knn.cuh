@@ -1,5 +1,7 @@
 // knn.cuh -- shared declarations of the exact vector scan (vector_scan_v1).
 #pragma once
+#include <mutex>
+
 #include "common.cuh"
 
 namespace yb {
@@ -29,6 +31,7 @@ struct Corpus {
     cudaEvent_t ev_scan[2] = {nullptr, nullptr};  // around the full-corpus filtered scan launch
     bool scan_timed = false;
     float last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    std::mutex mu;   // public entry points on one corpus are serialised (the workspace buffers are per corpus)
     size_t elem() const { return dtype == YAMS_B200_F16 ? 2 : 4; }
 };
 
