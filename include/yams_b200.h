@@ -159,6 +159,12 @@ YAMS_B200_API yams_status_t yams_b200_chunk_boundaries(void* self, const uint8_t
                                                        const yams_cdc_config* cfg,
                                                        yams_chunk_desc** out, size_t* out_n);
 
+/* SHA-256 of n SEPARATE host messages in one device pass (IContentHasher::hash per span, hasher.h:14-46;
+ * ChunkValidator::validateChunks hashes chunks fetched one by one, src/integrity/chunk_validator.cpp:173-213).
+ * digests: n x 32 bytes. */
+YAMS_B200_API yams_status_t yams_b200_sha256_many(void* self, const uint8_t* const* msgs, const size_t* lens,
+                                                  size_t n, uint8_t* digests);
+
 /* calculateDeduplication (src/chunking/rabin_chunker.cpp:224-239): unique-hash accounting over a chunk table.
  * A chunk is "unique" the first time its digest appears.  chunks: HOST array (as returned by chunk_and_hash). */
 typedef struct yams_dedup_stats {
@@ -216,6 +222,8 @@ typedef struct yams_content_ingest_v1 {
     yams_status_t (*chunk_and_hash_batch)(void* self, const uint8_t* const* files, const size_t* lens,
                                           size_t n_files, const yams_cdc_config* cfg, yams_chunk_desc** out,
                                           size_t* out_n, uint64_t* out_first);
+    yams_status_t (*sha256_many)(void* self, const uint8_t* const* msgs, const size_t* lens, size_t n,
+                                 uint8_t* digests);
     yams_status_t (*digest_set_create)(void* self, uint64_t capacity_hint, yams_b200_digest_set** out);
     yams_status_t (*digest_set_insert)(yams_b200_digest_set* s, const uint8_t* digests, size_t stride,
                                        size_t n, uint8_t* out_existed, uint64_t* out_new);

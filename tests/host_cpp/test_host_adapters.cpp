@@ -113,6 +113,18 @@ int main() {
             for (size_t j = 0; j < want.size(); ++j) CHECK(res[i][j].offset == want[j].offset && res[i][j].size == want[j].size && res[i][j].hash == want[j].hash);
         }
     }
+    // ---- validateChunks: re-hash stored chunks, flag the corrupted one ----
+    {
+        std::vector<std::pair<std::span<const std::byte>, std::string>> stored;
+        for (size_t i = 0; i < std::min<size_t>(full.size(), 40); ++i) stored.emplace_back(std::span<const std::byte>(full[i].data), full[i].hash);
+        std::vector<std::byte> bad(full[3].data);
+        bad[bad.size() / 2] ^= std::byte{0x01};
+        stored[3].first = std::span<const std::byte>(bad);
+        auto rep = validateChunks(stored);
+        CHECK(rep.size() == stored.size());
+        for (size_t i = 0; i < rep.size(); ++i) CHECK(rep[i].isValid == (i != 3));
+        CHECK(rep[3].errorMessage.rfind("Hash mismatch", 0) == 0);
+    }
     // ---- dedup accounting + the exists/store loop over repeated content ----
     {
         std::vector<std::byte> twice(data.begin(), data.end());

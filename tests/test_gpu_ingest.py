@@ -329,3 +329,16 @@ def test_chunk_and_hash_batch_group_splitting(oracle):
     env = dict(os.environ, YAMS_B200_BATCH_MIB="1")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert "BATCH OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_sha256_many_separate_messages(Y, oracle):
+    """IContentHasher::hash over separately held spans / ChunkValidator::validateChunks (chunk_validator.cpp:173-213)."""
+    O = oracle
+    rng = np.random.default_rng(31)
+    sizes = [0, 1, 55, 56, 63, 64, 65, 119, 120, 1000, 0, 65536, (1 << 20) + 7, 5 << 20, 3]
+    msgs = [rng.integers(0, 256, size=n, dtype=np.uint8) for n in sizes]
+    got = Y.sha256_many(msgs)
+    for i, m in enumerate(msgs):
+        assert bytes(got[i]) == O.sha256(m), (i, sizes[i])
+    assert Y.sha256_many([]).shape == (0, 32)
+    assert bytes(Y.sha256_many([b"abc"])[0]).hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"

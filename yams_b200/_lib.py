@@ -67,6 +67,7 @@ SYMBOLS = {
     "yams_b200_chunk_boundaries": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(CdcConfig), _descpp, _szp]),
     "yams_b200_chunk_and_hash_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t,
                                                  C.POINTER(CdcConfig), C.POINTER(C.POINTER(ChunkDesc)), C.POINTER(C.c_size_t), u64p]),
+    "yams_b200_sha256_many": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_void_p]),
     "yams_b200_digest_set_create": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     "yams_b200_digest_set_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, u64p]),
     "yams_b200_digest_set_contains": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]),
@@ -206,6 +207,18 @@ def chunk_and_hash_batch(files, cfg: Optional[CdcConfig] = None):
     _check(rc, "chunk_and_hash_batch")
     table = _take(out_p, out_n)
     return [table[int(first[i]):int(first[i + 1])] for i in range(n)]
+
+
+def sha256_many(messages) -> np.ndarray:
+    """SHA-256 of separate host buffers in one device pass -> uint8[n, 32]."""
+    arrs = [_as_u8(m) for m in messages]
+    n = len(arrs)
+    out = np.zeros((n, 32), dtype=np.uint8)
+    if n:
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data if a.size else None for a in arrs])
+        lens = (C.c_size_t * n)(*[a.size for a in arrs])
+        _check(lib().yams_b200_sha256_many(None, ptrs, lens, n, out.ctypes.data), "sha256_many")
+    return out
 
 
 def chunk_boundaries(data, cfg: Optional[CdcConfig] = None) -> np.ndarray:

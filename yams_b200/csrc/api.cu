@@ -160,6 +160,7 @@ int yams_plugin_init(const char* config_json, const void* host_context) {
     g_ingest_vt.sha256_batch = yams_b200_sha256_batch;
     g_ingest_vt.dedup_stats = yams_b200_dedup_stats;
     g_ingest_vt.chunk_and_hash_batch = yams_b200_chunk_and_hash_batch;
+    g_ingest_vt.sha256_many = yams_b200_sha256_many;
     g_ingest_vt.digest_set_create = yams_b200_digest_set_create;
     g_ingest_vt.digest_set_insert = yams_b200_digest_set_insert;
     g_ingest_vt.digest_set_contains = yams_b200_digest_set_contains;

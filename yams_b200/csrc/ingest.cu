@@ -940,6 +940,82 @@ yams_status_t yams_b200_sha256_batch(void* self, const uint8_t* base, size_t bas
     return rc;
 }
 
+// Many separate messages (IContentHasher::hash per span, ChunkValidator::validateChunks): packed 16-byte aligned into
+// the pooled staging buffer by the pinned upload path, hashed by one launch per <= 1 GiB group.
+yams_status_t yams_b200_sha256_many(void* self, const uint8_t* const* msgs, const size_t* lens, size_t n, uint8_t* digests) {
+    (void)self;
+    if (n == 0) return YAMS_OK;
+    YB_ARG(msgs && lens && digests, "null argument");
+    for (size_t i = 0; i < n; ++i) YB_ARG(msgs[i] || lens[i] == 0, "a message pointer is null");
+    yams_cdc_config cfg;
+    yams_b200_cdc_default_config(&cfg);
+    IngestRes* r = nullptr;
+    yams_status_t rc = acquire_res(&cfg, &r);
+    if (rc != YAMS_OK) return rc;
+    CdcStream& cs = r->cs;
+    cudaStream_t st = cs.st;
+    const uint64_t budget = batch_group_bytes();
+    size_t i0 = 0;
+    while (i0 < n && rc == YAMS_OK) {
+        // group [i0, i1): packed size within the budget (a single larger message forms its own group)
+        size_t i1 = i0;
+        uint64_t tot = 0;
+        std::vector<yams_chunk_desc> h;
+        while (i1 < n && (i1 == i0 || tot + lens[i1] + 16 <= budget) && h.size() < 0xFFFFFFF0ull) {
+            yams_chunk_desc d{};
+            d.offset = tot;
+            d.size = lens[i1];
+            h.push_back(d);
+            tot = (tot + lens[i1] + 15) & ~15ull;
+            ++i1;
+        }
+        const size_t m = i1 - i0;
+        rc = r->stage[0].reserve((size_t)tot + 256);
+        if (rc == YAMS_OK) rc = cs.descs.reserve(m * sizeof(yams_chunk_desc));
+        if (rc != YAMS_OK) break;
+        uint8_t* d_buf = r->stage[0].as<uint8_t>();
+        auto fill = [&](uint8_t* dst, uint64_t lo, uint64_t hi) {
+            // first message whose packed range ends beyond lo
+            size_t a = 0, b = m;
+            while (a < b) {
+                size_t mid = a + ((b - a) >> 1);
+                if (h[mid].offset + h[mid].size <= lo) a = mid + 1; else b = mid;
+            }
+            uint64_t p = lo;
+            for (size_t j = a; j < m && p < hi; ++j) {
+                if (h[j].offset > p) {   // alignment padding
+                    uint64_t e = std::min<uint64_t>(hi, h[j].offset);
+                    memset(dst + (p - lo), 0, (size_t)(e - p));
+                    p = e;
+                }
+                uint64_t e = std::min<uint64_t>(hi, h[j].offset + h[j].size);
+                if (e > p) {
+                    memcpy(dst + (p - lo), msgs[i0 + j] + (p - h[j].offset), (size_t)(e - p));
+                    p = e;
+                }
+            }
+            if (p < hi) memset(dst + (p - lo), 0, (size_t)(hi - p));
+        };
+        rc = staged_upload(r, d_buf, tot, fill, st);
+        if (rc != YAMS_OK) break;
+        cudaError_t e = cudaMemcpyAsync(cs.descs.p, h.data(), m * sizeof(yams_chunk_desc), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            rc = launch_sha256_chunks(d_buf, 0, cs.descs.as<yams_chunk_desc>(), 0, (uint32_t)m,
+                                      reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4), cs.dev->sm_count, st);
+        if (rc == YAMS_OK && e == cudaSuccess) e = cudaMemcpyAsync(h.data(), cs.descs.p, m * sizeof(yams_chunk_desc), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_last_error("sha256_many failed: %s", cudaGetErrorString(e));
+            rc = YAMS_ERR_INTERNAL;
+        }
+        if (rc == YAMS_OK)
+            for (size_t j = 0; j < m; ++j) memcpy(digests + 32 * (i0 + j), h[j].digest, 32);
+        i0 = i1;
+    }
+    release_res(r);
+    return rc;
+}
+
 yams_status_t yams_b200_dedup_stats(void* self, const yams_chunk_desc* chunks, size_t n, yams_dedup_stats* out) {
     (void)self;
     YB_ARG(out, "out is null");

@@ -216,9 +216,48 @@ public:
         return out;
     }
 
+    // separately held spans (no common base buffer): one device pass
+    static std::vector<std::string> hashSpans(const std::vector<std::span<const std::byte>>& spans) {
+        std::vector<const uint8_t*> ptrs(spans.size());
+        std::vector<size_t> lens(spans.size());
+        for (size_t i = 0; i < spans.size(); ++i) {
+            ptrs[i] = reinterpret_cast<const uint8_t*>(spans[i].data());
+            lens[i] = spans[i].size();
+        }
+        std::vector<uint8_t> dg(spans.size() * 32);
+        yams_status_t st = yams_b200_sha256_many(nullptr, ptrs.data(), lens.data(), spans.size(), dg.data());
+        if (st != YAMS_OK) throw_status("sha256_many", st);
+        std::vector<std::string> out(spans.size());
+        for (size_t i = 0; i < spans.size(); ++i) out[i] = bytesToHex(dg.data() + 32 * i, 32);
+        return out;
+    }
+
 private:
     std::vector<std::byte> buf_;
 };
+
+// ChunkValidator::validateChunks (src/integrity/chunk_validator.cpp:173-213): every chunk is re-hashed and compared
+// with the hash it is stored under.  One device pass instead of maxParallelValidations worker threads.
+struct ChunkValidationResult {   // include/yams/integrity/chunk_validator.h (fields used by callers)
+    std::string chunkHash;
+    bool isValid = false;
+    std::string errorMessage;
+    size_t chunkSize = 0;
+};
+inline std::vector<ChunkValidationResult> validateChunks(const std::vector<std::pair<std::span<const std::byte>, std::string>>& chunks) {
+    std::vector<std::span<const std::byte>> spans;
+    spans.reserve(chunks.size());
+    for (const auto& c : chunks) spans.push_back(c.first);
+    auto actual = B200ContentHasher::hashSpans(spans);
+    std::vector<ChunkValidationResult> out(chunks.size());
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        out[i].chunkHash = chunks[i].second;
+        out[i].chunkSize = chunks[i].first.size();
+        out[i].isValid = actual[i] == chunks[i].second;
+        if (!out[i].isValid) out[i].errorMessage = "Hash mismatch: expected " + chunks[i].second + ", got " + actual[i];
+    }
+    return out;
+}
 
 // The part of IVectorStore the hot path covers.  Records live in SQLite in the real backend; here a record is
 // (rowid, chunk_id) and `relevance_score` -- enough to express the tie-break contract of
