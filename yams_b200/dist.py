@@ -29,3 +29,17 @@ def allgather_partials(part_rowids, part_scores):
         dist.all_gather(ls, part_scores.contiguous())
         all_r, all_s = torch.stack(lr), torch.stack(ls)
     return all_r, all_s
+
+
+def split_allowed(allowed, rowid_lo: int, rowid_hi: int):
+    """Candidate sets on a row-sharded corpus: every rank keeps, of each query's ascending
+    allowed-rowid list, the part that falls into its own rowid range [rowid_lo, rowid_hi).  The per-rank partial
+    top-k are then gathered and merged exactly like the unfiltered scan."""
+    import numpy as np
+    out = []
+    for a in allowed:
+        a = np.asarray(a, dtype=np.int64)
+        lo = int(np.searchsorted(a, rowid_lo, side="left"))
+        hi = int(np.searchsorted(a, rowid_hi, side="left"))
+        out.append(a[lo:hi])
+    return out
