@@ -443,6 +443,22 @@ def main():
                         "roofline": ing["roofline"], "e2e": ing["e2e"], "gpu_launches": ing["gpu_launches"]})
             if "cpu_baseline" in ing:
                 out["cpu_baseline"] = ing["cpu_baseline"]
+        # side measurement, N=1 only, never allowed to break the line above: many small files through the batch entry
+        # (host buffers in ordinary pageable memory, chunk tables out) -- the shape of `yams add -r`
+        if rank == 0 and world == 1:
+            try:
+                nfiles, fsz = 4096, 64 << 10
+                pool = buf[: 64 * fsz].cpu().numpy().reshape(64, fsz)
+                files = [np.array(pool[i % 64], copy=True) for i in range(nfiles)]
+                Y.chunk_and_hash_batch(files[:64], cfg)
+                t0 = time.perf_counter()
+                tables = Y.chunk_and_hash_batch(files, cfg)
+                dt = time.perf_counter() - t0
+                ing["small_files_batch"] = {"files": nfiles, "file_bytes": fsz, "files_per_s": nfiles / dt, "gb_per_s": nfiles * fsz / dt / 1e9,
+                                            "chunks": int(sum(len(t) for t in tables)),
+                                            "note": "one chunk_and_hash_batch call, pageable host buffers, wall clock incl. upload and result copy"}
+            except Exception as e:   # noqa: BLE001
+                ing["small_files_batch"] = {"error": repr(e)[:200]}
         out["ingest"] = ing
         del buf
 

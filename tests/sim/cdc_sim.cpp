@@ -140,4 +140,88 @@ size_t sim_candidates(const uint8_t* data, size_t n, uint64_t window, uint64_t p
         }
     return cnt;
 }
+
+// Emulates chunk_and_hash_batch's device pass (ingest.cu run_batch_group): the files are laid out in one zeroed buffer
+// (256-byte aligned starts, >= 64 zero bytes in front of each), ONE candidate pass over the whole buffer, the merged
+// node table, the shared chain kernels, per-node emission.  out_first[f] = index of file f's first chunk.
+size_t sim_chunk_batch(const uint8_t* const* files, const size_t* lens, size_t nfiles, uint64_t window, uint64_t minc,
+                       uint64_t maxc, uint64_t poly, uint64_t mask, int variant, uint64_t* out_offsets, uint64_t* out_sizes,
+                       size_t cap, uint64_t* out_first) {
+    Params pr;
+    if (!resolve(window, minc, maxc, poly, mask, variant, &pr)) return (size_t)-1;
+    const CdcParams& P = pr.P;
+    const uint32_t nf = (uint32_t)nfiles;
+    std::vector<uint64_t> starts(nf), ends(nf);
+    uint64_t pos = 256;
+    for (uint32_t f = 0; f < nf; ++f) {
+        starts[f] = pos;
+        ends[f] = pos + lens[f];
+        pos += (lens[f] + 64 + 255) & ~255ull;
+    }
+    const uint64_t L = pos;
+    std::vector<uint8_t> buf((size_t)L + 256, 0);
+    for (uint32_t f = 0; f < nf; ++f)
+        if (lens[f]) memcpy(buf.data() + starts[f], files[f], lens[f]);
+    ByteView view{buf.data(), 0, 0};
+    std::vector<uint64_t> cand;
+    if (!pr.no_candidates)
+        for (uint64_t p = 0; p < L; ++p)
+            if (is_candidate(view, pr.T, P, p)) cand.push_back(p);
+    const uint32_t ncand = (uint32_t)cand.size();
+    uint64_t dummy = 0;
+    BatchLayout B{cand.empty() ? &dummy : cand.data(), ncand, starts.data(), ends.data(), nf};
+    const uint32_t nnodes = ncand + nf;
+    std::vector<uint64_t> npos(nnodes);
+    std::vector<uint32_t> nref(nnodes), root_node(nf), next(nnodes), forced(nnodes), cnt(nnodes), exit_(nnodes);
+    for (uint32_t j = 0; j < ncand; ++j) {
+        uint32_t node = batch_node_of_cand(B, j);
+        npos[node] = cand[j] + 1;
+        nref[node] = j;
+    }
+    for (uint32_t f = 0; f < nf; ++f) {
+        uint32_t node = batch_node_of_root(B, f);
+        npos[node] = starts[f];
+        nref[node] = kBatchRootFlag | f;
+        root_node[f] = node;
+    }
+    for (uint32_t i = 0; i < nnodes; ++i) {
+        BatchNext r = batch_next(B, P, i, npos[i], nref[i], root_node.data(), nnodes);
+        if (r.next <= i) return (size_t)-2;   // the chain must move forward
+        next[i] = r.next;
+        forced[i] = r.forced;
+        cnt[i] = r.count;
+    }
+    uint32_t nblocks = (nnodes + kNodeBlock - 1) / kNodeBlock;
+    for (uint32_t b = 0; b < nblocks; ++b) {
+        uint32_t bs = b * kNodeBlock, be = bs + kNodeBlock < nnodes ? bs + kNodeBlock : nnodes;
+        block_exit_seq(next.data() + bs, bs, be, exit_.data() + bs);
+    }
+    std::vector<uint32_t> entry(nblocks, kNoEntry);
+    for (uint32_t cur = 0; cur < nnodes; cur = exit_[cur]) entry[cur / kNodeBlock] = cur;
+    std::vector<uint8_t> onchain(nnodes, 0);
+    for (uint32_t b = 0; b < nblocks; ++b) {
+        uint32_t bs = b * kNodeBlock, be = bs + kNodeBlock < nnodes ? bs + kNodeBlock : nnodes;
+        if (entry[b] != kNoEntry) block_mark_seq(next.data() + bs, bs, be, entry[b], onchain.data() + bs);
+    }
+    std::vector<uint64_t> offsets(nnodes + 1, 0);
+    for (uint32_t i = 0; i < nnodes; ++i) offsets[i + 1] = offsets[i] + (onchain[i] ? cnt[i] : 0);
+    const size_t total = (size_t)offsets[nnodes];
+    for (uint32_t f = 0; f < nf; ++f) {
+        if (!onchain[root_node[f]]) return (size_t)-3;   // every root lies on the chain
+        out_first[f] = offsets[root_node[f]];
+    }
+    out_first[nf] = total;
+    for (uint32_t i = 0; i < nnodes; ++i) {
+        if (!onchain[i]) continue;
+        uint64_t base = offsets[i];
+        batch_emit(B, P, npos[i], forced[i], next[i] < nnodes ? npos[next[i]] : 0ull, [&](uint64_t k, uint64_t off, uint64_t size) {
+            uint32_t fup = upper_bound_u64(starts.data(), nf, off);
+            if (base + k < cap) {
+                out_offsets[base + k] = off - starts[fup - 1];   // batch_rebase_kernel
+                out_sizes[base + k] = size;
+            }
+        });
+    }
+    return total;
+}
 }

@@ -25,6 +25,9 @@ def sim():
     L.sim_chunk.restype = C.c_size_t
     L.sim_chunk.argtypes = [u8p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
                             C.c_size_t, u64p, u64p, C.c_size_t]
+    L.sim_chunk_batch.restype = C.c_size_t
+    L.sim_chunk_batch.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64,
+                                  C.c_uint64, C.c_uint64, C.c_int, u64p, u64p, C.c_size_t, u64p]
     L.sim_candidates.restype = C.c_size_t
     L.sim_candidates.argtypes = [u8p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, u64p, C.c_size_t]
     return L
@@ -86,3 +89,47 @@ def test_sim_many_candidates_cross_blocks(sim, oracle):
     for slice_ in (0, 100000):
         offs, sizes = run_sim(sim, O, data, cfg, slice_)
         assert np.array_equal(offs, want[0]) and np.array_equal(sizes, want[1])
+
+
+def test_sim_batch_of_files_equals_per_file_oracle(sim, oracle):
+    """chunk_and_hash_batch's selection logic (merged node table, dead links in the gaps, per-file tails) on the CPU."""
+    O = oracle
+    rng = np.random.default_rng(123)
+    for trial in range(25):
+        nfiles = int(rng.integers(1, 12))
+        files = []
+        for f in range(nfiles):
+            n = int(rng.choice([0, 1, 47, 48, 49, 500, 4096, int(rng.integers(0, 60000))]))
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                files.append(O.gen_bytes(int(rng.integers(1, 1 << 30)), 0, n))
+            elif kind == 1:
+                files.append(np.full(n, int(rng.choice([0x00, 0x42, 0xC5])), dtype=np.uint8))
+            else:
+                d = O.gen_bytes(int(rng.integers(1, 1 << 30)), 0, n)
+                if n:
+                    d[rng.integers(0, n, size=max(1, n // 30))] = 0xC5
+                files.append(d)
+        minc, maxc = int(rng.integers(0, 3000)), int(rng.integers(0, 9000))
+        variant = trial % 2
+        if variant == 1 and minc == 0 and maxc == 0:
+            maxc = 1
+        cfg = O.default_config(variant=variant, min_chunk=minc, max_chunk=maxc, window_size=int(rng.integers(0, 49)),
+                               mask=int(rng.choice([0x0, 0x3F, 0xFF, 0x1FFF, 0x303, 0x8000000000000001])))
+        if cfg.mask == 0:
+            files = [f[:3000] for f in files]
+        total = sum(f.size for f in files)
+        cap = total + 16 * nfiles + 16
+        offs = np.empty(cap, dtype=np.uint64)
+        sizes = np.empty(cap, dtype=np.uint64)
+        first = np.zeros(nfiles + 1, dtype=np.uint64)
+        ptrs = (C.c_void_p * nfiles)(*[f.ctypes.data if f.size else None for f in files])
+        lens = (C.c_size_t * nfiles)(*[f.size for f in files])
+        n = sim.sim_chunk_batch(ptrs, lens, nfiles, cfg.window_size, cfg.min_chunk, cfg.max_chunk, cfg.polynomial, cfg.mask,
+                                cfg.variant, O._p(offs, O.u64p), O._p(sizes, O.u64p), cap, O._p(first, O.u64p))
+        assert n < 2**63, (trial, n)
+        assert int(first[nfiles]) == n
+        for f in range(nfiles):
+            want = O.cdc_chunk(files[f], cfg, hash=False)
+            a, b = int(first[f]), int(first[f + 1])
+            assert np.array_equal(offs[a:b], want[0]) and np.array_equal(sizes[a:b], want[1]), (trial, f, files[f].size, minc, maxc, variant)

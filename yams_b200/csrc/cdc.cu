@@ -653,34 +653,18 @@ __global__ void cdc_emit_kernel(SelectArgs S, const uint32_t* __restrict__ next,
     }
 }
 
-// ---- cut selection over a batch of files (chunk_and_hash_batch) --------------------------------------------------
-// Nodes = file roots + candidate cuts, merged by buffer position (a root sorts before a candidate at the same
-// position).  next[] keeps the single-stream shape (strictly increasing), so cdc_exit/walk/mark are reused unchanged:
-// the chain runs root(0) -> cuts of file 0 -> root(1) -> ...; nodes lying in a gap or at a file's end are "dead"
-// (emit nothing, next = node + 1) and hand the chain over to the next root.
-__device__ __forceinline__ uint32_t upper_bound_u64(const uint64_t* a, uint32_t n, uint64_t key) {   // first idx with a[idx] > key
-    uint32_t lo = 0, hi = n;
-    while (lo < hi) {
-        uint32_t mid = lo + ((hi - lo) >> 1);
-        if (a[mid] <= key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
+// ---- cut selection over a batch of files (chunk_and_hash_batch): thin wrappers over cdc_logic.h ---------------------
 __global__ void batch_nodes_kernel(BatchArgs B, uint64_t* __restrict__ npos, uint32_t* __restrict__ nref, uint32_t* __restrict__ root_node) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < B.ncand) {
-        uint64_t p = B.cand[t] + 1;   // a cut after byte cand[t] starts the next chunk at cand[t] + 1
-        uint32_t node = t + upper_bound_u64(B.starts, B.nfiles, p);
-        npos[node] = p;
+    if (t < B.L.ncand) {
+        uint32_t node = batch_node_of_cand(B.L, t);
+        npos[node] = B.L.cand[t] + 1;   // a cut after byte cand[t] starts the next chunk at cand[t] + 1
         nref[node] = t;
-    } else if (t < B.ncand + B.nfiles) {
-        uint32_t f = t - B.ncand;
-        uint64_t s = B.starts[f];
-        uint32_t before = s == 0 ? 0u : lower_bound_u64(B.cand, 0, B.ncand, s - 1);   // candidates with cand + 1 < s
-        uint32_t node = f + before;
-        npos[node] = s;
-        nref[node] = 0x80000000u | f;
+    } else if (t < B.L.ncand + B.L.nfiles) {
+        uint32_t f = t - B.L.ncand;
+        uint32_t node = batch_node_of_root(B.L, f);
+        npos[node] = B.L.starts[f];
+        nref[node] = kBatchRootFlag | f;
         root_node[f] = node;
     }
 }
@@ -690,28 +674,10 @@ __global__ void batch_next_kernel(BatchArgs B, const uint64_t* __restrict__ npos
                                   uint32_t* __restrict__ forced, uint32_t* __restrict__ cnt) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnodes) return;
-    const uint64_t s = npos[i];
-    const uint32_t ref = nref[i];
-    const uint32_t fup = upper_bound_u64(B.starts, B.nfiles, s);   // files starting at or before s
-    uint32_t nx = i + 1, fo = 0, c = 0;
-    if (fup > 0 && s < B.ends[fup - 1]) {
-        const uint32_t f = fup - 1;
-        const uint64_t e = B.ends[f];
-        uint32_t hint = (ref & 0x80000000u) ? lower_bound_u64(B.cand, 0, B.ncand, s) : ref + 1;
-        NextCut r = next_cut(B.cand, B.ncand, hint, s, B.P);
-        if (r.j < B.ncand && B.cand[r.j] < e) {
-            nx = r.j + upper_bound_u64(B.starts, B.nfiles, B.cand[r.j] + 1);
-            fo = (uint32_t)r.forced;
-            c = fo + 1;
-        } else {
-            nx = f + 1 < B.nfiles ? root_node[f + 1] : nnodes;
-            fo = kBatchTail;
-            c = (uint32_t)((e - s + B.P.force - 1) / B.P.force);   // streaming_chunker.h:115-118: the remainder is emitted too
-        }
-    }
-    next[i] = nx;
-    forced[i] = fo;
-    cnt[i] = c;
+    BatchNext r = batch_next(B.L, B.P, i, npos[i], nref[i], root_node, nnodes);
+    next[i] = r.next;
+    forced[i] = r.forced;
+    cnt[i] = r.count;
 }
 
 __global__ void batch_mask_counts_kernel(const uint8_t* __restrict__ onchain, uint32_t* __restrict__ cnt, uint32_t nnodes) {
@@ -724,32 +690,12 @@ __global__ void batch_emit_kernel(BatchArgs B, const uint64_t* __restrict__ npos
                                   const uint32_t* __restrict__ offsets, uint32_t nnodes, yams_chunk_desc* __restrict__ out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nnodes || !onchain[i]) return;
-    const uint64_t s = npos[i];
-    const uint32_t fo = forced[i];
     yams_chunk_desc* o = out + offsets[i];
-    if (fo & kBatchTail) {
-        const uint32_t fup = upper_bound_u64(B.starts, B.nfiles, s);
-        if (fup == 0) return;
-        const uint64_t e = B.ends[fup - 1];
-        if (s >= e) return;
-        const uint64_t n = (e - s + B.P.force - 1) / B.P.force;
-        for (uint64_t t = 0; t < n; ++t) {
-            uint64_t cs = s + t * B.P.force;
-            o[t].offset = cs;
-            o[t].size = e - cs < B.P.force ? e - cs : B.P.force;
-        }
-    } else {
-        // live node with a candidate cut: `fo` forced chunks, then the chunk that ends at the cut (= start of next[i])
-        const uint32_t fup = upper_bound_u64(B.starts, B.nfiles, s);
-        if (fup == 0 || s >= B.ends[fup - 1]) return;   // dead node
-        for (uint32_t t = 0; t < fo; ++t) {
-            o[t].offset = s + (uint64_t)t * B.P.force;
-            o[t].size = B.P.force;
-        }
-        const uint64_t ls = s + (uint64_t)fo * B.P.force;
-        o[fo].offset = ls;
-        o[fo].size = npos[next[i]] - ls;
-    }
+    const uint32_t nx = next[i];
+    batch_emit(B.L, B.P, npos[i], forced[i], nx < nnodes ? npos[nx] : 0ull, [o](uint64_t k, uint64_t off, uint64_t size) {
+        o[k].offset = off;
+        o[k].size = size;
+    });
 }
 
 __global__ void batch_first_kernel(const uint32_t* __restrict__ root_node, const uint32_t* __restrict__ offsets, uint32_t nfiles,

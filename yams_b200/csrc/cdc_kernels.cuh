@@ -30,14 +30,9 @@ struct SelectArgs {
 // [starts[f], ends[f]); every file start is preceded by >= 64 zero bytes, so the rolling hash of the buffer equals the
 // hash of the file alone (the reference's ring buffer starts zeroed, chunker.h:150-154).
 struct BatchArgs {
-    const uint64_t* cand;     // ascending candidate positions of the whole buffer
-    uint32_t ncand;
-    const uint64_t* starts;   // ascending
-    const uint64_t* ends;
-    uint32_t nfiles;
+    BatchLayout L;            // candidates + file layout (cdc_logic.h)
     CdcParams P;
 };
-constexpr uint32_t kBatchTail = 0x80000000u;   // forced[] flag: the node's chunks run to the end of its file
 
 __global__ void batch_nodes_kernel(BatchArgs B, uint64_t* npos, uint32_t* nref, uint32_t* root_node);
 __global__ void batch_next_kernel(BatchArgs B, const uint64_t* npos, const uint32_t* nref, const uint32_t* root_node, uint32_t nnodes,

@@ -173,4 +173,82 @@ YB_HD uint64_t node_emit_count(uint32_t next_node, uint64_t forced, uint32_t end
     return final ? (rem + P.force - 1) / P.force : rem / P.force;
 }
 
+// ---- many files in one buffer (chunk_and_hash_batch) --------------------------------------------------------------
+// File f occupies buffer positions [starts[f], ends[f]) (ascending, zero gaps of >= 64 bytes in front of every file).
+// Nodes = file roots + candidate cuts merged by position (a root sorts before a candidate at the same position).
+// next[] keeps the single-stream shape (strictly increasing), so block_exit_seq / block_mark_seq are reused: the chain
+// runs root(0) -> cuts of file 0 -> root(1) -> ...; nodes lying in a gap or at a file's end are dead links.
+struct BatchLayout {
+    const uint64_t* cand;     // ascending candidate positions of the whole buffer
+    uint32_t ncand;
+    const uint64_t* starts;
+    const uint64_t* ends;
+    uint32_t nfiles;
+};
+constexpr uint32_t kBatchRootFlag = 0x80000000u;   // nref[]: node is the root of file (nref & 0x7FFFFFFF)
+constexpr uint32_t kBatchTail = 0x80000000u;       // forced[]: the node's chunks run to the end of its file
+
+YB_HD uint32_t upper_bound_u64(const uint64_t* a, uint32_t n, uint64_t key) {   // first idx with a[idx] > key
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (a[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// node index of candidate j (the chunk that starts at cand[j] + 1)
+YB_HD uint32_t batch_node_of_cand(const BatchLayout& B, uint32_t j) { return j + upper_bound_u64(B.starts, B.nfiles, B.cand[j] + 1); }
+// node index of the root of file f
+YB_HD uint32_t batch_node_of_root(const BatchLayout& B, uint32_t f) {
+    uint64_t s = B.starts[f];
+    return f + (s == 0 ? 0u : lower_bound_u64(B.cand, 0, B.ncand, s - 1));   // candidates with cand + 1 < s
+}
+struct BatchNext {
+    uint32_t next;     // node index, nnodes = END
+    uint32_t forced;   // forced chunks before the candidate cut, or kBatchTail
+    uint32_t count;    // chunks this node emits when it is on the chain
+};
+// s = start position of the node, ref = nref[] of the node, root_node[] = node index of every file root
+YB_HD BatchNext batch_next(const BatchLayout& B, const CdcParams& P, uint32_t node, uint64_t s, uint32_t ref, const uint32_t* root_node,
+                           uint32_t nnodes) {
+    BatchNext r;
+    r.next = node + 1;
+    r.forced = 0;
+    r.count = 0;
+    const uint32_t fup = upper_bound_u64(B.starts, B.nfiles, s);   // files starting at or before s
+    if (fup == 0 || s >= B.ends[fup - 1]) return r;                // gap / file end: dead link
+    const uint32_t f = fup - 1;
+    const uint64_t e = B.ends[f];
+    const uint32_t hint = (ref & kBatchRootFlag) ? lower_bound_u64(B.cand, 0, B.ncand, s) : ref + 1;
+    NextCut c = next_cut(B.cand, B.ncand, hint, s, P);
+    if (c.j < B.ncand && B.cand[c.j] < e) {
+        r.next = batch_node_of_cand(B, c.j);
+        r.forced = (uint32_t)c.forced;
+        r.count = r.forced + 1;
+    } else {
+        r.next = f + 1 < B.nfiles ? root_node[f + 1] : nnodes;
+        r.forced = kBatchTail;
+        r.count = (uint32_t)((e - s + P.force - 1) / P.force);   // streaming_chunker.h:115-118: the remainder is emitted too
+    }
+    return r;
+}
+// Chunks of an on-chain node: emit(k, offset, size) for k = 0 .. count-1.  next_pos = start position of next[node].
+template <typename EmitT>
+YB_HD void batch_emit(const BatchLayout& B, const CdcParams& P, uint64_t s, uint32_t forced, uint64_t next_pos, EmitT emit) {
+    const uint32_t fup = upper_bound_u64(B.starts, B.nfiles, s);
+    if (fup == 0 || s >= B.ends[fup - 1]) return;   // dead link
+    if (forced & kBatchTail) {
+        const uint64_t e = B.ends[fup - 1];
+        const uint64_t n = (e - s + P.force - 1) / P.force;
+        for (uint64_t t = 0; t < n; ++t) {
+            uint64_t cs = s + t * P.force;
+            emit(t, cs, e - cs < P.force ? e - cs : P.force);
+        }
+    } else {
+        for (uint32_t t = 0; t < forced; ++t) emit((uint64_t)t, s + (uint64_t)t * P.force, P.force);
+        const uint64_t ls = s + (uint64_t)forced * P.force;
+        emit((uint64_t)forced, ls, next_pos - ls);
+    }
+}
+
 }  // namespace yb

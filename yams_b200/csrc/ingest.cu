@@ -514,7 +514,7 @@ static yams_status_t run_batch_group(IngestRes* r, const uint8_t* const* files, 
     if (!cs.cand.p && (rc = cs.cand.reserve(8)) != YAMS_OK) return rc;
     uint64_t* d_sc = cs.scalars.as<uint64_t>();
     volatile uint64_t* h_sc = cs.h_scalars.as<uint64_t>();
-    BatchArgs B{cs.cand.as<uint64_t>(), ncand, cs.fileinfo.as<uint64_t>(), cs.fileinfo.as<uint64_t>() + nf, nf, cs.P};
+    BatchArgs B{BatchLayout{cs.cand.as<uint64_t>(), ncand, cs.fileinfo.as<uint64_t>(), cs.fileinfo.as<uint64_t>() + nf, nf}, cs.P};
     const uint32_t tgrid = (nnodes + 255) / 256;
     batch_nodes_kernel<<<tgrid, 256, 0, st>>>(B, cs.npos.as<uint64_t>(), cs.nref.as<uint32_t>(), cs.roots.as<uint32_t>());
     batch_next_kernel<<<tgrid, 256, 0, st>>>(B, cs.npos.as<uint64_t>(), cs.nref.as<uint32_t>(), cs.roots.as<uint32_t>(), nnodes,
