@@ -1694,12 +1694,14 @@ yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim,
     if (rc == YAMS_OK) rc = d_od.reserve((size_t)m * 4);
     if (rc == YAMS_OK) {
         std::vector<int64_t> rid_h((size_t)m);
+        std::vector<float> packed;   // rows passing the rowid range, packed on the host: one copy instead of one per row
         if (use_range) {
+            packed.resize((size_t)m * dim);
             for (uint64_t j = 0; j < m; ++j) {
-                cudaMemcpyAsync(d_rows.as<float>() + (size_t)j * dim, rows + (size_t)keep[j] * dim, (size_t)dim * 4,
-                                cudaMemcpyHostToDevice, st);
+                memcpy(packed.data() + (size_t)j * dim, rows + (size_t)keep[j] * dim, (size_t)dim * 4);
                 rid_h[j] = rowids ? rowids[keep[j]] : (int64_t)keep[j];
             }
+            cudaMemcpyAsync(d_rows.p, packed.data(), (size_t)m * dim * 4, cudaMemcpyHostToDevice, st);
         } else {
             cudaMemcpyAsync(d_rows.p, rows, (size_t)m * dim * 4, cudaMemcpyHostToDevice, st);
             for (uint64_t j = 0; j < m; ++j) rid_h[j] = rowids ? rowids[j] : (int64_t)j;
