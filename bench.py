@@ -459,6 +459,23 @@ def main():
                                             "note": "one chunk_and_hash_batch call, pageable host buffers, wall clock incl. upload and result copy"}
             except Exception as e:   # noqa: BLE001
                 ing["small_files_batch"] = {"error": repr(e)[:200]}
+            # the step after chunking: exists/store over the whole chunk table as one digest-set call
+            try:
+                ds = Y.DigestSet(capacity_hint=len(ch))
+                t0 = time.perf_counter()
+                existed, fresh = ds.insert(ch)
+                dt = time.perf_counter() - t0
+                dev_ms = ds.last_ms()
+                t0 = time.perf_counter()
+                again = ds.contains(ch)
+                dt2 = time.perf_counter() - t0
+                ing["digest_set"] = {"digests": int(len(ch)), "new": int(fresh), "insert_ms_host_call": dt * 1e3, "insert_ms_device": dev_ms,
+                                     "contains_ms_host_call": dt2 * 1e3, "contains_ms_device": ds.last_ms(),
+                                     "all_found_afterwards": bool(again.all()),
+                                     "note": "exists-then-store over the C3 chunk table (content_store_impl.cpp:245-288 as one call)"}
+                ds.close()
+            except Exception as e:   # noqa: BLE001
+                ing["digest_set"] = {"error": repr(e)[:200]}
         out["ingest"] = ing
         del buf
 
