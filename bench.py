@@ -450,13 +450,14 @@ def main():
                 nfiles, fsz = 4096, 64 << 10
                 pool = buf[: 64 * fsz].cpu().numpy().reshape(64, fsz)
                 files = [np.array(pool[i % 64], copy=True) for i in range(nfiles)]
-                Y.chunk_and_hash_batch(files[:64], cfg)
+                Y.chunk_and_hash_batch(files, cfg)            # sizes the pooled pinned / device staging buffers
                 t0 = time.perf_counter()
                 tables = Y.chunk_and_hash_batch(files, cfg)
                 dt = time.perf_counter() - t0
                 ing["small_files_batch"] = {"files": nfiles, "file_bytes": fsz, "files_per_s": nfiles / dt, "gb_per_s": nfiles * fsz / dt / 1e9,
                                             "chunks": int(sum(len(t) for t in tables)),
-                                            "note": "one chunk_and_hash_batch call, pageable host buffers, wall clock incl. upload and result copy"}
+                                            "note": "one chunk_and_hash_batch call through the ctypes mirror, pageable host buffers, wall clock incl. upload and "
+                                                    "result copy (C++ caller: profiles/r1_j_small_files_batch.md)"}
             except Exception as e:   # noqa: BLE001
                 ing["small_files_batch"] = {"error": repr(e)[:200]}
             # the step after chunking: exists/store over the whole chunk table as one digest-set call
