@@ -2,7 +2,7 @@
 // `storage_->exists(hash)` / `storage_->store(hash, ...)` loop that follows chunking in the reference
 // (/root/reference/src/api/content_store_impl.cpp:245-288; storage_engine.cpp:281-305), SURVEY.md §8f N1.
 //
-// Layout in HBM: `store` = every digest ever offered, 32 B each, append-only; `table` = open-addressing array of
+// Layout in HBM: `store` = every digest that was new when it was offered, 32 B each, append-only; `table` = open-addressing array of
 // uint32 indices into `store` (0xFFFFFFFF = empty, load factor <= 0.5, linear probing from splitmix64 of the first
 // 16 digest bytes).  One thread per digest; a probe is one 4-byte read plus, on a hit, one 32-byte compare.
 //
@@ -70,28 +70,6 @@ __global__ void digest_claim_kernel(const Digest* __restrict__ store, uint32_t f
     }
 }
 
-// resolve: existed[i] = the slot of digest i is owned by somebody else (an older entry or an earlier one of the batch)
-__global__ void digest_resolve_kernel(const Digest* __restrict__ store, uint32_t first, uint32_t n, const uint32_t* __restrict__ table,
-                                      uint64_t slots, uint8_t* __restrict__ existed, unsigned long long* __restrict__ n_new) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned fresh = 0;
-    if (i < n) {
-        const uint32_t idx = first + i;
-        const Digest mine = store[idx];
-        uint64_t slot = digest_slot(mine, slots);
-        for (;;) {
-            uint32_t cur = table[slot];
-            if (cur == idx) { fresh = 1; break; }
-            if (cur == kEmptySlot) break;   // cannot happen after the claim pass
-            if (digest_eq(store[cur], mine)) break;
-            slot = (slot + 1) & (slots - 1);
-        }
-        existed[i] = fresh ? 0 : 1;
-    }
-    unsigned m = __ballot_sync(0xffffffffu, fresh);
-    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_new, (unsigned long long)__popc(m));
-}
-
 // read-only membership of staged digests (they sit in scratch, not in the store)
 __global__ void digest_contains_kernel(const Digest* __restrict__ store, const Digest* __restrict__ probe, uint32_t n,
                                        const uint32_t* __restrict__ table, uint64_t slots, uint8_t* __restrict__ out) {
@@ -109,6 +87,48 @@ __global__ void digest_contains_kernel(const Digest* __restrict__ store, const D
     out[i] = hit;
 }
 
+// staged digests that are not in the table yet are appended to the store at base + pos[i] (pos = exclusive scan of
+// fresh[]); slot_of[i] remembers the store index so that the resolve pass can tell "mine" from "an earlier twin"
+__global__ void digest_fresh_flags_kernel(const uint8_t* __restrict__ present, uint32_t n, uint32_t* __restrict__ fresh) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) fresh[i] = present[i] ? 0u : 1u;
+}
+__global__ void digest_append_kernel(const Digest* __restrict__ probe, const uint32_t* __restrict__ fresh, const uint32_t* __restrict__ pos,
+                                     uint32_t n, uint32_t base, Digest* __restrict__ store, uint32_t* __restrict__ index_of) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (fresh[i]) {
+        store[base + pos[i]] = probe[i];
+        index_of[i] = base + pos[i];
+    } else {
+        index_of[i] = kEmptySlot;
+    }
+}
+// existed[i]: present before the call, or the table slot of its digest is owned by an earlier twin of this batch
+__global__ void digest_resolve2_kernel(const Digest* __restrict__ store, const Digest* __restrict__ probe, const uint32_t* __restrict__ index_of,
+                                       uint32_t n, const uint32_t* __restrict__ table, uint64_t slots, uint8_t* __restrict__ existed,
+                                       unsigned long long* __restrict__ n_new) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned fresh = 0;
+    if (i < n) {
+        const uint32_t idx = index_of[i];
+        if (idx != kEmptySlot) {
+            const Digest mine = probe[i];
+            uint64_t slot = digest_slot(mine, slots);
+            for (;;) {
+                uint32_t cur = table[slot];
+                if (cur == idx) { fresh = 1; break; }
+                if (cur == kEmptySlot) break;   // cannot happen after the claim pass
+                if (digest_eq(store[cur], mine)) break;
+                slot = (slot + 1) & (slots - 1);
+            }
+        }
+        existed[i] = fresh ? 0 : 1;
+    }
+    unsigned m = __ballot_sync(0xffffffffu, fresh);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(n_new, (unsigned long long)__popc(m));
+}
+
 }  // namespace yb
 
 using namespace yb;
@@ -116,9 +136,9 @@ using namespace yb;
 struct yams_b200_digest_set {
     DeviceCtx* dev = nullptr;
     cudaStream_t st = nullptr;
-    DevBuf store, table, stage, flags, probe, counter;
+    DevBuf store, table, stage, flags, probe, counter, fresh, pos, index_of, scan_scratch;
     HostBuf pin;
-    uint64_t entries = 0;   // digests in `store` (every digest ever offered, duplicates included)
+    uint64_t entries = 0;   // digests in `store`: every digest that was new when offered (+ twins inside one batch)
     uint64_t unique = 0;    // distinct digests == set size
     uint64_t slots = 0;
     float last_ms = 0.f;    // device time of the last insert/contains (staging + kernels, no PCIe)
@@ -185,7 +205,8 @@ yams_status_t yams_b200_digest_set_create(void* self, uint64_t capacity_hint, ya
 void yams_b200_digest_set_destroy(yams_b200_digest_set* s) {
     if (!s) return;
     if (s->st) cudaStreamSynchronize(s->st);
-    for (DevBuf* b : {&s->store, &s->table, &s->stage, &s->flags, &s->probe, &s->counter}) b->release();
+    for (DevBuf* b : {&s->store, &s->table, &s->stage, &s->flags, &s->probe, &s->counter, &s->fresh, &s->pos, &s->index_of, &s->scan_scratch})
+        b->release();
     s->pin.release();
     for (auto& e : s->ev)
         if (e) cudaEventDestroy(e);
@@ -209,28 +230,49 @@ yams_status_t yams_b200_digest_set_insert(yams_b200_digest_set* s, const uint8_t
     YB_ARG(n < (1ull << 31), "batch too large");
     std::lock_guard<std::mutex> lk(s->mu);
     yams_status_t rc;
+    // the store only ever receives digests that are not in the set yet, so re-offering known content (the common case
+    // of a daily `yams add` over an unchanged tree) does not grow it
     if ((rc = set_grow(s, s->entries + n)) != YAMS_OK) return rc;
     const size_t in_bytes = (n - 1) * stride + 32;
     if ((rc = s->stage.reserve(in_bytes)) != YAMS_OK) return rc;
+    if ((rc = s->probe.reserve(n * 32)) != YAMS_OK) return rc;
     if ((rc = s->flags.reserve(n)) != YAMS_OK) return rc;
+    if ((rc = s->fresh.reserve(n * 4)) != YAMS_OK) return rc;
+    if ((rc = s->pos.reserve(n * 4)) != YAMS_OK) return rc;
+    if ((rc = s->index_of.reserve(n * 4)) != YAMS_OK) return rc;
+    if ((rc = s->counter.reserve(16)) != YAMS_OK) return rc;
     cudaStream_t st = s->st;
     YB_CUDA(cudaMemcpyAsync(s->stage.p, digests, in_bytes, cudaMemcpyHostToDevice, st));
-    YB_CUDA(cudaMemsetAsync(s->counter.p, 0, 8, st));
+    unsigned long long* d_new = s->counter.as<unsigned long long>();
+    uint64_t* d_total = reinterpret_cast<uint64_t*>(d_new + 1);
+    YB_CUDA(cudaMemsetAsync(s->counter.p, 0, 16, st));
     const unsigned grid = (unsigned)((n + 255) / 256);
     const uint32_t base = (uint32_t)s->entries;
     YB_CUDA(cudaEventRecord(s->ev[0], st));
-    digest_stage_kernel<<<grid, 256, 0, st>>>(s->stage.as<uint8_t>(), stride, (uint32_t)n, s->store.as<Digest>(), base);
-    digest_claim_kernel<<<grid, 256, 0, st>>>(s->store.as<Digest>(), base, (uint32_t)n, base, s->table.as<uint32_t>(), s->slots);
-    digest_resolve_kernel<<<grid, 256, 0, st>>>(s->store.as<Digest>(), base, (uint32_t)n, s->table.as<uint32_t>(), s->slots,
-                                                s->flags.as<uint8_t>(), s->counter.as<unsigned long long>());
+    digest_stage_kernel<<<grid, 256, 0, st>>>(s->stage.as<uint8_t>(), stride, (uint32_t)n, s->probe.as<Digest>(), 0);
+    digest_contains_kernel<<<grid, 256, 0, st>>>(s->store.as<Digest>(), s->probe.as<Digest>(), (uint32_t)n, s->table.as<uint32_t>(),
+                                                 s->slots, s->flags.as<uint8_t>());
+    digest_fresh_flags_kernel<<<grid, 256, 0, st>>>(s->flags.as<uint8_t>(), (uint32_t)n, s->fresh.as<uint32_t>());
+    if ((rc = exclusive_scan_u32(s->fresh.as<uint32_t>(), s->pos.as<uint32_t>(), n, d_total, s->scan_scratch, st)) != YAMS_OK) return rc;
+    digest_append_kernel<<<grid, 256, 0, st>>>(s->probe.as<Digest>(), s->fresh.as<uint32_t>(), s->pos.as<uint32_t>(), (uint32_t)n, base,
+                                               s->store.as<Digest>(), s->index_of.as<uint32_t>());
+    uint64_t appended = 0;
+    YB_CUDA(cudaMemcpyAsync(&appended, d_total, 8, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    if (appended) {
+        digest_claim_kernel<<<(unsigned)((appended + 255) / 256), 256, 0, st>>>(s->store.as<Digest>(), base, (uint32_t)appended, base,
+                                                                               s->table.as<uint32_t>(), s->slots);
+    }
+    digest_resolve2_kernel<<<grid, 256, 0, st>>>(s->store.as<Digest>(), s->probe.as<Digest>(), s->index_of.as<uint32_t>(), (uint32_t)n,
+                                                 s->table.as<uint32_t>(), s->slots, s->flags.as<uint8_t>(), d_new);
     YB_CUDA(cudaEventRecord(s->ev[1], st));
     YB_CUDA(cudaGetLastError());
     unsigned long long fresh = 0;
-    YB_CUDA(cudaMemcpyAsync(&fresh, s->counter.p, 8, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaMemcpyAsync(&fresh, d_new, 8, cudaMemcpyDeviceToHost, st));
     if (out_existed) YB_CUDA(cudaMemcpyAsync(out_existed, s->flags.p, n, cudaMemcpyDeviceToHost, st));
     YB_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&s->last_ms, s->ev[0], s->ev[1]);
-    s->entries += n;
+    s->entries += appended;
     s->unique += fresh;
     if (out_new) *out_new = fresh;
     return YAMS_OK;

@@ -277,7 +277,7 @@ static std::vector<IngestRes*> g_pool;
 // one parked resource set per concurrently ingesting host thread (`yams add` workers); creating/destroying one costs
 // cudaMalloc/cudaFree/cudaMallocHost calls that serialise the whole device
 static size_t pool_max() {
-    static const size_t v = [] { const char* e = getenv("YAMS_B200_POOL_MAX"); long x = e ? atol(e) : 64; return (size_t)(x < 1 ? 1 : x); }();
+    static const size_t v = [] { const char* e = getenv("YAMS_B200_POOL_MAX"); long x = e ? atol(e) : 16; return (size_t)(x < 1 ? 1 : x); }();
     return v;
 }
 
