@@ -73,6 +73,20 @@ def test_no_cpu_fallback_without_gpu(Y):
         Y.Corpus(8)
     rc, _ = Y.vec_distance_l2([1.0, 2.0], [1.0, 2.0])
     assert rc != 0
+    # every other compute entry fails loudly as well -- nothing is answered on the CPU
+    import numpy as np
+    for call in (lambda: Y.chunk_and_hash_batch([b"abc", b"defg"]),
+                 lambda: Y.chunk_boundaries(b"abc"),
+                 lambda: Y.sha256_many([b"abc"]),
+                 lambda: Y.sha256_batch(np.frombuffer(b"abcdef", dtype=np.uint8), [0], [3]),
+                 lambda: Y.dedup_stats(np.zeros(2, dtype=Y.lib_chunk_dtype())),
+                 lambda: Y.DigestSet(),
+                 lambda: Y.IngestSession().feed(b"abc"),
+                 lambda: Y.batch_distance(np.ones(4, np.float32), np.ones((3, 4), np.float32)),
+                 lambda: Y.compute_cosine_similarity([1.0, 2.0], [2.0, 1.0]),
+                 lambda: Y.vec0_exact(np.ones(4, np.float32), np.ones((3, 4), np.float32))):
+        with pytest.raises(Y.YamsB200Error):
+            call()
     assert "no CUDA device" in Y.health()["last_error"]
 
 

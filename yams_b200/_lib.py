@@ -162,6 +162,11 @@ def default_config(variant: int = STREAMING, **kw) -> CdcConfig:
     return cfg
 
 
+def lib_chunk_dtype():
+    """numpy dtype of yams_chunk_desc (offset, size, digest[32])."""
+    return CHUNK_DTYPE
+
+
 def _as_u8(data) -> np.ndarray:
     if isinstance(data, np.ndarray):
         return np.ascontiguousarray(data, dtype=np.uint8)
