@@ -289,7 +289,7 @@ YAMS_B200_API void yams_b200_corpus_destroy(yams_b200_corpus* c);
  * allowed_rowids[allowed_offsets[i] .. allowed_offsets[i+1]) (ascending) -- CandidateFilterMode::
  * Exact (src/vector/vector_database.cpp:570-597). allowed_offsets has Q+1 entries.
  * Outputs (caller-owned HOST): out_rowids/out_scores Q x k (unused slots: rowid -1, score 0),
- * out_counts Q, out_flags Q (nullable). */
+ * out_counts Q, out_flags Q (nullable). * k <= 3072 (cosine) / 4096 (L2). */
 YAMS_B200_API yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32_t nq,
                                              uint32_t k, float threshold,
                                              const int64_t* allowed_rowids,

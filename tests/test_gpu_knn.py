@@ -527,3 +527,20 @@ def test_concurrent_searches_on_one_corpus(Y, oracle):
     for i in range(len(batches)):
         assert np.array_equal(got[i][0], want[i][0]) and np.array_equal(got[i][1], want[i][1])
     c.close()
+
+
+def test_large_k(Y, oracle):
+    """k in the thousands (rerank windows): K' = k + k/4 survivors are ordered in shared memory (limit k <= 3072)."""
+    O = oracle
+    n, d = 90_000, 32
+    rows = O.f16_from_float(O.gen_rows_f32(42, 0, n, d)).reshape(n, d)
+    c = Y.Corpus(d, Y.F16, Y.COSINE)
+    c.append(rows.view(np.float16))
+    queries = O.gen_rows_f32(43, 0, 3, d)
+    for k in (769, 2000, 3072):
+        rid, sc, cnt, _ = c.search(queries, k, threshold=-1.0)
+        rc, wr, ws, wc = O.exact_scan_cosine_batch(rows, queries, k)
+        assert np.array_equal(cnt, wc) and np.array_equal(rid, wr) and np.array_equal(sc, ws), k
+    with pytest.raises(Y.YamsB200Error):
+        c.search(queries, 3073)
+    c.close()

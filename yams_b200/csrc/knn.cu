@@ -286,7 +286,7 @@ __device__ __forceinline__ float fkey_inv(uint32_t k) {
 }
 
 constexpr int SEL_THREADS = 256;
-constexpr int SEL_MAXK = 1024;
+constexpr int SEL_MAXK = 4096;       // survivors per query the select / final kernels can order in shared memory
 
 struct SelectIn {
     const float* dense;     // mode dense: scores[q * ld + i], row = row_start + i * row_stride
@@ -925,6 +925,7 @@ namespace yb {
 yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaStream_t st);
 bool tcgen05_supported(const Corpus* c, uint32_t nq);
 
+constexpr uint32_t kMaxK = 3072;          // K' = k + max(16, k/4) rounded to 32 must fit SEL_MAXK
 constexpr uint32_t kSampleRows = 65536;   // strided sample that calibrates the per-query thresholds
 constexpr uint32_t kSampleRank = 8;       // threshold = 8th best score of the sample
 constexpr float kTauMargin = 2e-3f;       // absorbs stage-1 rounding (fp16 queries on the tensor path)
@@ -1411,7 +1412,7 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
     // k == 0 first and returns empty): mirror that order
     if (k == 0) return YAMS_OK;
     YB_ARG(out_rowids && out_scores, "null output");
-    YB_ARG(k <= 768, "k > 768 is not supported by the fused top-k path");
+    YB_ARG(k <= kMaxK, "k > 3072 is not supported by the fused top-k path");
     if ((rc = prepare_queries(c, queries, false, nq)) != YAMS_OK) return rc;
     YB_CUDA(cudaEventRecord(c->ev[0], c->st));
     // device outputs

@@ -326,7 +326,7 @@ public:
         if (k == 0) return {};
         std::vector<int64_t> allowed = lookupCandidateRowids(candidate_hashes);
         uint64_t offs[2] = {0, allowed.size()};
-        size_t kk = std::min<size_t>(768, k + 8);
+        size_t kk = std::min<size_t>(3072, k + 8);
         std::vector<int64_t> rid(kk);
         std::vector<float> sc(kk);
         uint32_t cnt = 0;
@@ -384,8 +384,8 @@ public:
             if (st != YAMS_OK) throw_status("search", st);
             bool need_more = false;
             for (size_t q = 0; q < queries.size(); ++q)
-                if ((flg[q] & YAMS_B200_FLAG_TIE_AT_K) && cnt[q] == kk && kk < 768) need_more = true;
-            if (need_more) { kk = std::min<size_t>(768, kk * 2); continue; }
+                if ((flg[q] & YAMS_B200_FLAG_TIE_AT_K) && cnt[q] == kk && kk < 3072) need_more = true;
+            if (need_more) { kk = std::min<size_t>(3072, kk * 2); continue; }
             for (size_t q = 0; q < queries.size(); ++q) {
                 std::vector<VectorHit> hits(cnt[q]);
                 for (uint32_t i = 0; i < cnt[q]; ++i) {
