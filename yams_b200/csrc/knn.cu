@@ -1413,6 +1413,7 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
     if (k == 0) return YAMS_OK;
     YB_ARG(out_rowids && out_scores, "null output");
     YB_ARG(k <= kMaxK, "k > 3072 is not supported by the fused top-k path");
+    YB_ARG(nq <= 65535, "at most 65535 queries per call (split larger batches)");   // per-query grid dimensions
     if ((rc = prepare_queries(c, queries, false, nq)) != YAMS_OK) return rc;
     YB_CUDA(cudaEventRecord(c->ev[0], c->st));
     // device outputs
@@ -1583,6 +1584,7 @@ yams_status_t yams_b200_search_device(yams_b200_corpus* c, const float* d_querie
     YB_ARG(c && d_queries && d_out_rowids && d_out_scores, "null argument");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_ARG(k > 0 && k <= 768, "k must be in 1..768");
+    YB_ARG(nq <= 65535, "at most 65535 queries per call (split larger batches)");
     if (nq == 0) return YAMS_OK;
     yams_status_t rc;
     if ((rc = prepare_queries(c, d_queries, true, nq)) != YAMS_OK) return rc;
