@@ -255,6 +255,19 @@ def cdc_chunk(data, cfg: CdcConfig, hash: bool = True):
         cap = n
 
 
+def ref_dedup_stats(data, cfg: CdcConfig, variant: Optional[int] = None) -> dict:
+    """The reference's own calculateDeduplication over the reference chunker's output (oracle/_ref)."""
+    a = _bytes_arr(data)
+    out = (C.c_uint64 * 4)()
+    v = cfg.variant if variant is None else variant
+    R = ref()
+    R.ref_dedup_stats.argtypes = [u8p, C.c_size_t, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_int,
+                                  C.POINTER(C.c_uint64)]
+    R.ref_dedup_stats.restype = None
+    R.ref_dedup_stats(_data_ptr(a), a.size, cfg.window_size, cfg.min_chunk, cfg.max_chunk, cfg.polynomial, cfg.mask, v, out)
+    return {"totalSize": int(out[0]), "uniqueSize": int(out[1]), "chunkCount": int(out[2]), "uniqueChunks": int(out[3])}
+
+
 def ref_chunk(data, cfg: CdcConfig, variant: Optional[int] = None, hash: bool = True):
     """Reference StreamingChunker (variant 0) / RabinChunker lazy (1) / RabinChunker full (2)."""
     R = ref()

@@ -66,6 +66,27 @@ size_t ref_chunk(const uint8_t* data, size_t n, uint64_t window, uint64_t minc, 
     return chunks.size();
 }
 
+// calculateDeduplication (rabin_chunker.cpp:224-239) over the chunks of the reference chunker itself.
+// out[4] = totalSize, uniqueSize, chunkCount, uniqueChunks
+void ref_dedup_stats(const uint8_t* data, size_t n, uint64_t window, uint64_t minc, uint64_t maxc, uint64_t poly,
+                     uint64_t mask, int variant, uint64_t* out) {
+    auto cfg = make_cfg(window, minc, maxc, poly, mask);
+    std::span<const std::byte> span(reinterpret_cast<const std::byte*>(data), n);
+    std::vector<yams::chunking::Chunk> chunks;
+    if (variant == 0) {
+        yams::chunking::StreamingChunker ch(cfg);
+        chunks = ch.chunkData(span);
+    } else {
+        yams::chunking::RabinChunker ch(cfg);
+        chunks = ch.chunkDataLazy(span);
+    }
+    yams::chunking::DeduplicationStats st = yams::chunking::calculateDeduplication(chunks);
+    out[0] = st.totalSize;
+    out[1] = st.uniqueSize;
+    out[2] = st.chunkCount;
+    out[3] = st.uniqueChunks;
+}
+
 // SHA256Hasher::hash (static one-shot) -> 64-char lowercase hex + NUL
 void ref_sha256_hex(const uint8_t* data, size_t n, char* out_hex65) {
     auto h = yams::crypto::SHA256Hasher::hash(
