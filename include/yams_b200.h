@@ -15,6 +15,12 @@
  *
  * There is NO CPU fallback: every compute entry point returns YAMS_ERR_INTERNAL (and says why in the
  * health JSON) when no sm_100 device is usable.
+ *
+ * Threading (model_provider_v1.h:45 "all functions must be thread-safe unless documented"): every entry point may
+ * be called from any host thread.  Calls on one corpus or one digest set are serialised by a per-handle mutex; the
+ * handle-less ingest entries (chunk_and_hash*, sha256_*) draw a private device workspace from a pool, so concurrent
+ * callers run on separate CUDA streams; an ingest SESSION (ingest_open..ingest_close) belongs to one thread at a time.
+ * Input pointers are borrowed for the duration of the call only.
  */
 #ifndef YAMS_B200_H
 #define YAMS_B200_H
