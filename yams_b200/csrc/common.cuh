@@ -5,6 +5,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <exception>
+#include <new>
+
 #include <string>
 
 #include "../../include/yams_b200.h"
@@ -33,6 +36,21 @@ void note_global_error(const char* text);  // remembered for yams_plugin_get_hea
             return YAMS_ERR_INVALID_ARG;                    \
         }                                                   \
     } while (0)
+
+// No exception may cross the C boundary (the reference catches at its C entry points too,
+// third_party/sqlite-vec-cpp/src/sqlite_vec_c_api.cpp:30-53): host-side allocations (std::vector, std::thread) inside an
+// extern "C" entry are wrapped by YB_TRY ... YB_CATCH.
+#define YB_TRY try {
+#define YB_CATCH                                                      \
+    }                                                                 \
+    catch (const std::bad_alloc&) {                                   \
+        ::yb::set_last_error("out of host memory");                   \
+        return YAMS_ERR_INTERNAL;                                     \
+    }                                                                 \
+    catch (const std::exception& e) {                                 \
+        ::yb::set_last_error("unexpected host exception: %s", e.what()); \
+        return YAMS_ERR_INTERNAL;                                     \
+    }
 
 // Growable device buffer (never shrinks); contents are NOT preserved across growth unless asked.
 struct DevBuf {

@@ -177,6 +177,7 @@ static yams_status_t set_grow(yams_b200_digest_set* s, uint64_t need_entries) {
 extern "C" {
 
 yams_status_t yams_b200_digest_set_create(void* self, uint64_t capacity_hint, yams_b200_digest_set** out) {
+    YB_TRY
     (void)self;
     YB_ARG(out, "out is null");
     *out = nullptr;
@@ -200,6 +201,7 @@ yams_status_t yams_b200_digest_set_create(void* self, uint64_t capacity_hint, ya
     }
     *out = s;
     return YAMS_OK;
+    YB_CATCH
 }
 
 void yams_b200_digest_set_destroy(yams_b200_digest_set* s) {
@@ -223,6 +225,7 @@ yams_status_t yams_b200_digest_set_size(yams_b200_digest_set* s, uint64_t* out) 
 
 yams_status_t yams_b200_digest_set_insert(yams_b200_digest_set* s, const uint8_t* digests, size_t stride, size_t n,
                                           uint8_t* out_existed, uint64_t* out_new) {
+    YB_TRY
     YB_ARG(s, "set is null");
     if (out_new) *out_new = 0;
     if (n == 0) return YAMS_OK;
@@ -276,10 +279,12 @@ yams_status_t yams_b200_digest_set_insert(yams_b200_digest_set* s, const uint8_t
     s->unique += fresh;
     if (out_new) *out_new = fresh;
     return YAMS_OK;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_digest_set_contains(yams_b200_digest_set* s, const uint8_t* digests, size_t stride, size_t n,
                                             uint8_t* out_exists) {
+    YB_TRY
     YB_ARG(s, "set is null");
     if (n == 0) return YAMS_OK;
     YB_ARG(digests && stride >= 32 && out_exists, "bad argument");
@@ -303,6 +308,7 @@ yams_status_t yams_b200_digest_set_contains(yams_b200_digest_set* s, const uint8
     YB_CUDA(cudaStreamSynchronize(st));
     cudaEventElapsedTime(&s->last_ms, s->ev[0], s->ev[1]);
     return YAMS_OK;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_digest_set_last_ms(yams_b200_digest_set* s, float* out_ms) {

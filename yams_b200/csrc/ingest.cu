@@ -741,6 +741,7 @@ void yams_b200_cdc_default_config(yams_cdc_config* cfg) {
 
 yams_status_t yams_b200_chunk_and_hash(void* self, const uint8_t* data, size_t len, const yams_cdc_config* cfg,
                                        yams_chunk_desc** out, size_t* out_n) {
+    YB_TRY
     (void)self;
     YB_ARG(out && out_n, "out / out_n is null");
     *out = nullptr;
@@ -748,10 +749,12 @@ yams_status_t yams_b200_chunk_and_hash(void* self, const uint8_t* data, size_t l
     YB_ARG(data || len == 0, "data is null");
     YB_ARG(cfg, "cfg is null");
     return run_host(data, len, cfg, true, out, out_n);
+    YB_CATCH
 }
 
 yams_status_t yams_b200_chunk_boundaries(void* self, const uint8_t* data, size_t len, const yams_cdc_config* cfg,
                                          yams_chunk_desc** out, size_t* out_n) {
+    YB_TRY
     (void)self;
     YB_ARG(out && out_n, "out / out_n is null");
     *out = nullptr;
@@ -762,10 +765,12 @@ yams_status_t yams_b200_chunk_boundaries(void* self, const uint8_t* data, size_t
     if (rc == YAMS_OK)
         for (size_t i = 0; i < *out_n; ++i) memset((*out)[i].digest, 0, 32);
     return rc;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_chunk_and_hash_device(void* self, const uint8_t* d_data, size_t len,
                                               const yams_cdc_config* cfg, yams_chunk_desc** out, size_t* out_n) {
+    YB_TRY
     (void)self;
     YB_ARG(out && out_n, "out / out_n is null");
     *out = nullptr;
@@ -773,10 +778,12 @@ yams_status_t yams_b200_chunk_and_hash_device(void* self, const uint8_t* d_data,
     YB_ARG(d_data || len == 0, "d_data is null");
     YB_ARG(cfg, "cfg is null");
     return run_device(d_data, len, cfg, true, out, out_n);
+    YB_CATCH
 }
 
 yams_status_t yams_b200_chunk_and_hash_batch(void* self, const uint8_t* const* files, const size_t* lens, size_t n_files,
                                              const yams_cdc_config* cfg, yams_chunk_desc** out, size_t* out_n, uint64_t* out_first) {
+    YB_TRY
     (void)self;
     YB_ARG(out && out_n, "out / out_n is null");
     *out = nullptr;
@@ -830,6 +837,7 @@ yams_status_t yams_b200_chunk_and_hash_batch(void* self, const uint8_t* const* f
         *out_n = all.size();
     }
     return YAMS_OK;
+    YB_CATCH
 }
 
 void yams_b200_free_chunks(void* self, yams_chunk_desc* chunks, size_t n) {
@@ -839,15 +847,18 @@ void yams_b200_free_chunks(void* self, yams_chunk_desc* chunks, size_t n) {
 }
 
 yams_status_t yams_b200_ingest_open(void* self, const yams_cdc_config* cfg, yams_b200_ingest** out) {
+    YB_TRY
     (void)self;
     YB_ARG(out, "out is null");
     *out = nullptr;
     YB_ARG(cfg, "cfg is null");
     return session_open(cfg, true, out);
+    YB_CATCH
 }
 
 yams_status_t yams_b200_ingest_feed(yams_b200_ingest* s, const uint8_t* data, size_t len, yams_chunk_desc** out,
                                     size_t* out_n) {
+    YB_TRY
     YB_ARG(s && out && out_n, "null argument");
     *out = nullptr;
     *out_n = 0;
@@ -855,15 +866,18 @@ yams_status_t yams_b200_ingest_feed(yams_b200_ingest* s, const uint8_t* data, si
     yams_status_t rc = session_feed(s, data, len, false);
     if (rc != YAMS_OK) return rc;
     return session_take(s, out, out_n);
+    YB_CATCH
 }
 
 yams_status_t yams_b200_ingest_finish(yams_b200_ingest* s, yams_chunk_desc** out, size_t* out_n) {
+    YB_TRY
     YB_ARG(s && out && out_n, "null argument");
     *out = nullptr;
     *out_n = 0;
     yams_status_t rc = session_feed(s, nullptr, 0, true);
     if (rc != YAMS_OK) return rc;
     return session_take(s, out, out_n);
+    YB_CATCH
 }
 
 void yams_b200_ingest_close(yams_b200_ingest* s) { session_close(s); }
@@ -903,6 +917,7 @@ static yams_status_t sha_batch_impl(const uint8_t* d_base, size_t base_len, cons
 yams_status_t yams_b200_sha256_batch_device(void* self, const uint8_t* d_base, size_t base_len,
                                             const uint64_t* offsets, const uint64_t* sizes, size_t n,
                                             uint8_t* digests) {
+    YB_TRY
     (void)self;
     if (n == 0) return YAMS_OK;
     YB_ARG(offsets && sizes && digests, "null argument");
@@ -915,10 +930,12 @@ yams_status_t yams_b200_sha256_batch_device(void* self, const uint8_t* d_base, s
     rc = sha_batch_impl(d_base, base_len, offsets, sizes, n, digests, dev, st);
     cudaStreamDestroy(st);
     return rc;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_sha256_batch(void* self, const uint8_t* base, size_t base_len, const uint64_t* offsets,
                                      const uint64_t* sizes, size_t n, uint8_t* digests) {
+    YB_TRY
     (void)self;
     if (n == 0) return YAMS_OK;
     YB_ARG(offsets && sizes && digests, "null argument");
@@ -938,11 +955,13 @@ yams_status_t yams_b200_sha256_batch(void* self, const uint8_t* base, size_t bas
     d_base.release();
     cudaStreamDestroy(st);
     return rc;
+    YB_CATCH
 }
 
 // Many separate messages (IContentHasher::hash per span, ChunkValidator::validateChunks): packed 16-byte aligned into
 // the pooled staging buffer by the pinned upload path, hashed by one launch per <= 1 GiB group.
 yams_status_t yams_b200_sha256_many(void* self, const uint8_t* const* msgs, const size_t* lens, size_t n, uint8_t* digests) {
+    YB_TRY
     (void)self;
     if (n == 0) return YAMS_OK;
     YB_ARG(msgs && lens && digests, "null argument");
@@ -1014,9 +1033,11 @@ yams_status_t yams_b200_sha256_many(void* self, const uint8_t* const* msgs, cons
     }
     release_res(r);
     return rc;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_dedup_stats(void* self, const yams_chunk_desc* chunks, size_t n, yams_dedup_stats* out) {
+    YB_TRY
     (void)self;
     YB_ARG(out, "out is null");
     memset(out, 0, sizeof(*out));
@@ -1052,6 +1073,7 @@ yams_status_t yams_b200_dedup_stats(void* self, const yams_chunk_desc* chunks, s
     for (DevBuf* b : {&d_descs, &d_table, &d_out}) b->release();
     cudaStreamDestroy(st);
     return rc;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_ingest_last_timings(void* self, float out_ms[8]) {

@@ -1201,6 +1201,7 @@ extern "C" {
 
 yams_status_t yams_b200_corpus_create(void* self, uint32_t dim, int dtype, int metric, uint64_t capacity_hint,
                                       yams_b200_corpus** out) {
+    YB_TRY
     (void)self;
     YB_ARG(out, "out is null");
     *out = nullptr;
@@ -1232,6 +1233,7 @@ yams_status_t yams_b200_corpus_create(void* self, uint32_t dim, int dtype, int m
     }
     *out = c;
     return YAMS_OK;
+    YB_CATCH
 }
 
 void yams_b200_corpus_destroy(yams_b200_corpus* c) {
@@ -1250,6 +1252,7 @@ void yams_b200_corpus_destroy(yams_b200_corpus* c) {
 }
 
 yams_status_t yams_b200_corpus_append(yams_b200_corpus* c, const void* rows, uint64_t n, const int64_t* rowids) {
+    YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     if (n == 0) return YAMS_OK;
@@ -1260,9 +1263,11 @@ yams_status_t yams_b200_corpus_append(yams_b200_corpus* c, const void* rows, uin
     size_t rb = (size_t)c->dim * c->elem();
     YB_CUDA(cudaMemcpyAsync(c->rows.as<uint8_t>() + (size_t)c->n * rb, rows, (size_t)n * rb, cudaMemcpyHostToDevice, c->st));
     return corpus_finish_append(c, n, rowids);
+    YB_CATCH
 }
 
 yams_status_t yams_b200_corpus_append_f32_as_f16(yams_b200_corpus* c, const float* rows, uint64_t n, const int64_t* rowids) {
+    YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_ARG(c->dtype == YAMS_B200_F16, "corpus is not fp16");
@@ -1277,9 +1282,11 @@ yams_status_t yams_b200_corpus_append_f32_as_f16(yams_b200_corpus* c, const floa
     convert_f32_to_f16_trunc_kernel<<<(unsigned)std::min<size_t>((cnt + 255) / 256, 65535), 256, 0, c->st>>>(
         c->dense.as<float>(), c->rows.as<uint16_t>() + (size_t)c->n * c->dim, cnt);
     return corpus_finish_append(c, n, rowids);
+    YB_CATCH
 }
 
 yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t seed, uint64_t first_row, uint64_t n) {
+    YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     if (n == 0) return YAMS_OK;
@@ -1305,9 +1312,11 @@ yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t se
     YB_CUDA(cudaStreamSynchronize(c->st));
     c->n += n;
     return YAMS_OK;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_corpus_remove(yams_b200_corpus* c, const int64_t* rowids, uint64_t n, uint64_t* out_removed) {
+    YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     if (out_removed) *out_removed = 0;
@@ -1347,6 +1356,7 @@ yams_status_t yams_b200_corpus_remove(yams_b200_corpus* c, const int64_t* rowids
     c->last_rowid = last;
     c->rowids_dense = false;
     return YAMS_OK;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_corpus_clear(yams_b200_corpus* c) {
@@ -1397,6 +1407,7 @@ static yams_status_t prepare_queries(yams_b200_corpus* c, const float* q_src, bo
 yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32_t nq, uint32_t k, float threshold,
                                const int64_t* allowed_rowids, const uint64_t* allowed_offsets, int64_t* out_rowids,
                                float* out_scores, uint32_t* out_counts, uint64_t* out_flags) {
+    YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     if (nq == 0) return YAMS_OK;
@@ -1505,11 +1516,13 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
         }
     }
     return rc;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, const float* query, float threshold,
                                             const int64_t* allowed_rowids, uint64_t n_allowed, int64_t* out_rowids,
                                             float* out_scores, uint64_t* out_count) {
+    YB_TRY
     YB_ARG(c && query && out_count, "null argument");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     *out_count = 0;
@@ -1577,10 +1590,12 @@ yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, const float* qu
     }
     *out_count = h_cnt;
     return YAMS_OK;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_search_device(yams_b200_corpus* c, const float* d_queries, uint32_t nq, uint32_t k, float threshold,
                                       int64_t* d_out_rowids, float* d_out_scores) {
+    YB_TRY
     YB_ARG(c && d_queries && d_out_rowids && d_out_scores, "null argument");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_ARG(k > 0 && k <= 768, "k must be in 1..768");
@@ -1600,6 +1615,7 @@ yams_status_t yams_b200_search_device(yams_b200_corpus* c, const float* d_querie
     YB_CUDA(cudaEventRecord(c->ev[2], c->st));
     c->last_ms[4] = tensor ? 1.f : 0.f;
     return YAMS_OK;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_merge_partials_device(yams_b200_corpus* c, const int64_t* d_rowids, const float* d_scores,
@@ -1661,6 +1677,7 @@ yams_status_t yams_b200_debug_stage1_scores(yams_b200_corpus* c, const float* qu
 yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim, const float* rows, const int64_t* rowids,
                                    uint64_t n, uint64_t k, int use_range, int64_t rowid_lo, int64_t rowid_hi,
                                    int64_t* out_rowids, float* out_dist, uint64_t* out_count) {
+    YB_TRY
     (void)self;
     YB_ARG(out_count, "out_count is null");
     *out_count = 0;
@@ -1733,11 +1750,13 @@ yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim,
     for (DevBuf* b : {&d_rows, &d_q, &d_dist, &d_keys, &d_rid, &d_or, &d_od}) b->release();
     cudaStreamDestroy(st);
     return rc;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_batch_distance(void* self, int metric, const float* query, uint32_t dim, const float* database,
                                        uint64_t n, int mode, uint64_t k, float threshold, uint64_t* out_idx, float* out_dist,
                                        uint64_t* out_count) {
+    YB_TRY
     (void)self;
     YB_ARG(out_count, "out_count is null");
     *out_count = 0;
@@ -1813,9 +1832,11 @@ yams_status_t yams_b200_batch_distance(void* self, int metric, const float* quer
     for (DevBuf* b : {&d_rows, &d_q, &d_dist, &d_keys, &d_oi, &d_od, &d_cnt}) b->release();
     cudaStreamDestroy(st);
     return rc;
+    YB_CATCH
 }
 
 yams_status_t yams_b200_compute_cosine_similarity(void* self, const float* a, size_t na, const float* b, size_t nb, double* out) {
+    YB_TRY
     (void)self;
     YB_ARG(out, "out is null");
     *out = 0.0;
@@ -1840,6 +1861,7 @@ yams_status_t yams_b200_compute_cosine_similarity(void* self, const float* a, si
     d_ab.release();
     d_o.release();
     return rc;
+    YB_CATCH
 }
 
 }  // extern "C"
