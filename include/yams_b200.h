@@ -257,8 +257,9 @@ typedef struct yams_b200_corpus yams_b200_corpus; /* opaque device-resident mirr
 YAMS_B200_API yams_status_t yams_b200_corpus_create(void* self, uint32_t dim, int dtype, int metric,
                                                     uint64_t capacity_hint, yams_b200_corpus** out);
 /* rows: HOST pointer, n x dim elements of the corpus dtype; rowids nullable (then consecutive,
- * continuing from the current size). Rowids must be appended in ascending order (the reference
- * scans ORDER BY rowid, sqlite_vec_backend.cpp:4175). */
+ * continuing from the current size). Rowids must be non-negative (-1 marks an unused result slot) and appended in
+ * strictly ascending order (the reference scans ORDER BY rowid, sqlite_vec_backend.cpp:4175). A rejected batch leaves
+ * the corpus unchanged. */
 YAMS_B200_API yams_status_t yams_b200_corpus_append(yams_b200_corpus* c, const void* rows, uint64_t n,
                                                     const int64_t* rowids);
 /* fp32 HOST rows converted with the reference's TRUNCATING float16_t::from_float
@@ -281,14 +282,21 @@ YAMS_B200_API void yams_b200_corpus_destroy(yams_b200_corpus* c);
 
 #define YAMS_B200_FLAG_TIE_AT_K 1ull       /* equal scores straddle the k boundary: the host   */
                                            /* adapter must re-break by chunk_id (:4218-4223)   */
-#define YAMS_B200_FLAG_FALLBACK_PATH 2ull  /* query was answered by the exhaustive path        */
+#define YAMS_B200_FLAG_FALLBACK_PATH 2ull  /* the fast path could not PROVE its answer exact;   */
+                                           /* the query was answered by an exhaustive level     */
 
 /* Exact top-k of every query against the corpus (bruteForceSearchUnlocked fast path semantics,
  * sqlite_vec_backend.cpp:4203-4331):
  *   cosine: sim = float(dot / (|row| * |q|)) accumulated in double; rows with a non-finite element
  *   or |row|^2 <= 1e-12 are skipped; sim < threshold dropped; order (sim desc, rowid asc).
- *   l2 (vec0 surface): dist = sqrtf(sum (q-r)^2) in float; order (dist asc, rowid asc); threshold
- *   ignored.
+ *   l2 (vec0 surface, vec0_module.hpp:376-430): dist = sqrtf(sum (q-r)^2) in float, evaluated as the reference build does
+ *   (AVX lane order when dim % 16 == 0, simd/avx.hpp:20-66); order (dist asc, rowid asc); threshold ignored.
+ * How "exact" is guaranteed: a tensor-core pass ranks all rows by an approximate score with a known error bound eps, the
+ * best K' = k + max(16, k/4) rows are re-scored exactly, and a device-side certificate checks that no other row can
+ * reach the k-th exact score (bound + eps < k-th score).  A query that fails the check (near-duplicate rows, an
+ * overflowing or short candidate list) is re-run exhaustively inside the same call -- CUDA-core scores of all rows +
+ * exact re-scoring of the best 4096, then, if even that cannot be certified, the exact score of every row -- and carries
+ * YAMS_B200_FLAG_FALLBACK_PATH.  The returned ids/scores are the reference's in every case.
  * queries: HOST, Q x dim fp32 row-major.  A query that is non-finite or has |q|^2 < 1e-10 makes
  * the whole call return YAMS_ERR_INVALID_ARG (:4127-4130).  k == 0 -> all counts 0 (:4123-4126).
  * allowed_rowids: nullable; when given, query i may only match rowids in
@@ -312,12 +320,25 @@ YAMS_B200_API yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, c
                                                           int64_t* out_rowids, float* out_scores,
                                                           uint64_t* out_count);
 
-/* Device-pointer form for multi-GPU sharding: queries and outputs are DEVICE pointers, the call
- * is enqueued on the corpus stream and returns after enqueueing; outputs are the rank-local partial
- * top-k in the padded Q x k layout (unused: score -inf / +inf(l2), rowid -1). */
+/* Device-pointer form for multi-GPU sharding: queries and outputs are DEVICE pointers, the whole pipeline is enqueued on
+ * the corpus stream and the call returns WITHOUT synchronising (query validity, list overflow and the exactness
+ * certificate are evaluated on the device and parked in a status block).  Outputs are the rank-local partial top-k in
+ * the padded Q x k layout (unused: score -inf / +inf(l2), rowid -1).
+ * yams_b200_search_device_finish waits for the stream, returns YAMS_ERR_INVALID_ARG if a query was non-finite / zero,
+ * and re-runs the queries the certificate rejected through the exhaustive levels, patching the device outputs in place
+ * (*out_resolved = how many; 0 for ordinary data).  A caller that pipelines batches calls it before it consumes the
+ * outputs of that batch; only the most recent search_device of a corpus can be finished. */
 YAMS_B200_API yams_status_t yams_b200_search_device(yams_b200_corpus* c, const float* d_queries,
                                                     uint32_t nq, uint32_t k, float threshold,
                                                     int64_t* d_out_rowids, float* d_out_scores);
+YAMS_B200_API yams_status_t yams_b200_search_device_finish(yams_b200_corpus* c, uint32_t* out_resolved);
+/* The exhaustive reference inside the library: exact score of EVERY row (the reference's loop, row-parallel) + a global
+ * sort, no tensor-core stage, no thresholds.  Same outputs as yams_b200_search.  This is what the fast path is checked
+ * against at corpus sizes a CPU oracle cannot reach (bench.py parity_full, tests); ~3 ms per query per 10 M rows. */
+YAMS_B200_API yams_status_t yams_b200_search_exhaustive(yams_b200_corpus* c, const float* queries, uint32_t nq,
+                                                        uint32_t k, float threshold, int64_t* out_rowids,
+                                                        float* out_scores, uint32_t* out_counts,
+                                                        uint64_t* out_flags);
 /* Merge R partial results laid out [R][Q][k] (as produced by an all-gather of search_device
  * outputs) into the global top-k, same order. All DEVICE pointers. */
 YAMS_B200_API yams_status_t yams_b200_merge_partials_device(yams_b200_corpus* c,
@@ -327,6 +348,14 @@ YAMS_B200_API yams_status_t yams_b200_merge_partials_device(yams_b200_corpus* c,
                                                             int64_t* d_out_rowids,
                                                             float* d_out_scores,
                                                             uint32_t* d_out_counts);
+/* Same merge over the PACKED record an all-gather of one buffer produces: rank r's record is
+ * [nq*k int64 rowids][nq*k float scores] (12*nq*k bytes), records back to back.  search_device writes
+ * such a record when d_out_scores = (float*)(d_out_rowids + nq*k).  stream: cudaStream_t to launch on (NULL = the
+ * corpus stream) so that gather + merge of batch i can overlap the scan of batch i+1. */
+YAMS_B200_API yams_status_t yams_b200_merge_packed_device(yams_b200_corpus* c, const void* d_packed,
+                                                          uint32_t nranks, uint32_t nq, uint32_t k,
+                                                          int64_t* d_out_rowids, float* d_out_scores,
+                                                          uint32_t* d_out_counts, void* stream);
 YAMS_B200_API yams_status_t yams_b200_corpus_sync(yams_b200_corpus* c);
 /* raw cudaStream_t of the corpus (for event timing by the bench) */
 YAMS_B200_API void* yams_b200_corpus_stream(yams_b200_corpus* c);
@@ -363,7 +392,8 @@ YAMS_B200_API yams_status_t yams_b200_compute_cosine_similarity(void* self, cons
 
 /* [0] stage-1 scan ms, [1] rescoring+select ms, [2] total device ms, [3] h2d+d2h ms of the last
  * yams_b200_search on this corpus; [4] = which stage-1 kernel ran (0 cuda-core, 1 tcgen05);
- * [5] = duration of the full-corpus filtered scan launch alone (the dominant kernel) */
+ * [5] = duration of the full-corpus filtered scan launch alone (the dominant kernel);
+ * [6] = queries of that call the certificate sent to the exhaustive levels */
 YAMS_B200_API yams_status_t yams_b200_search_last_timings(yams_b200_corpus* c, float out_ms[8]);
 
 typedef struct yams_vector_scan_v1 {
@@ -420,6 +450,9 @@ YAMS_B200_API yams_status_t yams_b200_synth_bytes_device(uint64_t seed, uint64_t
 YAMS_B200_API yams_status_t yams_b200_debug_stage1_scores(yams_b200_corpus* c, const float* queries, uint32_t nq,
                                                           int engine, uint64_t row_start, uint64_t row_stride,
                                                           uint64_t nrows, float* out);
+
+/* diagnostics: the per-query stage-1 error bound eps[q] of the last search / debug_stage1_scores call (HOST out) */
+YAMS_B200_API yams_status_t yams_b200_debug_last_eps(yams_b200_corpus* c, uint32_t nq, float* out);
 
 /* ---- misc ------------------------------------------------------------------------------------ */
 YAMS_B200_API int yams_b200_device_count(void);

@@ -98,6 +98,66 @@ int main() {
     cs.deleteVector("c0");
     hits = cs.searchSimilar({1, 0, 0, 0}, 1, -1.0f);
     CHECK(cs.size() == 2 && hits.size() == 1 && hits[0].chunk_id == "c4");
+    // ---- every argument of IVectorStore::searchSimilar (vector_store.h:44-49) + VectorSearchDiagnostics ----
+    {
+        B200VectorStore ms(4);
+        std::vector<float> mrow = {1, 0, 0, 0, /**/ 0.9f, 0.1f, 0, 0, /**/ 0.5f, 0.5f, 0, 0, /**/ 0, 0, 0, 0, /**/ 0.8f, 0.2f, 0, 0, /**/ 0.7f, 0.3f, 0, 0};
+        ms.insertVectorsBatch(mrow, {1, 2, 3, 4, 5, 6}, {"m0", "m1", "m2", "m3", "m4", "m5"}, {"docA", "docA", "docB", "docB", "docB", "docC"},
+                              {{{"lang", "en"}}, {{"lang", "de"}}, {{"lang", "en"}}, {{"lang", "en"}}, {{"lang", "en"}, {"kind", "code"}}, {}});
+        VectorSearchDiagnostics dg;
+        auto h = ms.searchSimilar({1, 0, 0, 0}, 10, -1.0f, std::string("docB"), {}, {}, &dg);   // WHERE document_hash = 'docB'
+        CHECK(h.size() == 2 && h[0].chunk_id == "m4" && h[1].chunk_id == "m2");                 // m3 is a zero row: skipped
+        CHECK(dg.usedExactScan && dg.rowsVisitedObserved && dg.rowsVisited == 3 && dg.exactDistanceEvaluations == 2 && dg.returnedRows == 2);
+        dg = {};
+        h = ms.searchSimilar({1, 0, 0, 0}, 10, -1.0f, std::nullopt, {}, {{"lang", "en"}}, &dg);     // metadata filter over the whole table
+        CHECK(h.size() == 3 && h[0].chunk_id == "m0" && h[1].chunk_id == "m4" && h[2].chunk_id == "m2");
+        CHECK(dg.rowsVisited == 6 && dg.exactDistanceEvaluations == 3 && dg.returnedRows == 3);
+        h = ms.searchSimilar({1, 0, 0, 0}, 10, -1.0f, std::nullopt, {"docA", "docB"}, {{"lang", "en"}, {"kind", "code"}});
+        CHECK(h.size() == 1 && h[0].chunk_id == "m4");
+        h = ms.searchSimilar({1, 0, 0, 0}, 10, -1.0f, std::string("docC"), {"docA"}, {});          // document_hash outside the candidate set
+        CHECK(h.empty());
+        dg = {};
+        h = ms.searchSimilar({1, 0, 0, 0}, 2, -1.0f, std::nullopt, {}, {}, &dg);
+        CHECK(h.size() == 2 && h[0].chunk_id == "m0" && h[1].chunk_id == "m1" && dg.rowsVisited == 6 && dg.exactDistanceEvaluations == 5);
+    }
+    // ---- fp16 store (BASELINE config C2's layout) fed with the fp32 rows the reference holds: same neighbours as the fp32 store ----
+    {
+        const uint32_t D = 64, N = 3000;
+        std::vector<float> big(N * D);
+        uint64_t sd = 99;
+        for (auto& v : big) { sd = sd * 6364136223846793005ULL + 1442695040888963407ULL; v = (float)((sd >> 40) & 0xFFFF) / 65536.0f - 0.5f; }
+        std::vector<int64_t> ids(N);
+        std::vector<std::string> cids(N);
+        for (uint32_t i = 0; i < N; ++i) { ids[i] = 100 + i; cids[i] = "k" + std::to_string(i); }
+        B200VectorStore s32(D, YAMS_B200_F32), s16(D, YAMS_B200_F16);
+        s32.insertVectorsBatch(big, ids, cids);
+        s16.insertVectorsBatch(big, ids, cids);
+        std::vector<float> q(big.begin() + 17 * D, big.begin() + 18 * D);
+        auto a32 = s32.searchSimilar(q, 5, -1.0f), a16 = s16.searchSimilar(q, 5, -1.0f);
+        CHECK(a32.size() == 5 && a16.size() == 5 && a32[0].chunk_id == "k17" && a16[0].chunk_id == "k17");
+        for (int i = 0; i < 5; ++i) CHECK(std::fabs(a32[i].relevance_score - a16[i].relevance_score) < 2e-3f);   // truncated halves: ranks 2.. may swap, scores cannot move
+    }
+    // ---- an equal-score run longer than the slack: widened until the chunk_id order is right (:4218-4223) ----
+    {
+        B200VectorStore ts(4);
+        const int T = 40;
+        std::vector<float> trow;
+        std::vector<int64_t> tid;
+        std::vector<std::string> tcid;
+        for (int i = 0; i < T; ++i) {
+            trow.insert(trow.end(), {2.0f, 0, 0, 0});
+            tid.push_back(i + 1);
+            char buf[16];
+            snprintf(buf, sizeof buf, "t%03d", T - i);      // chunk_id order is the reverse of the rowid order
+            tcid.push_back(buf);
+        }
+        ts.insertVectorsBatch(trow, tid, tcid);
+        auto th = ts.searchSimilar({1, 0, 0, 0}, 3, -1.0f);
+        CHECK(th.size() == 3 && th[0].chunk_id == "t001" && th[1].chunk_id == "t002" && th[2].chunk_id == "t003");
+        bool k_threw = false;
+        try { ts.searchSimilar({1, 0, 0, 0}, 4000, -1.0f); } catch (const std::invalid_argument& e) { k_threw = std::string(e.what()).find("3072") != std::string::npos; }
+        CHECK(k_threw);
+    }
     CHECK(computeCosineSimilarity({1, 2, 3}, {1, 2, 3, 4}) == 0.0);
     CHECK(std::fabs(computeCosineSimilarity({1, 0}, {1, 1}) - 0.70710678118654757) < 1e-15);
     // ---- many buffers in one device pass == one chunkDataLazy per buffer ----

@@ -306,6 +306,19 @@ def test_cpp_host_adapters(Y, tmp_path):
     assert out.returncode == 0 and "ALL OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_plugin_loader_walks_the_vtables(Y, tmp_path):
+    """dlopen(RTLD_LAZY | RTLD_LOCAL) + dlsym of the 8 envelope symbols + get_interface + a chunk and a search through the
+    returned vtables, exactly as the daemon's AbiPluginLoader reaches a plugin (abi_plugin_loader.cpp:303-341,657-680)."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_plugin_loader")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++20", "-O1", os.path.join(root, "tests", "host_cpp", "test_plugin_loader.cpp"),
+                           "-o", exe, "-ldl"])
+    out = subprocess.run([exe, os.path.join(root, "yams_b200", "libyams_b200.so")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "LOADER OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_all_matching_candidate_rows(Y, oracle):
     """ExactRowSelection::AllMatching (sqlite_vec_backend.cpp:4283-4288,4315-4316): every passing candidate row."""
     O = oracle

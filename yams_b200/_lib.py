@@ -14,6 +14,7 @@ _SO = os.path.join(HERE, "libyams_b200.so")
 STREAMING, RABIN = 0, 1
 F32, F16 = 0, 1
 COSINE, L2 = 0, 1
+FLAG_TIE_AT_K, FLAG_FALLBACK_PATH = 1, 2
 
 u8p = C.POINTER(C.c_uint8)
 u32p = C.POINTER(C.c_uint32)
@@ -91,6 +92,10 @@ SYMBOLS = {
     "yams_b200_search": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_float, i64p, u64p, i64p, f32p, u32p, u64p]),
     "yams_b200_search_all_matching": (C.c_int, [C.c_void_p, f32p, C.c_float, i64p, C.c_uint64, i64p, f32p, u64p]),
     "yams_b200_search_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_void_p, C.c_void_p]),
+    "yams_b200_search_device_finish": (C.c_int, [C.c_void_p, u32p]),
+    "yams_b200_search_exhaustive": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_float, i64p, f32p, u32p, u64p]),
+    "yams_b200_merge_packed_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p,
+                                                C.c_void_p, C.c_void_p]),
     "yams_b200_merge_partials_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32,
                                                   C.c_void_p, C.c_void_p, C.c_void_p]),
     "yams_b200_corpus_sync": (C.c_int, [C.c_void_p]),
@@ -102,6 +107,7 @@ SYMBOLS = {
     "sqlite3_vec_distance_cosine": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, f32p]),
     "yams_b200_synth_bytes_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "yams_b200_debug_stage1_scores": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
+    "yams_b200_debug_last_eps": (C.c_int, [C.c_void_p, C.c_uint32, f32p]),
     "yams_b200_device_count": (C.c_int, []),
     "yams_b200_last_error": (C.c_char_p, []),
 }
@@ -403,6 +409,32 @@ class Corpus:
     def search_device(self, d_queries: int, nq: int, k: int, threshold: float, d_out_rowids: int, d_out_scores: int):
         _check(lib().yams_b200_search_device(self._h, d_queries, nq, k, threshold, d_out_rowids, d_out_scores), "search_device")
 
+    def search_device_finish(self) -> int:
+        """Blocks until the last search_device is done; raises on invalid queries; -> queries resolved exhaustively."""
+        n = C.c_uint32(0)
+        _check(lib().yams_b200_search_device_finish(self._h, C.byref(n)), "search_device_finish")
+        return n.value
+
+    def search_exhaustive(self, queries: np.ndarray, k: int, threshold: float = -1.0):
+        """The library's own exhaustive reference (exact score of every row + global sort); same outputs as search."""
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq = q.shape[0]
+        out_r = np.full((nq, k), -1, dtype=np.int64)
+        out_s = np.zeros((nq, k), dtype=np.float32)
+        out_c = np.zeros(nq, dtype=np.uint32)
+        out_f = np.zeros(nq, dtype=np.uint64)
+        _check(lib().yams_b200_search_exhaustive(self._h, q.ctypes.data_as(f32p), nq, k, threshold, out_r.ctypes.data_as(i64p),
+                                                 out_s.ctypes.data_as(f32p), out_c.ctypes.data_as(u32p), out_f.ctypes.data_as(u64p)),
+               "search_exhaustive")
+        return out_r, out_s, out_c, out_f
+
+    def merge_packed_device(self, d_packed: int, nranks: int, nq: int, k: int, d_out_rowids: int, d_out_scores: int,
+                            d_out_counts: int = 0, stream: int = 0):
+        _check(lib().yams_b200_merge_packed_device(self._h, d_packed, nranks, nq, k, d_out_rowids, d_out_scores,
+                                                   d_out_counts or None, stream or None), "merge_packed_device")
+
     def merge_partials_device(self, d_rowids: int, d_scores: int, nranks: int, nq: int, k: int, d_out_rowids: int,
                               d_out_scores: int, d_out_counts: int = 0):
         _check(lib().yams_b200_merge_partials_device(self._h, d_rowids, d_scores, nranks, nq, k, d_out_rowids, d_out_scores,
@@ -416,6 +448,11 @@ class Corpus:
                                                    nrows, out.ctypes.data_as(f32p)), "debug_stage1_scores")
         return out
 
+    def debug_last_eps(self, nq: int) -> np.ndarray:
+        out = np.empty(nq, dtype=np.float32)
+        _check(lib().yams_b200_debug_last_eps(self._h, nq, out.ctypes.data_as(f32p)), "debug_last_eps")
+        return out
+
     def sync(self):
         _check(lib().yams_b200_corpus_sync(self._h), "corpus_sync")
 
@@ -427,7 +464,7 @@ class Corpus:
         ms = (C.c_float * 8)()
         lib().yams_b200_search_last_timings(self._h, ms)
         return {"stage1_ms": ms[0], "stage2_ms": ms[1], "total_ms": ms[2], "scan_kernel_ms": ms[5],
-                "engine": "tcgen05" if ms[4] else "cuda-core"}
+                "engine": "tcgen05" if ms[4] else "cuda-core", "resolved_exhaustively": int(ms[6])}
 
     def close(self):
         if self._h:

@@ -114,6 +114,13 @@ struct DeviceCtx {
 yams_status_t ensure_device(DeviceCtx** out);
 void set_requested_device(int dev);
 
+// Every handle-based entry point binds the handle's device on the calling thread first (the header promises "any host
+// thread"; a fresh thread starts on device 0 whatever the plugin was initialised with).
+#define YB_BIND(h)                                                   \
+    do {                                                             \
+        if ((h)->dev) cudaSetDevice((h)->dev->device);               \
+    } while (0)
+
 // exclusive scan of n uint32 values (in may alias out); *d_total (device, uint64) receives the sum
 yams_status_t exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, uint64_t* d_total,
                                  DevBuf& scratch, cudaStream_t st);

@@ -89,27 +89,55 @@ __global__ void synth_fill_kernel(uint64_t seed, uint64_t first_row, uint64_t n,
     }
 }
 
+// nonnegative floats order like their bit patterns: atomic max through the integer view
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+    if (v == v) atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+
 // per-row validity + 1/|row| exactly as the reference evaluates it (sqlite_vec_backend.cpp:4253-4269):
-// sequential double accumulation; rows with a non-finite element or |row|^2 <= 1e-12 get 0
+// sequential double accumulation; rows with a non-finite element or |row|^2 <= 1e-12 get 0.
+// L2 corpora (vec0 surface, no skip rules) keep |row|^2 in the same slot instead: stage 1 ranks by 2 q.r - |row|^2.
+// stats[0] = max |row|, stats[1] = max |row - tf32(row)| (fp32 corpora read by the tf32 tensor-core engine),
+// stats[2] = max of that residual relative to |row|: the inputs of the stage-1 error bound
 __global__ void row_stats_kernel(const void* __restrict__ rows, int dtype, uint32_t d, uint64_t first, uint64_t n,
-                                 float* __restrict__ inv_norm) {
+                                 float* __restrict__ inv_norm, int metric, float* __restrict__ stats) {
     uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n) return;
     uint64_t base = (first + r) * (uint64_t)d;
-    double ss = 0.0;
+    double ss = 0.0, res = 0.0;
     bool finite = true;
     for (uint32_t c = 0; c < d; ++c) {
         float v = load_elem(rows, dtype, base + c);
         if (!isfinite(v)) { finite = false; break; }
         ss += (double)v * (double)v;
+        if (dtype == YAMS_B200_F32) {
+            float t = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+            res += (double)t * (double)t;
+        }
     }
-    inv_norm[first + r] = (finite && ss > 1e-12) ? (float)(1.0 / sqrt(ss)) : 0.0f;
+    if (metric == YAMS_B200_L2) inv_norm[first + r] = finite ? (float)ss : INFINITY;
+    else inv_norm[first + r] = (finite && ss > 1e-12) ? (float)(1.0 / sqrt(ss)) : 0.0f;
+    if (finite && ss > 0.0) {
+        float nrm = (float)sqrt(ss), rs = (float)sqrt(res);
+        atomic_max_nonneg(&stats[0], nrm * 1.0000002f);
+        atomic_max_nonneg(&stats[1], rs * 1.0000002f);
+        if (ss > 1e-12) atomic_max_nonneg(&stats[2], (rs / nrm) * 1.0000002f);
+    }
 }
 
-// queries: flags[q] = 1 if non-finite or |q|^2 < 1e-10 (sqlite_vec_backend.cpp:204-235,4127);
-// qnorm[q] = sqrt(sum (double)q^2) (:4204-4209), qinv[q] = 1/qnorm as float
+// Device-side status of one search call (read by the host once, after everything is enqueued)
+struct ScanStatus {
+    uint32_t n_invalid;   // queries the reference rejects (non-finite or zero norm, sqlite_vec_backend.cpp:4127-4130)
+    uint32_t n_bad;       // queries whose fast-path result could not be certified exact -> resolved by the exhaustive levels
+    uint32_t n_bad2;      // ... of which level 1 could not certify either -> full exact pass
+    uint32_t pad;
+    // followed by uint32_t bad[nq], bad2[nq]
+};
+
+// queries: invalid if non-finite or (cosine) |q|^2 < 1e-10 (sqlite_vec_backend.cpp:204-235,4127);
+// qnorm[q] = sqrt(sum (double)q^2) (:4204-4209), qinv[q] = 1/qnorm as float (1 for L2: queries stay unscaled)
 __global__ void query_prep_kernel(const float* __restrict__ q, uint32_t nq, uint32_t d, double* __restrict__ qnorm,
-                                  float* __restrict__ qinv, uint32_t* __restrict__ flags) {
+                                  float* __restrict__ qinv, int metric, ScanStatus* __restrict__ status) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nq) return;
     double ss = 0.0;
@@ -119,11 +147,25 @@ __global__ void query_prep_kernel(const float* __restrict__ q, uint32_t nq, uint
         if (!isfinite(v)) finite = false;
         ss += (double)v * (double)v;
     }
-    bool bad = !finite || ss < 1e-10;
-    flags[i] = bad ? 1u : 0u;
+    bool bad = !finite || (metric == YAMS_B200_COSINE && ss < 1e-10);
+    if (bad) atomicAdd(&status->n_invalid, 1u);
     double nrm = sqrt(ss);
     qnorm[i] = nrm;
-    qinv[i] = bad ? 0.0f : (float)(1.0 / nrm);
+    qinv[i] = metric == YAMS_B200_L2 ? 1.0f : (bad ? 0.0f : (float)(1.0 / nrm));
+}
+
+// error bound of the CUDA-core engine's stage-1 score (fp32 FMA chain over d products, Cauchy-Schwarz on sum |q_i r_i|;
+// the float roundings of 1/|row|, 1/|q| or |row|^2 are covered by the +4):
+//   cosine: |s~ - s| <= 2^-24 (d + 4);   L2 (s = 2 q.r - |r|^2): <= 2^-23 (d + 4) |q| Rmax + 2^-22 Rmax^2
+__global__ void eps_cc_kernel(const double* __restrict__ qnorm, uint32_t nq, uint32_t d, int metric, float r_max,
+                              float* __restrict__ eps, int keep_larger) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const float u = 5.9604645e-08f;   // 2^-24
+    float e;
+    if (metric == YAMS_B200_L2) e = 2.f * u * (float)(d + 4) * (float)qnorm[i] * r_max + 4.f * u * r_max * r_max + 1e-30f;
+    else e = u * (float)(d + 4) + 1e-7f;
+    eps[i] = keep_larger ? fmaxf(eps[i], e) : e;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -240,7 +282,9 @@ __global__ void __launch_bounds__(CC_THREADS, 2) stage1_cc_kernel(Stage1Args a, 
         for (int j = 0; j < 4; ++j) {
             uint32_t q = q0 + tx * 4 + j;
             if (q >= a.nq) continue;
-            float s = inr > 0.f ? acc[i][j] * inr * a.qinv[q] : -INFINITY;
+            float s;
+            if (a.metric == YAMS_B200_L2) s = fmaf(2.f, acc[i][j], -inr);           // 2 q.r - |r|^2 (slot holds |r|^2)
+            else s = inr > 0.f ? acc[i][j] * inr * a.qinv[q] : -INFINITY;
             if (FILTER) {
                 bool pass = s > a.tau[q];
                 if (pass && a.mask) pass = (a.mask[(uint64_t)q * a.mask_ld + (grow >> 5)] >> (grow & 31)) & 1u;
@@ -297,6 +341,7 @@ struct SelectIn {
     const uint32_t* counts;
     uint32_t cap;
     const uint32_t* qmap;   // nullable: CTA b handles query qmap[b] for the list/out side
+    const float* tau;       // nullable (list mode): rows that never reached the list scored <= tau[q]
 };
 
 __device__ __forceinline__ uint64_t sel_key(const SelectIn& in, uint32_t qsrc, uint64_t i) {
@@ -314,16 +359,21 @@ __device__ __forceinline__ uint64_t sel_key(const SelectIn& in, uint32_t qsrc, u
 }
 
 // tau_only: writes the K-th largest score to out_tau[q] (-inf when fewer than K items)
-// else    : writes the top-K (sorted desc; ties -> smaller row first) to out_sel[q*K ..], count to out_n[q]
+// else    : writes the top-K (sorted desc; ties -> smaller row first) to out_sel[b*K ..], count to out_n[b], and
+//           out_bound[b] = an upper bound of the stage-1 score of every row that was NOT selected (the input of the
+//           exactness certificate in final_kernel): the K-th selected score when the list was longer than K, else the
+//           list threshold tau (rows that never reached the list), -inf when no other row exists, +inf when the list
+//           overflowed its capacity (unknown rows were dropped)
 __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, uint32_t K, int tau_only, float* __restrict__ out_tau,
-                                                                  Cand* __restrict__ out_sel, uint32_t* __restrict__ out_n) {
+                                                                  Cand* __restrict__ out_sel, uint32_t* __restrict__ out_n,
+                                                                  float* __restrict__ out_bound) {
     __shared__ uint32_t hist[256];
     __shared__ uint64_t s_prefix;
     __shared__ uint32_t s_want;
     __shared__ uint32_t s_cnt;
     __shared__ uint64_t buf[SEL_MAXK];
     const uint32_t b = blockIdx.x;
-    const uint32_t qdst = in.qmap ? in.qmap[b] : b;
+    const uint32_t qdst = in.qmap ? in.qmap[b] : b;   // tau_only output slot / list-side query
     const uint32_t qsrc = in.dense ? b : qdst;
     uint64_t L = in.dense ? in.dense_len : (uint64_t)min(in.counts[qsrc], in.cap);
     // radix select of the K-th largest key among L > K items; result in s_prefix
@@ -409,9 +459,19 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, u
         Cand c;
         c.score = fkey_inv((uint32_t)(key >> 32));
         c.row = 0xFFFFFFFFu - (uint32_t)key;
-        out_sel[(uint64_t)qdst * K + i] = c;
+        out_sel[(uint64_t)b * K + i] = c;
     }
-    if (threadIdx.x == 0) out_n[qdst] = nout;
+    if (threadIdx.x == 0) {
+        out_n[b] = nout;
+        if (out_bound) {
+            float bd;
+            if (!in.dense && in.counts[qsrc] > in.cap) bd = INFINITY;
+            else if (L > K && K > 0) bd = fkey_inv((uint32_t)(buf[K - 1] >> 32));
+            else if (L > K) bd = INFINITY;
+            else bd = (!in.dense && in.tau) ? in.tau[qsrc] : -INFINITY;
+            out_bound[b] = bd;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -422,65 +482,118 @@ struct Exact {
     uint32_t row;
 };
 
-// one thread per (query, survivor): sqlite_vec_backend.cpp:4253-4279 evaluated in the same order
+// one thread per (query, survivor).
+// cosine: sqlite_vec_backend.cpp:4253-4279 evaluated in the same order (sequential double accumulation, skip rules, float cast)
+// L2    : distances::l2_distance<float> as the reference BUILD evaluates it (YAMS compiles sqlite-vec-cpp with AVX,
+//         src/vector/meson.build:79-87): dim >= 16 && dim % 16 == 0 -> simd/avx.hpp:20-66 (eight lane-strided float partial
+//         sums, separate multiply and add, lanes summed left to right), else the scalar loop l2.hpp:108-118; sim = -dist.
+// Entry b of sel/out belongs to query qmap[b] (or b).
 __global__ void rescore_kernel(const void* __restrict__ rows, int dtype, uint32_t d, const float* __restrict__ q32,
                                const double* __restrict__ qnorm, const Cand* __restrict__ sel, const uint32_t* __restrict__ sel_n,
-                               uint32_t Kp, uint32_t nq, float threshold, Exact* __restrict__ out,
-                               const uint32_t* __restrict__ mask = nullptr, uint64_t mask_ld = 0) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nq * Kp) return;
-    uint32_t q = t / Kp, j = t % Kp;
+                               uint32_t Kp, uint32_t nq, float threshold, Exact* __restrict__ out, int metric,
+                               const uint32_t* __restrict__ qmap, const uint32_t* __restrict__ mask, uint64_t mask_ld) {
+    uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (uint64_t)nq * Kp) return;
+    uint32_t b = (uint32_t)(t / Kp), j = (uint32_t)(t % Kp);
+    const uint32_t q = qmap ? qmap[b] : b;
     Exact e;
     e.sim = __int_as_float(0x7FC00000);
     e.row = 0xFFFFFFFFu;
-    bool take = j < sel_n[q] && sel[(uint64_t)q * Kp + j].row != 0xFFFFFFFFu;
+    bool take = j < sel_n[b] && sel[(uint64_t)b * Kp + j].row != 0xFFFFFFFFu;
     if (take && mask) {   // candidate-set mode: a row outside the allowed set is never a result
-        uint32_t row = sel[(uint64_t)q * Kp + j].row;
+        uint32_t row = sel[(uint64_t)b * Kp + j].row;
         take = (mask[(uint64_t)q * mask_ld + (row >> 5)] >> (row & 31)) & 1u;
     }
     if (take) {
-        uint32_t row = sel[(uint64_t)q * Kp + j].row;
+        uint32_t row = sel[(uint64_t)b * Kp + j].row;
         uint64_t base = (uint64_t)row * d;
         const float* qv = q32 + (uint64_t)q * d;
-        double norm_sq = 0.0, dot = 0.0;
-        bool finite = true;
-        for (uint32_t c = 0; c < d; ++c) {
-            float v = load_elem(rows, dtype, base + c);
-            if (!isfinite(v)) { finite = false; break; }
-            double sv = (double)v, qd = (double)qv[c];
-            norm_sq += sv * sv;
-            dot += sv * qd;
-        }
-        if (finite && norm_sq > 1e-12) {
-            double denom = sqrt(norm_sq) * qnorm[q];
-            double simd = denom > 0.0 ? dot / denom : 0.0;
-            if (isfinite(simd)) {
-                float sim = (float)simd;
-                if (!(sim < threshold)) {
-                    e.sim = sim;
-                    e.row = row;
+        if (metric == YAMS_B200_L2) {
+            float sum;
+            if (d >= 16 && d % 16 == 0) {
+                float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                for (uint32_t c = 0; c < d; c += 8) {
+#pragma unroll
+                    for (int l = 0; l < 8; ++l) {
+                        float df = __fsub_rn(qv[c + l], load_elem(rows, dtype, base + c + l));
+                        p[l] = __fadd_rn(p[l], __fmul_rn(df, df));
+                    }
+                }
+                sum = p[0];
+#pragma unroll
+                for (int l = 1; l < 8; ++l) sum = __fadd_rn(sum, p[l]);
+            } else {
+                sum = 0.f;
+                for (uint32_t c = 0; c < d; ++c) {
+                    float df = __fsub_rn(qv[c], load_elem(rows, dtype, base + c));
+                    sum = __fadd_rn(sum, __fmul_rn(df, df));
+                }
+            }
+            float dist = sqrtf(sum);
+            if (dist == dist) {
+                e.sim = -dist;
+                e.row = row;
+            }
+        } else {
+            double norm_sq = 0.0, dot = 0.0;
+            bool finite = true;
+            for (uint32_t c = 0; c < d; ++c) {
+                float v = load_elem(rows, dtype, base + c);
+                if (!isfinite(v)) { finite = false; break; }
+                double sv = (double)v, qd = (double)qv[c];
+                norm_sq += sv * sv;
+                dot += sv * qd;
+            }
+            if (finite && norm_sq > 1e-12) {
+                double denom = sqrt(norm_sq) * qnorm[q];
+                double simd = denom > 0.0 ? dot / denom : 0.0;
+                if (isfinite(simd)) {
+                    float sim = (float)simd;
+                    if (!(sim < threshold)) {
+                        e.sim = sim;
+                        e.row = row;
+                    }
                 }
             }
         }
     }
-    out[(uint64_t)q * Kp + j] = e;
+    out[(uint64_t)b * Kp + j] = e;
 }
 
-// one CTA per query: order survivors by (sim desc, row asc), emit k
+// The exactness certificate.  Stage 1 ranks rows by an approximate score s~ with |s~ - s| <= eps[q];
+// only the top-K' by s~ are re-scored exactly.  Every row that was NOT re-scored has s~ <= bound (topk_select_kernel), hence
+// a true score <= bound + eps.  The emitted top-k is provably the reference's top-k iff no such row can reach the k-th exact
+// score (or, with fewer than k valid survivors, the caller's threshold):
+//   cosine:  bound + eps <  (valid >= k ? sim_k : threshold)
+//   L2    :  |q|^2 - bound - eps > dist_k^2          (s~ = 2 q.r - |r|^2, so d^2 = |q|^2 - s)
+// Otherwise the query is queued for the exhaustive levels (status->bad / bad2) and flagged.
+struct CertArgs {
+    const float* bound;       // per CTA
+    const float* eps;         // per query
+    const double* qnorm;      // per query (L2)
+    float threshold;
+    int metric;
+    ScanStatus* status;       // nullable: no certificate (results already exhaustive)
+    int level;                // 0: failures go to bad[], 1: to bad2[]
+    uint32_t nq_total;        // capacity of each list
+};
+
+// one CTA per query: order survivors by (sim desc, row asc), emit k, certify.  CTA b serves query qmap[b] (or b).
 __global__ void __launch_bounds__(SEL_THREADS) final_kernel(const Exact* __restrict__ ex, const uint32_t* __restrict__ ex_n,
                                                             uint32_t Kp, uint32_t k,
                                                             const int64_t* __restrict__ rowids, int negate,
                                                             int64_t* __restrict__ out_rowids, float* __restrict__ out_scores,
                                                             uint32_t* __restrict__ out_counts, uint64_t* __restrict__ out_flags,
-                                                            float pad_score) {
+                                                            float pad_score, const uint32_t* __restrict__ qmap, CertArgs cert) {
     __shared__ uint64_t buf[SEL_MAXK];
-    const uint32_t q = blockIdx.x;
+    const uint32_t b = blockIdx.x;
+    const uint32_t q = qmap ? qmap[b] : b;
     uint32_t np2 = 1;
     while (np2 < Kp) np2 <<= 1;
     for (uint32_t i = threadIdx.x; i < np2; i += SEL_THREADS) {
         uint64_t key = 0;
-        if (i < Kp && (!ex_n || i < ex_n[q])) {
-            Exact e = ex[(uint64_t)q * Kp + i];
+        if (i < Kp && (!ex_n || i < ex_n[b])) {
+            Exact e = ex[(uint64_t)b * Kp + i];
             if (e.sim == e.sim) key = ((uint64_t)fkey(e.sim) << 32) | (uint64_t)(0xFFFFFFFFu - e.row);
         }
         buf[i] = key;
@@ -522,11 +635,63 @@ __global__ void __launch_bounds__(SEL_THREADS) final_kernel(const Exact* __restr
     }
     if (threadIdx.x == 0) {
         if (out_counts) out_counts[q] = nout;
-        if (out_flags) {
-            uint64_t f = 0;
-            if (valid > k && k > 0 && (buf[k - 1] >> 32) == (buf[k] >> 32)) f |= YAMS_B200_FLAG_TIE_AT_K;
-            out_flags[q] |= f;
+        uint64_t f = 0;
+        if (valid > k && k > 0 && (buf[k - 1] >> 32) == (buf[k] >> 32)) f |= YAMS_B200_FLAG_TIE_AT_K;
+        if (cert.status && k > 0) {
+            const float bd = cert.bound[b];
+            bool certified = true;
+            if (bd > -INFINITY) {
+                const float e = cert.eps[q];
+                if (cert.metric == YAMS_B200_L2) {
+                    certified = false;
+                    if (valid >= k) {
+                        const float dk = -fkey_inv((uint32_t)(buf[k - 1] >> 32));
+                        const double qq = cert.qnorm[q] * cert.qnorm[q];
+                        // distances are floats of a float sum: allow their own rounding (d * 2^-24 relative, generously)
+                        const double dk2 = (double)dk * (double)dk * 1.0001 + 1e-30;
+                        certified = qq - (double)bd - (double)e > dk2;
+                    }
+                } else {
+                    const float lvl = valid >= k ? fkey_inv((uint32_t)(buf[k - 1] >> 32)) : cert.threshold;
+                    certified = bd + e < lvl;
+                }
+            }
+            if (!certified) {
+                f |= YAMS_B200_FLAG_FALLBACK_PATH;
+                uint32_t* cnt = cert.level == 0 ? &cert.status->n_bad : &cert.status->n_bad2;
+                uint32_t* list = reinterpret_cast<uint32_t*>(cert.status + 1) + (cert.level == 0 ? 0u : cert.nq_total);
+                uint32_t pos = atomicAdd(cnt, 1u);
+                if (pos < cert.nq_total) list[pos] = q;
+            }
         }
+        if (cert.level >= 1) f |= YAMS_B200_FLAG_FALLBACK_PATH;   // answered by an exhaustive level
+        if (out_flags) out_flags[q] = f;
+    }
+}
+
+// level 2 (full exact pass): keys sorted descending -> the k best of ONE query
+__global__ void emit_sorted_kernel(const uint64_t* __restrict__ keys, uint64_t nkeys, uint32_t k, uint32_t q,
+                                   const int64_t* __restrict__ rowids, int negate, float pad_score, int64_t* __restrict__ out_rowids,
+                                   float* __restrict__ out_scores, uint32_t* __restrict__ out_counts, uint64_t* __restrict__ out_flags) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < k) {
+        uint64_t key = i < nkeys ? keys[i] : 0;
+        if (key) {
+            float s = fkey_inv((uint32_t)(key >> 32));
+            out_rowids[(uint64_t)q * k + i] = rowids[0xFFFFFFFFu - (uint32_t)key];
+            out_scores[(uint64_t)q * k + i] = negate ? -s : s;
+        } else {
+            out_rowids[(uint64_t)q * k + i] = -1;
+            out_scores[(uint64_t)q * k + i] = pad_score;
+        }
+    }
+    if (i == 0) {
+        uint32_t cnt = 0;
+        while (cnt < k && cnt < nkeys && keys[cnt]) ++cnt;
+        if (out_counts) out_counts[q] = cnt;
+        uint64_t f = YAMS_B200_FLAG_FALLBACK_PATH;
+        if (cnt == k && k < nkeys && keys[k] && (keys[k - 1] >> 32) == (keys[k] >> 32)) f |= YAMS_B200_FLAG_TIE_AT_K;
+        if (out_flags) out_flags[q] = f;
     }
 }
 
@@ -534,8 +699,7 @@ __global__ void __launch_bounds__(SEL_THREADS) final_kernel(const Exact* __restr
 // candidate-set mask: bit (q, row) set when rowids[row] is in query q's allowed list
 // ---------------------------------------------------------------------------------------------------
 __global__ void build_mask_kernel(const int64_t* __restrict__ allowed, const uint64_t* __restrict__ offsets, uint32_t nq,
-                                  const int64_t* __restrict__ rowids, uint64_t n, uint32_t* __restrict__ mask, uint64_t mask_ld,
-                                  uint32_t* __restrict__ per_query) {
+                                  const int64_t* __restrict__ rowids, uint64_t n, uint32_t* __restrict__ mask, uint64_t mask_ld) {
     uint32_t q = blockIdx.y;
     uint64_t lo = offsets[q], hi = offsets[q + 1];
     for (uint64_t i = lo + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (uint64_t)gridDim.x * blockDim.x) {
@@ -545,10 +709,7 @@ __global__ void build_mask_kernel(const int64_t* __restrict__ allowed, const uin
             uint64_t m = a + ((b - a) >> 1);
             if (rowids[m] < want) a = m + 1; else b = m;
         }
-        if (a < n && rowids[a] == want) {
-            uint32_t old = atomicOr(&mask[(uint64_t)q * mask_ld + (a >> 5)], 1u << (a & 31));
-            if (!((old >> (a & 31)) & 1u)) atomicAdd(&per_query[q], 1u);
-        }
+        if (a < n && rowids[a] == want) atomicOr(&mask[(uint64_t)q * mask_ld + (a >> 5)], 1u << (a & 31));
     }
 }
 
@@ -748,6 +909,7 @@ __global__ void unpack_keys_kernel(const uint64_t* __restrict__ keys, uint64_t m
 // multi-GPU: merge R partial top-k lists per query
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SEL_THREADS) merge_partials_kernel(const int64_t* __restrict__ rowids, const float* __restrict__ scores,
+                                                                     uint64_t rank_stride_r, uint64_t rank_stride_s,
                                                                      uint32_t R, uint32_t nq, uint32_t k, int l2,
                                                                      int64_t* __restrict__ out_rowids, float* __restrict__ out_scores,
                                                                      uint32_t* __restrict__ out_counts) {
@@ -763,9 +925,9 @@ __global__ void __launch_bounds__(SEL_THREADS) merge_partials_kernel(const int64
         int64_t r = INT64_MAX;
         if (i < total) {
             uint32_t rk = i / k, j = i % k;
-            size_t idx = ((size_t)rk * nq + q) * k + j;
-            r = rowids[idx];
-            s = scores[idx];
+            size_t idx = (size_t)q * k + j;
+            r = rowids[(size_t)rk * rank_stride_r + idx];
+            s = scores[(size_t)rk * rank_stride_s + idx];
             if (l2) s = -s;
             if (r < 0) { s = -INFINITY; r = INT64_MAX; }
         }
@@ -928,9 +1090,12 @@ bool tcgen05_supported(const Corpus* c, uint32_t nq);
 constexpr uint32_t kMaxK = 3072;          // K' = k + max(16, k/4) rounded to 32 must fit SEL_MAXK
 constexpr uint32_t kSampleRows = 65536;   // strided sample that calibrates the per-query thresholds
 constexpr uint32_t kSampleRank = 8;       // threshold = 8th best score of the sample
-constexpr float kTauMargin = 2e-3f;       // absorbs stage-1 rounding (fp16 queries on the tensor path)
+constexpr float kTauMargin = 2e-3f;       // cosine: keeps the candidate lists comfortably longer than K' (not needed for
+                                          // exactness -- the certificate covers rows below the threshold)
 constexpr uint32_t kCandCap = 8192;       // candidate list capacity per query
 constexpr uint32_t kDenseLimit = 65536;   // corpora up to this many rows are scored densely
+constexpr uint32_t kLevel1K = SEL_MAXK;   // survivors re-scored per query by exhaustive level 1
+constexpr uint32_t kLevel1Group = 8;      // queries per level-1 group: group * n floats of scratch
 
 static uint32_t survivors_for(uint32_t k) {
     uint32_t slack = std::max<uint32_t>(16, k / 4);
@@ -943,82 +1108,126 @@ static yams_status_t corpus_reserve(Corpus* c, uint64_t n_total) {
     if ((rc = c->rows.reserve((size_t)n_total * c->dim * c->elem() + 256, true, c->st)) != YAMS_OK) return rc;
     if ((rc = c->rowids.reserve((size_t)n_total * 8 + 256, true, c->st)) != YAMS_OK) return rc;
     if ((rc = c->inv_norm.reserve((size_t)n_total * 4 + 256, true, c->st)) != YAMS_OK) return rc;
+    if (!c->stats.p) {
+        if ((rc = c->stats.reserve(16)) != YAMS_OK) return rc;
+        YB_CUDA(cudaMemsetAsync(c->stats.p, 0, 16, c->st));
+    }
     return YAMS_OK;
 }
 
-static yams_status_t corpus_finish_append(Corpus* c, uint64_t n_new, const int64_t* rowids_host) {
-    // rowids
+// row statistics of the n_new rows already copied behind the current end + commit of the append.
+// Nothing of the corpus state changes unless every check passed (a rejected batch leaves the corpus as it was).
+static yams_status_t corpus_finish_append(Corpus* c, uint64_t n_new, const int64_t* rowids_host, int64_t first_synthetic = -1) {
     int64_t* d_rid = c->rowids.as<int64_t>() + c->n;
+    int64_t last = c->last_rowid;
+    bool dense = c->rowids_dense;
     if (rowids_host) {
         for (uint64_t i = 0; i < n_new; ++i) {
-            YB_ARG(rowids_host[i] > c->last_rowid, "rowids must be appended in strictly ascending order");
-            if (c->n + i > 0 && rowids_host[i] != c->last_rowid + 1) c->rowids_dense = false;
-            c->last_rowid = rowids_host[i];
+            YB_ARG(rowids_host[i] >= 0, "rowids must be non-negative (-1 marks an unused result slot)");
+            YB_ARG(rowids_host[i] > last, "rowids must be appended in strictly ascending order");
+            if (c->n + i > 0 && rowids_host[i] != last + 1) dense = false;
+            last = rowids_host[i];
         }
         YB_CUDA(cudaMemcpyAsync(d_rid, rowids_host, (size_t)n_new * 8, cudaMemcpyHostToDevice, c->st));
     } else {
-        int64_t first = c->n == 0 ? 0 : c->last_rowid + 1;
+        int64_t first = first_synthetic >= 0 ? first_synthetic : (c->n == 0 ? 0 : last + 1);
+        YB_ARG(first > last || c->n == 0, "rowids must be appended in strictly ascending order");
+        if (c->n > 0 && first != last + 1) dense = false;
         iota_rowids_kernel<<<(unsigned)std::min<uint64_t>((n_new + 255) / 256, 4096), 256, 0, c->st>>>(d_rid, n_new, first);
-        c->last_rowid = first + (int64_t)n_new - 1;
+        last = first + (int64_t)n_new - 1;
     }
     row_stats_kernel<<<(unsigned)((n_new + 127) / 128), 128, 0, c->st>>>(c->rows.p, c->dtype, c->dim, c->n, n_new,
-                                                                       c->inv_norm.as<float>());
+                                                                       c->inv_norm.as<float>(), c->metric, c->stats.as<float>());
     YB_CUDA(cudaGetLastError());
+    float h_stats[4] = {0, 0, 0, 0};
+    YB_CUDA(cudaMemcpyAsync(h_stats, c->stats.p, 12, cudaMemcpyDeviceToHost, c->st));
     YB_CUDA(cudaStreamSynchronize(c->st));
+    c->r_max = h_stats[0];
+    c->dr_abs_max = h_stats[1];
+    c->dr_rel_max = h_stats[2];
+    c->last_rowid = last;
+    c->rowids_dense = dense;
     c->n += n_new;
     return YAMS_OK;
 }
 
-// Runs the whole cosine pipeline for nq queries already resident at c->q32 (device) and writes the
-// padded [nq][k] result into device buffers.
-// Candidate sets (CandidateFilterMode::Exact) come in one of two forms:
-//   d_mask  : bit matrix [nq][mask_ld*32] of allowed rows + h_allowed[q] = allowed rows of query q  -> masked corpus pass
-//   direct  : device lists (ascending rowids, d_offsets[nq+1]) small enough that scoring the listed rows one by one is
-//             cheaper than a corpus pass                                                             -> gather_score_kernel
+// Small candidate sets (CandidateFilterMode::Exact): device lists (ascending rowids, d_offsets[nq+1]) short enough that
+// scoring the listed rows one by one is cheaper than a corpus pass -> gather_score_kernel
 struct DirectLists {
     const int64_t* d_allowed = nullptr;
     const uint64_t* d_offsets = nullptr;
     uint64_t total = 0;
     uint32_t max_len = 0;
 };
-static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, float threshold, const uint32_t* d_mask,
-                                          uint64_t mask_ld, const uint32_t* h_allowed, int64_t* d_out_rowids, float* d_out_scores,
-                                          uint32_t* d_out_counts, uint64_t* d_out_flags, bool use_tensor,
-                                          const DirectLists* direct = nullptr) {
-    yams_status_t rc;
-    cudaStream_t st = c->st;
-    const uint32_t Kp = survivors_for(k);
-    const uint64_t n = c->n;
-    c->scan_timed = false;
-    float* d_qinv = c->qinv.as<float>();
-    double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());           // nq doubles
-    uint32_t* d_counts = c->counts.as<uint32_t>();
-    Stage1Args a{};
+
+struct ScanPlan {
+    uint32_t nq = 0, k = 0;
+    float threshold = -1.f;
+    const uint32_t* d_mask = nullptr;   // bit matrix [nq][mask_ld*32] of allowed rows -> masked corpus pass
+    uint64_t mask_ld = 0;
+    const DirectLists* direct = nullptr;
+    bool use_tensor = false;
+};
+
+static ScanStatus* status_of(Corpus* c) { return c->status.as<ScanStatus>(); }
+
+static void fill_stage1_common(Corpus* c, Stage1Args& a, uint32_t nq) {
     a.rows = c->rows.p;
     a.inv_norm = c->inv_norm.as<float>();
     a.dim = c->dim;
     a.dtype = c->dtype;
     a.q32 = c->q32.as<float>();
-    a.qinv = d_qinv;
+    a.qinv = c->qinv.as<float>();
     a.nq = nq;
-    auto run_stage1 = [&](const Stage1Args& args, bool filter) -> yams_status_t {
-        if (use_tensor) {
+    a.metric = c->metric;
+    a.eps = c->eps.as<float>();
+    a.r_max = c->r_max;
+    a.dr_abs_max = c->dr_abs_max;
+    a.dr_rel_max = c->dr_rel_max;
+}
+
+// Enqueues the whole pipeline for the nq queries already prepared on the device (prepare_queries) and writes the padded
+// [nq][k] result into device buffers.  NO host synchronisation: list overflow, short lists and stage-1 rounding are all
+// caught by the certificate in final_kernel, which queues such queries in the ScanStatus block for resolve_uncertain().
+static yams_status_t scan_enqueue(Corpus* c, const ScanPlan& p, int64_t* d_out_rowids, float* d_out_scores, uint32_t* d_out_counts,
+                                  uint64_t* d_out_flags) {
+    yams_status_t rc;
+    cudaStream_t st = c->st;
+    const uint32_t nq = p.nq, k = p.k;
+    const uint32_t Kp = survivors_for(k);
+    const uint64_t n = c->n;
+    const bool l2 = c->metric == YAMS_B200_L2;
+    c->scan_timed = false;
+    double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());           // nq doubles
+    uint32_t* d_counts = c->counts.as<uint32_t>();
+    Stage1Args a{};
+    fill_stage1_common(c, a, nq);
+    bool qprep_done = false, tensor_used = false, cc_used = false;
+    auto run_stage1 = [&](Stage1Args args, bool filter) -> yams_status_t {
+        if (p.use_tensor) {
+            args.skip_qprep = qprep_done;
             yams_status_t r = stage1_tcgen05(c, args, filter, st);
+            if (r == YAMS_OK) { qprep_done = true; tensor_used = true; }
             if (r != YAMS_ERR_UNSUPPORTED) return r;
         }
+        cc_used = true;
         return stage1_cuda_core(args, filter, st);
     };
     if ((rc = c->sel.reserve((size_t)nq * Kp * sizeof(Cand) + (size_t)nq * 4)) != YAMS_OK) return rc;
+    if ((rc = c->bound.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
+    if ((rc = c->eps.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
+    a.eps = c->eps.as<float>();
     Cand* d_sel = c->sel.as<Cand>();
     uint32_t* d_sel_n = reinterpret_cast<uint32_t*>(d_sel + (size_t)nq * Kp);
+    float* d_bound = c->bound.as<float>();
     YB_CUDA(cudaMemsetAsync(d_sel_n, 0, (size_t)nq * 4, st));
-    if (d_out_flags) YB_CUDA(cudaMemsetAsync(d_out_flags, 0, (size_t)nq * 8, st));
+    fill_f32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_bound, nq, -INFINITY);
 
-    std::vector<uint32_t> bad;  // queries that need the exhaustive path
     if (n == 0) {
-        // nothing to score
-    } else if (direct) {
+        // nothing to score: every list is empty, bound = -inf
+    } else if (p.direct) {
         // ---- small candidate sets: score the listed rows only ----
+        const DirectLists* direct = p.direct;
         const uint32_t cap = std::max<uint32_t>(direct->max_len, 1);
         if ((rc = c->cands.reserve((size_t)nq * cap * sizeof(Cand))) != YAMS_OK) return rc;
         list_lengths_kernel<<<(nq + 255) / 256, 256, 0, st>>>(direct->d_offsets, nq, d_counts);
@@ -1027,7 +1236,7 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
             const bool v8 = c->dtype == YAMS_B200_F16 && c->dim % 8 == 0, v4 = c->dtype == YAMS_B200_F32 && c->dim % 4 == 0;
 #define YB_GATHER(V)                                                                                                              \
     gather_score_kernel<V><<<grid, 256, 0, st>>>(c->rows.p, c->dtype, c->dim, c->inv_norm.as<float>(), c->rowids.as<int64_t>(), n, \
-                                                 a.q32, d_qinv, direct->d_allowed, direct->d_offsets, nq, direct->total,           \
+                                                 a.q32, a.qinv, direct->d_allowed, direct->d_offsets, nq, direct->total,           \
                                                  c->cands.as<Cand>(), cap)
             YB_CUDA(cudaEventRecord(c->ev_scan[0], st));
             if (v8) YB_GATHER(8); else if (v4) YB_GATHER(4); else YB_GATHER(0);
@@ -1035,10 +1244,11 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
             YB_CUDA(cudaEventRecord(c->ev_scan[1], st));
             c->scan_timed = true;
         }
+        cc_used = true;   // fp32 CUDA-core dot products: same error bound as the CUDA-core engine
         SelectIn in{};
         in.cands = c->cands.as<Cand>(); in.counts = d_counts; in.cap = cap;
-        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
-    } else if (!d_mask && n <= kDenseLimit) {
+        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n, d_bound);
+    } else if (!p.d_mask && n <= kDenseLimit) {
         // ---- dense: every score materialised, exact top-K' straight from the matrix ----
         if ((rc = c->dense.reserve((size_t)nq * n * 4)) != YAMS_OK) return rc;
         a.row_start = 0; a.row_stride = 1; a.nrows = n;
@@ -1046,7 +1256,7 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
         if ((rc = run_stage1(a, false)) != YAMS_OK) return rc;
         SelectIn in{};
         in.dense = c->dense.as<float>(); in.ld = n; in.row_start = 0; in.row_stride = 1; in.dense_len = n;
-        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
+        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n, d_bound);
     } else {
         uint32_t cap;
         if ((rc = c->tau.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
@@ -1065,112 +1275,153 @@ static yams_status_t search_cosine_device(Corpus* c, uint32_t nq, uint32_t k, fl
             s1.row_start = 0; s1.row_stride = stride; s1.nrows = S;
             s1.out_scores = c->sample_scores.as<float>(); s1.ld = S;
             if ((rc = run_stage1(s1, false)) != YAMS_OK) return rc;
-            if (d_mask)
-                mask_scores_kernel<<<dim3((unsigned)((S + 255) / 256), nq), 256, 0, st>>>(c->sample_scores.as<float>(), S, S, stride, d_mask,
-                                                                                         mask_ld, nullptr);
+            if (p.d_mask)
+                mask_scores_kernel<<<dim3((unsigned)((S + 255) / 256), nq), 256, 0, st>>>(c->sample_scores.as<float>(), S, S, stride,
+                                                                                         p.d_mask, p.mask_ld, nullptr);
             SelectIn in{};
             in.dense = c->sample_scores.as<float>(); in.ld = S; in.row_start = 0; in.row_stride = stride; in.dense_len = S;
-            topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, m, 1, d_tau, nullptr, nullptr);
-            // never filter above what the caller's own threshold would keep
-            tau_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_tau, nq, kTauMargin, -INFINITY);
+            topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, m, 1, d_tau, nullptr, nullptr, nullptr);
+            if (!l2) tau_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_tau, nq, kTauMargin, -INFINITY);
         }
         if ((rc = c->cands.reserve((size_t)nq * cap * sizeof(Cand))) != YAMS_OK) return rc;
         YB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, st));
         Stage1Args f = a;
         f.row_start = 0; f.row_stride = 1; f.nrows = n;
         f.tau = d_tau; f.cands = c->cands.as<Cand>(); f.cap = cap; f.counts = d_counts;
-        f.mask = d_mask; f.mask_ld = mask_ld;
+        f.mask = p.d_mask; f.mask_ld = p.mask_ld;
         YB_CUDA(cudaEventRecord(c->ev_scan[0], st));
         if ((rc = run_stage1(f, true)) != YAMS_OK) return rc;
         YB_CUDA(cudaEventRecord(c->ev_scan[1], st));
         c->scan_timed = true;
         SelectIn in{};
-        in.cands = c->cands.as<Cand>(); in.counts = d_counts; in.cap = cap;
-        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
-        {
-            // verify every list: overflow or too few survivors -> exhaustive path for that query
-            uint32_t* h_counts = c->h_pin.as<uint32_t>() + nq;   // [0, nq) may hold the caller's h_allowed
-            YB_CUDA(cudaMemcpyAsync(h_counts, d_counts, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-            YB_CUDA(cudaStreamSynchronize(st));
-            for (uint32_t q = 0; q < nq; ++q) {
-                uint64_t need = std::min<uint64_t>(Kp, d_mask ? (uint64_t)h_allowed[q] : n);
-                if (h_counts[q] > cap || h_counts[q] < need) bad.push_back(q);
-            }
-        }
+        in.cands = c->cands.as<Cand>(); in.counts = d_counts; in.cap = cap; in.tau = d_tau;
+        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n, d_bound);
     }
-    // ---- exhaustive path for the (rare) queries whose threshold was off ----
-    if (!bad.empty()) {
-        const uint32_t G = 8;  // queries per group: G * n floats of scratch
-        if ((rc = c->dense.reserve((size_t)G * n * 4 + (size_t)G * c->dim * 4 + (size_t)G * 8)) != YAMS_OK) return rc;
-        float* d_scores = c->dense.as<float>();
-        float* d_qg = d_scores + (size_t)G * n;
-        float* d_qinv_g = d_qg + (size_t)G * c->dim;
-        uint32_t* d_qmap = reinterpret_cast<uint32_t*>(d_qinv_g + G);
-        for (size_t g0 = 0; g0 < bad.size(); g0 += G) {
-            uint32_t g = (uint32_t)std::min<size_t>(G, bad.size() - g0);
-            for (uint32_t i = 0; i < g; ++i) {
-                YB_CUDA(cudaMemcpyAsync(d_qg + (size_t)i * c->dim, a.q32 + (size_t)bad[g0 + i] * c->dim, (size_t)c->dim * 4,
-                                        cudaMemcpyDeviceToDevice, st));
-                YB_CUDA(cudaMemcpyAsync(d_qinv_g + i, d_qinv + bad[g0 + i], 4, cudaMemcpyDeviceToDevice, st));
-            }
-            YB_CUDA(cudaMemcpyAsync(d_qmap, bad.data() + g0, (size_t)g * 4, cudaMemcpyHostToDevice, st));
-            Stage1Args e = a;
-            e.q32 = d_qg; e.qinv = d_qinv_g; e.nq = g;
-            e.row_start = 0; e.row_stride = 1; e.nrows = n; e.out_scores = d_scores; e.ld = n;
-            if ((rc = stage1_cuda_core(e, false, st)) != YAMS_OK) return rc;
-            if (d_mask)
-                mask_scores_kernel<<<dim3((unsigned)std::min<uint64_t>((n + 255) / 256, 65535), g), 256, 0, st>>>(d_scores, n, n, 1, d_mask,
-                                                                                                                 mask_ld, d_qmap);
-            SelectIn in{};
-            in.dense = d_scores; in.ld = n; in.row_start = 0; in.row_stride = 1; in.dense_len = n; in.qmap = d_qmap;
-            topk_select_kernel<<<g, SEL_THREADS, 0, st>>>(in, Kp, 0, nullptr, d_sel, d_sel_n);
-            YB_CUDA(cudaStreamSynchronize(st));  // d_qmap / bad.data() reuse
-        }
-        if (d_out_flags) {
-            std::vector<uint64_t> hf(nq, 0);
-            for (uint32_t q : bad) hf[q] = YAMS_B200_FLAG_FALLBACK_PATH;
-            YB_CUDA(cudaMemcpyAsync(d_out_flags, hf.data(), (size_t)nq * 8, cudaMemcpyHostToDevice, st));
-            YB_CUDA(cudaStreamSynchronize(st));
-        }
-    }
+    // error bound of the engine(s) that produced the ranking
+    if (cc_used || !tensor_used)
+        eps_cc_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_qnorm, nq, c->dim, c->metric, c->r_max, c->eps.as<float>(), tensor_used ? 1 : 0);
     YB_CUDA(cudaEventRecord(c->ev[1], st));
-    // ---- stage 2 ----
+    // ---- stage 2: exact re-scoring, ordering, certificate ----
     if ((rc = c->outbuf.reserve((size_t)nq * Kp * sizeof(Exact))) != YAMS_OK) return rc;
     Exact* d_ex = c->outbuf.as<Exact>();
-    uint32_t tot = nq * Kp;
-    rescore_kernel<<<(tot + 127) / 128, 128, 0, st>>>(c->rows.p, c->dtype, c->dim, a.q32, d_qnorm, d_sel, d_sel_n, Kp, nq,
-                                                      threshold, d_ex, d_mask, mask_ld);
-    final_kernel<<<nq, SEL_THREADS, 0, st>>>(d_ex, nullptr, Kp, k, c->rowids.as<int64_t>(), 0, d_out_rowids, d_out_scores,
-                                             d_out_counts, d_out_flags, -INFINITY);
+    uint64_t tot = (uint64_t)nq * Kp;
+    rescore_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(c->rows.p, c->dtype, c->dim, a.q32, d_qnorm, d_sel, d_sel_n, Kp, nq,
+                                                                  p.threshold, d_ex, c->metric, nullptr, p.d_mask, p.mask_ld);
+    CertArgs cert{};
+    cert.bound = d_bound; cert.eps = c->eps.as<float>(); cert.qnorm = d_qnorm; cert.threshold = p.threshold;
+    cert.metric = c->metric; cert.status = status_of(c); cert.level = 0; cert.nq_total = nq;
+    final_kernel<<<nq, SEL_THREADS, 0, st>>>(d_ex, nullptr, Kp, k, c->rowids.as<int64_t>(), l2 ? 1 : 0, d_out_rowids, d_out_scores,
+                                             d_out_counts, d_out_flags, l2 ? INFINITY : -INFINITY, nullptr, cert);
     YB_CUDA(cudaGetLastError());
     return YAMS_OK;
 }
 
-// L2 (vec0 semantics) over the corpus: dense distances + exact top-k (k <= SEL_MAXK)
-static yams_status_t search_l2_device(Corpus* c, uint32_t nq, uint32_t k, int64_t* d_out_rowids, float* d_out_scores,
-                                      uint32_t* d_out_counts) {
+// Level 2: exact score of EVERY row for one query (the reference's own loop, row-parallel) + a global sort.
+static yams_status_t exact_all_rows(Corpus* c, const ScanPlan& p, uint32_t q, int64_t* d_out_rowids, float* d_out_scores,
+                                    uint32_t* d_out_counts, uint64_t* d_out_flags) {
+    yams_status_t rc;
+    cudaStream_t st = c->st;
+    const uint64_t m = c->n;
+    const bool l2 = c->metric == YAMS_B200_L2;
+    uint64_t np2 = 1;
+    while (np2 < std::max<uint64_t>(m, 1)) np2 <<= 1;
+    if ((rc = c->sel.reserve((size_t)m * sizeof(Cand) + 64)) != YAMS_OK) return rc;
+    if ((rc = c->outbuf.reserve((size_t)m * sizeof(Exact) + 64)) != YAMS_OK) return rc;
+    if ((rc = c->dense.reserve((size_t)np2 * 8 + 64)) != YAMS_OK) return rc;
+    if ((rc = c->lvl.reserve(64)) != YAMS_OK) return rc;
+    Cand* d_sel = c->sel.as<Cand>();
+    uint64_t* d_keys = c->dense.as<uint64_t>();
+    uint32_t* d_small = c->lvl.as<uint32_t>();     // [0] = survivors (m), [1] = query index
+    uint32_t h_small[2] = {(uint32_t)m, q};
+    YB_CUDA(cudaMemcpyAsync(d_small, h_small, 8, cudaMemcpyHostToDevice, st));
+    unsigned g = (unsigned)std::min<uint64_t>((np2 + 255) / 256, 65535);
+    double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());
+    if (m) {
+        iota_sel_kernel<<<g, 256, 0, st>>>(d_sel, m);
+        rescore_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(c->rows.p, c->dtype, c->dim, c->q32.as<float>(), d_qnorm, d_sel, d_small,
+                                                                   (uint32_t)m, 1, p.threshold, c->outbuf.as<Exact>(), c->metric, d_small + 1,
+                                                                   p.d_mask, p.mask_ld);
+    }
+    exact_keys_kernel<<<g, 256, 0, st>>>(c->outbuf.as<Exact>(), m, np2, d_keys);
+    for (uint64_t size = 2; size <= np2; size <<= 1)
+        for (uint64_t stride = size >> 1; stride > 0; stride >>= 1) bitonic_step_kernel<<<g, 256, 0, st>>>(d_keys, np2, size, stride);
+    emit_sorted_kernel<<<(p.k + 255) / 256, 256, 0, st>>>(d_keys, np2, p.k, q, c->rowids.as<int64_t>(), l2 ? 1 : 0, l2 ? INFINITY : -INFINITY,
+                                                          d_out_rowids, d_out_scores, d_out_counts, d_out_flags);
+    YB_CUDA(cudaGetLastError());
+    YB_CUDA(cudaStreamSynchronize(st));   // h_small / scratch reuse
+    return YAMS_OK;
+}
+
+// Blocking: answers the queries the certificate rejected.
+//   level 1: dense stage-1 scores of ALL rows with the CUDA-core engine (error bound eps_cc, ~1e-5), exact re-scoring of the
+//            best kLevel1K (4096) rows instead of K', same certificate;
+//   level 2: whatever level 1 cannot certify either (more than ~4000 rows within eps of the k-th score: a corpus of
+//            duplicates) is answered by the exact score of every row.
+static yams_status_t resolve_uncertain(Corpus* c, const ScanPlan& p, const uint32_t* bad, uint32_t n_bad, int64_t* d_out_rowids,
+                                       float* d_out_scores, uint32_t* d_out_counts, uint64_t* d_out_flags) {
     yams_status_t rc;
     cudaStream_t st = c->st;
     const uint64_t n = c->n;
-    YB_ARG(k <= SEL_MAXK, "k too large for the L2 top-k path");
-    if ((rc = c->dense.reserve((size_t)nq * std::max<uint64_t>(n, 1) * 4)) != YAMS_OK) return rc;
-    if ((rc = c->sel.reserve((size_t)nq * std::max<uint32_t>(k, 1) * sizeof(Cand) + (size_t)nq * 4)) != YAMS_OK) return rc;
-    Cand* d_sel = c->sel.as<Cand>();
-    uint32_t* d_sel_n = reinterpret_cast<uint32_t*>(d_sel + (size_t)nq * std::max<uint32_t>(k, 1));
-    YB_CUDA(cudaMemsetAsync(d_sel_n, 0, (size_t)nq * 4, st));
-    if (n) {
-        dim3 grid((unsigned)((n * 32 + 255) / 256), nq);
-        l2_dense_kernel<<<grid, 256, 0, st>>>(c->rows.p, c->dtype, c->dim, n, c->q32.as<float>(), nq, c->dense.as<float>());
+    const uint32_t k = p.k, G = kLevel1Group, K1 = kLevel1K;
+    const bool l2 = c->metric == YAMS_B200_L2;
+    if (n_bad == 0) return YAMS_OK;
+    if ((rc = c->dense.reserve((size_t)G * n * 4 + (size_t)G * c->dim * 4 + (size_t)G * 8 + 64)) != YAMS_OK) return rc;
+    if ((rc = c->lvl.reserve((size_t)G * K1 * (sizeof(Cand) + sizeof(Exact)) + (size_t)G * 16 + 64)) != YAMS_OK) return rc;
+    if ((rc = c->eps2.reserve((size_t)p.nq * 4)) != YAMS_OK) return rc;
+    float* d_scores = c->dense.as<float>();
+    float* d_qg = d_scores + (size_t)G * n;
+    float* d_qinv_g = d_qg + (size_t)G * c->dim;
+    uint32_t* d_qmap = reinterpret_cast<uint32_t*>(d_qinv_g + G);
+    Cand* d_sel1 = c->lvl.as<Cand>();
+    Exact* d_ex1 = reinterpret_cast<Exact*>(d_sel1 + (size_t)G * K1);
+    uint32_t* d_sel1_n = reinterpret_cast<uint32_t*>(d_ex1 + (size_t)G * K1);
+    float* d_bound1 = reinterpret_cast<float*>(d_sel1_n + G);
+    double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());
+    eps_cc_kernel<<<(p.nq + 255) / 256, 256, 0, st>>>(d_qnorm, p.nq, c->dim, c->metric, c->r_max, c->eps2.as<float>(), 0);
+    Stage1Args a{};
+    fill_stage1_common(c, a, p.nq);
+    for (uint32_t g0 = 0; g0 < n_bad; g0 += G) {
+        uint32_t g = std::min<uint32_t>(G, n_bad - g0);
+        for (uint32_t i = 0; i < g; ++i) {
+            YB_CUDA(cudaMemcpyAsync(d_qg + (size_t)i * c->dim, a.q32 + (size_t)bad[g0 + i] * c->dim, (size_t)c->dim * 4,
+                                    cudaMemcpyDeviceToDevice, st));
+            YB_CUDA(cudaMemcpyAsync(d_qinv_g + i, a.qinv + bad[g0 + i], 4, cudaMemcpyDeviceToDevice, st));
+        }
+        YB_CUDA(cudaMemcpyAsync(d_qmap, bad + g0, (size_t)g * 4, cudaMemcpyHostToDevice, st));
+        Stage1Args e = a;
+        e.q32 = d_qg; e.qinv = d_qinv_g; e.nq = g;
+        e.row_start = 0; e.row_stride = 1; e.nrows = n; e.out_scores = d_scores; e.ld = n;
+        if ((rc = stage1_cuda_core(e, false, st)) != YAMS_OK) return rc;
+        if (p.d_mask)
+            mask_scores_kernel<<<dim3((unsigned)std::min<uint64_t>((n + 255) / 256, 65535), g), 256, 0, st>>>(d_scores, n, n, 1, p.d_mask,
+                                                                                                             p.mask_ld, d_qmap);
         SelectIn in{};
-        in.dense = c->dense.as<float>(); in.ld = n; in.row_start = 0; in.row_stride = 1; in.dense_len = n;
-        topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, k, 0, nullptr, d_sel, d_sel_n);
+        in.dense = d_scores; in.ld = n; in.row_start = 0; in.row_stride = 1; in.dense_len = n;
+        topk_select_kernel<<<g, SEL_THREADS, 0, st>>>(in, K1, 0, nullptr, d_sel1, d_sel1_n, d_bound1);
+        uint64_t tot = (uint64_t)g * K1;
+        rescore_kernel<<<(unsigned)((tot + 127) / 128), 128, 0, st>>>(c->rows.p, c->dtype, c->dim, a.q32, d_qnorm, d_sel1, d_sel1_n, K1, g,
+                                                                      p.threshold, d_ex1, c->metric, d_qmap, p.d_mask, p.mask_ld);
+        CertArgs cert{};
+        cert.bound = d_bound1; cert.eps = c->eps2.as<float>(); cert.qnorm = d_qnorm; cert.threshold = p.threshold;
+        cert.metric = c->metric; cert.status = status_of(c); cert.level = 1; cert.nq_total = p.nq;
+        final_kernel<<<g, SEL_THREADS, 0, st>>>(d_ex1, d_sel1_n, K1, k, c->rowids.as<int64_t>(), l2 ? 1 : 0, d_out_rowids, d_out_scores,
+                                                d_out_counts, d_out_flags, l2 ? INFINITY : -INFINITY, d_qmap, cert);
+        YB_CUDA(cudaGetLastError());
+        YB_CUDA(cudaStreamSynchronize(st));  // d_qmap / bad reuse
     }
-    // reuse final_kernel: Exact has the same layout as Cand (score, row); scores are negated distances
-    static_assert(sizeof(Exact) == sizeof(Cand), "layout");
-    final_kernel<<<nq, SEL_THREADS, 0, st>>>(reinterpret_cast<const Exact*>(d_sel), d_sel_n, std::max<uint32_t>(k, 1), k,
-                                             c->rowids.as<int64_t>(), 1, d_out_rowids, d_out_scores, d_out_counts, nullptr,
-                                             INFINITY);
-    YB_CUDA(cudaGetLastError());
+    // level 2 for what is left
+    uint32_t n_bad2 = 0;
+    YB_CUDA(cudaMemcpyAsync(&n_bad2, &status_of(c)->n_bad2, 4, cudaMemcpyDeviceToHost, st));
+    YB_CUDA(cudaStreamSynchronize(st));
+    if (n_bad2) {
+        n_bad2 = std::min(n_bad2, p.nq);
+        std::vector<uint32_t> bad2(n_bad2);
+        const uint32_t* d_list2 = reinterpret_cast<const uint32_t*>(status_of(c) + 1) + p.nq;
+        YB_CUDA(cudaMemcpyAsync(bad2.data(), d_list2, (size_t)n_bad2 * 4, cudaMemcpyDeviceToHost, st));
+        YB_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t q : bad2)
+            if ((rc = exact_all_rows(c, p, q, d_out_rowids, d_out_scores, d_out_counts, d_out_flags)) != YAMS_OK) return rc;
+    }
     return YAMS_OK;
 }
 
@@ -1240,7 +1491,8 @@ void yams_b200_corpus_destroy(yams_b200_corpus* c) {
     if (!c) return;
     if (c->st) cudaStreamSynchronize(c->st);
     for (DevBuf* b : {&c->rows, &c->rowids, &c->inv_norm, &c->q32, &c->q16, &c->qinv, &c->tau, &c->counts, &c->cands,
-                      &c->sample_scores, &c->sel, &c->outbuf, &c->dense, &c->mask, &c->misc, &c->dout})
+                      &c->sample_scores, &c->sel, &c->outbuf, &c->dense, &c->mask, &c->misc, &c->dout, &c->stats, &c->status,
+                      &c->bound, &c->eps, &c->eps2, &c->lvl})
         b->release();
     c->h_pin.release();
     for (auto& e : c->ev)
@@ -1255,6 +1507,7 @@ yams_status_t yams_b200_corpus_append(yams_b200_corpus* c, const void* rows, uin
     YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
     if (n == 0) return YAMS_OK;
     YB_ARG(rows, "rows is null");
     YB_ARG(c->n + n < 0xFFFFFFFFull, "corpus is limited to 2^32-1 rows per GPU");
@@ -1270,6 +1523,7 @@ yams_status_t yams_b200_corpus_append_f32_as_f16(yams_b200_corpus* c, const floa
     YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
     YB_ARG(c->dtype == YAMS_B200_F16, "corpus is not fp16");
     if (n == 0) return YAMS_OK;
     YB_ARG(rows, "rows is null");
@@ -1289,6 +1543,7 @@ yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t se
     YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
     if (n == 0) return YAMS_OK;
     YB_ARG(c->n + n < 0xFFFFFFFFull, "corpus is limited to 2^32-1 rows per GPU");
     yams_status_t rc = corpus_reserve(c, c->n + n);
@@ -1301,17 +1556,7 @@ yams_status_t yams_b200_corpus_append_synthetic(yams_b200_corpus* c, uint64_t se
                                                                c->rows.as<uint8_t>() + (size_t)c->n * rb, c->dtype);
     YB_CUDA(cudaGetLastError());
     // rowid = first_row + i
-    std::vector<int64_t> none;
-    int64_t first = (int64_t)first_row;
-    YB_ARG(first > c->last_rowid, "rowids must be appended in strictly ascending order");
-    if (c->n > 0 && first != c->last_rowid + 1) c->rowids_dense = false;
-    iota_rowids_kernel<<<(unsigned)std::min<uint64_t>((n + 255) / 256, 4096), 256, 0, c->st>>>(c->rowids.as<int64_t>() + c->n, n, first);
-    c->last_rowid = first + (int64_t)n - 1;
-    row_stats_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c->st>>>(c->rows.p, c->dtype, c->dim, c->n, n, c->inv_norm.as<float>());
-    YB_CUDA(cudaGetLastError());
-    YB_CUDA(cudaStreamSynchronize(c->st));
-    c->n += n;
-    return YAMS_OK;
+    return corpus_finish_append(c, n, nullptr, (int64_t)first_row);
     YB_CATCH
 }
 
@@ -1319,6 +1564,7 @@ yams_status_t yams_b200_corpus_remove(yams_b200_corpus* c, const int64_t* rowids
     YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
     if (out_removed) *out_removed = 0;
     if (n == 0 || c->n == 0) return YAMS_OK;
     YB_ARG(rowids, "rowids is null");
@@ -1362,9 +1608,13 @@ yams_status_t yams_b200_corpus_remove(yams_b200_corpus* c, const int64_t* rowids
 yams_status_t yams_b200_corpus_clear(yams_b200_corpus* c) {
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
     c->n = 0;
     c->last_rowid = INT64_MIN;
     c->rowids_dense = true;
+    c->pending.active = false;
+    c->r_max = c->dr_abs_max = c->dr_rel_max = 0.f;
+    if (c->stats.p) YB_CUDA(cudaMemsetAsync(c->stats.p, 0, 16, c->st));
     return YAMS_OK;
 }
 
@@ -1377,13 +1627,15 @@ yams_status_t yams_b200_corpus_size(const yams_b200_corpus* c, uint64_t* out_n) 
 yams_status_t yams_b200_corpus_sync(yams_b200_corpus* c) {
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
     YB_CUDA(cudaStreamSynchronize(c->st));
     return YAMS_OK;
 }
 
 void* yams_b200_corpus_stream(yams_b200_corpus* c) { return c ? (void*)c->st : nullptr; }
 
-// uploads / validates queries; leaves q32, qinv, qnorm(misc) on the device
+// uploads the queries and enqueues their preparation: q32, qinv, qnorm (misc) on the device, status block zeroed,
+// invalid queries counted in status->n_invalid (read by the host together with the results -- no synchronisation here)
 static yams_status_t prepare_queries(yams_b200_corpus* c, const float* q_src, bool src_is_device, uint32_t nq) {
     yams_status_t rc;
     size_t qb = (size_t)nq * c->dim * 4;
@@ -1391,16 +1643,33 @@ static yams_status_t prepare_queries(yams_b200_corpus* c, const float* q_src, bo
     if ((rc = c->qinv.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
     if ((rc = c->misc.reserve((size_t)nq * 8 + (size_t)nq * 4)) != YAMS_OK) return rc;
     if ((rc = c->counts.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
-    if ((rc = c->h_pin.reserve((size_t)nq * 16)) != YAMS_OK) return rc;
+    if ((rc = c->status.reserve(sizeof(ScanStatus) + (size_t)nq * 8)) != YAMS_OK) return rc;
+    if ((rc = c->h_pin.reserve(sizeof(ScanStatus) + (size_t)nq * 8 + 64)) != YAMS_OK) return rc;
+    YB_CUDA(cudaMemsetAsync(c->status.p, 0, sizeof(ScanStatus), c->st));
     YB_CUDA(cudaMemcpyAsync(c->q32.p, q_src, qb, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
     double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());
-    uint32_t* d_flags = reinterpret_cast<uint32_t*>(c->misc.as<uint8_t>() + (size_t)nq * 8);
-    query_prep_kernel<<<(nq + 63) / 64, 64, 0, c->st>>>(c->q32.as<float>(), nq, c->dim, d_qnorm, c->qinv.as<float>(), d_flags);
-    uint32_t* h_flags = c->h_pin.as<uint32_t>();
-    YB_CUDA(cudaMemcpyAsync(h_flags, d_flags, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->st));
-    YB_CUDA(cudaStreamSynchronize(c->st));
-    for (uint32_t q = 0; q < nq; ++q)
-        YB_ARG(h_flags[q] == 0, "exact vector search requires a finite, non-zero query embedding");
+    query_prep_kernel<<<(nq + 63) / 64, 64, 0, c->st>>>(c->q32.as<float>(), nq, c->dim, d_qnorm, c->qinv.as<float>(), c->metric,
+                                                        status_of(c));
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
+}
+
+// After the stream has been synchronised: the status block of the call (pinned copy) -> invalid queries are an error,
+// uncertain queries are resolved by the exhaustive levels (results patched in the device output buffers).
+static yams_status_t finish_scan(yams_b200_corpus* c, const ScanPlan& p, int64_t* d_or, float* d_os, uint32_t* d_oc, uint64_t* d_of,
+                                 uint32_t* out_resolved) {
+    const ScanStatus* hs = c->h_pin.as<ScanStatus>();
+    if (out_resolved) *out_resolved = 0;
+    YB_ARG(hs->n_invalid == 0, "exact vector search requires a finite, non-zero query embedding");
+    uint32_t n_bad = std::min(hs->n_bad, p.nq);
+    if (n_bad == 0) return YAMS_OK;
+    std::vector<uint32_t> bad(reinterpret_cast<const uint32_t*>(hs + 1), reinterpret_cast<const uint32_t*>(hs + 1) + n_bad);
+    std::sort(bad.begin(), bad.end());
+    if (out_resolved) *out_resolved = n_bad;
+    return resolve_uncertain(c, p, bad.data(), n_bad, d_or, d_os, d_oc, d_of);
+}
+static yams_status_t enqueue_status_readback(yams_b200_corpus* c, uint32_t nq) {
+    YB_CUDA(cudaMemcpyAsync(c->h_pin.p, c->status.p, sizeof(ScanStatus) + (size_t)nq * 4, cudaMemcpyDeviceToHost, c->st));
     return YAMS_OK;
 }
 
@@ -1410,6 +1679,7 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
     YB_TRY
     YB_ARG(c, "corpus is null");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
     if (nq == 0) return YAMS_OK;
     YB_ARG(queries && out_counts, "null argument");
     YB_ARG(!allowed_rowids || allowed_offsets, "allowed_offsets missing");
@@ -1419,12 +1689,14 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
     yams_status_t rc;
     cudaEvent_t w0 = c->ev[3];
     YB_CUDA(cudaEventRecord(w0, c->st));
-    // the reference validates the query before looking at k (sqlite_vec_backend.cpp:4123-4130 checks
-    // k == 0 first and returns empty): mirror that order
+    // the reference looks at k before it validates the query (sqlite_vec_backend.cpp:4123-4130: k == 0 returns
+    // empty first): mirror that order
     if (k == 0) return YAMS_OK;
     YB_ARG(out_rowids && out_scores, "null output");
-    YB_ARG(k <= kMaxK, "k > 3072 is not supported by the fused top-k path");
+    YB_ARG(k <= kMaxK, "k > 3072 is not supported by the fused top-k path (page larger requests)");
     YB_ARG(nq <= 65535, "at most 65535 queries per call (split larger batches)");   // per-query grid dimensions
+    YB_ARG(!allowed_offsets || c->metric == YAMS_B200_COSINE, "candidate sets are only supported for the cosine metric");
+    c->pending.active = false;
     if ((rc = prepare_queries(c, queries, false, nq)) != YAMS_OK) return rc;
     YB_CUDA(cudaEventRecord(c->ev[0], c->st));
     // device outputs
@@ -1435,87 +1707,120 @@ yams_status_t yams_b200_search(yams_b200_corpus* c, const float* queries, uint32
     uint64_t* d_of = reinterpret_cast<uint64_t*>(d_or + (size_t)nq * k);
     float* d_os = reinterpret_cast<float*>(d_of + nq);
     uint32_t* d_oc = reinterpret_cast<uint32_t*>(d_os + (size_t)nq * k);
-    const bool tensor = tcgen05_supported(c, nq);
-    if (c->metric == YAMS_B200_COSINE) {
-        const uint32_t* d_mask = nullptr;
-        uint64_t mask_ld = 0;
-        const uint32_t* h_allowed = nullptr;
-        DirectLists lists;
-        bool direct = false;
-        if (allowed_offsets && c->n) {
-            // small ascending lists: score the listed rows directly instead of passing over the corpus.  Break-even
-            // (DESIGN.md §4.4): a corpus pass costs ~max(1, nq/400) row reads per row, a gathered row about two.
-            const uint64_t total = allowed_offsets[nq];
-            direct = total <= std::max<uint64_t>(c->n / 2, c->n / 400 * nq) && total < (1ull << 31);
-            for (uint32_t q = 0; q < nq && direct; ++q) {
-                uint64_t lo = allowed_offsets[q], hi = allowed_offsets[q + 1];
-                direct = hi >= lo && hi - lo < 0xFFFFFFFFull;
-                for (uint64_t i = lo + 1; i < hi && direct; ++i) direct = allowed_rowids[i - 1] <= allowed_rowids[i];
-                if (direct) lists.max_len = std::max<uint32_t>(lists.max_len, (uint32_t)(hi - lo));
-            }
+    ScanPlan plan;
+    plan.nq = nq; plan.k = k; plan.threshold = threshold;
+    plan.use_tensor = tcgen05_supported(c, nq);
+    DirectLists lists;
+    bool direct = false;
+    if (allowed_offsets && c->n) {
+        // small ascending lists: score the listed rows directly instead of passing over the corpus.  Break-even
+        // (DESIGN.md §4.4): a corpus pass costs ~max(1, nq/400) row reads per row, a gathered row about two.
+        const uint64_t total = allowed_offsets[nq];
+        direct = total <= std::max<uint64_t>(c->n / 2, c->n / 400 * nq) && total < (1ull << 31);
+        for (uint32_t q = 0; q < nq && direct; ++q) {
+            uint64_t lo = allowed_offsets[q], hi = allowed_offsets[q + 1];
+            direct = hi >= lo && hi - lo < 0xFFFFFFFFull;
+            for (uint64_t i = lo + 1; i < hi && direct; ++i) direct = allowed_rowids[i - 1] <= allowed_rowids[i];
+            if (direct) lists.max_len = std::max<uint32_t>(lists.max_len, (uint32_t)(hi - lo));
         }
-        if (direct) {
-            const uint64_t total = allowed_offsets[nq];
-            if ((rc = c->mask.reserve((size_t)total * 8 + (size_t)(nq + 1) * 8 + 64)) != YAMS_OK) return rc;
-            int64_t* d_allowed = c->mask.as<int64_t>();
-            uint64_t* d_offs = reinterpret_cast<uint64_t*>(d_allowed + total);
-            if (total) YB_CUDA(cudaMemcpyAsync(d_allowed, allowed_rowids, (size_t)total * 8, cudaMemcpyHostToDevice, c->st));
-            YB_CUDA(cudaMemcpyAsync(d_offs, allowed_offsets, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->st));
-            lists.d_allowed = d_allowed;
-            lists.d_offsets = d_offs;
-            lists.total = total;
-        } else if (allowed_offsets && c->n) {
-            uint64_t total = allowed_offsets[nq];
-            mask_ld = (c->n + 31) / 32;
-            size_t mb = (size_t)nq * mask_ld * 4;
-            if ((rc = c->mask.reserve(mb + (size_t)total * 8 + (size_t)(nq + 1) * 8 + (size_t)nq * 4 + 64)) != YAMS_OK) {
-                return rc;
-            }
-            uint32_t* dm = c->mask.as<uint32_t>();
-            int64_t* d_allowed = reinterpret_cast<int64_t*>(c->mask.as<uint8_t>() + ((mb + 7) & ~(size_t)7));
-            uint64_t* d_offs = reinterpret_cast<uint64_t*>(d_allowed + total);
-            uint32_t* d_pq = reinterpret_cast<uint32_t*>(d_offs + nq + 1);
-            cudaMemsetAsync(dm, 0, mb, c->st);
-            cudaMemsetAsync(d_pq, 0, (size_t)nq * 4, c->st);
-            if (total) cudaMemcpyAsync(d_allowed, allowed_rowids, (size_t)total * 8, cudaMemcpyHostToDevice, c->st);
-            cudaMemcpyAsync(d_offs, allowed_offsets, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->st);
-            dim3 grid(64, nq);
-            build_mask_kernel<<<grid, 256, 0, c->st>>>(d_allowed, d_offs, nq, c->rowids.as<int64_t>(), c->n, dm, mask_ld, d_pq);
-            uint32_t* h_pq = c->h_pin.as<uint32_t>();
-            cudaMemcpyAsync(h_pq, d_pq, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->st);
-            if (cudaStreamSynchronize(c->st) != cudaSuccess) {
-                set_last_error("mask build failed");
-                return YAMS_ERR_INTERNAL;
-            }
-            h_allowed = h_pq;
-            d_mask = dm;
-        }
-        rc = search_cosine_device(c, nq, k, threshold, d_mask, mask_ld, h_allowed, d_or, d_os, d_oc, d_of, tensor,
-                                  direct ? &lists : nullptr);
-    } else {
-        YB_ARG(!allowed_offsets, "candidate sets are only supported for the cosine metric");
-        cudaMemsetAsync(d_of, 0, (size_t)nq * 8, c->st);
-        YB_CUDA(cudaEventRecord(c->ev[1], c->st));
-        rc = search_l2_device(c, nq, k, d_or, d_os, d_oc);
     }
-    if (rc == YAMS_OK) {
-        cudaEventRecord(c->ev[2], c->st);
+    if (direct) {
+        const uint64_t total = allowed_offsets[nq];
+        if ((rc = c->mask.reserve((size_t)total * 8 + (size_t)(nq + 1) * 8 + 64)) != YAMS_OK) return rc;
+        int64_t* d_allowed = c->mask.as<int64_t>();
+        uint64_t* d_offs = reinterpret_cast<uint64_t*>(d_allowed + total);
+        if (total) YB_CUDA(cudaMemcpyAsync(d_allowed, allowed_rowids, (size_t)total * 8, cudaMemcpyHostToDevice, c->st));
+        YB_CUDA(cudaMemcpyAsync(d_offs, allowed_offsets, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->st));
+        lists.d_allowed = d_allowed;
+        lists.d_offsets = d_offs;
+        lists.total = total;
+        plan.direct = &lists;
+    } else if (allowed_offsets && c->n) {
+        uint64_t total = allowed_offsets[nq];
+        uint64_t mask_ld = (c->n + 31) / 32;
+        size_t mb = (size_t)nq * mask_ld * 4;
+        if ((rc = c->mask.reserve(mb + (size_t)total * 8 + (size_t)(nq + 1) * 8 + 64)) != YAMS_OK) return rc;
+        uint32_t* dm = c->mask.as<uint32_t>();
+        int64_t* d_allowed = reinterpret_cast<int64_t*>(c->mask.as<uint8_t>() + ((mb + 7) & ~(size_t)7));
+        uint64_t* d_offs = reinterpret_cast<uint64_t*>(d_allowed + total);
+        YB_CUDA(cudaMemsetAsync(dm, 0, mb, c->st));
+        if (total) YB_CUDA(cudaMemcpyAsync(d_allowed, allowed_rowids, (size_t)total * 8, cudaMemcpyHostToDevice, c->st));
+        YB_CUDA(cudaMemcpyAsync(d_offs, allowed_offsets, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->st));
+        dim3 grid(64, nq);
+        build_mask_kernel<<<grid, 256, 0, c->st>>>(d_allowed, d_offs, nq, c->rowids.as<int64_t>(), c->n, dm, mask_ld);
+        plan.d_mask = dm;
+        plan.mask_ld = mask_ld;
+    }
+    if ((rc = scan_enqueue(c, plan, d_or, d_os, d_oc, d_of)) != YAMS_OK) return rc;
+    cudaEventRecord(c->ev[2], c->st);
+    if ((rc = enqueue_status_readback(c, nq)) != YAMS_OK) return rc;
+    auto copy_out = [&]() -> cudaError_t {
         cudaError_t e = cudaMemcpyAsync(out_rowids, d_or, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(out_counts, d_oc, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->st);
         if (e == cudaSuccess && out_flags) e = cudaMemcpyAsync(out_flags, d_of, (size_t)nq * 8, cudaMemcpyDeviceToHost, c->st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->st);
-        if (e != cudaSuccess) {
-            set_last_error("search failed: %s", cudaGetErrorString(e));
-            rc = YAMS_ERR_INTERNAL;
-        } else {
-            cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
-            cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]);
-            cudaEventElapsedTime(&c->last_ms[2], c->ev[0], c->ev[2]);
-            c->last_ms[4] = tensor ? 1.f : 0.f;
-        }
+        return e;
+    };
+    cudaError_t e = copy_out();
+    if (e != cudaSuccess) {
+        set_last_error("search failed: %s", cudaGetErrorString(e));
+        return YAMS_ERR_INTERNAL;
     }
-    return rc;
+    cudaEventElapsedTime(&c->last_ms[0], c->ev[0], c->ev[1]);
+    cudaEventElapsedTime(&c->last_ms[1], c->ev[1], c->ev[2]);
+    cudaEventElapsedTime(&c->last_ms[2], c->ev[0], c->ev[2]);
+    c->last_ms[4] = plan.use_tensor ? 1.f : 0.f;
+    uint32_t resolved = 0;
+    rc = finish_scan(c, plan, d_or, d_os, d_oc, d_of, &resolved);
+    c->last_ms[6] = (float)resolved;
+    if (rc != YAMS_OK) {
+        for (uint32_t q = 0; q < nq; ++q) out_counts[q] = 0;
+        return rc;
+    }
+    if (resolved && (e = copy_out()) != cudaSuccess) {
+        set_last_error("search failed: %s", cudaGetErrorString(e));
+        return YAMS_ERR_INTERNAL;
+    }
+    return YAMS_OK;
+    YB_CATCH
+}
+
+// The full exact pass (level 2 of the fallback chain) for EVERY query: the reference's own loop evaluated for all rows,
+// no stage 1, no thresholds, no certificate needed.  It is what bench.py and the tests check the fast path against at
+// sizes the CPU oracle cannot reach; ~3 ms per query per 10 M rows.
+yams_status_t yams_b200_search_exhaustive(yams_b200_corpus* c, const float* queries, uint32_t nq, uint32_t k, float threshold,
+                                          int64_t* out_rowids, float* out_scores, uint32_t* out_counts, uint64_t* out_flags) {
+    YB_TRY
+    YB_ARG(c, "corpus is null");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
+    if (nq == 0) return YAMS_OK;
+    YB_ARG(queries && out_counts && out_rowids && out_scores, "null argument");
+    YB_ARG(k > 0 && k <= kMaxK, "k must be in 1..3072");
+    YB_ARG(nq <= 65535, "at most 65535 queries per call");
+    yams_status_t rc;
+    c->pending.active = false;
+    if ((rc = prepare_queries(c, queries, false, nq)) != YAMS_OK) return rc;
+    size_t ob = (size_t)nq * k * 12 + (size_t)nq * 4 + (size_t)nq * 8 + 64;
+    if ((rc = c->dout.reserve(ob)) != YAMS_OK) return rc;
+    int64_t* d_or = c->dout.as<int64_t>();
+    uint64_t* d_of = reinterpret_cast<uint64_t*>(d_or + (size_t)nq * k);
+    float* d_os = reinterpret_cast<float*>(d_of + nq);
+    uint32_t* d_oc = reinterpret_cast<uint32_t*>(d_os + (size_t)nq * k);
+    if ((rc = enqueue_status_readback(c, 0)) != YAMS_OK) return rc;
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    YB_ARG(c->h_pin.as<ScanStatus>()->n_invalid == 0, "exact vector search requires a finite, non-zero query embedding");
+    ScanPlan plan;
+    plan.nq = nq; plan.k = k; plan.threshold = threshold;
+    for (uint32_t q = 0; q < nq; ++q)
+        if ((rc = exact_all_rows(c, plan, q, d_or, d_os, d_oc, d_of)) != YAMS_OK) return rc;
+    YB_CUDA(cudaMemcpyAsync(out_rowids, d_or, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, c->st));
+    YB_CUDA(cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, c->st));
+    YB_CUDA(cudaMemcpyAsync(out_counts, d_oc, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->st));
+    if (out_flags) YB_CUDA(cudaMemcpyAsync(out_flags, d_of, (size_t)nq * 8, cudaMemcpyDeviceToHost, c->st));
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    return YAMS_OK;
     YB_CATCH
 }
 
@@ -1525,7 +1830,9 @@ yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, const float* qu
     YB_TRY
     YB_ARG(c && query && out_count, "null argument");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
     *out_count = 0;
+    c->pending.active = false;
     YB_ARG(c->metric == YAMS_B200_COSINE, "all-matching selection is defined for the cosine scan");
     // the reference gathers the candidate rowids into a set (:4412-4448): duplicates count once
     std::vector<int64_t> uniq;
@@ -1542,7 +1849,11 @@ yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, const float* qu
     }
     const uint64_t m = allowed_rowids ? n_allowed : c->n;
     yams_status_t rc;
-    if ((rc = prepare_queries(c, query, false, 1)) != YAMS_OK) return rc;   // InvalidArgument for a bad query (:4127)
+    if ((rc = prepare_queries(c, query, false, 1)) != YAMS_OK) return rc;
+    if ((rc = enqueue_status_readback(c, 0)) != YAMS_OK) return rc;
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    YB_ARG(c->h_pin.as<ScanStatus>()->n_invalid == 0,
+           "exact vector search requires a finite, non-zero query embedding");   // InvalidArgument for a bad query (:4127)
     if (m == 0 || c->n == 0) return YAMS_OK;
     YB_ARG(out_rowids && out_scores, "null output");
     YB_ARG(m < (1ull << 31), "candidate set too large");
@@ -1571,7 +1882,8 @@ yams_status_t yams_b200_search_all_matching(yams_b200_corpus* c, const float* qu
     YB_CUDA(cudaMemcpyAsync(d_seln, &mm, 4, cudaMemcpyHostToDevice, st));
     double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());
     rescore_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(c->rows.p, c->dtype, c->dim, c->q32.as<float>(), d_qnorm, d_sel, d_seln,
-                                                               (uint32_t)m, 1, threshold, c->outbuf.as<Exact>());
+                                                               (uint32_t)m, 1, threshold, c->outbuf.as<Exact>(), YAMS_B200_COSINE, nullptr,
+                                                               nullptr, 0);
     exact_keys_kernel<<<g, 256, 0, st>>>(c->outbuf.as<Exact>(), m, np2, d_keys);
     for (uint64_t size = 2; size <= np2; size <<= 1)
         for (uint64_t stride = size >> 1; stride > 0; stride >>= 1) bitonic_step_kernel<<<g, 256, 0, st>>>(d_keys, np2, size, stride);
@@ -1598,24 +1910,58 @@ yams_status_t yams_b200_search_device(yams_b200_corpus* c, const float* d_querie
     YB_TRY
     YB_ARG(c && d_queries && d_out_rowids && d_out_scores, "null argument");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
     YB_ARG(k > 0 && k <= 768, "k must be in 1..768");
     YB_ARG(nq <= 65535, "at most 65535 queries per call (split larger batches)");
     if (nq == 0) return YAMS_OK;
     yams_status_t rc;
+    c->pending.active = false;
     if ((rc = prepare_queries(c, d_queries, true, nq)) != YAMS_OK) return rc;
     YB_CUDA(cudaEventRecord(c->ev[0], c->st));
-    const bool tensor = tcgen05_supported(c, nq);
-    if (c->metric == YAMS_B200_COSINE)
-        rc = search_cosine_device(c, nq, k, threshold, nullptr, 0, 0, d_out_rowids, d_out_scores, nullptr, nullptr, tensor);
-    else {
-        YB_CUDA(cudaEventRecord(c->ev[1], c->st));
-        rc = search_l2_device(c, nq, k, d_out_rowids, d_out_scores, nullptr);
-    }
-    if (rc != YAMS_OK) return rc;
+    ScanPlan plan;
+    plan.nq = nq; plan.k = k; plan.threshold = threshold;
+    plan.use_tensor = tcgen05_supported(c, nq);
+    if ((rc = scan_enqueue(c, plan, d_out_rowids, d_out_scores, nullptr, nullptr)) != YAMS_OK) return rc;
     YB_CUDA(cudaEventRecord(c->ev[2], c->st));
-    c->last_ms[4] = tensor ? 1.f : 0.f;
+    if ((rc = enqueue_status_readback(c, nq)) != YAMS_OK) return rc;
+    c->last_ms[4] = plan.use_tensor ? 1.f : 0.f;
+    c->pending.active = true;
+    c->pending.nq = nq;
+    c->pending.k = k;
+    c->pending.threshold = threshold;
+    c->pending.d_out_rowids = d_out_rowids;
+    c->pending.d_out_scores = d_out_scores;
     return YAMS_OK;
     YB_CATCH
+}
+
+yams_status_t yams_b200_search_device_finish(yams_b200_corpus* c, uint32_t* out_resolved) {
+    YB_TRY
+    YB_ARG(c, "corpus is null");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
+    if (out_resolved) *out_resolved = 0;
+    if (!c->pending.active) return YAMS_OK;
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    c->pending.active = false;
+    ScanPlan plan;
+    plan.nq = c->pending.nq; plan.k = c->pending.k; plan.threshold = c->pending.threshold;
+    return finish_scan(c, plan, c->pending.d_out_rowids, c->pending.d_out_scores, nullptr, nullptr, out_resolved);
+    YB_CATCH
+}
+
+static yams_status_t merge_launch(yams_b200_corpus* c, const int64_t* d_rowids, const float* d_scores, uint64_t rank_stride_r,
+                                  uint64_t rank_stride_s, uint32_t nranks, uint32_t nq, uint32_t k, int64_t* d_out_rowids,
+                                  float* d_out_scores, uint32_t* d_out_counts, cudaStream_t st) {
+    YB_ARG(nranks >= 1 && k >= 1, "bad shape");
+    uint32_t total = nranks * k, np2 = 1;
+    while (np2 < total) np2 <<= 1;
+    YB_ARG(np2 <= 4096, "nranks * k too large to merge in one CTA");
+    size_t smem = (((size_t)np2 * 4 + 7) & ~(size_t)7) + (size_t)np2 * 8;
+    merge_partials_kernel<<<nq, SEL_THREADS, smem, st>>>(d_rowids, d_scores, rank_stride_r, rank_stride_s, nranks, nq, k,
+                                                         c->metric == YAMS_B200_L2, d_out_rowids, d_out_scores, d_out_counts);
+    YB_CUDA(cudaGetLastError());
+    return YAMS_OK;
 }
 
 yams_status_t yams_b200_merge_partials_device(yams_b200_corpus* c, const int64_t* d_rowids, const float* d_scores,
@@ -1623,15 +1969,22 @@ yams_status_t yams_b200_merge_partials_device(yams_b200_corpus* c, const int64_t
                                               float* d_out_scores, uint32_t* d_out_counts) {
     YB_ARG(c && d_rowids && d_scores && d_out_rowids && d_out_scores, "null argument");
     std::lock_guard<std::mutex> corpus_lock(c->mu);
-    YB_ARG(nranks >= 1 && k >= 1, "bad shape");
-    uint32_t total = nranks * k, np2 = 1;
-    while (np2 < total) np2 <<= 1;
-    YB_ARG(np2 <= 4096, "nranks * k too large to merge in one CTA");
-    size_t smem = (((size_t)np2 * 4 + 7) & ~(size_t)7) + (size_t)np2 * 8;
-    merge_partials_kernel<<<nq, SEL_THREADS, smem, c->st>>>(d_rowids, d_scores, nranks, nq, k, c->metric == YAMS_B200_L2,
-                                                            d_out_rowids, d_out_scores, d_out_counts);
-    YB_CUDA(cudaGetLastError());
-    return YAMS_OK;
+    YB_BIND(c);
+    return merge_launch(c, d_rowids, d_scores, (uint64_t)nq * k, (uint64_t)nq * k, nranks, nq, k, d_out_rowids, d_out_scores,
+                        d_out_counts, c->st);
+}
+
+yams_status_t yams_b200_merge_packed_device(yams_b200_corpus* c, const void* d_packed, uint32_t nranks, uint32_t nq, uint32_t k,
+                                            int64_t* d_out_rowids, float* d_out_scores, uint32_t* d_out_counts, void* stream) {
+    YB_ARG(c && d_packed && d_out_rowids && d_out_scores, "null argument");
+    YB_BIND(c);
+    // one rank's record: [nq*k int64 rowids][nq*k float scores] = 12 * nq * k bytes
+    const uint8_t* base = static_cast<const uint8_t*>(d_packed);
+    const uint64_t rec = (uint64_t)nq * k * 12;
+    YB_ARG(rec % 8 == 0, "nq * k must be even for the packed layout");
+    return merge_launch(c, reinterpret_cast<const int64_t*>(base), reinterpret_cast<const float*>(base + (uint64_t)nq * k * 8),
+                        rec / 8, rec / 4, nranks, nq, k, d_out_rowids, d_out_scores, d_out_counts,
+                        stream ? static_cast<cudaStream_t>(stream) : c->st);
 }
 
 yams_status_t yams_b200_search_last_timings(yams_b200_corpus* c, float out_ms[8]) {
@@ -1655,21 +2008,37 @@ yams_status_t yams_b200_debug_stage1_scores(yams_b200_corpus* c, const float* qu
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_ARG(row_start + (nrows - 1) * row_stride < c->n, "rows out of range");
     yams_status_t rc;
+    YB_BIND(c);
+    c->pending.active = false;
     if ((rc = prepare_queries(c, queries, false, nq)) != YAMS_OK) return rc;
     if ((rc = c->dense.reserve((size_t)nq * nrows * 4)) != YAMS_OK) return rc;
+    if ((rc = c->eps.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
     YB_CUDA(cudaMemsetAsync(c->dense.p, 0xFF, (size_t)nq * nrows * 4, c->st));
     Stage1Args a{};
-    a.rows = c->rows.p; a.inv_norm = c->inv_norm.as<float>(); a.dim = c->dim; a.dtype = c->dtype;
-    a.q32 = c->q32.as<float>(); a.qinv = c->qinv.as<float>(); a.nq = nq;
+    fill_stage1_common(c, a, nq);
     a.row_start = row_start; a.row_stride = row_stride; a.nrows = nrows;
     a.out_scores = c->dense.as<float>(); a.ld = nrows;
     if (engine == 1) {
         rc = stage1_tcgen05(c, a, false, c->st);
     } else {
         rc = stage1_cuda_core(a, false, c->st);
+        eps_cc_kernel<<<(nq + 255) / 256, 256, 0, c->st>>>(reinterpret_cast<double*>(c->misc.as<uint8_t>()), nq, c->dim, c->metric, c->r_max,
+                                                           c->eps.as<float>(), 0);
     }
     if (rc != YAMS_OK) return rc;
     YB_CUDA(cudaMemcpyAsync(out, c->dense.p, (size_t)nq * nrows * 4, cudaMemcpyDeviceToHost, c->st));
+    YB_CUDA(cudaStreamSynchronize(c->st));
+    return YAMS_OK;
+}
+
+// diagnostics: the per-query stage-1 error bound eps[q] (certificate input) computed by the last search /
+// debug_stage1_scores call on this corpus
+yams_status_t yams_b200_debug_last_eps(yams_b200_corpus* c, uint32_t nq, float* out) {
+    YB_ARG(c && out && nq > 0, "bad argument");
+    std::lock_guard<std::mutex> corpus_lock(c->mu);
+    YB_BIND(c);
+    YB_ARG(c->eps.cap >= (size_t)nq * 4, "no search with that many queries has run");
+    YB_CUDA(cudaMemcpyAsync(out, c->eps.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, c->st));
     YB_CUDA(cudaStreamSynchronize(c->st));
     return YAMS_OK;
 }

@@ -23,10 +23,23 @@ struct Corpus {
     bool rowids_dense = true;  // rowid[i] == rowid[0] + i
     DevBuf rows;       // n x dim elements
     DevBuf rowids;     // n x int64
-    DevBuf inv_norm;   // n x float: 1/|row| (double math), 0 for rows the reference skips
+    DevBuf inv_norm;   // n x float. cosine: 1/|row| (double math), 0 for rows the reference skips; L2: |row|^2
+    DevBuf stats;      // 3 floats: max |row|, max |row - tf32(row)|, max of that residual relative to |row| (row_stats_kernel)
+    float r_max = 0.f, dr_abs_max = 0.f, dr_rel_max = 0.f;   // host copies of stats (upper bounds; removals keep them)
     // search workspace
     DevBuf q32, q16, qinv, tau, counts, cands, sample_scores, sel, outbuf, dense, mask, misc, dout;
+    DevBuf status;     // ScanStatus + bad[nq] + bad2[nq] of the call in flight
+    DevBuf bound, eps, eps2;   // per query: certificate inputs (knn.cu final_kernel)
+    DevBuf lvl;        // exhaustive level 1 workspace
     HostBuf h_pin;
+    // the call enqueued by search_device and not yet finished (search_device_finish)
+    struct Pending {
+        bool active = false;
+        uint32_t nq = 0, k = 0;
+        float threshold = 0.f;
+        int64_t* d_out_rowids = nullptr;
+        float* d_out_scores = nullptr;
+    } pending;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev_scan[2] = {nullptr, nullptr};  // around the full-corpus filtered scan launch
     bool scan_timed = false;
@@ -35,8 +48,9 @@ struct Corpus {
     size_t elem() const { return dtype == YAMS_B200_F16 ? 2 : 4; }
 };
 
-// Stage-1 engine interface: scores of `nrows` corpus rows (row_start + i*row_stride) against nq
-// queries; cosine scaling (inv_norm[row] * qinv[q]) applied.
+// Stage-1 engine interface: approximate scores of `nrows` corpus rows (row_start + i*row_stride) against nq queries.
+//   cosine: score = q.r * inv_norm[row] * qinv[q]          (-inf for rows the reference skips)
+//   L2    : score = 2 q.r - |row|^2  (inv_norm[] holds |row|^2; larger = closer; |q|^2 is constant per query)
 //   STORE : out_scores[q * ld + i] = score
 //   FILTER: rows with score > tau[q] (and mask bit set, if mask) are appended to cands[q][..cap)
 struct Stage1Args {
@@ -60,6 +74,12 @@ struct Stage1Args {
     uint32_t* counts;
     const uint32_t* mask;   // nullable: bit (q * mask_ld*32 + row)
     uint64_t mask_ld;       // words per query
+    int metric;             // YAMS_B200_COSINE / YAMS_B200_L2
+    // tensor engine: operand-typed queries + the per-query error bound eps[] (|score~ - score| <= eps[q], the input of the
+    // exactness certificate) are prepared by the first call of a search and reused by the following ones
+    bool skip_qprep;
+    float* eps;             // nq floats, written by the engine's query preparation
+    float r_max, dr_abs_max, dr_rel_max;   // corpus norm statistics (Corpus)
 };
 
 yams_status_t stage1_cuda_core(const Stage1Args& a, bool filter, cudaStream_t st);

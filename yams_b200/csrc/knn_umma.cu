@@ -157,6 +157,11 @@ struct UmmaArgs {
     uint32_t b_stage;     // bytes of one B stage held by ONE CTA = (n_tile / CTAS) * 128
     uint32_t idesc;
     unsigned long long* prof;   // nullable diagnostics: per CTA {producer wait, mma wait full, mma wait tempty, epi wait, epi work, total}
+    // experiment knobs (tools/exp_umma.py; all 0 in production)
+    uint32_t mode;        // 0 normal; 1 loads only (no MMAs); 2 MMAs only (ring filled once, then no loads)
+    uint32_t nopf;        // 1: no L2 prefetch of the next row tile
+    uint32_t peer_arrive; // CTAS == 2: the peer CTA arrives on the leader's full barrier (count 2) instead of count 1
+    uint32_t epi_relaxed; // CTAS == 2: accumulator hand-back without a cluster-scope release
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -173,6 +178,14 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
     uint32_t raddr;
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+// same without the cluster-scope release (a cluster-scope release drains the SM's outstanding memory traffic and costs
+// thousands of cycles next to in-flight TMA loads): enough for hand-backs whose data travelled through tcgen05/TMEM and
+// were ordered by tcgen05.fence::before_thread_sync
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t rank) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(rank));
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
 }
 // 2-SM TMA load: bytes are credited to the barrier of the pair's leader CTA (peer bit cleared)
 __device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -249,7 +262,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
         for (uint32_t s = 0; s < u.stages; ++s) {
-            mbar_init(&full[s], CTAS);          // leader's expect_tx arrive (+ the peer's remote arrive)
+            mbar_init(&full[s], (CTAS == 2 && u.peer_arrive) ? 2 : 1);   // leader's expect_tx arrive (+ the peer's remote arrive)
             mbar_init(&empty[s], 1);
         }
         mbar_init(&tfull[0], 1);
@@ -287,7 +300,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     if (warp == 0) {
         // ===================== TMA producer (every CTA loads its own rows and its share of the queries) =====
         if (lane == 0) {
-            uint32_t s = 0, ph = 0;
+            uint32_t s = 0, ph = 0, iter = 0;
             long long w_prod = 0;
             // A CTA (pair) owns whole row tiles and runs every query tile against each: the corpus tile is fetched
             // from HBM once and re-read from L2 by the same SM; the next row tile is prefetched into L2 meanwhile.
@@ -301,9 +314,12 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                         mbar_wait(&empty[s], ph ^ 1, &w_prod);
                         uint8_t* sa = tiles + (size_t)s * stage_bytes;
                         uint8_t* sb = sa + UM_A_STAGE;
-                        if (CTAS == 2) {
+                        if (u.mode == 2 && iter >= u.stages) {   // experiment: operands stay in place, barriers only
+                            if (leader) mbar_arrive(&full[s]);
+                            else if (u.peer_arrive) mbar_arrive_remote(&full[s], 0);
+                        } else if (CTAS == 2) {
                             if (leader) mbar_expect_tx(&full[s], stage_bytes * 2);
-                            else mbar_arrive_remote(&full[s], 0);
+                            else if (u.peer_arrive) mbar_arrive_remote(&full[s], 0);
                             tma_load_2d_2sm(sa, &tmA, &full[s], (int)(kb * u.block_k), a_row);
                             tma_load_2d_2sm(sb, &tmB, &full[s], (int)(kb * u.block_k), b_row);
                         } else {
@@ -311,7 +327,8 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             tma_load_2d(sa, &tmA, &full[s], (int)(kb * u.block_k), a_row);
                             tma_load_2d(sb, &tmB, &full[s], (int)(kb * u.block_k), b_row);
                         }
-                        if (qt == 0 && have_next) tma_prefetch_2d(&tmA, (int)(kb * u.block_k), a_next);
+                        ++iter;
+                        if (qt == 0 && have_next && !u.nopf) tma_prefetch_2d(&tmA, (int)(kb * u.block_k), a_next);
                         if (++s == u.stages) { s = 0; ph ^= 1; }
                     }
                 }
@@ -335,6 +352,12 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
                     const uint64_t adesc = make_smem_desc(sa);
                     const uint64_t bdesc = make_smem_desc(sa + UM_A_STAGE);
+                    if (u.mode == 1) {   // experiment: loads only
+                        mbar_arrive(&empty[s]);
+                        if (CTAS == 2) mbar_arrive_remote(&empty[s], 1);
+                        if (++s == u.stages) { s = 0; ph ^= 1; }
+                        continue;
+                    }
 #pragma unroll
                     for (uint32_t k = 0; k < UM_MMAS_PER_KBLOCK; ++k) {
                         // advance 32 bytes (16 fp16 / 8 tf32) along K inside the swizzle row: +2 in 16-byte units
@@ -351,7 +374,10 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     if (CTAS == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
                     if (++s == u.stages) { s = 0; ph ^= 1; }
                 }
-                if (CTAS == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);   // accumulator complete
+                if (u.mode == 1) {
+                    mbar_arrive(&tfull[as]);
+                    if (CTAS == 2) mbar_arrive_remote(&tfull[as], 1);
+                } else if (CTAS == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);   // accumulator complete
             }
             if (u.prof) {
                 u.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
@@ -412,13 +438,21 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (profiling) t_head += clock64() - t_h0;
             mbar_wait(&tfull[as], aph, &w_epi);
             tcgen05_fence_after();
-            if (FILTER) {
+            // score = acc * alpha + beta.  cosine: alpha = 1/|row| (0 marks a row the reference skips), beta = 0;
+            // L2: alpha = 2, beta = -|row|^2 (the row slot holds |row|^2; +inf marks a non-finite row)
+            const bool l2 = u.a.metric == YAMS_B200_L2;
+            const float alpha = l2 ? 2.f : inr;
+            const float beta = l2 ? -inr : 0.f;
+            const bool rowok = rvalid && (l2 ? inr < INFINITY : inr > 0.f);
+            if (u.mode == 1) {
+                // experiment: no accumulators to read
+            } else if (FILTER) {
                 const float* tau_t = tau_all + q0;
-                // conservative row-level bound: score > tau_q  =>  acc > tmin * |row| (slightly relaxed)
+                // conservative row-level bound: acc * alpha + beta > tau_q  =>  acc > (tmin - beta) / alpha (slightly relaxed)
                 float bound = INFINITY;
-                if (rvalid && inr > 0.f) {
-                    float b0 = tmin_s[qt] * (1.0f / inr);
-                    bound = b0 - fabsf(b0) * 1e-6f - 1e-30f;
+                if (rowok) {
+                    float b0 = (tmin_s[qt] - beta) * (1.0f / alpha);
+                    bound = b0 - (fabsf(tmin_s[qt]) + fabsf(beta)) * (2e-6f / alpha) - 1e-30f;
                 }
                 auto process = [&](const uint32_t (&v)[32], uint32_t c0) {
                     float m = __uint_as_float(v[0]);
@@ -433,10 +467,10 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
                         for (int c = 0; c < 32; c += 4) {
                             const float4 t4 = *reinterpret_cast<const float4*>(tau_t + c0 + c);
-                            pm |= (__uint_as_float(v[c + 0]) * inr > t4.x ? 1u : 0u) << (c + 0);
-                            pm |= (__uint_as_float(v[c + 1]) * inr > t4.y ? 1u : 0u) << (c + 1);
-                            pm |= (__uint_as_float(v[c + 2]) * inr > t4.z ? 1u : 0u) << (c + 2);
-                            pm |= (__uint_as_float(v[c + 3]) * inr > t4.w ? 1u : 0u) << (c + 3);
+                            pm |= (fmaf(__uint_as_float(v[c + 0]), alpha, beta) > t4.x ? 1u : 0u) << (c + 0);
+                            pm |= (fmaf(__uint_as_float(v[c + 1]), alpha, beta) > t4.y ? 1u : 0u) << (c + 1);
+                            pm |= (fmaf(__uint_as_float(v[c + 2]), alpha, beta) > t4.z ? 1u : 0u) << (c + 2);
+                            pm |= (fmaf(__uint_as_float(v[c + 3]), alpha, beta) > t4.w ? 1u : 0u) << (c + 3);
                         }
                         // survivors (about one per entry): compact loop, the column is extracted with a select tree
                         // so the code stays small (an unrolled per-column body thrashed the instruction cache)
@@ -452,7 +486,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                             for (int i = 0; i < 4; ++i) x4[i] = (c & 4) ? x8[i + 4] : x8[i];
 #pragma unroll
                             for (int i = 0; i < 2; ++i) x2[i] = (c & 2) ? x4[i + 2] : x4[i];
-                            const float sc = __uint_as_float((c & 1) ? x2[1] : x2[0]) * inr;
+                            const float sc = fmaf(__uint_as_float((c & 1) ? x2[1] : x2[0]), alpha, beta);
                             const uint32_t q = q0 + c0 + (uint32_t)c;
                             if (direct) {
                                 uint32_t w = __ldg(&u.a.mask[(uint64_t)q * u.a.mask_ld + (grow >> 5)]);
@@ -517,7 +551,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
                     for (int c = 0; c < 32; ++c) {
                         const uint32_t q = q0 + c0 + c;
                         if (q < u.a.nq)
-                            u.a.out_scores[(uint64_t)q * u.a.ld + li] = inr > 0.f ? __uint_as_float(v[c]) * inr : -INFINITY;
+                            u.a.out_scores[(uint64_t)q * u.a.ld + li] = rowok ? fmaf(__uint_as_float(v[c]), alpha, beta) : -INFINITY;
                     }
                 }
             }
@@ -525,7 +559,9 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (CTAS == 2) mbar_arrive_remote(&tempty[as], 0); else mbar_arrive(&tempty[as]);
+                if (CTAS == 2) {
+                    if (u.epi_relaxed) mbar_arrive_remote_relaxed(&tempty[as], 0); else mbar_arrive_remote(&tempty[as], 0);
+                } else mbar_arrive(&tempty[as]);
             }
             if (FILTER && !direct && *my_cnt >= (UM_EPI_CAP * 3) / 4) flush();   // warp-uniform (smem value)
             li = li_next;
@@ -554,13 +590,52 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     }
 }
 
-// queries -> fp16, pre-scaled by 1/|q|
-__global__ void queries_to_f16_kernel(const float* __restrict__ q32, const float* __restrict__ qinv, uint32_t nq, uint32_t d,
-                                      __half* __restrict__ out) {
-    uint64_t total = (uint64_t)nq * d;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t q = (uint32_t)(i / d);
-        out[i] = __float2half_rn(q32[i] * qinv[q]);
+// Query preparation, one CTA per query: the operand-typed copy the tensor cores read (fp16, or fp32 read as tf32), pre-scaled
+// by 1/|q| for the cosine metric, and the per-query stage-1 error bound eps[q] that the exactness certificate uses.
+// With x = the scaled query, y = what the tensor core multiplies (fp16-rounded / tf32-truncated x), dq = |x - y|, and the
+// rows r read as r' (exact for fp16 rows; tf32-truncated for fp32 rows, residual norms tracked per corpus):
+//   |x.r - y.r'| <= dq |r'| + |x| |r - r'|            (Cauchy-Schwarz with the ACTUAL rounding residuals)
+//   cosine (|x| = 1, score = x.r / |r|):  eps = 1.25 (dq + dr_rel_max) + 2^-23 (d + 4)
+//   L2 (score = 2 x.r - |r|^2)         :  eps = 2.5 (dq Rmax + |x| dr_abs_max) + 2^-22 (d + 4) |x| Rmax + 2^-22 Rmax^2
+// The 1.25 covers the second-order term and the fp32 accumulation inside the tensor core is the 2^-23 (d + 4) term.
+template <bool TF32>
+__global__ void __launch_bounds__(128) queries_prep_kernel(const float* __restrict__ q32, const float* __restrict__ qinv, uint32_t nq,
+                                                           uint32_t d, void* __restrict__ out, int metric, float r_max, float dr_abs_max,
+                                                           float dr_rel_max, float* __restrict__ eps) {
+    const uint32_t q = blockIdx.x;
+    const float scale = qinv[q];   // 1 for L2
+    float ss = 0.f, xx = 0.f;
+    for (uint32_t c = threadIdx.x; c < d; c += 128) {
+        const float x = q32[(uint64_t)q * d + c] * scale;
+        float y;
+        if (TF32) {
+            reinterpret_cast<float*>(out)[(uint64_t)q * d + c] = x;
+            y = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+        } else {
+            const __half h = __float2half_rn(x);
+            reinterpret_cast<__half*>(out)[(uint64_t)q * d + c] = h;
+            y = __half2float(h);
+        }
+        const float r = x - y;
+        ss = fmaf(r, r, ss);
+        xx = fmaf(x, x, xx);
+    }
+    __shared__ float red[2][4];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        xx += __shfl_xor_sync(0xffffffffu, xx, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = ss; red[1][threadIdx.x >> 5] = xx; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const float dq = sqrtf(red[0][0] + red[0][1] + red[0][2] + red[0][3]) * 1.000001f;
+        const float xn = sqrtf(red[1][0] + red[1][1] + red[1][2] + red[1][3]) * 1.000001f;
+        const float u = 1.1920929e-07f;   // 2^-23
+        float e;
+        if (metric == YAMS_B200_L2) e = 2.5f * (dq * r_max + xn * dr_abs_max) + 2.f * u * (float)(d + 4) * xn * r_max + 2.f * u * r_max * r_max + 1e-30f;
+        else e = 1.25f * (dq + xn * dr_rel_max) + u * (float)(d + 4) + 1e-7f;
+        eps[q] = e;
     }
 }
 
@@ -582,14 +657,6 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// queries pre-scaled by 1/|q|, kept in fp32 (tf32 engine)
-__global__ void queries_scale_f32_kernel(const float* __restrict__ q32, const float* __restrict__ qinv, uint32_t nq, uint32_t d,
-                                         float* __restrict__ out) {
-    uint64_t total = (uint64_t)nq * d;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
-        out[i] = q32[i] * qinv[(uint32_t)(i / d)];
-}
-
 static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,
                         uint32_t box_inner, uint32_t box_outer, bool f32 = false) {
     EncodeTiledFn fn = get_encode_fn();
@@ -607,7 +674,7 @@ static bool make_map_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64
 bool tcgen05_supported(const Corpus* c, uint32_t nq) {
     (void)nq;
     if (getenv("YAMS_B200_DISABLE_TCGEN05")) return false;
-    if (c->metric != YAMS_B200_COSINE || get_encode_fn() == nullptr) return false;
+    if (get_encode_fn() == nullptr) return false;
     // fp16 rows: kind::f16; fp32 rows (the reference's BLOB layout): kind::tf32.  TMA needs 16-byte row pitches.
     return c->dtype == YAMS_B200_F16 ? (c->dim % 8 == 0) : (c->dim % 4 == 0 && !getenv("YAMS_B200_DISABLE_TF32"));
 }
@@ -624,16 +691,25 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     size_t qb = (size_t)a.nq * a.dim * esz;
     if ((rc = c->q16.reserve(qb + 256)) != YAMS_OK) return rc;
     void* d_q16 = c->q16.p;
-    const unsigned qgrid = (unsigned)std::min<uint64_t>(((uint64_t)a.nq * a.dim + 255) / 256, 4096);
-    if (tf32) queries_scale_f32_kernel<<<qgrid, 256, 0, st>>>(a.q32, a.qinv, a.nq, a.dim, c->q16.as<float>());
-    else queries_to_f16_kernel<<<qgrid, 256, 0, st>>>(a.q32, a.qinv, a.nq, a.dim, c->q16.as<__half>());
+    if (!a.skip_qprep) {
+        if (!a.eps) return YAMS_ERR_UNSUPPORTED;
+        if (tf32) queries_prep_kernel<true><<<a.nq, 128, 0, st>>>(a.q32, a.qinv, a.nq, a.dim, d_q16, a.metric, a.r_max, a.dr_abs_max,
+                                                                   a.dr_rel_max, a.eps);
+        else queries_prep_kernel<false><<<a.nq, 128, 0, st>>>(a.q32, a.qinv, a.nq, a.dim, d_q16, a.metric, a.r_max, 0.f, 0.f, a.eps);
+    }
 
-    static const int ctas_env = [] { const char* e = getenv("YAMS_B200_UMMA_CTAS"); return e ? atoi(e) : 1; }();
+    auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
+    const int ctas_env = env_int("YAMS_B200_UMMA_CTAS", 1);
     const int ctas = (ctas_env == 1 || c->dev->sm_count < 2) ? 1 : 2;
     UmmaArgs u{};
     u.a = a;
+    u.mode = (uint32_t)env_int("YAMS_B200_UMMA_MODE", 0);
+    u.nopf = (uint32_t)env_int("YAMS_B200_UMMA_NOPF", 0);
+    u.peer_arrive = (uint32_t)env_int("YAMS_B200_UMMA_PEER_ARRIVE", 0);
+    u.epi_relaxed = (uint32_t)env_int("YAMS_B200_UMMA_EPI_RELAXED", 1);
     const uint32_t nmult = 16 * ctas;   // each CTA's share of the query tile must be a multiple of 8 rows (16 for M=128)
-    u.n_tile = a.nq >= UM_MAX_N ? UM_MAX_N : ((a.nq + nmult - 1) / nmult) * nmult;
+    const uint32_t max_n = (uint32_t)std::min(UM_MAX_N, std::max(32, env_int("YAMS_B200_UMMA_NTILE", UM_MAX_N)));
+    u.n_tile = a.nq >= max_n ? max_n : ((a.nq + nmult - 1) / nmult) * nmult;
     u.nqt = (a.nq + u.n_tile - 1) / u.n_tile;
     const uint32_t rows_per_unit = UM_BLOCK_M * ctas;
     u.nrt = (uint32_t)((a.nrows + rows_per_unit - 1) / rows_per_unit);
@@ -645,6 +721,7 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     if (u.nqt > 32 || (size_t)u.nqt * u.n_tile > 4096) return YAMS_ERR_UNSUPPORTED;   // thresholds live in shared memory
     const uint32_t budget = 224 * 1024 - (uint32_t)(32 * 4 + 16 + (((size_t)u.nqt * u.n_tile + 31) & ~(size_t)31) * 4 + 4 * UM_EPI_CAP * sizeof(EpiEntry)) - 2048;
     u.stages = std::min<uint32_t>(8, budget / stage_bytes);
+    if (int st_env = env_int("YAMS_B200_UMMA_STAGES", 0)) u.stages = std::min<uint32_t>(u.stages, (uint32_t)st_env);
     if (u.stages < 2) return YAMS_ERR_UNSUPPORTED;
     // instruction descriptor: D=f32 (bits 4-5), A/B format (bits 7-9 / 10-12: 0 = f16, 2 = tf32), both K-major,
     // N = n_tile (bits 17-22, /8), M = 128 per CTA (bits 24-28, /16)

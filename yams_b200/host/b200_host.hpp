@@ -14,6 +14,9 @@
 #include <span>
 #include <stdexcept>
 #include <algorithm>
+#include <cmath>
+#include <map>
+#include <optional>
 #include <string>
 #include <unordered_map>
 #include <unordered_set>
@@ -260,17 +263,32 @@ inline std::vector<ChunkValidationResult> validateChunks(const std::vector<std::
 }
 
 // The part of IVectorStore the hot path covers.  Records live in SQLite in the real backend; here a record is
-// (rowid, chunk_id) and `relevance_score` -- enough to express the tie-break contract of
-// sqlite_vec_backend.cpp:4218-4223 (similarity desc, then chunk_id asc).
+// (rowid, chunk_id, document_hash, metadata) and `relevance_score` -- enough to express the WHERE clause of
+// bruteForceSearchUnlocked (sqlite_vec_backend.cpp:4138-4175), its metadata filter (:4349-4360) and the tie-break
+// contract of :4218-4223 (similarity desc, then chunk_id asc).
 struct VectorHit {
     int64_t rowid = -1;
     std::string chunk_id;
     float relevance_score = 0.f;
 };
 
+// The fields of VectorSearchDiagnostics (include/yams/vector/vector_types.h:180-203) the exact scan fills
+// (sqlite_vec_backend.cpp:4131-4135, 4336-4338, 4368-4370, 4404-4406)
+struct VectorSearchDiagnostics {
+    bool usedExactScan = false;
+    bool rowsVisitedObserved = false;
+    bool exactDistanceEvaluationsObserved = false;
+    size_t rowsVisited = 0;
+    size_t exactDistanceEvaluations = 0;
+    size_t returnedRows = 0;
+    size_t resolvedExhaustively = 0;   // extension: queries the device certificate sent to the exhaustive levels
+};
+
 class B200VectorStore {
 public:
-    B200VectorStore(uint32_t dim, int dtype = YAMS_B200_F32, int metric = YAMS_B200_COSINE) : dim_(dim) {
+    static constexpr size_t kMaxDeviceK = 3072;   // yams_b200_search limit (include/yams_b200.h)
+
+    B200VectorStore(uint32_t dim, int dtype = YAMS_B200_F32, int metric = YAMS_B200_COSINE) : dim_(dim), dtype_(dtype) {
         yams_status_t st = yams_b200_corpus_create(nullptr, dim, dtype, metric, 0, &c_);
         if (st != YAMS_OK) throw_status("corpus_create", st);
     }
@@ -278,10 +296,14 @@ public:
     B200VectorStore(const B200VectorStore&) = delete;
     B200VectorStore& operator=(const B200VectorStore&) = delete;
 
-    // insertVectorsBatch: rows are fp32 (the reference BLOB layout); rowids ascending
+    // insertVectorsBatch: rows are fp32 (the reference BLOB layout, sqlite_vec_backend.cpp:343-363); rowids ascending.
+    // An fp16 store converts on the device with the reference's truncating float16_t::from_float.
     void insertVectorsBatch(const std::vector<float>& rows, const std::vector<int64_t>& rowids, const std::vector<std::string>& chunk_ids,
-                            const std::vector<std::string>& document_hashes = {}) {
-        yams_status_t st = yams_b200_corpus_append(c_, rows.data(), rowids.size(), rowids.data());
+                            const std::vector<std::string>& document_hashes = {},
+                            const std::vector<std::map<std::string, std::string>>& metadata = {}) {
+        if (rows.size() != rowids.size() * dim_ || chunk_ids.size() != rowids.size()) throw std::invalid_argument("insertVectorsBatch: shape mismatch");
+        yams_status_t st = dtype_ == YAMS_B200_F16 ? yams_b200_corpus_append_f32_as_f16(c_, rows.data(), rowids.size(), rowids.data())
+                                                   : yams_b200_corpus_append(c_, rows.data(), rowids.size(), rowids.data());
         if (st != YAMS_OK) throw_status("corpus_append", st);
         for (size_t i = 0; i < rowids.size(); ++i) {
             chunk_of_[rowids[i]] = chunk_ids[i];
@@ -289,7 +311,19 @@ public:
                 doc_of_[rowids[i]] = document_hashes[i];
                 rows_of_doc_[document_hashes[i]].push_back(rowids[i]);
             }
+            if (i < metadata.size() && !metadata[i].empty()) meta_of_[rowids[i]] = metadata[i];
+            // rows the scan skips (isZeroNormEmbedding / isFiniteEmbedding, sqlite_vec_backend.cpp:204-235): only needed
+            // to report exactDistanceEvaluations the way the reference counts it
+            const float* r = rows.data() + i * dim_;
+            double ss = 0.0;
+            bool finite = true;
+            for (uint32_t c = 0; c < dim_; ++c) {
+                finite = finite && std::isfinite(r[c]);
+                ss += (double)r[c] * (double)r[c];
+            }
+            if (!finite || ss <= 1e-12) skipped_.insert(rowids[i]);
         }
+        all_rowids_.insert(all_rowids_.end(), rowids.begin(), rowids.end());
     }
 
     // deleteVector(chunk_id) / deleteVectorsByDocument(document_hash) (vector_store.h:39-40): the device mirror drops
@@ -319,92 +353,63 @@ public:
         return out;
     }
 
-    // searchExactCandidatesWithDiagnostics (vector_store.h:121-129): exact top-k within the candidate documents
-    std::vector<VectorHit> searchExactCandidates(const std::vector<float>& query, size_t k, float similarity_threshold,
-                                                 const std::unordered_set<std::string>& candidate_hashes) {
+    // searchSimilar (vector_store.h:44-49) with every argument of the reference: `document_hash`, `candidate_hashes`
+    // and `metadata_filters` become ONE allowed-rowid set (the WHERE clause of :4138-4175 intersected with the metadata
+    // predicate of :4349-4360) that the device scan honours.  InvalidArgument (std::invalid_argument here) for a
+    // non-finite or zero-norm query; k == 0 -> empty.
+    std::vector<VectorHit> searchSimilar(const std::vector<float>& query, size_t k, float similarity_threshold = 0.0f,
+                                         const std::optional<std::string>& document_hash = std::nullopt,
+                                         const std::unordered_set<std::string>& candidate_hashes = {},
+                                         const std::map<std::string, std::string>& metadata_filters = {},
+                                         VectorSearchDiagnostics* diagnostics = nullptr) {
         if (query.size() != dim_) throw std::invalid_argument("query dimension mismatch");
         if (k == 0) return {};
-        std::vector<int64_t> allowed = lookupCandidateRowids(candidate_hashes);
-        uint64_t offs[2] = {0, allowed.size()};
-        size_t kk = std::min<size_t>(3072, k + 8);
-        std::vector<int64_t> rid(kk);
-        std::vector<float> sc(kk);
-        uint32_t cnt = 0;
-        uint64_t flg = 0;
-        int64_t none = 0;
-        yams_status_t st = yams_b200_search(c_, query.data(), 1, (uint32_t)kk, similarity_threshold, allowed.empty() ? &none : allowed.data(),
-                                            offs, rid.data(), sc.data(), &cnt, &flg);
-        if (st == YAMS_ERR_INVALID_ARG) throw std::invalid_argument("Exact vector search requires a finite, non-zero query embedding");
-        if (st != YAMS_OK) throw_status("search", st);
-        return materialise(rid.data(), sc.data(), cnt, k);
+        std::optional<std::vector<int64_t>> allowed = allowedRows(document_hash, candidate_hashes, metadata_filters, diagnostics);
+        auto all = searchImpl(query.data(), 1, k, similarity_threshold, allowed ? &*allowed : nullptr, diagnostics);
+        return all.empty() ? std::vector<VectorHit>{} : std::move(all[0]);
+    }
+
+    // searchExactCandidatesWithDiagnostics (vector_store.h:121-129): exact top-k within the candidate documents
+    std::vector<VectorHit> searchExactCandidates(const std::vector<float>& query, size_t k, float similarity_threshold,
+                                                 const std::unordered_set<std::string>& candidate_hashes,
+                                                 VectorSearchDiagnostics* diagnostics = nullptr) {
+        if (query.size() != dim_) throw std::invalid_argument("query dimension mismatch");
+        if (k == 0) return {};
+        std::optional<std::vector<int64_t>> allowed = allowedRows(std::nullopt, candidate_hashes, {}, diagnostics);
+        if (!allowed) allowed.emplace();   // an empty candidate set selects nothing here (the seam is candidate-only)
+        auto all = searchImpl(query.data(), 1, k, similarity_threshold, &*allowed, diagnostics);
+        return all.empty() ? std::vector<VectorHit>{} : std::move(all[0]);
     }
 
     // searchAllExactCandidateRowsWithDiagnostics (vector_store.h:131-138): every passing row of the candidate documents
     std::vector<VectorHit> searchAllExactCandidateRows(const std::vector<float>& query, float similarity_threshold,
-                                                       const std::unordered_set<std::string>& candidate_hashes) {
+                                                       const std::unordered_set<std::string>& candidate_hashes,
+                                                       VectorSearchDiagnostics* diagnostics = nullptr) {
         if (query.size() != dim_) throw std::invalid_argument("query dimension mismatch");
-        std::vector<int64_t> allowed = lookupCandidateRowids(candidate_hashes);
-        if (allowed.empty()) return {};
-        std::vector<int64_t> rid(allowed.size());
-        std::vector<float> sc(allowed.size());
-        uint64_t cnt = 0;
-        yams_status_t st = yams_b200_search_all_matching(c_, query.data(), similarity_threshold, allowed.data(), allowed.size(), rid.data(),
-                                                         sc.data(), &cnt);
-        if (st == YAMS_ERR_INVALID_ARG) throw std::invalid_argument("Exact vector search requires a finite, non-zero query embedding");
-        if (st != YAMS_OK) throw_status("search_all_matching", st);
-        return materialise(rid.data(), sc.data(), (uint32_t)cnt, (size_t)cnt);
+        std::optional<std::vector<int64_t>> allowed = allowedRows(std::nullopt, candidate_hashes, {}, diagnostics);
+        if (!allowed || allowed->empty()) return {};
+        auto hits = allMatching(query.data(), similarity_threshold, *allowed);
+        if (diagnostics) diagnostics->returnedRows = hits.size();
+        return hits;
     }
 
-    // searchSimilar (vector_store.h:44-49): InvalidArgument (std::invalid_argument here) for a non-finite or
-    // zero-norm query; k == 0 -> empty.
-    std::vector<VectorHit> searchSimilar(const std::vector<float>& query, size_t k, float similarity_threshold = 0.0f) {
-        auto all = searchSimilarBatch({query}, k, similarity_threshold);
-        return all.empty() ? std::vector<VectorHit>{} : all[0];
-    }
-
+    // searchSimilarBatch (vector_store.h:51-53; the reference loops over the queries, :4531-4546): one device call
     std::vector<std::vector<VectorHit>> searchSimilarBatch(const std::vector<std::vector<float>>& queries, size_t k,
-                                                           float similarity_threshold = 0.0f) {
+                                                           float similarity_threshold = 0.0f, VectorSearchDiagnostics* diagnostics = nullptr) {
         std::vector<std::vector<VectorHit>> out(queries.size());
         if (queries.empty() || k == 0) return out;
         std::vector<float> flat;
+        flat.reserve(queries.size() * dim_);
         for (const auto& q : queries) {
             if (q.size() != dim_) throw std::invalid_argument("All query embeddings must have the same dimension");  // :1620-1627
             flat.insert(flat.end(), q.begin(), q.end());
         }
-        // ask for slack so that an equal-score run straddling k can be re-ordered by chunk_id on the host
-        size_t kk = k + 8;
-        for (int attempt = 0; attempt < 4; ++attempt) {
-            std::vector<int64_t> rid(queries.size() * kk);
-            std::vector<float> sc(queries.size() * kk);
-            std::vector<uint32_t> cnt(queries.size());
-            std::vector<uint64_t> flg(queries.size());
-            yams_status_t st = yams_b200_search(c_, flat.data(), (uint32_t)queries.size(), (uint32_t)kk, similarity_threshold, nullptr,
-                                                nullptr, rid.data(), sc.data(), cnt.data(), flg.data());
-            if (st == YAMS_ERR_INVALID_ARG) throw std::invalid_argument("Exact vector search requires a finite, non-zero query embedding");
-            if (st != YAMS_OK) throw_status("search", st);
-            bool need_more = false;
-            for (size_t q = 0; q < queries.size(); ++q)
-                if ((flg[q] & YAMS_B200_FLAG_TIE_AT_K) && cnt[q] == kk && kk < 3072) need_more = true;
-            if (need_more) { kk = std::min<size_t>(3072, kk * 2); continue; }
-            for (size_t q = 0; q < queries.size(); ++q) {
-                std::vector<VectorHit> hits(cnt[q]);
-                for (uint32_t i = 0; i < cnt[q]; ++i) {
-                    hits[i].rowid = rid[q * kk + i];
-                    hits[i].relevance_score = sc[q * kk + i];
-                    auto it = chunk_of_.find(hits[i].rowid);
-                    hits[i].chunk_id = it == chunk_of_.end() ? std::string() : it->second;
-                }
-                // sqlite_vec_backend.cpp:4218-4223: similarity desc, then chunk_id asc
-                std::stable_sort(hits.begin(), hits.end(), [](const VectorHit& a, const VectorHit& b) {
-                    if (a.relevance_score != b.relevance_score) return a.relevance_score > b.relevance_score;
-                    return a.chunk_id < b.chunk_id;
-                });
-                if (hits.size() > k) hits.resize(k);
-                out[q] = std::move(hits);
-            }
-            return out;
+        if (diagnostics) {
+            noteScan(diagnostics);
+            diagnostics->rowsVisited += all_rowids_.size() * queries.size();
+            diagnostics->exactDistanceEvaluations += (all_rowids_.size() - skipped_.size()) * queries.size();
         }
-        throw std::runtime_error("too many equal-score rows at the k boundary");
+        return searchImpl(flat.data(), queries.size(), k, similarity_threshold, nullptr, diagnostics);
     }
 
     size_t size() const {
@@ -414,6 +419,125 @@ public:
     }
 
 private:
+    static void noteScan(VectorSearchDiagnostics* d) {
+        d->usedExactScan = true;
+        d->rowsVisitedObserved = true;
+        d->exactDistanceEvaluationsObserved = true;
+    }
+    // The rows `SELECT ... WHERE [document_hash = ?] [AND document_hash IN (...)]` visits, minus those failing the
+    // metadata predicate; nullopt = no restriction at all.  Fills rowsVisited / exactDistanceEvaluations like the reference
+    // counts them (visited = rows the statement yields; evaluated = rows that reach the similarity computation).
+    std::optional<std::vector<int64_t>> allowedRows(const std::optional<std::string>& document_hash,
+                                                    const std::unordered_set<std::string>& candidate_hashes,
+                                                    const std::map<std::string, std::string>& metadata_filters,
+                                                    VectorSearchDiagnostics* d) const {
+        const bool restricted = document_hash.has_value() || !candidate_hashes.empty();
+        std::vector<int64_t> rows;
+        if (restricted) {
+            if (document_hash && (candidate_hashes.empty() || candidate_hashes.count(*document_hash))) {
+                auto it = rows_of_doc_.find(*document_hash);
+                if (it != rows_of_doc_.end()) rows = it->second;
+                std::sort(rows.begin(), rows.end());
+            } else if (!document_hash) {
+                rows = lookupCandidateRowids(candidate_hashes);
+            }
+        } else if (!metadata_filters.empty()) {
+            rows = all_rowids_;
+        }
+        const size_t visited = (restricted || !metadata_filters.empty()) ? rows.size() : all_rowids_.size();
+        if (!metadata_filters.empty()) {
+            std::vector<int64_t> kept;
+            for (int64_t r : rows) {
+                auto m = meta_of_.find(r);
+                bool match = true;
+                for (const auto& [key, value] : metadata_filters) {
+                    if (m == meta_of_.end()) { match = false; break; }
+                    auto f = m->second.find(key);
+                    if (f == m->second.end() || f->second != value) { match = false; break; }
+                }
+                if (match) kept.push_back(r);
+            }
+            rows.swap(kept);
+        }
+        if (d) {
+            noteScan(d);
+            d->rowsVisited += visited;
+            size_t evaluated = (restricted || !metadata_filters.empty()) ? rows.size() : all_rowids_.size();
+            if (restricted || !metadata_filters.empty()) {
+                for (int64_t r : rows) evaluated -= skipped_.count(r);
+            } else {
+                evaluated -= skipped_.size();
+            }
+            d->exactDistanceEvaluations += evaluated;
+        }
+        if (!restricted && metadata_filters.empty()) return std::nullopt;
+        return rows;
+    }
+
+    std::vector<VectorHit> allMatching(const float* query, float threshold, const std::vector<int64_t>& allowed) {
+        std::vector<int64_t> rid(allowed.size());
+        std::vector<float> sc(allowed.size());
+        uint64_t cnt = 0;
+        yams_status_t st = yams_b200_search_all_matching(c_, query, threshold, allowed.data(), allowed.size(), rid.data(), sc.data(), &cnt);
+        if (st == YAMS_ERR_INVALID_ARG) throw std::invalid_argument("Exact vector search requires a finite, non-zero query embedding");
+        if (st != YAMS_OK) throw_status("search_all_matching", st);
+        return materialise(rid.data(), sc.data(), (uint32_t)cnt, (size_t)cnt);
+    }
+
+    // One device call for nq queries (optionally all restricted to the same allowed-rowid set).  The device breaks equal
+    // scores by rowid and raises TIE_AT_K when an equal-score run straddles the requested count; the reference breaks by
+    // chunk_id (:4218-4223), so the request carries slack and is widened until the run fits (at most kMaxDeviceK rows;
+    // beyond that the whole candidate set is fetched with the AllMatching selection and cut here).
+    std::vector<std::vector<VectorHit>> searchImpl(const float* flat, size_t nq, size_t k, float threshold, const std::vector<int64_t>* allowed,
+                                                   VectorSearchDiagnostics* d) {
+        if (k > kMaxDeviceK)
+            throw std::invalid_argument("k exceeds the device top-k limit of 3072 rows per query; page the request or use the all-matching selection");
+        std::vector<std::vector<VectorHit>> out(nq);
+        std::vector<uint64_t> offs;
+        int64_t none = 0;
+        if (allowed) {
+            offs.resize(nq + 1);
+            for (size_t q = 0; q <= nq; ++q) offs[q] = q * allowed->size();
+        }
+        std::vector<int64_t> allowed_rep;
+        if (allowed && nq > 1) {
+            allowed_rep.reserve(allowed->size() * nq);
+            for (size_t q = 0; q < nq; ++q) allowed_rep.insert(allowed_rep.end(), allowed->begin(), allowed->end());
+        }
+        const int64_t* al = !allowed ? nullptr : (allowed->empty() ? &none : (nq > 1 ? allowed_rep.data() : allowed->data()));
+        size_t kk = std::min(kMaxDeviceK, k + 8);
+        for (;;) {
+            std::vector<int64_t> rid(nq * kk);
+            std::vector<float> sc(nq * kk);
+            std::vector<uint32_t> cnt(nq);
+            std::vector<uint64_t> flg(nq);
+            yams_status_t st = yams_b200_search(c_, flat, (uint32_t)nq, (uint32_t)kk, threshold, al, allowed ? offs.data() : nullptr, rid.data(),
+                                                sc.data(), cnt.data(), flg.data());
+            if (st == YAMS_ERR_INVALID_ARG) throw std::invalid_argument("Exact vector search requires a finite, non-zero query embedding");
+            if (st != YAMS_OK) throw_status("search", st);
+            bool widen = false;
+            for (size_t q = 0; q < nq; ++q)
+                if ((flg[q] & YAMS_B200_FLAG_TIE_AT_K) && cnt[q] == kk && kk < kMaxDeviceK) widen = true;
+            if (widen) { kk = std::min(kMaxDeviceK, kk * 2); continue; }
+            for (size_t q = 0; q < nq; ++q) {
+                if ((flg[q] & YAMS_B200_FLAG_TIE_AT_K) && cnt[q] == kk) {
+                    // an equal-score run longer than the device can return: take every matching row and cut here
+                    std::vector<int64_t> everything = allowed ? *allowed : all_rowids_;
+                    std::sort(everything.begin(), everything.end());
+                    out[q] = allMatching(flat + q * dim_, threshold, everything);
+                    if (out[q].size() > k) out[q].resize(k);
+                } else {
+                    out[q] = materialise(rid.data() + q * kk, sc.data() + q * kk, cnt[q], k);
+                }
+                if (d) {
+                    d->returnedRows += out[q].size();
+                    if (flg[q] & YAMS_B200_FLAG_FALLBACK_PATH) ++d->resolvedExhaustively;
+                }
+            }
+            return out;
+        }
+    }
+
     // records for the winners + the chunk_id tie-break of sqlite_vec_backend.cpp:4218-4223
     std::vector<VectorHit> materialise(const int64_t* rid, const float* sc, uint32_t cnt, size_t k) const {
         std::vector<VectorHit> hits(cnt);
@@ -434,8 +558,12 @@ private:
         if (gone.empty()) return;
         yams_status_t st = yams_b200_corpus_remove(c_, gone.data(), gone.size(), nullptr);
         if (st != YAMS_OK) throw_status("corpus_remove", st);
+        std::unordered_set<int64_t> g(gone.begin(), gone.end());
+        all_rowids_.erase(std::remove_if(all_rowids_.begin(), all_rowids_.end(), [&](int64_t r) { return g.count(r) != 0; }), all_rowids_.end());
         for (int64_t r : gone) {
             chunk_of_.erase(r);
+            meta_of_.erase(r);
+            skipped_.erase(r);
             auto d = doc_of_.find(r);
             if (d != doc_of_.end()) {
                 auto& v = rows_of_doc_[d->second];
@@ -447,8 +575,12 @@ private:
     }
     yams_b200_corpus* c_ = nullptr;
     uint32_t dim_;
+    int dtype_;
+    std::vector<int64_t> all_rowids_;   // ascending (append order)
+    std::unordered_set<int64_t> skipped_;
     std::unordered_map<int64_t, std::string> chunk_of_;
     std::unordered_map<int64_t, std::string> doc_of_;
+    std::unordered_map<int64_t, std::map<std::string, std::string>> meta_of_;
     std::unordered_map<std::string, std::vector<int64_t>> rows_of_doc_;
 };
 
