@@ -444,6 +444,11 @@ YAMS_B200_API int sqlite3_vec_distance_cosine(const void* vec1, size_t size1, co
 YAMS_B200_API yams_status_t yams_b200_synth_bytes_device(uint64_t seed, uint64_t start, uint64_t n,
                                                          uint8_t* d_out);
 
+/* rows [first_row, first_row + n) of the synthetic vector generator (x = (splitmix64(seed ^ (row*dim + c)) >> 40) * 2^-23 - 1,
+ * L2-normalised in fp32; bit-identical to oracle yo_gen_rows_f32) as fp32 into a DEVICE buffer of n x dim floats */
+YAMS_B200_API yams_status_t yams_b200_synth_rows_device(uint64_t seed, uint64_t first_row, uint64_t n, uint32_t dim,
+                                                        float* d_out);
+
 /* diagnostics: dense stage-1 (approximate) scores of rows row_start + i*row_stride, i < nrows, with the
  * chosen engine (0 = CUDA-core, 1 = tcgen05); out[q * nrows + i] on the HOST. YAMS_ERR_UNSUPPORTED when the
  * engine cannot take the shape. */

@@ -107,6 +107,7 @@ SYMBOLS = {
     "sqlite3_vec_distance_cosine": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, f32p]),
     "yams_b200_synth_bytes_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "yams_b200_debug_stage1_scores": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
+    "yams_b200_synth_rows_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "yams_b200_debug_last_eps": (C.c_int, [C.c_void_p, C.c_uint32, f32p]),
     "yams_b200_device_count": (C.c_int, []),
     "yams_b200_last_error": (C.c_char_p, []),
@@ -320,6 +321,11 @@ def sha256_batch_device(dev_ptr: int, base_len: int, offsets, sizes) -> np.ndarr
 
 def synth_bytes_device(seed: int, start: int, n: int, dev_ptr: int):
     _check(lib().yams_b200_synth_bytes_device(seed, start, n, dev_ptr), "synth_bytes_device")
+
+
+def synth_rows_device(seed: int, first_row: int, n: int, dim: int, dev_ptr: int):
+    """n x dim fp32 rows of the synthetic vector generator into a device buffer."""
+    _check(lib().yams_b200_synth_rows_device(seed, first_row, n, dim, dev_ptr), "synth_rows_device")
 
 
 class Corpus:

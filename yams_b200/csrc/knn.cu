@@ -2031,6 +2031,29 @@ yams_status_t yams_b200_debug_stage1_scores(yams_b200_corpus* c, const float* qu
     return YAMS_OK;
 }
 
+// bench / test utility: n synthetic rows of the SURVEY.md §8d generator (bit-identical to oracle yo_gen_rows_f32) as fp32
+// into a DEVICE buffer -- the query batches of bench.py are produced by the library itself, not by the checker
+yams_status_t yams_b200_synth_rows_device(uint64_t seed, uint64_t first_row, uint64_t n, uint32_t dim, float* d_out) {
+    YB_TRY
+    YB_ARG(d_out && dim > 0, "bad argument");
+    if (n == 0) return YAMS_OK;
+    DeviceCtx* dev = nullptr;
+    yams_status_t rc = ensure_device(&dev);
+    if (rc != YAMS_OK) return rc;
+    float* d_inv = nullptr;
+    YB_CUDA(cudaMalloc(&d_inv, (size_t)n * 4));
+    synth_rownorm_kernel<<<(unsigned)((n + 127) / 128), 128>>>(seed, first_row, n, dim, d_inv);
+    synth_fill_kernel<<<dev->sm_count * 16, 256>>>(seed, first_row, n, dim, d_inv, d_out, YAMS_B200_F32);
+    cudaError_t e = cudaDeviceSynchronize();
+    cudaFree(d_inv);
+    if (e != cudaSuccess) {
+        set_last_error("synth_rows_device failed: %s", cudaGetErrorString(e));
+        return YAMS_ERR_INTERNAL;
+    }
+    return YAMS_OK;
+    YB_CATCH
+}
+
 // diagnostics: the per-query stage-1 error bound eps[q] (certificate input) computed by the last search /
 // debug_stage1_scores call on this corpus
 yams_status_t yams_b200_debug_last_eps(yams_b200_corpus* c, uint32_t nq, float* out) {
