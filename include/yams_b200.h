@@ -370,8 +370,9 @@ YAMS_B200_API yams_status_t yams_b200_vec0_exact(void* self, const float* query,
                                                  int64_t* out_rowids, float* out_dist,
                                                  uint64_t* out_count);
 
-/* sqlite-vec-cpp batch surface (distances/batch.hpp:24-146): ONE query against n contiguous fp32 rows, float
- * accumulation like distances/{cosine,l2}.hpp (cosine DISTANCE = 1 - cos, 1.0 when the norm product < 1e-8).
+/* sqlite-vec-cpp batch surface (distances/batch.hpp:24-146): ONE query against n contiguous fp32 rows, float accumulation
+ * in the operation ORDER of the reference build (AVX lane order, simd/avx.hpp; see csrc/ref_order.cuh), so distances are
+ * bit-identical to distances::{cosine,l2}_distance<float> (cosine DISTANCE = 1 - cos, 1.0 when the norm product < 1e-8).
  *   mode ALL      batch_distance / batch_distance_contiguous / batch_distance_parallel: out_dist[n] in row order
  *   mode TOP_K    batch_top_k: indices of the k smallest distances, ascending (ties by index -- a legal refinement
  *                 of the reference's unstable partial_sort); out_idx[min(k,n)], out_dist optional
@@ -389,6 +390,10 @@ YAMS_B200_API yams_status_t yams_b200_batch_distance(void* self, int metric, con
  * 0 on a size mismatch, an empty vector or a zero norm. Sequential double accumulation -> bit-identical. */
 YAMS_B200_API yams_status_t yams_b200_compute_cosine_similarity(void* self, const float* a, size_t na,
                                                                 const float* b, size_t nb, double* out);
+/* The rerank loops that call computeCosineSimilarity once per candidate (sqlite_vec_backend.cpp:4025,4374,4507) as ONE
+ * device pass: n pairs (a_i, b_i), row-major a[n][dim] and b[n][dim] HOST arrays -> out[n]. Same arithmetic per pair. */
+YAMS_B200_API yams_status_t yams_b200_compute_cosine_similarity_many(void* self, const float* a, const float* b,
+                                                                     size_t n, size_t dim, double* out);
 
 /* [0] stage-1 scan ms, [1] rescoring+select ms, [2] total device ms, [3] h2d+d2h ms of the last
  * yams_b200_search on this corpus; [4] = which stage-1 kernel ran (0 cuda-core, 1 tcgen05);
@@ -425,19 +430,29 @@ typedef struct yams_vector_scan_v1 {
                                     uint64_t* out_count);
     yams_status_t (*compute_cosine_similarity)(void* self, const float* a, size_t na, const float* b,
                                                size_t nb, double* out);
+    yams_status_t (*compute_cosine_similarity_many)(void* self, const float* a, const float* b, size_t n,
+                                                    size_t dim, double* out);
+    yams_status_t (*search_exhaustive)(yams_b200_corpus* c, const float* queries, uint32_t nq, uint32_t k,
+                                       float threshold, int64_t* out_rowids, float* out_scores,
+                                       uint32_t* out_counts, uint64_t* out_flags);
 } yams_vector_scan_v1;
 
 /* ---- sqlite-vec-cpp C API kept bit-for-bit in signature and error behaviour ------------------
  * third_party/sqlite-vec-cpp/src/sqlite_vec_c_api.cpp:57-105 (declared sqlite_vec.hpp:34-50):
  * sizes in BYTES, returns SQLITE_OK(0) / SQLITE_ERROR(1) on null pointer or dimension mismatch.
- * These are pairwise host-side operators (two small blobs); they are computed on the host by the
- * adapter in float exactly as distances/{l2,cosine}.hpp scalar paths do -- a GPU launch per pair
- * would be pure overhead. (sqlite3_vec_init needs sqlite3.h, absent in this image: see
- * INTEGRATION.md.) */
+ * The library has no CPU arithmetic at all: a pair is evaluated by one device thread in the operation order of the
+ * reference build (csrc/ref_order.cuh), through a pooled workspace (pinned staging + stream; no allocation per call).
+ * One pair costs a launch round trip (~20 us) -- callers with many pairs should use yams_b200_batch_distance /
+ * yams_b200_compute_cosine_similarity_many.  The SQL registration (sqlite3_vec_init, vec_distance_l2/cosine/l1 scalar
+ * functions) is csrc/sqlite_glue.cpp, compiled only where sqlite3.h exists. */
 YAMS_B200_API int sqlite3_vec_distance_l2(const void* vec1, size_t size1, const void* vec2,
                                           size_t size2, float* result);
 YAMS_B200_API int sqlite3_vec_distance_cosine(const void* vec1, size_t size1, const void* vec2,
                                               size_t size2, float* result);
+/* same contract for the L1 metric of the SQL scalar vec_distance_l1 (sqlite/functions.hpp:144-208, distances/l1.hpp:62-92);
+ * the reference C API has no such symbol -- the SQL glue (csrc/sqlite_glue.cpp) needs it */
+YAMS_B200_API int yams_b200_vec_distance_l1(const void* vec1, size_t size1, const void* vec2, size_t size2,
+                                            float* result);
 
 /* ---- bench / test utilities (SURVEY.md §8d synthetic inputs, generated straight into HBM) ------ */
 /* byte[i] = (splitmix64(seed ^ (i>>3)) >> (8*(i&7))) & 0xFF for stream positions [start, start+n) */

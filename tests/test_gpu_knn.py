@@ -319,6 +319,60 @@ def test_plugin_loader_walks_the_vtables(Y, tmp_path):
     assert out.returncode == 0 and "LOADER OK" in out.stdout, out.stdout + out.stderr
 
 
+def test_sqlite_glue_through_a_stand_in_sqlite(Y, tmp_path):
+    """csrc/sqlite_glue.cpp (sqlite3_vec_init + vec_distance_l2/cosine/l1 SQL scalars; reference: sqlite_vec_c_api.cpp:15-55,
+    sqlite/functions.hpp:76-278) compiled against the stand-in sqlite3.h of tests/host_cpp/mock_sqlite3 and driven like SQL would."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "test_sqlite_glue")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "tests", "host_cpp", "mock_sqlite3"),
+                           os.path.join(root, "yams_b200", "csrc", "sqlite_glue.cpp"), os.path.join(root, "tests", "host_cpp", "test_sqlite_glue.cpp"),
+                           "-o", exe, "-L" + os.path.join(root, "yams_b200"), "-lyams_b200", "-Wl,-rpath," + os.path.join(root, "yams_b200")])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "GLUE OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_pairwise_and_batch_operators_are_bit_identical_to_the_reference_build(Y, oracle):
+    """R5/R6/R7: distances::{l2,cosine}_distance<float> in the operation order of the reference build (AVX lanes, FMA contraction
+    where the compiler applies it) -- compared bit for bit with the reference compiled in place, at dims that take every path."""
+    O = oracle
+    if not O.ref_available():
+        pytest.skip("needs the reference compiled in place")
+    R = O.ref()
+    rng = np.random.default_rng(9)
+    for d in (1, 5, 7, 8, 13, 16, 31, 32, 100, 384, 768, 1536):
+        for _ in range(6):
+            a = rng.normal(size=d).astype(np.float32)
+            b = rng.normal(size=d).astype(np.float32)
+            rc, got = Y.vec_distance_l2(a, b)
+            assert rc == 0 and np.float32(got) == np.float32(R.ref_l2_distance(O._p(a, O.f32p), O._p(b, O.f32p), d)), ("l2", d)
+            rc, got = Y.vec_distance_cosine(a, b)
+            assert rc == 0 and np.float32(got) == np.float32(R.ref_cosine_distance(O._p(a, O.f32p), O._p(b, O.f32p), d)), ("cos", d)
+    for d, n in ((768, 4000), (100, 3000), (16, 500)):
+        rows = rng.normal(size=(n, d)).astype(np.float32)
+        q = rng.normal(size=d).astype(np.float32)
+        for metric, om, fn in ((Y.COSINE, O.METRIC_COSINE, R.ref_cosine_distance), (Y.L2, O.METRIC_L2, R.ref_l2_distance)):
+            got = Y.batch_distance(q, rows, metric=metric, mode=Y.BATCH_ALL)
+            want = np.array([fn(O._p(q, O.f32p), O._p(np.ascontiguousarray(rows[i]), O.f32p), d) for i in range(n)], dtype=np.float32)
+            assert np.array_equal(got, want), (metric, d)
+            idx, dist = Y.batch_distance(q, rows, metric=metric, mode=Y.BATCH_TOP_K, k=10)
+            ri, rd = O.batch_top_k(q, rows, 10, metric=om, use_ref=True)
+            assert np.array_equal(dist, rd) and (list(idx) == list(ri) or len(set(rd)) < 10)
+    # L1 (the SQL scalar vec_distance_l1): both paths of distances/l1.hpp against a float64 evaluation
+    for d in (3, 7, 8, 100):
+        a = rng.normal(size=d).astype(np.float32)
+        b = rng.normal(size=d).astype(np.float32)
+        rc, got = Y.vec_distance_l1(a, b)
+        assert rc == 0 and abs(got - np.abs(a.astype(np.float64) - b.astype(np.float64)).sum()) < 1e-4 * d
+    # computeCosineSimilarity for many pairs in one pass == one call per pair
+    A = rng.normal(size=(50, 384)).astype(np.float32)
+    B = rng.normal(size=(50, 384)).astype(np.float32)
+    many = Y.compute_cosine_similarity_many(A, B)
+    assert all(many[i] == Y.compute_cosine_similarity(A[i], B[i]) == O.lib().yo_cosine_similarity_f64(O._p(A[i], O.f32p), O._p(B[i], O.f32p), 384)
+               for i in range(50))
+
+
 def test_all_matching_candidate_rows(Y, oracle):
     """ExactRowSelection::AllMatching (sqlite_vec_backend.cpp:4283-4288,4315-4316): every passing candidate row."""
     O = oracle

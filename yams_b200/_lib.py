@@ -87,6 +87,7 @@ SYMBOLS = {
                                            C.c_float, u64p, f32p, u64p]),
     "yams_b200_compute_cosine_similarity": (C.c_int, [C.c_void_p, f32p, C.c_size_t, f32p, C.c_size_t,
                                                       C.POINTER(C.c_double)]),
+    "yams_b200_compute_cosine_similarity_many": (C.c_int, [C.c_void_p, f32p, f32p, C.c_size_t, C.c_size_t, C.POINTER(C.c_double)]),
     "yams_b200_corpus_size": (C.c_int, [C.c_void_p, u64p]),
     "yams_b200_corpus_destroy": (None, [C.c_void_p]),
     "yams_b200_search": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_float, i64p, u64p, i64p, f32p, u32p, u64p]),
@@ -105,6 +106,7 @@ SYMBOLS = {
     "yams_b200_search_last_timings": (C.c_int, [C.c_void_p, f32p]),
     "sqlite3_vec_distance_l2": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, f32p]),
     "sqlite3_vec_distance_cosine": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, f32p]),
+    "yams_b200_vec_distance_l1": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, f32p]),
     "yams_b200_synth_bytes_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "yams_b200_debug_stage1_scores": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
     "yams_b200_synth_rows_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
@@ -589,6 +591,17 @@ def compute_cosine_similarity(a, b) -> float:
     return out.value
 
 
+def compute_cosine_similarity_many(a, b) -> np.ndarray:
+    """n pairs in one device pass: a[n, d], b[n, d] -> float64[n]."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    assert a.shape == b.shape and a.ndim == 2
+    out = np.zeros(a.shape[0], dtype=np.float64)
+    _check(lib().yams_b200_compute_cosine_similarity_many(None, a.ctypes.data_as(f32p), b.ctypes.data_as(f32p), a.shape[0], a.shape[1],
+                                                          out.ctypes.data_as(C.POINTER(C.c_double))), "compute_cosine_similarity_many")
+    return out
+
+
 def _pair(fn, a, b):
     a = np.ascontiguousarray(a, dtype=np.float32)
     b = np.ascontiguousarray(b, dtype=np.float32)
@@ -603,3 +616,7 @@ def vec_distance_l2(a, b):
 
 def vec_distance_cosine(a, b):
     return _pair(lib().sqlite3_vec_distance_cosine, a, b)
+
+
+def vec_distance_l1(a, b):
+    return _pair(lib().yams_b200_vec_distance_l1, a, b)

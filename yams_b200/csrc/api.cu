@@ -5,7 +5,10 @@
 
 #include <mutex>
 
+#include <vector>
+
 #include "common.cuh"
+#include "ref_order.cuh"
 
 namespace yb {
 
@@ -74,35 +77,46 @@ yams_status_t ensure_device(DeviceCtx** out) {
     return YAMS_OK;
 }
 
-// single-warp pairwise kernels for the sqlite-vec-cpp scalar operator surface
+static std::mutex g_ws_mu;
+static std::vector<OpWs*> g_ws_free;
+
+OpWs* opws_acquire() {
+    DeviceCtx* dev = nullptr;
+    if (ensure_device(&dev) != YAMS_OK) return nullptr;   // also binds the device on this thread
+    {
+        std::lock_guard<std::mutex> lk(g_ws_mu);
+        if (!g_ws_free.empty()) {
+            OpWs* w = g_ws_free.back();
+            g_ws_free.pop_back();
+            return w;
+        }
+    }
+    OpWs* w = new (std::nothrow) OpWs();
+    if (!w) return nullptr;
+    if (cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking) != cudaSuccess) {
+        set_last_error("cudaStreamCreate failed");
+        delete w;
+        return nullptr;
+    }
+    return w;
+}
+void opws_release(OpWs* w) {
+    std::lock_guard<std::mutex> lk(g_ws_mu);
+    if (g_ws_free.size() < 16) {
+        g_ws_free.push_back(w);
+        return;
+    }
+    for (auto& b : w->d) b.release();
+    w->h.release();
+    cudaStreamDestroy(w->st);
+    delete w;
+}
+
+// pairwise operators of the sqlite-vec-cpp C API: one thread evaluates the pair in the reference build's operation order
 __global__ void pair_distance_kernel(const float* __restrict__ a, const float* __restrict__ b, uint32_t d, int metric,
                                      float* __restrict__ out) {
-    // float accumulation like distances/{l2,cosine}.hpp; lane-strided partial sums + shuffle tree
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (uint32_t i = threadIdx.x; i < d; i += 32) {
-        float x = a[i], y = b[i];
-        if (metric == YAMS_B200_L2) {
-            float df = x - y;
-            s0 += df * df;
-        } else {
-            s0 += x * y;
-            s1 += x * x;
-            s2 += y * y;
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (threadIdx.x == 0) {
-        if (metric == YAMS_B200_L2) {
-            *out = sqrtf(s0);
-        } else {
-            float denom = sqrtf(s1) * sqrtf(s2);
-            *out = denom < 1e-8f ? 1.0f : 1.0f - (s0 / denom);  // cosine.hpp:64-68
-        }
-    }
+    F32At fa{a}, fb{b};
+    *out = metric == YAMS_B200_L2 ? ref_l2_distance(fa, fb, d) : (metric == 2 ? ref_l1_distance(fa, fb, d) : ref_cosine_distance(fa, fb, d));
 }
 
 static int pair_distance(const void* v1, size_t size1, const void* v2, size_t size2, float* result, int metric) {
@@ -110,18 +124,21 @@ static int pair_distance(const void* v1, size_t size1, const void* v2, size_t si
     if (!v1 || !v2 || !result) return 1;
     size_t d1 = size1 / sizeof(float), d2 = size2 / sizeof(float);
     if (d1 != d2) return 1;
-    DeviceCtx* dev = nullptr;
-    if (ensure_device(&dev) != YAMS_OK) return 1;
-    float* d_buf = nullptr;
-    if (cudaMalloc(&d_buf, (2 * d1 + 1) * sizeof(float) + 16) != cudaSuccess) return 1;
-    int rc = 1;
-    if (cudaMemcpy(d_buf, v1, d1 * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
-        cudaMemcpy(d_buf + d1, v2, d1 * 4, cudaMemcpyHostToDevice) == cudaSuccess) {
-        pair_distance_kernel<<<1, 32>>>(d_buf, d_buf + d1, (uint32_t)d1, metric, d_buf + 2 * d1);
-        if (cudaMemcpy(result, d_buf + 2 * d1, 4, cudaMemcpyDeviceToHost) == cudaSuccess) rc = 0;
-    }
-    cudaFree(d_buf);
-    return rc;
+    OpWsLease lease;
+    OpWs* w = lease.w;
+    if (!w) return 1;
+    const size_t bytes = (2 * d1 + 4) * sizeof(float);
+    if (w->d[0].reserve(bytes) != YAMS_OK || w->h.reserve(bytes) != YAMS_OK) return 1;
+    float* hp = w->h.as<float>();
+    memcpy(hp, v1, d1 * 4);
+    memcpy(hp + d1, v2, d1 * 4);
+    float* dp = w->d[0].as<float>();
+    if (cudaMemcpyAsync(dp, hp, 2 * d1 * 4, cudaMemcpyHostToDevice, w->st) != cudaSuccess) return 1;
+    pair_distance_kernel<<<1, 1, 0, w->st>>>(dp, dp + d1, (uint32_t)d1, metric, dp + 2 * d1);
+    if (cudaMemcpyAsync(hp + 2 * d1, dp + 2 * d1, 4, cudaMemcpyDeviceToHost, w->st) != cudaSuccess) return 1;
+    if (cudaStreamSynchronize(w->st) != cudaSuccess) return 1;
+    *result = hp[2 * d1];
+    return 0;
 }
 
 }  // namespace yb
@@ -179,6 +196,8 @@ int yams_plugin_init(const char* config_json, const void* host_context) {
     g_scan_vt.search_all_matching = yams_b200_search_all_matching;
     g_scan_vt.batch_distance = yams_b200_batch_distance;
     g_scan_vt.compute_cosine_similarity = yams_b200_compute_cosine_similarity;
+    g_scan_vt.compute_cosine_similarity_many = yams_b200_compute_cosine_similarity_many;
+    g_scan_vt.search_exhaustive = yams_b200_search_exhaustive;
     DeviceCtx* dev = nullptr;
     if (ensure_device(&dev) != YAMS_OK) return YAMS_PLUGIN_ERR_INIT_FAILED;  // no CPU fallback
     g_inited = true;
@@ -231,6 +250,9 @@ int sqlite3_vec_distance_l2(const void* vec1, size_t size1, const void* vec2, si
 }
 int sqlite3_vec_distance_cosine(const void* vec1, size_t size1, const void* vec2, size_t size2, float* result) {
     return pair_distance(vec1, size1, vec2, size2, result, YAMS_B200_COSINE);
+}
+int yams_b200_vec_distance_l1(const void* vec1, size_t size1, const void* vec2, size_t size2, float* result) {
+    return pair_distance(vec1, size1, vec2, size2, result, 2);
 }
 
 int yams_b200_device_count(void) {

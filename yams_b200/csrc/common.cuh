@@ -121,6 +121,24 @@ void set_requested_device(int dev);
         if ((h)->dev) cudaSetDevice((h)->dev->device);               \
     } while (0)
 
+// Pooled workspace of the small host-pointer operators (pairwise distances, computeCosineSimilarity, vec0_exact,
+// batch_distance): a stream, a few growable device buffers and one pinned staging buffer, parked between calls so that
+// no call pays cudaMalloc / cudaStreamCreate.  Concurrent callers get separate workspaces.
+struct OpWs {
+    cudaStream_t st = nullptr;
+    DevBuf d[8];
+    HostBuf h;
+};
+OpWs* opws_acquire();             // nullptr (+ last error set) when no device / stream can be had
+void opws_release(OpWs* w);
+struct OpWsLease {
+    OpWs* w;
+    OpWsLease() : w(opws_acquire()) {}
+    ~OpWsLease() { if (w) opws_release(w); }
+    OpWsLease(const OpWsLease&) = delete;
+    OpWsLease& operator=(const OpWsLease&) = delete;
+};
+
 // exclusive scan of n uint32 values (in may alias out); *d_total (device, uint64) receives the sum
 yams_status_t exclusive_scan_u32(const uint32_t* d_in, uint32_t* d_out, size_t n, uint64_t* d_total,
                                  DevBuf& scratch, cudaStream_t st);

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "knn.cuh"
+#include "ref_order.cuh"
 
 namespace yb {
 
@@ -509,27 +510,9 @@ __global__ void rescore_kernel(const void* __restrict__ rows, int dtype, uint32_
         uint64_t base = (uint64_t)row * d;
         const float* qv = q32 + (uint64_t)q * d;
         if (metric == YAMS_B200_L2) {
-            float sum;
-            if (d >= 16 && d % 16 == 0) {
-                float p[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                for (uint32_t c = 0; c < d; c += 8) {
-#pragma unroll
-                    for (int l = 0; l < 8; ++l) {
-                        float df = __fsub_rn(qv[c + l], load_elem(rows, dtype, base + c + l));
-                        p[l] = __fadd_rn(p[l], __fmul_rn(df, df));
-                    }
-                }
-                sum = p[0];
-#pragma unroll
-                for (int l = 1; l < 8; ++l) sum = __fadd_rn(sum, p[l]);
-            } else {
-                sum = 0.f;
-                for (uint32_t c = 0; c < d; ++c) {
-                    float df = __fsub_rn(qv[c], load_elem(rows, dtype, base + c));
-                    sum = __fadd_rn(sum, __fmul_rn(df, df));
-                }
-            }
-            float dist = sqrtf(sum);
+            auto row_at = [&](uint32_t c) { return load_elem(rows, dtype, base + c); };
+            auto q_at = [&](uint32_t c) { return qv[c]; };
+            float dist = ref_l2_distance(q_at, row_at, d);
             if (dist == dist) {
                 e.sim = -dist;
                 e.row = row;
@@ -791,61 +774,16 @@ __global__ void list_lengths_kernel(const uint64_t* __restrict__ offsets, uint32
 }
 
 // ---------------------------------------------------------------------------------------------------
-// L2 surface (vec0_run_exact_query): float accumulation + sqrt; warp per row
+// sqlite-vec-cpp operator surface (vec0_run_exact_query, distances/batch.hpp): one thread per row evaluates the float
+// distance in the reference build's own operation order (ref_order.cuh) -> bit-identical results.  NEGATED distance out so
+// that the descending key sort used everywhere else yields ascending distances.
 // ---------------------------------------------------------------------------------------------------
-__global__ void l2_dense_kernel(const void* __restrict__ rows, int dtype, uint32_t d, uint64_t n, const float* __restrict__ q32,
-                                uint32_t nq, float* __restrict__ out /* [q][n], NEGATED distance */) {
-    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    uint32_t q = blockIdx.y;
-    if (warp >= n || q >= nq) return;
-    const float* qv = q32 + (uint64_t)q * d;
-    float s = 0.f;
-    for (uint32_t c = lane; c < d; c += 32) {
-        float df = qv[c] - load_elem(rows, dtype, warp * d + c);
-        s = fmaf(df, df, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) out[(uint64_t)q * n + warp] = -sqrtf(s);
-}
-
-// batch.hpp surface: one warp per row, float accumulation (cosine.hpp:48-69, l2.hpp:108-118); NEGATED distance out
-// so that the descending key sort used everywhere else yields ascending distances
 __global__ void batch_dist_kernel(const float* __restrict__ rows, uint32_t d, uint64_t n, const float* __restrict__ q, int metric,
                                   float* __restrict__ out_neg) {
-    uint64_t warp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    uint32_t lane = threadIdx.x & 31;
-    if (warp >= n) return;
-    const float* r = rows + warp * d;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f;
-    for (uint32_t c = lane; c < d; c += 32) {
-        float x = q[c], y = r[c];
-        if (metric == YAMS_B200_L2) {
-            float df = x - y;
-            s0 = fmaf(df, df, s0);
-        } else {
-            s0 = fmaf(x, y, s0);
-            s1 = fmaf(x, x, s1);
-            s2 = fmaf(y, y, s2);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) {
-        float dist;
-        if (metric == YAMS_B200_L2) {
-            dist = sqrtf(s0);
-        } else {
-            float denom = sqrtf(s1) * sqrtf(s2);
-            dist = denom < 1e-8f ? 1.0f : 1.0f - (s0 / denom);
-        }
-        out_neg[warp] = -dist;
-    }
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    F32At qa{q}, ra{rows + r * d};
+    out_neg[r] = -(metric == YAMS_B200_L2 ? ref_l2_distance(qa, ra, d) : ref_cosine_distance(qa, ra, d));
 }
 // keys for the FILTERED mode: rows failing dist < threshold get key 0 (sort last)
 __global__ void make_keys_filtered_kernel(const float* __restrict__ neg_dist, uint64_t n, uint64_t np2, float threshold,
@@ -868,7 +806,13 @@ __global__ void negate_kernel(float* p, uint64_t n) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = -p[i];
 }
 // computeCosineSimilarity (vector_database.cpp:1786-1810): one thread, the reference's accumulation order
-__global__ void cosine_similarity_f64_kernel(const float* __restrict__ a, const float* __restrict__ b, uint64_t d, double* out) {
+__global__ void cosine_similarity_f64_kernel(const float* __restrict__ a_all, const float* __restrict__ b_all, uint64_t n, uint64_t d,
+                                             double* __restrict__ out_all) {
+    const uint64_t p = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const float* a = a_all + p * d;
+    const float* b = b_all + p * d;
+    double* out = out_all + p;
     double dp = 0.0, na = 0.0, nb = 0.0;
     for (uint64_t i = 0; i < d; ++i) {
         double x = (double)a[i], y = (double)b[i];
@@ -2077,9 +2021,7 @@ yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim,
     if (n == 0) return YAMS_OK;
     YB_ARG(rows && out_rowids && out_dist, "null argument");
     YB_ARG(n < 0xFFFFFFFFull, "too many rows");
-    DeviceCtx* dev = nullptr;
-    yams_status_t rc = ensure_device(&dev);
-    if (rc != YAMS_OK) return rc;
+    yams_status_t rc = YAMS_OK;
     // rowid range filter (vec0_module.hpp:399-401) is applied on the host side of the copy: only rows in
     // range are uploaded (pure data movement, no arithmetic)
     std::vector<uint32_t> keep;
@@ -2092,11 +2034,13 @@ yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim,
         if (keep.empty()) return YAMS_OK;
     }
     uint64_t m = use_range ? keep.size() : n;
-    cudaStream_t st;
-    YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    OpWsLease lease;
+    if (!lease.w) return YAMS_ERR_INTERNAL;
+    cudaStream_t st = lease.w->st;
     uint64_t np2 = 1;
     while (np2 < m) np2 <<= 1;
-    DevBuf d_rows, d_q, d_dist, d_keys, d_rid, d_or, d_od;
+    DevBuf &d_rows = lease.w->d[0], &d_q = lease.w->d[1], &d_dist = lease.w->d[2], &d_keys = lease.w->d[3], &d_rid = lease.w->d[4],
+           &d_or = lease.w->d[5], &d_od = lease.w->d[6];
     rc = d_rows.reserve((size_t)m * dim * 4);
     if (rc == YAMS_OK) rc = d_q.reserve((size_t)dim * 4);
     if (rc == YAMS_OK) rc = d_dist.reserve((size_t)m * 4);
@@ -2120,8 +2064,7 @@ yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim,
         }
         cudaMemcpyAsync(d_rid.p, rid_h.data(), (size_t)m * 8, cudaMemcpyHostToDevice, st);
         cudaMemcpyAsync(d_q.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, st);
-        dim3 grid((unsigned)((m * 32 + 255) / 256), 1);
-        l2_dense_kernel<<<grid, 256, 0, st>>>(d_rows.p, YAMS_B200_F32, dim, m, d_q.as<float>(), 1, d_dist.as<float>());
+        batch_dist_kernel<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_rows.as<float>(), dim, m, d_q.as<float>(), YAMS_B200_L2, d_dist.as<float>());
         unsigned g = (unsigned)std::min<uint64_t>((np2 + 255) / 256, 65535);
         make_keys_kernel<<<g, 256, 0, st>>>(d_dist.as<float>(), m, np2, d_keys.as<uint64_t>());
         for (uint64_t size = 2; size <= np2; size <<= 1)
@@ -2139,8 +2082,6 @@ yams_status_t yams_b200_vec0_exact(void* self, const float* query, uint32_t dim,
             *out_count = outn;
         }
     }
-    for (DevBuf* b : {&d_rows, &d_q, &d_dist, &d_keys, &d_rid, &d_or, &d_od}) b->release();
-    cudaStreamDestroy(st);
     return rc;
     YB_CATCH
 }
@@ -2160,14 +2101,14 @@ yams_status_t yams_b200_batch_distance(void* self, int metric, const float* quer
     YB_ARG(n < 0xFFFFFFFFull, "too many rows");
     YB_ARG(mode == YAMS_B200_BATCH_ALL ? out_dist != nullptr : out_idx != nullptr, "null output");
     YB_ARG(mode != YAMS_B200_BATCH_FILTERED || out_dist, "null output");
-    DeviceCtx* dev = nullptr;
-    yams_status_t rc = ensure_device(&dev);
-    if (rc != YAMS_OK) return rc;
-    cudaStream_t st;
-    YB_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    OpWsLease lease;
+    if (!lease.w) return YAMS_ERR_INTERNAL;
+    cudaStream_t st = lease.w->st;
+    yams_status_t rc;
     uint64_t np2 = 1;
     while (np2 < n) np2 <<= 1;
-    DevBuf d_rows, d_q, d_dist, d_keys, d_oi, d_od, d_cnt;
+    DevBuf &d_rows = lease.w->d[0], &d_q = lease.w->d[1], &d_dist = lease.w->d[2], &d_keys = lease.w->d[3], &d_oi = lease.w->d[4],
+           &d_od = lease.w->d[5], &d_cnt = lease.w->d[6];
     rc = d_rows.reserve((size_t)n * dim * 4);
     if (rc == YAMS_OK) rc = d_q.reserve((size_t)dim * 4);
     if (rc == YAMS_OK) rc = d_dist.reserve((size_t)n * 4);
@@ -2180,8 +2121,7 @@ yams_status_t yams_b200_batch_distance(void* self, int metric, const float* quer
     if (rc == YAMS_OK) {
         cudaError_t e = cudaMemcpyAsync(d_rows.p, database, (size_t)n * dim * 4, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(d_q.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, st);
-        batch_dist_kernel<<<(unsigned)((n * 32 + 255) / 256), 256, 0, st>>>(d_rows.as<float>(), dim, n, d_q.as<float>(), metric,
-                                                                           d_dist.as<float>());
+        batch_dist_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(d_rows.as<float>(), dim, n, d_q.as<float>(), metric, d_dist.as<float>());
         unsigned g = (unsigned)std::min<uint64_t>((np2 + 255) / 256, 65535);
         uint64_t outn = n;
         if (mode == YAMS_B200_BATCH_ALL) {
@@ -2221,10 +2161,29 @@ yams_status_t yams_b200_batch_distance(void* self, int metric, const float* quer
             *out_count = outn;
         }
     }
-    for (DevBuf* b : {&d_rows, &d_q, &d_dist, &d_keys, &d_oi, &d_od, &d_cnt}) b->release();
-    cudaStreamDestroy(st);
     return rc;
     YB_CATCH
+}
+
+// n pairs (a_i, b_i) of d floats each -> n doubles; one thread per pair, the reference's accumulation order
+static yams_status_t cosine_similarity_pairs(const float* a, const float* b, size_t n, size_t d, double* out) {
+    OpWsLease lease;
+    OpWs* w = lease.w;
+    if (!w) return YAMS_ERR_INTERNAL;
+    yams_status_t rc;
+    const size_t vb = n * d * 4;
+    if ((rc = w->d[0].reserve(2 * vb + n * 8 + 64)) != YAMS_OK) return rc;
+    if ((rc = w->h.reserve(n * 8 + 64)) != YAMS_OK) return rc;
+    float* da = w->d[0].as<float>();
+    float* db = da + n * d;
+    double* dout = reinterpret_cast<double*>(w->d[0].as<uint8_t>() + ((2 * vb + 7) & ~(size_t)7));
+    YB_CUDA(cudaMemcpyAsync(da, a, vb, cudaMemcpyHostToDevice, w->st));
+    YB_CUDA(cudaMemcpyAsync(db, b, vb, cudaMemcpyHostToDevice, w->st));
+    cosine_similarity_f64_kernel<<<(unsigned)((n + 63) / 64), 64, 0, w->st>>>(da, db, n, d, dout);
+    YB_CUDA(cudaMemcpyAsync(w->h.p, dout, n * 8, cudaMemcpyDeviceToHost, w->st));
+    YB_CUDA(cudaStreamSynchronize(w->st));
+    memcpy(out, w->h.p, n * 8);
+    return YAMS_OK;
 }
 
 yams_status_t yams_b200_compute_cosine_similarity(void* self, const float* a, size_t na, const float* b, size_t nb, double* out) {
@@ -2234,25 +2193,23 @@ yams_status_t yams_b200_compute_cosine_similarity(void* self, const float* a, si
     *out = 0.0;
     if (na != nb || na == 0) return YAMS_OK;   // vector_database.cpp:1788-1790
     YB_ARG(a && b, "null vector");
-    DeviceCtx* dev = nullptr;
-    yams_status_t rc = ensure_device(&dev);
-    if (rc != YAMS_OK) return rc;
-    DevBuf d_ab, d_o;
-    rc = d_ab.reserve(na * 8);
-    if (rc == YAMS_OK) rc = d_o.reserve(8);
-    if (rc == YAMS_OK) {
-        cudaError_t e = cudaMemcpy(d_ab.p, a, na * 4, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(d_ab.as<float>() + na, b, na * 4, cudaMemcpyHostToDevice);
-        cosine_similarity_f64_kernel<<<1, 1>>>(d_ab.as<float>(), d_ab.as<float>() + na, na, d_o.as<double>());
-        if (e == cudaSuccess) e = cudaMemcpy(out, d_o.p, 8, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) {
-            set_last_error("compute_cosine_similarity failed: %s", cudaGetErrorString(e));
-            rc = YAMS_ERR_INTERNAL;
-        }
+    return cosine_similarity_pairs(a, b, 1, na, out);
+    YB_CATCH
+}
+
+// The rerank loops that call computeCosineSimilarity once per candidate (sqlite_vec_backend.cpp:4025,4374,4507) as ONE device
+// pass: n pairs, row-major a[n][dim] / b[n][dim] (pass the same query n times, or n different pairs).
+yams_status_t yams_b200_compute_cosine_similarity_many(void* self, const float* a, const float* b, size_t n, size_t dim, double* out) {
+    YB_TRY
+    (void)self;
+    YB_ARG(out || n == 0, "out is null");
+    if (n == 0) return YAMS_OK;
+    if (dim == 0) {
+        for (size_t i = 0; i < n; ++i) out[i] = 0.0;
+        return YAMS_OK;
     }
-    d_ab.release();
-    d_o.release();
-    return rc;
+    YB_ARG(a && b, "null vector");
+    return cosine_similarity_pairs(a, b, n, dim, out);
     YB_CATCH
 }
 
