@@ -204,6 +204,33 @@ YAMS_B200_API yams_status_t yams_b200_digest_set_size(yams_b200_digest_set* s, u
 YAMS_B200_API yams_status_t yams_b200_digest_set_last_ms(yams_b200_digest_set* s, float* out_ms);
 YAMS_B200_API void yams_b200_digest_set_destroy(yams_b200_digest_set* s);
 
+/* ---- manifest of one file ---------------------------------------------------------------
+ * The consumer of the chunk table: ManifestManager::createManifest (src/manifest/manifest_manager.cpp:411-436) turns it
+ * into ChunkRef{hash (64 lowercase hex chars), offset, u32 size, flags} (include/yams/manifest/manifest_manager.h:48-61)
+ * and seals it with calculateChecksum (:705-730): a bit-serial CRC-32 over fileHash || to_string(fileSize) || for each
+ * chunk hash || to_string(offset) || to_string(size) -- ~80 text bytes per chunk on one dependent chain.  Here the hex
+ * rendering, the per-record CRCs and their GF(2) combination run on the device; the checksum is bit-identical. */
+typedef struct yams_chunk_ref {
+    char hash[64];      /* lowercase hex, NOT NUL-terminated (HASH_STRING_SIZE, core/types.h:279) */
+    uint64_t offset;
+    uint32_t size;      /* static_cast<uint32_t>(chunk.size), manifest_manager.h:209 */
+    uint32_t flags;
+} yams_chunk_ref;
+typedef struct yams_manifest_summary {
+    uint32_t checksum;             /* Manifest::checksum */
+    uint32_t valid;                /* Manifest::isValid (manifest_manager.h:98-104) && the offset / size rules of validateManifest (:452-468) */
+    uint32_t offsets_sequential;   /* every chunk.offset == running sum of the sizes */
+    uint32_t sizes_valid;          /* every size > 0 and representable in 32 bits */
+    uint64_t chunk_count;
+    uint64_t total_size;           /* Manifest::calculateTotalSize */
+    uint64_t checksum_text_bytes;  /* length of the text the CRC ran over */
+} yams_manifest_summary;
+/* chunks: HOST table as returned by chunk_and_hash (n may be 0); file_digest: SHA-256 of the whole file (FileInfo::hash,
+ * raw 32 bytes); out_refs: nullable HOST array of n entries. */
+YAMS_B200_API yams_status_t yams_b200_manifest_build(void* self, const yams_chunk_desc* chunks, size_t n,
+                                                     const uint8_t file_digest[32], uint64_t file_size,
+                                                     yams_chunk_ref* out_refs, yams_manifest_summary* out);
+
 /* Per-stage device timings (ms) of the last chunk_and_hash* call on this thread's context:
  * [0] candidate scan, [1] cut selection, [2] sha256, [3] total device, [4] h2d (0 for _device) */
 YAMS_B200_API yams_status_t yams_b200_ingest_last_timings(void* self, float out_ms[8]);
@@ -237,6 +264,8 @@ typedef struct yams_content_ingest_v1 {
                                          size_t n, uint8_t* out_exists);
     yams_status_t (*digest_set_size)(yams_b200_digest_set* s, uint64_t* out);
     void (*digest_set_destroy)(yams_b200_digest_set* s);
+    yams_status_t (*manifest_build)(void* self, const yams_chunk_desc* chunks, size_t n, const uint8_t file_digest[32],
+                                    uint64_t file_size, yams_chunk_ref* out_refs, yams_manifest_summary* out);
 } yams_content_ingest_v1;
 
 /* =============================================================================================

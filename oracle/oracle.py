@@ -288,6 +288,27 @@ def ref_chunk(data, cfg: CdcConfig, variant: Optional[int] = None, hash: bool = 
         cap = n
 
 
+def manifest_checksum(file_digest, file_size: int, digests: np.ndarray, offsets, sizes, use_ref: bool = False):
+    """ManifestManager::calculateChecksum; use_ref -> the reference's own createManifest (returns (checksum, valid))."""
+    fd = np.ascontiguousarray(np.frombuffer(bytes(file_digest), dtype=np.uint8))
+    dg = np.ascontiguousarray(digests, dtype=np.uint8).reshape(-1, 32)
+    of = np.ascontiguousarray(offsets, dtype=np.uint64)
+    sz = np.ascontiguousarray(sizes, dtype=np.uint64)
+    n = len(of)
+    if use_ref:
+        R = ref()
+        R.ref_manifest_checksum.restype = C.c_uint32
+        R.ref_manifest_checksum.argtypes = [u8p, C.c_uint64, u8p, u64p, u64p, C.c_size_t, C.POINTER(C.c_int)]
+        valid = C.c_int(0)
+        crc = R.ref_manifest_checksum(_p(fd, u8p), file_size, _p(dg, u8p) if n else C.cast(C.c_void_p(0), u8p), _p(of, u64p), _p(sz, u64p), n,
+                                      C.byref(valid))
+        return int(crc), int(valid.value)
+    L = lib()
+    L.yo_manifest_checksum.restype = C.c_uint32
+    L.yo_manifest_checksum.argtypes = [u8p, C.c_uint64, u8p, u64p, u64p, C.c_size_t]
+    return int(L.yo_manifest_checksum(_p(fd, u8p), file_size, _p(dg, u8p) if n else C.cast(C.c_void_p(0), u8p), _p(of, u64p), _p(sz, u64p), n))
+
+
 def exact_scan_cosine(rows: np.ndarray, query: np.ndarray, k: int, threshold: float = -1.0,
                       rowids: Optional[np.ndarray] = None, tie_rank: Optional[np.ndarray] = None,
                       allowed: Optional[np.ndarray] = None, all_matching: bool = False):

@@ -13,6 +13,7 @@
 #include <sqlite-vec-cpp/distances/batch.hpp>
 #include <sqlite-vec-cpp/distances/cosine.hpp>
 #include <sqlite-vec-cpp/distances/l2.hpp>
+#include <yams/manifest/manifest_manager.h>
 #include <sqlite-vec-cpp/utils/float16.hpp>
 
 #include <algorithm>
@@ -85,6 +86,36 @@ void ref_dedup_stats(const uint8_t* data, size_t n, uint64_t window, uint64_t mi
     out[1] = st.uniqueSize;
     out[2] = st.chunkCount;
     out[3] = st.uniqueChunks;
+}
+
+// ManifestManager::createManifest (src/manifest/manifest_manager.cpp:411-436) over a chunk table given as raw digests:
+// returns Manifest::checksum (calculateChecksum :705-730); *out_valid = validateManifest (:438-486) of that manifest.
+uint32_t ref_manifest_checksum(const uint8_t* file_digest32, uint64_t file_size, const uint8_t* digests /* n x 32 */,
+                               const uint64_t* offsets, const uint64_t* sizes, size_t n, int* out_valid) {
+    auto hex = [](const uint8_t* d) {
+        static const char* k = "0123456789abcdef";
+        std::string s(64, '0');
+        for (int i = 0; i < 32; ++i) { s[2 * i] = k[d[i] >> 4]; s[2 * i + 1] = k[d[i] & 15]; }
+        return s;
+    };
+    yams::FileInfo info;
+    info.hash = hex(file_digest32);
+    info.size = file_size;
+    info.originalName = "x";
+    std::vector<yams::manifest::ChunkRef> refs(n);
+    for (size_t i = 0; i < n; ++i) {
+        refs[i].hash = hex(digests + 32 * i);
+        refs[i].offset = offsets[i];
+        refs[i].size = static_cast<uint32_t>(sizes[i]);
+    }
+    yams::manifest::ManifestManager mm{yams::manifest::ManifestManager::Config{}};
+    auto res = mm.createManifest(info, refs);
+    if (!res) { if (out_valid) *out_valid = -1; return 0; }
+    if (out_valid) {
+        auto v = mm.validateManifest(res.value());
+        *out_valid = v ? (v.value() ? 1 : 0) : -1;
+    }
+    return res.value().checksum;
 }
 
 // SHA256Hasher::hash (static one-shot) -> 64-char lowercase hex + NUL

@@ -6,6 +6,7 @@
 
 #include <math.h>
 #include <stdlib.h>
+#include <stdio.h>
 #include <string.h>
 
 /* ============================== CDC ====================================================== */
@@ -625,6 +626,37 @@ size_t yo_batch_top_k(const float* query, const float* rows, size_t n, size_t d,
     }
     free(res);
     return m;
+}
+
+/* ============================== manifest checksum ========================================= */
+
+static uint32_t crc_text(uint32_t crc, const char* s, size_t n) {
+    /* src/manifest/manifest_manager.cpp:711-718 (hash_string): bit-serial reflected CRC-32 step per character */
+    for (size_t i = 0; i < n; ++i) {
+        crc ^= (uint32_t)(int)s[i];
+        for (int b = 0; b < 8; ++b) crc = (crc >> 1) ^ (0xEDB88320u * (crc & 1u));
+    }
+    return crc;
+}
+
+uint32_t yo_manifest_checksum(const uint8_t* file_digest32, uint64_t file_size, const uint8_t* digests,
+                              const uint64_t* offsets, const uint64_t* sizes, size_t n) {
+    /* ManifestManager::calculateChecksum, src/manifest/manifest_manager.cpp:705-730:
+     * fileHash, to_string(fileSize), then per chunk hash, to_string(offset), to_string(size) (ChunkRef::size is uint32) */
+    static const char* hexd = "0123456789abcdef";
+    char hex[64], num[32];
+    uint32_t crc = 0xFFFFFFFFu;
+    for (int i = 0; i < 32; ++i) { hex[2 * i] = hexd[file_digest32[i] >> 4]; hex[2 * i + 1] = hexd[file_digest32[i] & 15]; }
+    crc = crc_text(crc, hex, 64);
+    crc = crc_text(crc, num, (size_t)snprintf(num, sizeof num, "%llu", (unsigned long long)file_size));
+    for (size_t c = 0; c < n; ++c) {
+        const uint8_t* d = digests + 32 * c;
+        for (int i = 0; i < 32; ++i) { hex[2 * i] = hexd[d[i] >> 4]; hex[2 * i + 1] = hexd[d[i] & 15]; }
+        crc = crc_text(crc, hex, 64);
+        crc = crc_text(crc, num, (size_t)snprintf(num, sizeof num, "%llu", (unsigned long long)offsets[c]));
+        crc = crc_text(crc, num, (size_t)snprintf(num, sizeof num, "%u", (unsigned)(uint32_t)sizes[c]));
+    }
+    return ~crc;
 }
 
 /* ============================== synthetic inputs ========================================== */

@@ -140,6 +140,10 @@ void yo_gen_bytes(uint64_t seed, uint64_t start, size_t n, uint8_t* out);
  * fp32 (sum in double, scale in float); first_row lets callers generate slices. */
 void yo_gen_rows_f32(uint64_t seed, uint64_t first_row, size_t n, size_t d, float* out);
 
+/* ManifestManager::calculateChecksum (src/manifest/manifest_manager.cpp:705-730) over raw digests + (offset, size) */
+uint32_t yo_manifest_checksum(const uint8_t* file_digest32, uint64_t file_size, const uint8_t* digests,
+                              const uint64_t* offsets, const uint64_t* sizes, size_t n);
+
 #ifdef __cplusplus
 }
 #endif

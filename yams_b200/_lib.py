@@ -40,6 +40,13 @@ class ChunkDesc(C.Structure):
     _fields_ = [("offset", C.c_uint64), ("size", C.c_uint64), ("digest", C.c_uint8 * 32)]
 
 
+class ManifestSummary(C.Structure):
+    _fields_ = [("checksum", C.c_uint32), ("valid", C.c_uint32), ("offsets_sequential", C.c_uint32), ("sizes_valid", C.c_uint32),
+                ("chunk_count", C.c_uint64), ("total_size", C.c_uint64), ("checksum_text_bytes", C.c_uint64)]
+
+
+CHUNK_REF_DTYPE = np.dtype([("hash", "S64"), ("offset", "<u8"), ("size", "<u4"), ("flags", "<u4")])
+assert CHUNK_REF_DTYPE.itemsize == 80
 CHUNK_DTYPE = np.dtype([("offset", "<u8"), ("size", "<u8"), ("digest", "u1", (32,))])
 assert CHUNK_DTYPE.itemsize == C.sizeof(ChunkDesc) == 48
 
@@ -75,6 +82,7 @@ SYMBOLS = {
     "yams_b200_digest_set_size": (C.c_int, [C.c_void_p, u64p]),
     "yams_b200_digest_set_last_ms": (C.c_int, [C.c_void_p, f32p]),
     "yams_b200_digest_set_destroy": (None, [C.c_void_p]),
+    "yams_b200_manifest_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(ManifestSummary)]),
     "yams_b200_ingest_last_timings": (C.c_int, [C.c_void_p, f32p]),
     "yams_b200_dedup_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "yams_b200_corpus_create": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_uint64, C.POINTER(C.c_void_p)]),
@@ -253,6 +261,19 @@ def dedup_stats(chunks: np.ndarray) -> dict:
     total, unique, count, ucount = (int(x) for x in out)
     return {"totalSize": total, "uniqueSize": unique, "chunkCount": count, "uniqueChunks": ucount,
             "ratio": (1.0 - unique / total) if total else 0.0}
+
+
+def manifest_build(chunks: np.ndarray, file_digest, file_size: int, want_refs: bool = True):
+    """ManifestManager::createManifest over a chunk table: -> (ChunkRef table or None, summary dict incl. the CRC checksum)."""
+    arr = np.ascontiguousarray(chunks, dtype=CHUNK_DTYPE)
+    dg = np.ascontiguousarray(np.frombuffer(bytes(file_digest), dtype=np.uint8))
+    assert dg.size == 32
+    refs = np.zeros(max(len(arr), 1), dtype=CHUNK_REF_DTYPE) if want_refs else None
+    out = ManifestSummary()
+    _check(lib().yams_b200_manifest_build(None, arr.ctypes.data if len(arr) else None, len(arr), dg.ctypes.data, file_size,
+                                          refs.ctypes.data if want_refs else None, C.byref(out)), "manifest_build")
+    summary = {f[0]: int(getattr(out, f[0])) for f in ManifestSummary._fields_}
+    return (refs[:len(arr)] if want_refs else None), summary
 
 
 def ingest_last_timings() -> dict:

@@ -183,6 +183,7 @@ int yams_plugin_init(const char* config_json, const void* host_context) {
     g_ingest_vt.digest_set_contains = yams_b200_digest_set_contains;
     g_ingest_vt.digest_set_size = yams_b200_digest_set_size;
     g_ingest_vt.digest_set_destroy = yams_b200_digest_set_destroy;
+    g_ingest_vt.manifest_build = yams_b200_manifest_build;
     g_scan_vt.abi_version = YAMS_IFACE_VECTOR_SCAN_V1_VERSION;
     g_scan_vt.self = nullptr;
     g_scan_vt.corpus_create = yams_b200_corpus_create;
