@@ -343,6 +343,7 @@ struct SelectIn {
     uint32_t cap;
     const uint32_t* qmap;   // nullable: CTA b handles query qmap[b] for the list/out side
     const float* tau;       // nullable (list mode): rows that never reached the list scored <= tau[q]
+    float tau_margin;       // tau_only: subtracted from the selected score
 };
 
 __device__ __forceinline__ uint64_t sel_key(const SelectIn& in, uint32_t qsrc, uint64_t i) {
@@ -415,10 +416,59 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, u
             for (uint64_t i = threadIdx.x; i < L; i += SEL_THREADS) mn = min(mn, (uint32_t)(sel_key(in, qsrc, i) >> 32));
             atomicMin(&s_want, mn);
             __syncthreads();
-            if (threadIdx.x == 0) out_tau[qdst] = fkey_inv(s_want);
+            if (threadIdx.x == 0) out_tau[qdst] = fkey_inv(s_want) - in.tau_margin;
         } else {
-            radix_select(4);
-            if (threadIdx.x == 0) out_tau[qdst] = fkey_inv((uint32_t)s_prefix);
+            // Two passes instead of four: a 4096-bin histogram of the top 12 key bits locates the bin that holds the K-th
+            // best score; its (few) members are collected and sorted in shared memory.  A crowded bin (> 2048 members,
+            // e.g. constant scores) falls back to the plain 4-pass radix select.
+            uint32_t* h12 = reinterpret_cast<uint32_t*>(buf);            // [4096] counters
+            uint32_t* members = h12 + 4096;                               // [4096] score keys of the boundary bin
+            for (int i = threadIdx.x; i < 4096; i += SEL_THREADS) h12[i] = 0;
+            __syncthreads();
+            for (uint64_t i = threadIdx.x; i < L; i += SEL_THREADS) atomicAdd(&h12[(uint32_t)(sel_key(in, qsrc, i) >> 52)], 1u);
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t cum = 0;
+                int bsel = 0;
+                for (int bk = 4095; bk >= 0; --bk) {
+                    uint32_t h = h12[bk];
+                    if (cum + h >= K) { bsel = bk; break; }
+                    cum += h;
+                }
+                s_want = K - cum;               // rank inside the boundary bin (1-based)
+                s_prefix = (uint64_t)bsel;
+                s_cnt = 0;
+            }
+            __syncthreads();
+            const uint32_t bsel = (uint32_t)s_prefix, pop = h12[bsel];
+            if (pop <= 2048) {
+                uint32_t np2 = 1;
+                while (np2 < pop) np2 <<= 1;
+                __syncthreads();
+                for (uint32_t i = threadIdx.x; i < np2; i += SEL_THREADS) members[i] = 0;
+                __syncthreads();
+                for (uint64_t i = threadIdx.x; i < L; i += SEL_THREADS) {
+                    uint32_t fk = (uint32_t)(sel_key(in, qsrc, i) >> 32);
+                    if ((fk >> 20) == bsel) members[atomicAdd(&s_cnt, 1u)] = fk;
+                }
+                __syncthreads();
+                for (uint32_t size = 2; size <= np2; size <<= 1) {
+                    for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                        for (uint32_t t = threadIdx.x; t < np2 / 2; t += SEL_THREADS) {
+                            uint32_t lo = (t / stride) * (stride * 2) + (t % stride), hi = lo + stride;
+                            bool desc = ((lo & size) == 0);
+                            uint32_t x = members[lo], y = members[hi];
+                            if ((x < y) == desc) { members[lo] = y; members[hi] = x; }
+                        }
+                        __syncthreads();
+                    }
+                }
+                if (threadIdx.x == 0) out_tau[qdst] = fkey_inv(members[s_want - 1]) - in.tau_margin;
+            } else {
+                __syncthreads();
+                radix_select(4);
+                if (threadIdx.x == 0) out_tau[qdst] = fkey_inv((uint32_t)s_prefix) - in.tau_margin;
+            }
         }
         return;
     }
@@ -520,7 +570,43 @@ __global__ void rescore_kernel(const void* __restrict__ rows, int dtype, uint32_
         } else {
             double norm_sq = 0.0, dot = 0.0;
             bool finite = true;
-            for (uint32_t c = 0; c < d; ++c) {
+            // same element order as the reference's loop; only the loads are widened (16-byte row and query chunks)
+            uint32_t c = 0;
+            if (dtype == YAMS_B200_F16 && d % 8 == 0) {
+                const uint4* rp = reinterpret_cast<const uint4*>(static_cast<const __half*>(rows) + base);
+                const float4* qp = reinterpret_cast<const float4*>(qv);
+                for (; c < d; c += 8) {
+                    const uint4 raw = __ldg(rp + (c >> 3));
+                    const float4 q0 = __ldg(qp + (c >> 2)), q1 = __ldg(qp + (c >> 2) + 1);
+                    const __half2* h2 = reinterpret_cast<const __half2*>(&raw);
+                    const float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]), f2 = __half22float2(h2[2]), f3 = __half22float2(h2[3]);
+                    const float rv[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+                    const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        if (!isfinite(rv[e])) finite = false;
+                        const double sv = (double)rv[e];
+                        norm_sq += sv * sv;
+                        dot += sv * (double)qq[e];
+                    }
+                }
+            } else if (dtype == YAMS_B200_F32 && d % 4 == 0) {
+                const float4* rp = reinterpret_cast<const float4*>(static_cast<const float*>(rows) + base);
+                const float4* qp = reinterpret_cast<const float4*>(qv);
+                for (; c < d; c += 4) {
+                    const float4 r4 = __ldg(rp + (c >> 2)), q4 = __ldg(qp + (c >> 2));
+                    const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+                    const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (!isfinite(rv[e])) finite = false;
+                        const double sv = (double)rv[e];
+                        norm_sq += sv * sv;
+                        dot += sv * (double)qq[e];
+                    }
+                }
+            }
+            for (; c < d; ++c) {
                 float v = load_elem(rows, dtype, base + c);
                 if (!isfinite(v)) { finite = false; break; }
                 double sv = (double)v, qd = (double)qv[c];
@@ -1003,15 +1089,17 @@ __global__ void compact_scatter_kernel(UNIT* __restrict__ rows, uint64_t units_p
     for (uint64_t u = lane; u < units_per_row; u += 32) d[u] = t[u];
 }
 
-__global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
-}
-__global__ void tau_margin_kernel(float* tau, uint32_t nq, float margin, float floor_) {
+// per-query state of one scan: survivor counts, certificate bounds, candidate-list counters
+__global__ void scan_init_kernel(uint32_t nq, uint32_t* __restrict__ sel_n, float* __restrict__ bound, uint32_t* __restrict__ counts) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < nq) {
-        float t = tau[i] - margin;
-        tau[i] = t > floor_ ? t : floor_;
+        sel_n[i] = 0;
+        bound[i] = -INFINITY;
+        counts[i] = 0;
     }
+}
+__global__ void fill_f32_kernel(float* p, uint64_t n, float v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 __global__ void iota_rowids_kernel(int64_t* p, uint64_t n, int64_t first) {
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
@@ -1164,8 +1252,7 @@ static yams_status_t scan_enqueue(Corpus* c, const ScanPlan& p, int64_t* d_out_r
     Cand* d_sel = c->sel.as<Cand>();
     uint32_t* d_sel_n = reinterpret_cast<uint32_t*>(d_sel + (size_t)nq * Kp);
     float* d_bound = c->bound.as<float>();
-    YB_CUDA(cudaMemsetAsync(d_sel_n, 0, (size_t)nq * 4, st));
-    fill_f32_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_bound, nq, -INFINITY);
+    scan_init_kernel<<<(nq + 255) / 256, 256, 0, st>>>(nq, d_sel_n, d_bound, d_counts);
 
     if (n == 0) {
         // nothing to score: every list is empty, bound = -inf
@@ -1224,11 +1311,10 @@ static yams_status_t scan_enqueue(Corpus* c, const ScanPlan& p, int64_t* d_out_r
                                                                                          p.d_mask, p.mask_ld, nullptr);
             SelectIn in{};
             in.dense = c->sample_scores.as<float>(); in.ld = S; in.row_start = 0; in.row_stride = stride; in.dense_len = S;
+            in.tau_margin = l2 ? 0.f : kTauMargin;
             topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, m, 1, d_tau, nullptr, nullptr, nullptr);
-            if (!l2) tau_margin_kernel<<<(nq + 255) / 256, 256, 0, st>>>(d_tau, nq, kTauMargin, -INFINITY);
         }
         if ((rc = c->cands.reserve((size_t)nq * cap * sizeof(Cand))) != YAMS_OK) return rc;
-        YB_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)nq * 4, st));
         Stage1Args f = a;
         f.row_start = 0; f.row_stride = 1; f.nrows = n;
         f.tau = d_tau; f.cands = c->cands.as<Cand>(); f.cap = cap; f.counts = d_counts;

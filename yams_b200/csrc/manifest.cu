@@ -83,17 +83,24 @@ __device__ __forceinline__ CrcPart crc_join(const CrcTables* __restrict__ t, Crc
 __device__ __forceinline__ uint32_t crc_byte(const uint32_t* __restrict__ tab, uint32_t reg, uint32_t byte) {
     return (reg >> 8) ^ tab[(reg ^ byte) & 0xFFu];
 }
+// decimal text of v, most significant digit first, without a digit buffer
 __device__ __forceinline__ uint32_t crc_decimal(const uint32_t* __restrict__ tab, uint32_t reg, uint64_t v, uint32_t* len) {
-    char buf[20];
-    int n = 0;
-    do {
-        buf[n++] = (char)('0' + (int)(v % 10));
-        v /= 10;
-    } while (v);
-    *len += (uint32_t)n;
-    while (n) reg = crc_byte(tab, reg, (uint32_t)buf[--n]);
+    uint64_t p10 = 1;
+    uint32_t digits = 1;
+    while (digits < 20 && v / p10 >= 10) {
+        p10 *= 10;
+        ++digits;
+    }
+    *len += digits;
+    for (uint32_t i = 0; i < digits; ++i) {
+        const uint32_t dgt = (uint32_t)(v / p10);
+        reg = crc_byte(tab, reg, (uint32_t)'0' + dgt);
+        v -= (uint64_t)dgt * p10;
+        p10 /= 10;
+    }
     return reg;
 }
+__device__ __forceinline__ uint32_t hex_char(uint32_t nib) { return nib < 10 ? '0' + nib : 'a' + (nib - 10); }
 
 // record 0 = file header (fileHash || to_string(fileSize)); record i + 1 = chunk i
 __global__ void manifest_records_kernel(const yams_chunk_desc* __restrict__ chunks, uint32_t n, const uint8_t* __restrict__ file_digest,
@@ -104,39 +111,35 @@ __global__ void manifest_records_kernel(const yams_chunk_desc* __restrict__ chun
     __syncthreads();
     const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n) return;
-    const char* hexd = "0123456789abcdef";
     const uint8_t* dg = r == 0 ? file_digest : chunks[r - 1].digest;
     uint32_t reg = 0, len = 64;
-    char hex[64];
-#pragma unroll 4
-    for (int i = 0; i < 32; ++i) {
-        const uint8_t b = dg[i];
-        hex[2 * i] = hexd[b >> 4];
-        hex[2 * i + 1] = hexd[b & 15];
-        reg = crc_byte(tab, reg, (uint32_t)hex[2 * i]);
-        reg = crc_byte(tab, reg, (uint32_t)hex[2 * i + 1]);
+    uint32_t* ref_words = (refs && r > 0) ? reinterpret_cast<uint32_t*>(refs[r - 1].hash) : nullptr;   // 80-byte records: 4-byte aligned
+    for (int i = 0; i < 32; i += 2) {   // two digest bytes -> four hex characters = one 32-bit word of ChunkRef::hash
+        const uint32_t b0 = dg[i], b1 = dg[i + 1];
+        const uint32_t c0 = hex_char(b0 >> 4), c1 = hex_char(b0 & 15), c2 = hex_char(b1 >> 4), c3 = hex_char(b1 & 15);
+        reg = crc_byte(tab, reg, c0);
+        reg = crc_byte(tab, reg, c1);
+        reg = crc_byte(tab, reg, c2);
+        reg = crc_byte(tab, reg, c3);
+        if (ref_words) ref_words[i >> 1] = c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
     }
     if (r == 0) {
         reg = crc_decimal(tab, reg, file_size, &len);
     } else {
-        const yams_chunk_desc c = chunks[r - 1];
+        const uint64_t c_offset = chunks[r - 1].offset, c_size = chunks[r - 1].size;
         // ChunkRef::size is 32 bits (manifest_manager.h:51): createManifest's static_cast<uint32_t>(chunk.size)
-        const uint32_t sz32 = (uint32_t)c.size;
-        reg = crc_decimal(tab, reg, c.offset, &len);
+        const uint32_t sz32 = (uint32_t)c_size;
+        reg = crc_decimal(tab, reg, c_offset, &len);
         reg = crc_decimal(tab, reg, (uint64_t)sz32, &len);
         if (refs) {
-            yams_chunk_ref out;
-#pragma unroll
-            for (int i = 0; i < 64; ++i) out.hash[i] = hex[i];
-            out.offset = c.offset;
-            out.size = sz32;
-            out.flags = 0;
-            refs[r - 1] = out;
+            refs[r - 1].offset = c_offset;
+            refs[r - 1].size = sz32;
+            refs[r - 1].flags = 0;
         }
         // validateManifest (:452-461): offsets are the running sum of the sizes; ChunkRef::isValid: size > 0
         const uint64_t expect = r == 1 ? 0 : chunks[r - 2].offset + (uint64_t)(uint32_t)chunks[r - 2].size;
-        if (c.offset != expect) atomicAdd(&checks[0], 1ull);
-        if (sz32 == 0 || c.size != (uint64_t)sz32) atomicAdd(&checks[1], 1ull);
+        if (c_offset != expect) atomicAdd(&checks[0], 1ull);
+        if (sz32 == 0 || c_size != (uint64_t)sz32) atomicAdd(&checks[1], 1ull);
     }
     CrcPart p;
     p.len = len;
