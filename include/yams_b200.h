@@ -424,6 +424,34 @@ YAMS_B200_API yams_status_t yams_b200_compute_cosine_similarity(void* self, cons
 YAMS_B200_API yams_status_t yams_b200_compute_cosine_similarity_many(void* self, const float* a, const float* b,
                                                                      size_t n, size_t dim, double* out);
 
+/* ---- SimeonPqAdc engine -----------------------------------------------------------------
+ * The reference's default engine (src/vector/sqlite_vec_backend.cpp:3868-4056): a product-quantised index over the
+ * L2-normalised embeddings (third_party/simeon/include/simeon/pq.hpp:20-136: m sub-quantisers x k <= 256 centroids,
+ * one byte per subspace), scanned with an asymmetric-distance lookup table per query, the best
+ * max(k, k * rerank_factor) rows re-scored exactly.  Here the index lives beside a corpus: codes [rows][m] bytes in HBM
+ * (32 B per row at the defaults, 1/48 of the fp16 corpus), the exact rerank reads the corpus rows.
+ *   pq_build   rebuildSimeonPqIndex (:3540-3690) minus the training: rows with |row|^2 <= 1e-20 are left out, every other
+ *              row is normalised like normalizeEmbeddingInPlace (:213-226) and encoded like ProductQuantizer::encode
+ *              (simeon/src/pq.cpp:218-235) with the given codebooks [m][k][dim/m] (ProductQuantizer::import_codebooks; the
+ *              k-means training of <= 4096 samples stays where it is).  tie_break_keys: nullable, one per corpus row (the
+ *              FNV-1a of chunk_id the reference orders equal approximate scores by); NULL = row order.
+ *   pq_search  simeonPqSearchUnlocked: normalised query, lookup table (simd::dot order of the x86 build), ADC scores as
+ *              sequential float sums, best approxK by (score desc, tie key asc), exact double cosine of the ORIGINAL query
+ *              against the stored row (computeCosineSimilarity), threshold, order (similarity desc, rowid asc; TIE_AT_K
+ *              flag for the host's chunk_id re-break), k results.  Approximate scores, survivors and final scores are
+ *              bit-identical to the reference engine.  A query that cannot be normalised returns nothing.
+ * The index is invalidated by any corpus mutation (the reference marks it dirty): pq_search then returns INVALID_ARG. */
+typedef struct yams_b200_pq yams_b200_pq;
+YAMS_B200_API yams_status_t yams_b200_pq_build(yams_b200_corpus* c, uint32_t m, uint32_t k, const float* codebooks,
+                                               const uint64_t* tie_break_keys, yams_b200_pq** out);
+YAMS_B200_API yams_status_t yams_b200_pq_search(yams_b200_pq* pq, const float* queries, uint32_t nq, uint32_t k,
+                                                uint32_t rerank_factor, float threshold, int64_t* out_rowids,
+                                                float* out_scores, uint32_t* out_counts, uint64_t* out_flags);
+/* the index content, for parity checks: out_codes [n_indexed][m], out_rowids [n_indexed] (both nullable), *out_n */
+YAMS_B200_API yams_status_t yams_b200_pq_codes(yams_b200_pq* pq, uint8_t* out_codes, int64_t* out_rowids,
+                                               uint64_t* out_n);
+YAMS_B200_API void yams_b200_pq_destroy(yams_b200_pq* pq);
+
 /* [0] stage-1 scan ms, [1] rescoring+select ms, [2] total device ms, [3] h2d+d2h ms of the last
  * yams_b200_search on this corpus; [4] = which stage-1 kernel ran (0 cuda-core, 1 tcgen05);
  * [5] = duration of the full-corpus filtered scan launch alone (the dominant kernel);
@@ -464,6 +492,12 @@ typedef struct yams_vector_scan_v1 {
     yams_status_t (*search_exhaustive)(yams_b200_corpus* c, const float* queries, uint32_t nq, uint32_t k,
                                        float threshold, int64_t* out_rowids, float* out_scores,
                                        uint32_t* out_counts, uint64_t* out_flags);
+    yams_status_t (*pq_build)(yams_b200_corpus* c, uint32_t m, uint32_t k, const float* codebooks,
+                              const uint64_t* tie_break_keys, yams_b200_pq** out);
+    yams_status_t (*pq_search)(yams_b200_pq* pq, const float* queries, uint32_t nq, uint32_t k,
+                               uint32_t rerank_factor, float threshold, int64_t* out_rowids, float* out_scores,
+                               uint32_t* out_counts, uint64_t* out_flags);
+    void (*pq_destroy)(yams_b200_pq* pq);
 } yams_vector_scan_v1;
 
 /* ---- sqlite-vec-cpp C API kept bit-for-bit in signature and error behaviour ------------------

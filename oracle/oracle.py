@@ -309,6 +309,54 @@ def manifest_checksum(file_digest, file_size: int, digests: np.ndarray, offsets,
     return int(L.yo_manifest_checksum(_p(fd, u8p), file_size, _p(dg, u8p) if n else C.cast(C.c_void_p(0), u8p), _p(of, u64p), _p(sz, u64p), n))
 
 
+def _pq_fns():
+    R = ref()
+    R.ref_pq_encode.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint32, u8p]
+    R.ref_pq_scores.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p, u8p, C.c_size_t, f32p, f32p]
+    R.ref_pq_train.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint32, f32p]
+    return R
+
+
+def normalize_like_reference(rows: np.ndarray):
+    """normalizeEmbeddingInPlace (src/vector/sqlite_vec_backend.cpp:213-226): sequential double sum of squares, rows with
+    norm_sq <= 1e-20 rejected, inv = 1.0f / sqrt(float(norm_sq)), float scale.  -> (normalised rows of the accepted, accepted mask)"""
+    r = np.ascontiguousarray(rows, dtype=np.float32)
+    sq = np.cumsum(r.astype(np.float64) ** 2, axis=1)[:, -1]            # cumsum adds left to right, like the reference loop
+    ok = sq > 1e-20
+    inv = (np.float32(1.0) / np.sqrt(sq[ok].astype(np.float32))).astype(np.float32)
+    return (r[ok] * inv[:, None]).astype(np.float32), ok
+
+
+def pq_encode_ref(codebooks, dim, m, k, normalised_rows):
+    """simeon::ProductQuantizer::encode_batch (third_party/simeon/src/pq.cpp) compiled in place."""
+    R = _pq_fns()
+    v = np.ascontiguousarray(normalised_rows, dtype=np.float32)
+    cb = np.ascontiguousarray(codebooks, dtype=np.float32)
+    codes = np.zeros((len(v), m), dtype=np.uint8)
+    R.ref_pq_encode(_p(cb, f32p), dim, m, k, _p(v, f32p), len(v), _p(codes, u8p))
+    return codes
+
+
+def pq_scores_ref(codebooks, dim, m, k, normalised_query, codes):
+    """simeon::PQInnerProductQuery: (ADC inner products of every code row, the lookup table)."""
+    R = _pq_fns()
+    cb = np.ascontiguousarray(codebooks, dtype=np.float32)
+    q = np.ascontiguousarray(normalised_query, dtype=np.float32)
+    cd = np.ascontiguousarray(codes, dtype=np.uint8)
+    out = np.zeros(len(cd), dtype=np.float32)
+    lut = np.zeros(m * k, dtype=np.float32)
+    R.ref_pq_scores(_p(cb, f32p), dim, m, k, _p(q, f32p), _p(cd, u8p), len(cd), _p(out, f32p), _p(lut, f32p))
+    return out, lut
+
+
+def pq_train_ref(dim, m, k, training):
+    R = _pq_fns()
+    t = np.ascontiguousarray(training, dtype=np.float32)
+    cb = np.zeros(m * k * (dim // m), dtype=np.float32)
+    R.ref_pq_train(dim, m, k, _p(t, f32p), len(t), _p(cb, f32p))
+    return cb
+
+
 def exact_scan_cosine(rows: np.ndarray, query: np.ndarray, k: int, threshold: float = -1.0,
                       rowids: Optional[np.ndarray] = None, tie_rank: Optional[np.ndarray] = None,
                       allowed: Optional[np.ndarray] = None, all_matching: bool = False):

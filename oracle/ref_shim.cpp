@@ -2,7 +2,8 @@
 //
 // Compiled by oracle/Makefile together with the reference's own sources *where they lie* under
 // /root/reference (src/chunking/{rabin,streaming}_chunker.cpp, src/crypto/sha256_hasher.cpp and the
-// header-only third_party/sqlite-vec-cpp distances) into oracle/_ref/libyams_ref.so.  No reference
+// header-only third_party/sqlite-vec-cpp distances, src/manifest/manifest_manager.cpp, third_party/simeon/src/{pq,arch/avx2,
+// arch/scalar}.cpp) into oracle/_ref/libyams_ref.so.  No reference
 // source is copied into this repository; this file only *calls* the reference's public C++ API.
 // Used to (1) pin oracle/yams_oracle.c, (2) generate tests/golden/*, (3) serve as bench.py's
 // "reference" CPU arm when present.
@@ -14,12 +15,20 @@
 #include <sqlite-vec-cpp/distances/cosine.hpp>
 #include <sqlite-vec-cpp/distances/l2.hpp>
 #include <yams/manifest/manifest_manager.h>
+#include <simeon/pq.hpp>
+#include <simeon/simeon.hpp>
 #include <sqlite-vec-cpp/utils/float16.hpp>
 
 #include <algorithm>
 #include <cstring>
 #include <span>
 #include <vector>
+
+// simeon::active_simd_tier() is a compile-time constant (third_party/simeon/src/simeon.cpp:53-61): Avx2 on an x86 build with
+// SIMEON_HAS_AVX2, which is how this shim compiles the arch/ kernels.  Defined here instead of compiling simeon.cpp whole.
+namespace simeon {
+SimdTier active_simd_tier() noexcept { return SimdTier::Avx2; }
+}  // namespace simeon
 
 namespace {
 yams::chunking::ChunkingConfig make_cfg(uint64_t window, uint64_t minc, uint64_t maxc,
@@ -116,6 +125,30 @@ uint32_t ref_manifest_checksum(const uint8_t* file_digest32, uint64_t file_size,
         *out_valid = v ? (v.value() ? 1 : 0) : -1;
     }
     return res.value().checksum;
+}
+
+// ---- SimeonPqAdc pieces: simeon's own ProductQuantizer / PQInnerProductQuery (third_party/simeon/src/pq.cpp) ----
+// encode_batch of ALREADY NORMALISED rows with imported codebooks [m][k][dim/m]
+void ref_pq_encode(const float* codebooks, uint32_t dim, uint32_t m, uint32_t k, const float* vecs, uint32_t n, uint8_t* codes) {
+    simeon::ProductQuantizer pq(simeon::PQConfig{.dim = dim, .m = m, .k = k});
+    pq.import_codebooks(std::span<const float>(codebooks, (size_t)m * k * (dim / m)));
+    pq.encode_batch(vecs, n, codes);
+}
+// lookup table + ADC inner products of one (already normalised) query over n codes
+void ref_pq_scores(const float* codebooks, uint32_t dim, uint32_t m, uint32_t k, const float* query, const uint8_t* codes, size_t n,
+                   float* out_scores, float* out_lut) {
+    simeon::ProductQuantizer pq(simeon::PQConfig{.dim = dim, .m = m, .k = k});
+    pq.import_codebooks(std::span<const float>(codebooks, (size_t)m * k * (dim / m)));
+    simeon::PQInnerProductQuery qy(pq, query);
+    for (size_t i = 0; i < n; ++i) out_scores[i] = qy.inner_product(codes + i * m);
+    if (out_lut) std::memcpy(out_lut, qy.lut_ip().data(), qy.lut_ip().size() * sizeof(float));
+}
+// Lloyd training of the reference (ProductQuantizer::train) -> codebooks, for realistic test indexes
+void ref_pq_train(uint32_t dim, uint32_t m, uint32_t k, const float* training, uint32_t n_train, float* out_codebooks) {
+    simeon::ProductQuantizer pq(simeon::PQConfig{.dim = dim, .m = m, .k = k});
+    pq.train(training, n_train);
+    auto cb = pq.codebooks();
+    std::memcpy(out_codebooks, cb.data(), cb.size() * sizeof(float));
 }
 
 // SHA256Hasher::hash (static one-shot) -> 64-char lowercase hex + NUL

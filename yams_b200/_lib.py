@@ -118,6 +118,10 @@ SYMBOLS = {
     "yams_b200_synth_bytes_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "yams_b200_debug_stage1_scores": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
     "yams_b200_synth_rows_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "yams_b200_pq_build": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, f32p, u64p, C.POINTER(C.c_void_p)]),
+    "yams_b200_pq_search": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, i64p, f32p, u32p, u64p]),
+    "yams_b200_pq_codes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, u64p]),
+    "yams_b200_pq_destroy": (None, [C.c_void_p]),
     "yams_b200_debug_last_eps": (C.c_int, [C.c_void_p, C.c_uint32, f32p]),
     "yams_b200_device_count": (C.c_int, []),
     "yams_b200_last_error": (C.c_char_p, []),
@@ -499,6 +503,51 @@ class Corpus:
         if self._h:
             lib().yams_b200_corpus_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PqIndex:
+    """SimeonPqAdc index over a Corpus (codes in HBM beside the rows); search = ADC scan + exact rerank."""
+
+    def __init__(self, corpus: Corpus, m: int, k: int, codebooks: np.ndarray, tie_break_keys=None):
+        cb = np.ascontiguousarray(codebooks, dtype=np.float32)
+        assert cb.size == m * k * (corpus.dim // m)
+        tk = np.ascontiguousarray(tie_break_keys, dtype=np.uint64) if tie_break_keys is not None else None
+        self._h = C.c_void_p()
+        self.m, self.k, self._corpus = m, k, corpus
+        _check(lib().yams_b200_pq_build(corpus.handle, m, k, cb.ctypes.data_as(f32p), tk.ctypes.data_as(u64p) if tk is not None else None,
+                                        C.byref(self._h)), "pq_build")
+
+    def codes(self):
+        n = C.c_uint64(0)
+        _check(lib().yams_b200_pq_codes(self._h, None, None, C.byref(n)), "pq_codes")
+        codes = np.zeros((max(n.value, 1), self.m), dtype=np.uint8)
+        rowids = np.zeros(max(n.value, 1), dtype=np.int64)
+        _check(lib().yams_b200_pq_codes(self._h, codes.ctypes.data, rowids.ctypes.data, C.byref(n)), "pq_codes")
+        return codes[:n.value], rowids[:n.value]
+
+    def search(self, queries, k: int, rerank_factor: int = 2, threshold: float = 0.0):
+        q = np.ascontiguousarray(queries, dtype=np.float32)
+        if q.ndim == 1:
+            q = q[None, :]
+        nq = q.shape[0]
+        out_r = np.full((nq, max(k, 1)), -1, dtype=np.int64)
+        out_s = np.zeros((nq, max(k, 1)), dtype=np.float32)
+        out_c = np.zeros(nq, dtype=np.uint32)
+        out_f = np.zeros(nq, dtype=np.uint64)
+        _check(lib().yams_b200_pq_search(self._h, q.ctypes.data_as(f32p), nq, k, rerank_factor, threshold, out_r.ctypes.data_as(i64p),
+                                         out_s.ctypes.data_as(f32p), out_c.ctypes.data_as(u32p), out_f.ctypes.data_as(u64p)), "pq_search")
+        return out_r[:, :k], out_s[:, :k], out_c, out_f
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().yams_b200_pq_destroy(self._h)
+            self._h = None
 
     def __del__(self):
         try:

@@ -199,6 +199,9 @@ int yams_plugin_init(const char* config_json, const void* host_context) {
     g_scan_vt.compute_cosine_similarity = yams_b200_compute_cosine_similarity;
     g_scan_vt.compute_cosine_similarity_many = yams_b200_compute_cosine_similarity_many;
     g_scan_vt.search_exhaustive = yams_b200_search_exhaustive;
+    g_scan_vt.pq_build = yams_b200_pq_build;
+    g_scan_vt.pq_search = yams_b200_pq_search;
+    g_scan_vt.pq_destroy = yams_b200_pq_destroy;
     DeviceCtx* dev = nullptr;
     if (ensure_device(&dev) != YAMS_OK) return YAMS_PLUGIN_ERR_INIT_FAILED;  // no CPU fallback
     g_inited = true;

@@ -1111,7 +1111,6 @@ __global__ void iota_rowids_kernel(int64_t* p, uint64_t n, int64_t first) {
 // ===================================================================================================
 // host side: corpus mirror + search orchestration
 // ===================================================================================================
-struct yams_b200_corpus : public yb::Corpus {};
 
 namespace yb {
 
@@ -1180,6 +1179,7 @@ static yams_status_t corpus_finish_append(Corpus* c, uint64_t n_new, const int64
     c->last_rowid = last;
     c->rowids_dense = dense;
     c->n += n_new;
+    ++c->generation;
     return YAMS_OK;
 }
 
@@ -1344,6 +1344,20 @@ static yams_status_t scan_enqueue(Corpus* c, const ScanPlan& p, int64_t* d_out_r
                                              d_out_counts, d_out_flags, l2 ? INFINITY : -INFINITY, nullptr, cert);
     YB_CUDA(cudaGetLastError());
     return YAMS_OK;
+}
+
+// entry points for the other engines (pq.cu): exact top-K of per-query candidate lists, and the plain final ordering
+void launch_topk_lists(const Cand* lists, const uint32_t* counts, uint32_t cap, uint32_t nq, uint32_t K, Cand* out_sel, uint32_t* out_n,
+                       cudaStream_t st) {
+    SelectIn in{};
+    in.cands = lists; in.counts = counts; in.cap = cap;
+    topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, K, 0, nullptr, out_sel, out_n, nullptr);
+}
+void launch_final_plain(const void* exact, uint32_t Kp, uint32_t k, uint32_t nq, const int64_t* rowids, int64_t* out_rowids, float* out_scores,
+                        uint32_t* out_counts, uint64_t* out_flags, cudaStream_t st) {
+    CertArgs cert{};   // status == nullptr: no certificate (the caller's survivors are what the reference re-ranks, too)
+    final_kernel<<<nq, SEL_THREADS, 0, st>>>(static_cast<const Exact*>(exact), nullptr, Kp, k, rowids, 0, out_rowids, out_scores, out_counts,
+                                             out_flags, -INFINITY, nullptr, cert);
 }
 
 // Level 2: exact score of EVERY row for one query (the reference's own loop, row-parallel) + a global sort.
@@ -1629,6 +1643,7 @@ yams_status_t yams_b200_corpus_remove(yams_b200_corpus* c, const int64_t* rowids
     YB_CUDA(cudaStreamSynchronize(st));
     if (out_removed) *out_removed = c->n - kept;
     c->n = kept;
+    ++c->generation;
     c->last_rowid = last;
     c->rowids_dense = false;
     return YAMS_OK;
@@ -1640,6 +1655,7 @@ yams_status_t yams_b200_corpus_clear(yams_b200_corpus* c) {
     std::lock_guard<std::mutex> corpus_lock(c->mu);
     YB_BIND(c);
     c->n = 0;
+    ++c->generation;
     c->last_rowid = INT64_MIN;
     c->rowids_dense = true;
     c->pending.active = false;

@@ -19,6 +19,7 @@ struct Corpus {
     int dtype = YAMS_B200_F16;
     int metric = YAMS_B200_COSINE;
     uint64_t n = 0;
+    uint64_t generation = 0;   // bumped by every append / remove / clear: derived indexes (pq.cu) notice a stale corpus
     int64_t last_rowid = INT64_MIN;
     bool rowids_dense = true;  // rowid[i] == rowid[0] + i
     DevBuf rows;       // n x dim elements
@@ -85,3 +86,6 @@ struct Stage1Args {
 yams_status_t stage1_cuda_core(const Stage1Args& a, bool filter, cudaStream_t st);
 
 }  // namespace yb
+
+// the opaque handle of the C ABI
+struct yams_b200_corpus : public yb::Corpus {};
