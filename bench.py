@@ -521,6 +521,35 @@ def main():
                                           "corpus bytes / scan kernel time / measured copy bandwidth", "points": sweep}
             except Exception as e:   # noqa: BLE001
                 out["q_sweep"] = {"error": repr(e)[:200]}
+        if rank == 0 and world == 1 and not args.no_side and not f32:
+            try:   # N3: the SimeonPqAdc engine over the same corpus (32 B of codes per row) -- the latency engine
+                rng = np.random.default_rng(1)
+                m_pq, k_pq = 32, 256
+                cb = (rng.normal(size=(m_pq, k_pq, d // m_pq)) / np.sqrt(d)).astype(np.float32)
+                t0 = time.perf_counter()
+                pq = Y.PqIndex(corpus, m_pq, k_pq, cb)
+                build_s = time.perf_counter() - t0
+                pts = []
+                for q_n in (1, 16, 256):
+                    qs = q_host.numpy()[:q_n]
+                    pq.search(qs, k, rerank_factor=2, threshold=-1.0)
+                    t0 = time.perf_counter()
+                    for _ in range(5):
+                        pq.search(qs, k, rerank_factor=2, threshold=-1.0)
+                    pq_ms = (time.perf_counter() - t0) / 5 * 1e3
+                    corpus.search(qs, k, threshold=-1.0)
+                    t0 = time.perf_counter()
+                    for _ in range(5):
+                        corpus.search(qs, k, threshold=-1.0)
+                    ex_ms = (time.perf_counter() - t0) / 5 * 1e3
+                    pts.append({"queries": q_n, "pq_adc_ms_per_call": pq_ms, "exact_scan_ms_per_call": ex_ms,
+                                "pq_code_gbs": n * m_pq * q_n / pq_ms / 1e6})
+                out["pq_adc"] = {"workload": f"SimeonPqAdc over the same {n} x {d} corpus: m={m_pq}, k={k_pq} (defaults of VectorDatabaseConfig), rerank_factor 2, "
+                                             "host call incl. query upload and result copy; random (untrained) codebooks -- timing only, parity is in tests/test_gpu_pq.py",
+                                 "index_build_s": build_s, "code_bytes": n * m_pq, "points": pts}
+                pq.close()
+            except Exception as e:   # noqa: BLE001
+                out["pq_adc"] = {"error": repr(e)[:200]}
         corpus.close()
         del corpus
         torch.cuda.empty_cache()
