@@ -596,6 +596,44 @@ def test_concurrent_searches_on_one_corpus(Y, oracle):
     c.close()
 
 
+def test_worker_threads_bind_the_plugin_device(Y):
+    """A fresh host thread starts on CUDA device 0 whatever the plugin was initialised with: every handle-based entry must bind
+    the handle's device itself (model_provider_v1.h:45 "thread-safe unless documented").  Needs a second GPU."""
+    if Y.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = """
+import threading, sys
+import numpy as np
+sys.path.insert(0, %r)
+import yams_b200 as Y
+assert Y.plugin_init({"device": 1}) == 0, Y.health()
+assert Y.health()["device"] == 1
+c = Y.Corpus(64, Y.F16, Y.COSINE)
+c.append_synthetic(42, 0, 120000)
+q = np.random.default_rng(0).normal(size=(5, 64)).astype(np.float32)
+data = (np.arange(3 << 20, dtype=np.uint64) * 2654435761 >> 7).astype(np.uint8)
+want = c.search(q, 7)
+want_chunks = Y.chunk_and_hash(data)
+got = {}
+def work():
+    got["s"] = c.search(q, 7)                       # corpus handle created on device 1, called from a device-0 thread
+    got["c"] = Y.chunk_and_hash(data)               # pooled ingest workspace
+    got["a"] = c.search_all_matching(q[0], 0.2)
+    c.append_synthetic(42, 120000, 1000)
+    got["n"] = len(c)
+t = threading.Thread(target=work); t.start(); t.join()
+assert np.array_equal(got["s"][0], want[0]) and np.array_equal(got["s"][1], want[1])
+assert np.array_equal(got["c"], want_chunks) and got["n"] == 121000 and len(got["a"][0]) > 0
+print("THREADS OK")
+""" % root
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "THREADS OK" in out.stdout, out.stdout + out.stderr
+
+
 def test_large_k(Y, oracle):
     """k in the thousands (rerank windows): K' = k + k/4 survivors are ordered in shared memory (limit k <= 3072)."""
     O = oracle

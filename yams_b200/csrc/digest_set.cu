@@ -232,6 +232,7 @@ yams_status_t yams_b200_digest_set_insert(yams_b200_digest_set* s, const uint8_t
     YB_ARG(digests && stride >= 32, "bad digests/stride");
     YB_ARG(n < (1ull << 31), "batch too large");
     std::lock_guard<std::mutex> lk(s->mu);
+    YB_BIND(s);
     yams_status_t rc;
     // the store only ever receives digests that are not in the set yet, so re-offering known content (the common case
     // of a daily `yams add` over an unchanged tree) does not grow it
@@ -290,6 +291,7 @@ yams_status_t yams_b200_digest_set_contains(yams_b200_digest_set* s, const uint8
     YB_ARG(digests && stride >= 32 && out_exists, "bad argument");
     YB_ARG(n < (1ull << 31), "batch too large");
     std::lock_guard<std::mutex> lk(s->mu);
+    YB_BIND(s);
     yams_status_t rc;
     const size_t in_bytes = (n - 1) * stride + 32;
     if ((rc = s->stage.reserve(in_bytes)) != YAMS_OK) return rc;

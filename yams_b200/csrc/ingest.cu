@@ -284,6 +284,12 @@ static size_t pool_max() {
 static yams_status_t acquire_res(const yams_cdc_config* cfg, IngestRes** out) {
     IngestRes* r = nullptr;
     {
+        // a pooled resource may be picked up by a thread that never touched CUDA: bind the plugin's device first
+        DeviceCtx* dev = nullptr;
+        yams_status_t drc = ensure_device(&dev);
+        if (drc != YAMS_OK) return drc;
+    }
+    {
         std::lock_guard<std::mutex> lk(g_pool_mu);
         if (!g_pool.empty()) {
             r = g_pool.back();
@@ -860,6 +866,7 @@ yams_status_t yams_b200_ingest_feed(yams_b200_ingest* s, const uint8_t* data, si
                                     size_t* out_n) {
     YB_TRY
     YB_ARG(s && out && out_n, "null argument");
+    if (s->r && s->r->cs.dev) cudaSetDevice(s->r->cs.dev->device);   // a session may be fed from another thread than the one that opened it
     *out = nullptr;
     *out_n = 0;
     YB_ARG(data || len == 0, "data is null");
@@ -872,6 +879,7 @@ yams_status_t yams_b200_ingest_feed(yams_b200_ingest* s, const uint8_t* data, si
 yams_status_t yams_b200_ingest_finish(yams_b200_ingest* s, yams_chunk_desc** out, size_t* out_n) {
     YB_TRY
     YB_ARG(s && out && out_n, "null argument");
+    if (s->r && s->r->cs.dev) cudaSetDevice(s->r->cs.dev->device);   // a session may be fed from another thread than the one that opened it
     *out = nullptr;
     *out_n = 0;
     yams_status_t rc = session_feed(s, nullptr, 0, true);

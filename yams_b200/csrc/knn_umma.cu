@@ -699,7 +699,9 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     }
 
     auto env_int = [](const char* name, int dflt) { const char* e = getenv(name); return e ? atoi(e) : dflt; };
-    const int ctas_env = env_int("YAMS_B200_UMMA_CTAS", 2);   // 2-CTA pairs (cta_group::2, M = 256): ~3 % faster under the power cap
+    // 2-CTA pairs (cta_group::2, M = 256) for tensor-bound batches: ~3 % faster under the power cap (half the query-operand shared-memory
+    // reads).  HBM-bound batches (below ~2 query tiles) stream slightly faster with independent CTAs (measured 2.84 vs 2.89 ms per 10 M rows).
+    const int ctas_env = env_int("YAMS_B200_UMMA_CTAS", a.nq >= 512 ? 2 : 1);
     const int ctas = (ctas_env == 1 || c->dev->sm_count < 2) ? 1 : 2;
     UmmaArgs u{};
     u.a = a;
