@@ -452,6 +452,30 @@ YAMS_B200_API yams_status_t yams_b200_pq_codes(yams_b200_pq* pq, uint8_t* out_co
                                                uint64_t* out_n);
 YAMS_B200_API void yams_b200_pq_destroy(yams_b200_pq* pq);
 
+/* ---- Simeon text encoder, default profile ---------------------------------------------------
+ * third_party/simeon Encoder::encode (src/simeon.cpp:190-262) for the profile YAMS runs (`simeon-v1-384`, src/simeon.cpp:75-93;
+ * src/embedding_simeon/simeon_embedding_backend.cpp:118-135): byte n-grams of length ngram_min..ngram_max over the raw text,
+ * SplitMix64 hashing, integer count sketch (+-2 per gram), Achlioptas sparse projection (int64 sums, one float scale),
+ * L2 normalisation in the AVX2 tier's lane order.  Bit-identical to the reference encoder.  Other encoder modes (word /
+ * sub-word tokens, ASCII lowering, IDF / PMI weighting, FWHT or Gaussian projections, matryoshka) are not served here. */
+typedef struct yams_simeon_config {
+    uint32_t ngram_min, ngram_max;     /* 3, 5 */
+    uint32_t sketch_dim, output_dim;   /* 4096, 384 */
+    uint64_t hash_seed;                /* 0xA5A5A5A5A5A5A5A5 */
+    uint64_t projection_seed;          /* 0xDEADBEEFCAFEBABE */
+    int32_t l2_normalize;              /* 1 */
+    int32_t reserved;
+} yams_simeon_config;
+typedef struct yams_b200_encoder yams_b200_encoder;
+YAMS_B200_API void yams_b200_simeon_default_config(yams_simeon_config* cfg);
+YAMS_B200_API yams_status_t yams_b200_simeon_create(void* self, const yams_simeon_config* cfg /* NULL = default */,
+                                                    yams_b200_encoder** out);
+/* IEmbeddingBackend::generateEmbeddings (simeon_embedding_backend.cpp:194-209): n HOST texts (bytes, not NUL-terminated)
+ * -> out[n][output_dim] HOST floats, one device pass */
+YAMS_B200_API yams_status_t yams_b200_simeon_encode(yams_b200_encoder* e, const char* const* texts, const size_t* lens,
+                                                    size_t n, float* out);
+YAMS_B200_API void yams_b200_simeon_destroy(yams_b200_encoder* e);
+
 /* [0] stage-1 scan ms, [1] rescoring+select ms, [2] total device ms, [3] h2d+d2h ms of the last
  * yams_b200_search on this corpus; [4] = which stage-1 kernel ran (0 cuda-core, 1 tcgen05);
  * [5] = duration of the full-corpus filtered scan launch alone (the dominant kernel);

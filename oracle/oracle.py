@@ -309,6 +309,22 @@ def manifest_checksum(file_digest, file_size: int, digests: np.ndarray, offsets,
     return int(L.yo_manifest_checksum(_p(fd, u8p), file_size, _p(dg, u8p) if n else C.cast(C.c_void_p(0), u8p), _p(of, u64p), _p(sz, u64p), n))
 
 
+def simeon_encode_ref(texts, ngram_min=3, ngram_max=5, sketch_dim=4096, output_dim=384, hash_seed=0xA5A5A5A5A5A5A5A5,
+                      projection_seed=0xDEADBEEFCAFEBABE, l2_normalize=1) -> np.ndarray:
+    """simeon::Encoder::encode (third_party/simeon compiled in place) over a list of byte strings."""
+    R = ref()
+    R.ref_simeon_encode.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int,
+                                    C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, f32p]
+    raw = [t.encode("utf-8") if isinstance(t, str) else bytes(t) for t in texts]
+    n = len(raw)
+    out = np.zeros((n, output_dim), dtype=np.float32)
+    if n:
+        ptrs = (C.c_char_p * n)(*raw)
+        lens = (C.c_size_t * n)(*[len(r) for r in raw])
+        R.ref_simeon_encode(ngram_min, ngram_max, sketch_dim, output_dim, hash_seed, projection_seed, l2_normalize, ptrs, lens, n, _p(out, f32p))
+    return out
+
+
 def _pq_fns():
     R = ref()
     R.ref_pq_encode.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint32, u8p]

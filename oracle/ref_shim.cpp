@@ -24,12 +24,6 @@
 #include <span>
 #include <vector>
 
-// simeon::active_simd_tier() is a compile-time constant (third_party/simeon/src/simeon.cpp:53-61): Avx2 on an x86 build with
-// SIMEON_HAS_AVX2, which is how this shim compiles the arch/ kernels.  Defined here instead of compiling simeon.cpp whole.
-namespace simeon {
-SimdTier active_simd_tier() noexcept { return SimdTier::Avx2; }
-}  // namespace simeon
-
 namespace {
 yams::chunking::ChunkingConfig make_cfg(uint64_t window, uint64_t minc, uint64_t maxc,
                                         uint64_t poly, uint64_t mask) {
@@ -143,6 +137,21 @@ void ref_pq_scores(const float* codebooks, uint32_t dim, uint32_t m, uint32_t k,
     for (size_t i = 0; i < n; ++i) out_scores[i] = qy.inner_product(codes + i * m);
     if (out_lut) std::memcpy(out_lut, qy.lut_ip().data(), qy.lut_ip().size() * sizeof(float));
 }
+// simeon::Encoder of the profile YAMS runs (src/simeon.cpp:75-93 simeon_v1_384_config with the given overrides): n texts -> n x output_dim
+void ref_simeon_encode(uint32_t ngram_min, uint32_t ngram_max, uint32_t sketch_dim, uint32_t output_dim, uint64_t hash_seed,
+                       uint64_t projection_seed, int l2_normalize, const char* const* texts, const size_t* lens, size_t n, float* out) {
+    simeon::EncoderConfig cfg = simeon::simeon_v1_384_config();
+    cfg.ngram_min = ngram_min;
+    cfg.ngram_max = ngram_max;
+    cfg.sketch_dim = sketch_dim;
+    cfg.output_dim = output_dim;
+    cfg.hash_seed = hash_seed;
+    cfg.projection_seed = projection_seed;
+    cfg.l2_normalize = l2_normalize != 0;
+    simeon::Encoder enc(cfg);
+    for (size_t i = 0; i < n; ++i) enc.encode(std::string_view(texts[i], lens[i]), out + i * enc.output_dim());
+}
+
 // Lloyd training of the reference (ProductQuantizer::train) -> codebooks, for realistic test indexes
 void ref_pq_train(uint32_t dim, uint32_t m, uint32_t k, const float* training, uint32_t n_train, float* out_codebooks) {
     simeon::ProductQuantizer pq(simeon::PQConfig{.dim = dim, .m = m, .k = k});

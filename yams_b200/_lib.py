@@ -45,6 +45,11 @@ class ManifestSummary(C.Structure):
                 ("chunk_count", C.c_uint64), ("total_size", C.c_uint64), ("checksum_text_bytes", C.c_uint64)]
 
 
+class SimeonConfig(C.Structure):
+    _fields_ = [("ngram_min", C.c_uint32), ("ngram_max", C.c_uint32), ("sketch_dim", C.c_uint32), ("output_dim", C.c_uint32),
+                ("hash_seed", C.c_uint64), ("projection_seed", C.c_uint64), ("l2_normalize", C.c_int32), ("reserved", C.c_int32)]
+
+
 CHUNK_REF_DTYPE = np.dtype([("hash", "S64"), ("offset", "<u8"), ("size", "<u4"), ("flags", "<u4")])
 assert CHUNK_REF_DTYPE.itemsize == 80
 CHUNK_DTYPE = np.dtype([("offset", "<u8"), ("size", "<u8"), ("digest", "u1", (32,))])
@@ -118,6 +123,10 @@ SYMBOLS = {
     "yams_b200_synth_bytes_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p]),
     "yams_b200_debug_stage1_scores": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
     "yams_b200_synth_rows_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "yams_b200_simeon_default_config": (None, [C.POINTER(SimeonConfig)]),
+    "yams_b200_simeon_create": (C.c_int, [C.c_void_p, C.POINTER(SimeonConfig), C.POINTER(C.c_void_p)]),
+    "yams_b200_simeon_encode": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, f32p]),
+    "yams_b200_simeon_destroy": (None, [C.c_void_p]),
     "yams_b200_pq_build": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, f32p, u64p, C.POINTER(C.c_void_p)]),
     "yams_b200_pq_search": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_float, i64p, f32p, u32p, u64p]),
     "yams_b200_pq_codes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, u64p]),
@@ -503,6 +512,40 @@ class Corpus:
         if self._h:
             lib().yams_b200_corpus_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SimeonEncoder:
+    """The Simeon text encoder's default profile (byte n-grams -> count sketch -> Achlioptas projection -> L2)."""
+
+    def __init__(self, **overrides):
+        cfg = SimeonConfig()
+        lib().yams_b200_simeon_default_config(C.byref(cfg))
+        for k, v in overrides.items():
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self._h = C.c_void_p()
+        _check(lib().yams_b200_simeon_create(None, C.byref(cfg), C.byref(self._h)), "simeon_create")
+
+    def encode(self, texts) -> np.ndarray:
+        raw = [t.encode("utf-8") if isinstance(t, str) else bytes(t) for t in texts]
+        n = len(raw)
+        out = np.zeros((n, self.cfg.output_dim), dtype=np.float32)
+        if n:
+            ptrs = (C.c_char_p * n)(*raw)
+            lens = (C.c_size_t * n)(*[len(r) for r in raw])
+            _check(lib().yams_b200_simeon_encode(self._h, ptrs, lens, n, out.ctypes.data_as(f32p)), "simeon_encode")
+        return out
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().yams_b200_simeon_destroy(self._h)
+            self._h = None
 
     def __del__(self):
         try:
