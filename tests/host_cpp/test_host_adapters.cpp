@@ -198,6 +198,31 @@ int main() {
         auto again = index.addChunks(cc);
         CHECK(again.bytesStored == 0 && again.bytesDeduped == twice.size());
     }
+    // ---- manifest of the chunked buffer: refs mirror the table, the checksum is CRC-32 of the reference's text (zlib polynomial) ----
+    {
+        auto hasher_hex = B200ContentHasher::hash(std::span<const std::byte>(data));
+        auto m = createManifest(hasher_hex, data.size(), full);
+        CHECK(m.valid && m.chunks.size() == full.size() && m.chunks[3].hash == full[3].hash && m.chunks[3].offset == full[3].offset);
+        std::string text = hasher_hex + std::to_string(data.size());
+        for (const auto& c : full) text += c.hash + std::to_string(c.offset) + std::to_string((uint32_t)c.size);
+        uint32_t crc = 0xFFFFFFFFu;   // src/manifest/manifest_manager.cpp:705-730, the loop itself
+        for (char ch : text) { crc ^= (uint32_t)ch; for (int b = 0; b < 8; ++b) crc = (crc >> 1) ^ (0xEDB88320u * (crc & 1u)); }
+        CHECK(m.checksum == ~crc);
+        auto broken = full;
+        broken[2].offset += 1;
+        CHECK(!createManifest(hasher_hex, data.size(), broken).valid);
+    }
+    // ---- Simeon backend adapter: unit-norm embeddings, batch == single, the text itself is its own nearest neighbour ----
+    {
+        B200SimeonBackend sb;
+        std::vector<std::string> texts = {"content addressed storage", "vector similarity search", "", "content addressed storage!"};
+        auto embs = sb.generateEmbeddings(texts);
+        CHECK(sb.getEmbeddingDimension() == 384 && embs.size() == 4 && embs[0].size() == 384);
+        CHECK(sb.generateEmbedding(texts[1]) == embs[1]);
+        double n0 = 0, dot03 = 0, dot01 = 0, n2 = 0;
+        for (int i = 0; i < 384; ++i) { n0 += embs[0][i] * embs[0][i]; dot03 += embs[0][i] * embs[3][i]; dot01 += embs[0][i] * embs[1][i]; n2 += embs[2][i] * embs[2][i]; }
+        CHECK(std::fabs(n0 - 1.0) < 1e-5 && n2 == 0.0 && dot03 > 0.9 && dot01 < dot03);
+    }
     std::puts("ALL OK");
     return 0;
 }

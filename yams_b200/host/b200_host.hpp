@@ -584,6 +584,90 @@ private:
     std::unordered_map<std::string, std::vector<int64_t>> rows_of_doc_;
 };
 
+// IEmbeddingBackend-shaped adapter over the device encoder (src/embedding_simeon/simeon_embedding_backend.cpp:183-215): the default
+// Simeon profile only -- any other recipe stays on the reference's CPU encoder.
+class B200SimeonBackend {
+public:
+    explicit B200SimeonBackend(const yams_simeon_config* cfg = nullptr) {
+        yams_simeon_config c;
+        if (cfg) c = *cfg; else yams_b200_simeon_default_config(&c);
+        dim_ = c.output_dim;
+        yams_status_t st = yams_b200_simeon_create(nullptr, &c, &e_);
+        if (st != YAMS_OK) throw_status("simeon_create", st);
+    }
+    ~B200SimeonBackend() { yams_b200_simeon_destroy(e_); }
+    B200SimeonBackend(const B200SimeonBackend&) = delete;
+    B200SimeonBackend& operator=(const B200SimeonBackend&) = delete;
+    std::vector<float> generateEmbedding(const std::string& text) const {
+        auto all = generateEmbeddings(std::span<const std::string>(&text, 1));
+        return std::move(all[0]);
+    }
+    std::vector<std::vector<float>> generateEmbeddings(std::span<const std::string> texts) const {
+        std::vector<const char*> ptrs(texts.size());
+        std::vector<size_t> lens(texts.size());
+        for (size_t i = 0; i < texts.size(); ++i) { ptrs[i] = texts[i].data(); lens[i] = texts[i].size(); }
+        std::vector<float> flat(texts.size() * dim_);
+        yams_status_t st = yams_b200_simeon_encode(e_, ptrs.data(), lens.data(), texts.size(), flat.data());
+        if (st != YAMS_OK) throw_status("simeon_encode", st);
+        std::vector<std::vector<float>> out(texts.size());
+        for (size_t i = 0; i < texts.size(); ++i) out[i].assign(flat.begin() + i * dim_, flat.begin() + (i + 1) * dim_);
+        return out;
+    }
+    size_t getEmbeddingDimension() const { return dim_; }
+    std::string getBackendName() const { return "Simeon"; }
+
+private:
+    yams_b200_encoder* e_ = nullptr;
+    size_t dim_ = 0;
+};
+
+// ManifestManager::createManifest (src/manifest/manifest_manager.cpp:411-436) over a chunk table: ChunkRefs + checksum in one device call
+struct ManifestChunkRef {   // include/yams/manifest/manifest_manager.h:48-61
+    std::string hash;
+    uint64_t offset = 0;
+    uint32_t size = 0;
+    uint32_t flags = 0;
+};
+struct ManifestCore {
+    std::string fileHash;
+    uint64_t fileSize = 0;
+    std::vector<ManifestChunkRef> chunks;
+    uint32_t checksum = 0;
+    bool valid = false;   // Manifest::isValid && the offset / size rules of validateManifest
+};
+inline ManifestCore createManifest(const std::string& fileHashHex, uint64_t fileSize, const std::vector<Chunk>& chunks) {
+    if (fileHashHex.size() != 64) throw std::invalid_argument("file hash must be 64 hex characters");
+    auto nib = [](char c) -> int { return c >= '0' && c <= '9' ? c - '0' : c >= 'a' && c <= 'f' ? c - 'a' + 10 : c >= 'A' && c <= 'F' ? c - 'A' + 10 : -1; };
+    auto unhex = [&](const std::string& h, uint8_t* out) {
+        for (int i = 0; i < 32; ++i) {
+            int hi = nib(h[2 * i]), lo = nib(h[2 * i + 1]);
+            if (hi < 0 || lo < 0) throw std::invalid_argument("hash is not hex");
+            out[i] = (uint8_t)(hi * 16 + lo);
+        }
+    };
+    uint8_t fd[32];
+    unhex(fileHashHex, fd);
+    std::vector<yams_chunk_desc> table(chunks.size());
+    for (size_t i = 0; i < chunks.size(); ++i) {
+        if (chunks[i].hash.size() != 64) throw std::invalid_argument("chunk hash must be 64 hex characters");
+        table[i].offset = chunks[i].offset;
+        table[i].size = chunks[i].size;
+        unhex(chunks[i].hash, table[i].digest);
+    }
+    std::vector<yams_chunk_ref> refs(chunks.size());
+    yams_manifest_summary sum{};
+    yams_status_t st = yams_b200_manifest_build(nullptr, table.data(), table.size(), fd, fileSize, refs.data(), &sum);
+    if (st != YAMS_OK) throw_status("manifest_build", st);
+    ManifestCore m;
+    m.fileHash = fileHashHex;
+    m.fileSize = fileSize;
+    m.checksum = sum.checksum;
+    m.valid = sum.valid != 0;
+    m.chunks.resize(chunks.size());
+    for (size_t i = 0; i < chunks.size(); ++i) m.chunks[i] = {std::string(refs[i].hash, 64), refs[i].offset, refs[i].size, refs[i].flags};
+    return m;
+}
+
 // VectorDatabase::computeCosineSimilarity (vector_database.cpp:1786-1810)
 inline double computeCosineSimilarity(const std::vector<float>& a, const std::vector<float>& b) {
     double out = 0.0;
