@@ -244,17 +244,20 @@ __device__ __forceinline__ uint32_t fast_flags(uint32_t w, const uint32_t (&pat)
 template <int NFAST>
 __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(SinglePassArgs S) {
     extern __shared__ __align__(128) uint8_t sc_smem[];
-    uint8_t* bufs = sc_smem;                                                        // WS_WARPS x WS_STAGES x WS_BUF
-    uint64_t* T_s = reinterpret_cast<uint64_t*>(bufs + (size_t)WS_WARPS * WS_STAGES * WS_BUF);
-    uint64_t* bars = T_s + 256;                                                     // WS_WARPS x WS_STAGES
-    uint8_t* pass_s = reinterpret_cast<uint8_t*>(bars + WS_WARPS * WS_STAGES);      // 256
+    // warps per CTA is a launch parameter (16 when the scan runs alone, 8 when it shares the SMs with SHA-256 CTAs): the
+    // warps never synchronise with each other after the table is loaded
+    const int nwarps = (int)(blockDim.x >> 5);
+    uint8_t* bufs = sc_smem;                                                        // nwarps x WS_STAGES x WS_BUF
+    uint64_t* T_s = reinterpret_cast<uint64_t*>(bufs + (size_t)nwarps * WS_STAGES * WS_BUF);
+    uint64_t* bars = T_s + 256;                                                     // nwarps x WS_STAGES
+    uint8_t* pass_s = reinterpret_cast<uint8_t*>(bars + nwarps * WS_STAGES);        // 256
     uint16_t* T16_s = reinterpret_cast<uint16_t*>(pass_s + 256);                    // 256: low 16 bits of the table
-    uint32_t* wlist_s = reinterpret_cast<uint32_t*>(T16_s + 256);                   // WS_WARPS x WS_LIST confirmed candidates
-    uint32_t* wcnt_s = wlist_s + WS_WARPS * WS_LIST;                                // WS_WARPS counters
-    uint8_t* wqueue_s = reinterpret_cast<uint8_t*>(wcnt_s + WS_WARPS);              // WS_WARPS x 256 flagged units
+    uint32_t* wlist_s = reinterpret_cast<uint32_t*>(T16_s + 256);                   // nwarps x WS_LIST confirmed candidates
+    uint32_t* wcnt_s = wlist_s + nwarps * WS_LIST;                                  // nwarps counters
+    uint8_t* wqueue_s = reinterpret_cast<uint8_t*>(wcnt_s + nwarps);                // nwarps x 256 flagged units
     const ScanArgs& A = S.A;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < 256; i += WS_THREADS) {
+    for (int i = tid; i < 256; i += (int)blockDim.x) {
         uint64_t t = A.table[i];
         T_s[i] = t;
         uint64_t m0 = A.P.mask & 0xffull;
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) cdc_scan_single_pass_kernel(Sin
     }
     __syncthreads();
 
-    const uint32_t gw = blockIdx.x * WS_WARPS + warp;
+    const uint32_t gw = blockIdx.x * (uint32_t)nwarps + warp;
     const uint64_t t_begin64 = (uint64_t)gw * S.tiles_per_warp;
     const uint32_t t_begin = (uint32_t)(t_begin64 < S.ntiles ? t_begin64 : S.ntiles);
     const uint32_t t_end = (uint32_t)(t_begin64 + S.tiles_per_warp < S.ntiles ? t_begin64 + S.tiles_per_warp : S.ntiles);
@@ -521,7 +524,9 @@ __global__ void __launch_bounds__(1024) cdc_compact_kernel(const uint64_t* __res
 }
 
 yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm_count, uint64_t* cand_tmp, uint32_t* slice_counts,
-                                      uint32_t slice_cap, uint32_t nslices, uint64_t* cand, uint64_t* scalars, cudaStream_t st) {
+                                      uint32_t slice_cap, uint32_t nslices, uint64_t* cand, uint64_t* scalars, cudaStream_t st,
+                                      int warps_per_cta) {
+    const int W = (warps_per_cta >= 1 && warps_per_cta <= WS_WARPS) ? warps_per_cta : WS_WARPS;
     SinglePassArgs S{};
     S.A = A;
     S.ntiles = ntiles;
@@ -531,13 +536,13 @@ yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm
     S.end16 = A.scan_hi > A.origin ? A.origin + ((A.scan_hi - A.origin) & ~15ull) : A.origin;
     S.cand_tmp = cand_tmp;
     S.slice_counts = slice_counts;
-    size_t smem = (size_t)WS_WARPS * WS_STAGES * WS_BUF + 256 * 8 + (size_t)WS_WARPS * WS_STAGES * 8 + 256 + 512 +
-                  (size_t)WS_WARPS * (WS_LIST * 4 + 4 + 256) + 64;
-    unsigned nctas = (nslices + WS_WARPS - 1) / WS_WARPS;
+    size_t smem = (size_t)W * WS_STAGES * WS_BUF + 256 * 8 + (size_t)W * WS_STAGES * 8 + 256 + 512 +
+                  (size_t)W * (WS_LIST * 4 + 4 + 256) + 64;
+    unsigned nctas = (nslices + W - 1) / W;
 #define YB_LAUNCH_SCAN(NF)                                                                                                  \
     do {                                                                                                                    \
         YB_CUDA(cudaFuncSetAttribute(cdc_scan_single_pass_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        cdc_scan_single_pass_kernel<NF><<<nctas, WS_THREADS, smem, st>>>(S);                                                \
+        cdc_scan_single_pass_kernel<NF><<<nctas, W * 32, smem, st>>>(S);                                                \
     } while (0)
     switch (A.P.nfast) {
         case 1: YB_LAUNCH_SCAN(1); break;

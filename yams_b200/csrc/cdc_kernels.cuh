@@ -65,7 +65,8 @@ constexpr uint32_t kTileBytes = kScanThreads * 16 * kScanIters;   // 16 KiB
 constexpr uint32_t kSinglePassTile = 4096;
 constexpr uint32_t kSinglePassWarpsPerCta = 16;
 yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm_count, uint64_t* cand_tmp, uint32_t* slice_counts,
-                                      uint32_t slice_cap, uint32_t nslices, uint64_t* cand, uint64_t* scalars, cudaStream_t st);
+                                      uint32_t slice_cap, uint32_t nslices, uint64_t* cand, uint64_t* scalars, cudaStream_t st,
+                                      int warps_per_cta = 0);
 
 yams_status_t resolve_params(const yams_cdc_config* cfg, CdcParams* P, uint64_t table[256]);
 yams_status_t launch_sha256_chunks(const uint8_t* d_data, uint64_t base_pos, yams_chunk_desc* d_descs,

@@ -214,7 +214,9 @@ yams_status_t launch_sha256_chunks(const uint8_t* d_data, uint64_t base_pos, yam
     if (ctas > max_ctas) ctas = max_ctas;
     static const int variant = [] { const char* e = getenv("YAMS_B200_SHA_MADD"); return e ? atoi(e) : 1; }();
     static const int per_sm = [] { const char* e = getenv("YAMS_B200_SHA_CTAS"); int v = e ? atoi(e) : 4; return v < 3 ? 3 : (v > 6 ? 6 : v); }();
-    max_ctas = (uint32_t)sm_count * (uint32_t)per_sm;
+    // experiment knob: grid CTAs per SM independent of the occupancy variant (co-residency with the candidate scan)
+    static const int grid_per_sm = [] { const char* e = getenv("YAMS_B200_SHA_GRID"); return e ? atoi(e) : 0; }();
+    max_ctas = (uint32_t)sm_count * (uint32_t)(grid_per_sm > 0 ? grid_per_sm : per_sm);
     ctas = (warps_needed + kShaWarpsPerCta - 1) / kShaWarpsPerCta;
     if (ctas > max_ctas) ctas = max_ctas;
 #define YB_SHA(M, B) sha256_chunks_kernel<M, B><<<ctas, kShaWarpsPerCta * 32, 0, st>>>(d_data, base_pos, d_descs, first, n, d_counter, 1u)
