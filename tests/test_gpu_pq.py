@@ -110,3 +110,61 @@ def test_pq_over_an_fp16_corpus_and_row_order_ties(Y, oracle):
     assert list(rid[1, :2]) == [50, 100] and flags[1] & Y.FLAG_TIE_AT_K == 0
     pq.close()
     c.close()
+
+
+def _check_against_reference(O, pq, rows, rowids, tie_keys, codebooks, m, kc, queries, k, rerank, thr):
+    rid, sc, cnt, flags = pq.search(queries, k, rerank_factor=rerank, threshold=thr)
+    for qi in range(len(queries)):
+        wr, ws = reference_pq_search(O, rows, rowids, tie_keys, codebooks, m, kc, queries[qi], k, rerank, thr)
+        assert cnt[qi] == len(wr), (qi, k)
+        assert list(rid[qi, :len(wr)]) == wr, (qi, k)
+        assert np.array_equal(sc[qi, :len(wr)], np.array(ws, dtype=np.float32)), (qi, k)
+
+
+def test_pq_filtered_scan_large_index(Y, oracle):
+    """>= 64 tiles: the sampled-threshold (filtered) ADC pass replaces the per-tile sorting network; 1, 2 and 5 queries walk the
+    1-, 2- and 4-table CTA variants.  Small k (16 centroids) makes equal approximate scores common: tie keys decide."""
+    O = oracle
+    if not O.ref_available():
+        pytest.skip("needs simeon's pq.cpp compiled in place")
+    n, d, m, kc = 300_000, 64, 8, 16
+    rng = np.random.default_rng(11)
+    rows = O.gen_rows_f32(42, 0, n, d)
+    rows[1000:1064] = rows[2000]                                                    # a run of identical rows across the list boundary
+    rowids = np.arange(n, dtype=np.int64) + 3
+    tie_keys = rng.permutation(n).astype(np.uint64)
+    codebooks = (rng.normal(size=(m, kc, d // m)) / np.sqrt(d)).astype(np.float32).reshape(-1)
+    c = Y.Corpus(d, Y.F32, Y.COSINE)
+    c.append(rows, rowids=rowids)
+    pq = Y.PqIndex(c, m, kc, codebooks, tie_break_keys=tie_keys)
+    queries = O.gen_rows_f32(43, 0, 5, d)
+    queries[1] = rows[2000]
+    for nq in (1, 2, 5):
+        for k, rerank, thr in ((10, 2, -1.0), (40, 3, 0.0)):
+            _check_against_reference(O, pq, rows, rowids, tie_keys, codebooks, m, kc, queries[:nq], k, rerank, thr)
+    pq.close()
+    c.close()
+
+
+def test_pq_filtered_scan_overflow_falls_back(Y, oracle):
+    """The sampled tiles (every 4th of 74) hold only rows pointing away from the query, every other tile rows pointing at it:
+    the sample's threshold admits ~237 k rows into a 32 k list; the engine must notice and redo the selection unfiltered."""
+    O = oracle
+    if not O.ref_available():
+        pytest.skip("needs simeon's pq.cpp compiled in place")
+    n, d, m, kc = 300_000, 64, 8, 16
+    rng = np.random.default_rng(12)
+    query = O.gen_rows_f32(43, 0, 1, d)
+    noise = O.gen_rows_f32(42, 0, n, d)
+    tile = np.arange(n) // 4096
+    sign = np.where((tile % 4 == 0) & (tile < 64), -1.0, 1.0).astype(np.float32)[:, None]
+    rows = (noise * np.float32(0.7) + sign * query).astype(np.float32)
+    rowids = np.arange(n, dtype=np.int64)
+    tie_keys = np.arange(n, dtype=np.uint64)
+    codebooks = (rng.normal(size=(m, kc, d // m)) / np.sqrt(d)).astype(np.float32).reshape(-1)
+    c = Y.Corpus(d, Y.F32, Y.COSINE)
+    c.append(rows, rowids=rowids)
+    pq = Y.PqIndex(c, m, kc, codebooks, tie_break_keys=tie_keys)
+    _check_against_reference(O, pq, rows, rowids, tie_keys, codebooks, m, kc, query, 10, 2, -1.0)
+    pq.close()
+    c.close()

@@ -71,7 +71,10 @@ yams_status_t launch_scan_single_pass(const ScanArgs& A, uint32_t ntiles, int sm
 yams_status_t resolve_params(const yams_cdc_config* cfg, CdcParams* P, uint64_t table[256]);
 yams_status_t launch_sha256_chunks(const uint8_t* d_data, uint64_t base_pos, yams_chunk_desc* d_descs,
                                    uint32_t first, uint32_t n, unsigned int* d_counter, int sm_count,
-                                   cudaStream_t st);
+                                   cudaStream_t st, uint32_t* d_order_ws = nullptr, uint64_t total_bytes = 0,
+                                   int variant_per_sm = 0, int grid_per_sm = 0);
+// workspace of the longest-first order: 64 counters + one index per chunk
+inline size_t sha256_order_ws_bytes(uint64_t n) { return (size_t)(n + 64) * sizeof(uint32_t); }
 yams_status_t launch_dedup_stats(const yams_chunk_desc* d_descs, uint32_t n, uint32_t* d_table, uint64_t slots,
                                  unsigned long long* d_out, cudaStream_t st);
 yams_status_t launch_synth_bytes(uint64_t seed, uint64_t start, uint64_t n, uint8_t* d_out, int sm_count,

@@ -41,7 +41,7 @@ struct CdcStream {
     bool two_pass_only = false;  // YAMS_B200_TWO_PASS=1: skip the single-pass scan (diagnostics)
     uint32_t two_pass_fallbacks = 0;
     DevBuf table, tile_counts, tile_offsets, cand, cand_tmp, next, forced, exit_, entry, onchain, emit_counts,
-        emit_offsets, scan_scratch, descs, scalars;
+        emit_offsets, scan_scratch, descs, scalars, sha_order;
     DevBuf npos, nref, roots, fileinfo, first;   // chunk_and_hash_batch: merged node table, file layout, per-file chunk ranges
     HostBuf h_scalars;           // pinned: [0] ncand/ntotal, [1] new chunk start
     uint64_t ndescs = 0;         // chunks accumulated in `descs`
@@ -83,7 +83,7 @@ struct CdcStream {
     }
     void destroy() {
         for (DevBuf* b : {&table, &tile_counts, &tile_offsets, &cand, &cand_tmp, &next, &forced, &exit_, &entry, &onchain,
-                          &emit_counts, &emit_offsets, &scan_scratch, &descs, &scalars, &npos, &nref, &roots, &fileinfo, &first})
+                          &emit_counts, &emit_offsets, &scan_scratch, &descs, &scalars, &sha_order, &npos, &nref, &roots, &fileinfo, &first})
             b->release();
         h_scalars.release();
         for (auto& e : ev)
@@ -374,8 +374,11 @@ static yams_status_t run_device(const uint8_t* d_data, size_t len, const yams_cd
             set_last_error("too many chunks");
             rc = YAMS_ERR_INVALID_ARG;
         } else {
-            rc = launch_sha256_chunks(d_data, 0, cs.descs.as<yams_chunk_desc>(), 0, (uint32_t)cs.ndescs,
-                                      reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4), cs.dev->sm_count, cs.st);
+            rc = cs.sha_order.reserve(sha256_order_ws_bytes(cs.ndescs));
+            if (rc == YAMS_OK)
+                rc = launch_sha256_chunks(d_data, 0, cs.descs.as<yams_chunk_desc>(), 0, (uint32_t)cs.ndescs,
+                                          reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4), cs.dev->sm_count, cs.st,
+                                          cs.sha_order.as<uint32_t>(), len);
         }
     }
     cudaEventRecord(r->e2, cs.st);
@@ -546,8 +549,10 @@ static yams_status_t run_batch_group(IngestRes* r, const uint8_t* const* files, 
                                                              cs.first.as<uint64_t>());
     YB_CUDA(cudaEventRecord(cs.ev[2], st));
     if (hash && nnew) {
+        if ((rc = cs.sha_order.reserve(sha256_order_ws_bytes(nnew))) != YAMS_OK) return rc;
         if ((rc = launch_sha256_chunks(d_buf, 0, cs.descs.as<yams_chunk_desc>(), 0, (uint32_t)nnew,
-                                       reinterpret_cast<unsigned int*>(d_sc + 4), cs.dev->sm_count, st)) != YAMS_OK)
+                                       reinterpret_cast<unsigned int*>(d_sc + 4), cs.dev->sm_count, st, cs.sha_order.as<uint32_t>(),
+                                       L)) != YAMS_OK)
             return rc;
     }
     YB_CUDA(cudaEventRecord(cs.ev[3], st));
@@ -588,6 +593,7 @@ struct yams_b200_ingest {
     bool hash = true;
     bool finished = false;
     float ms_sha = 0;
+    uint64_t sha_pos = 0;         // stream position up to which chunks have been hashed (mean chunk size of a slice)
 };
 
 static yams_status_t session_open(const yams_cdc_config* cfg, bool hash, yams_b200_ingest** out) {
@@ -617,10 +623,14 @@ static yams_status_t session_sha(yams_b200_ingest* s, const uint8_t* data, uint6
     if (!s->hash || cs.ndescs <= first) return YAMS_OK;
     YB_ARG(cs.ndescs - first < 0xFFFFFFFFull, "too many chunks in one slice");
     YB_CUDA(cudaEventRecord(s->r->t0, cs.st));
-    yams_status_t rc = launch_sha256_chunks(data, base_pos, cs.descs.as<yams_chunk_desc>(), (uint32_t)first,
-                                            (uint32_t)(cs.ndescs - first),
-                                            reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4),
-                                            cs.dev->sm_count, cs.st);
+    yams_status_t rc = cs.sha_order.reserve(sha256_order_ws_bytes(cs.ndescs - first));
+    if (rc != YAMS_OK) return rc;
+    // mean chunk size of the slice: the new chunks end at the open chunk's start
+    const uint64_t slice_bytes = cs.chunk_start > s->sha_pos ? cs.chunk_start - s->sha_pos : 0;
+    s->sha_pos = cs.chunk_start;
+    rc = launch_sha256_chunks(data, base_pos, cs.descs.as<yams_chunk_desc>(), (uint32_t)first, (uint32_t)(cs.ndescs - first),
+                              reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4), cs.dev->sm_count, cs.st,
+                              cs.sha_order.as<uint32_t>(), slice_bytes);
     if (rc != YAMS_OK) return rc;
     YB_CUDA(cudaEventRecord(s->r->t1, cs.st));
     YB_CUDA(cudaEventSynchronize(s->r->t1));
@@ -1026,9 +1036,11 @@ yams_status_t yams_b200_sha256_many(void* self, const uint8_t* const* msgs, cons
         rc = staged_upload(r, d_buf, tot, fill, st);
         if (rc != YAMS_OK) break;
         cudaError_t e = cudaMemcpyAsync(cs.descs.p, h.data(), m * sizeof(yams_chunk_desc), cudaMemcpyHostToDevice, st);
-        if (e == cudaSuccess)
+        if (e == cudaSuccess) rc = cs.sha_order.reserve(sha256_order_ws_bytes(m));
+        if (e == cudaSuccess && rc == YAMS_OK)
             rc = launch_sha256_chunks(d_buf, 0, cs.descs.as<yams_chunk_desc>(), 0, (uint32_t)m,
-                                      reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4), cs.dev->sm_count, st);
+                                      reinterpret_cast<unsigned int*>(cs.scalars.as<uint64_t>() + 4), cs.dev->sm_count, st,
+                                      cs.sha_order.as<uint32_t>(), tot);
         if (rc == YAMS_OK && e == cudaSuccess) e = cudaMemcpyAsync(h.data(), cs.descs.p, m * sizeof(yams_chunk_desc), cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) {

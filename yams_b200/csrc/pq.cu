@@ -179,12 +179,12 @@ __global__ void __launch_bounds__(256) pq_lut_kernel(const float* __restrict__ q
 __global__ void __launch_bounds__(PQ_THREADS) pq_adc_kernel(const uint8_t* __restrict__ codes, uint64_t n_idx, uint32_t m, uint32_t k,
                                                             const float* __restrict__ lut_all, const uint32_t* __restrict__ tie_rank,
                                                             uint32_t approx, Cand* __restrict__ lists, uint32_t list_cap,
-                                                            uint32_t* __restrict__ counts) {
+                                                            uint32_t* __restrict__ counts, uint32_t tile_stride) {
     extern __shared__ unsigned char sm[];
     float* lut = reinterpret_cast<float*>(sm);                                     // m * k floats
     uint64_t* keys = reinterpret_cast<uint64_t*>(sm + (((size_t)m * k * 4 + 7) & ~(size_t)7));   // PQ_TILE keys
     const uint32_t q = blockIdx.y;
-    const uint64_t r0 = (uint64_t)blockIdx.x * PQ_TILE;
+    const uint64_t r0 = (uint64_t)blockIdx.x * tile_stride * PQ_TILE;
     const float* lq = lut_all + (size_t)q * m * k;
     for (uint32_t e = threadIdx.x; e < m * k; e += PQ_THREADS) lut[e] = lq[e];
     __syncthreads();
@@ -241,6 +241,112 @@ __global__ void __launch_bounds__(PQ_THREADS) pq_adc_kernel(const uint8_t* __res
         c.row = 0xFFFFFFFFu - (uint32_t)key;     // tie rank: topk_select orders equal scores by ascending `row`
         if (s_base + i < list_cap) lists[(size_t)q * list_cap + s_base + i] = c;
     }
+}
+
+// Threshold of the filtered scan: the approx-th best key of the sampled tiles (any lower bound of the global approx-th best
+// key keeps the selection exact); 0 = accept every row (fewer than approx sampled rows).
+__global__ void pq_tau_kernel(const Cand* __restrict__ sel, const uint32_t* __restrict__ sel_n, uint32_t approx, uint32_t nq,
+                              uint64_t* __restrict__ tau, uint32_t* __restrict__ counts) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint64_t t = 0;
+    if (sel_n[q] >= approx) {
+        const Cand c = sel[(size_t)q * approx + approx - 1];
+        uint32_t b = __float_as_uint(c.score);
+        b = (c.score != c.score) ? 0u : ((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+        t = ((uint64_t)b << 32) | (uint64_t)(0xFFFFFFFFu - c.row);
+    }
+    tau[q] = t;
+    counts[q] = 0;
+}
+
+// Filtered ADC scan: CTA (row range, group of QG queries) with the QG lookup tables in shared memory; every row's code bytes
+// are read once per group; rows whose key reaches the query's threshold are appended to its list.  Same float order as
+// pq_adc_kernel (sequential sum over the m sub-quantisers).
+template <int QG>
+__global__ void __launch_bounds__(PQ_THREADS) pq_adc_filter_kernel(const uint8_t* __restrict__ codes, uint64_t n_idx, uint32_t m, uint32_t k,
+                                                                   const float* __restrict__ lut_all, const uint32_t* __restrict__ tie_rank,
+                                                                   const uint64_t* __restrict__ tau, uint32_t nq, uint64_t rows_per_cta,
+                                                                   Cand* __restrict__ lists, uint32_t list_cap, uint32_t* __restrict__ counts) {
+    extern __shared__ unsigned char sm[];
+    float* lut = reinterpret_cast<float*>(sm);   // QG x m x k
+    const uint32_t q0 = blockIdx.y * QG;
+    const uint32_t lut_len = m * k;
+    for (uint32_t e = threadIdx.x; e < lut_len * QG; e += PQ_THREADS) {
+        const uint32_t g = e / lut_len;
+        lut[e] = (q0 + g < nq) ? lut_all[(size_t)(q0 + g) * lut_len + (e - g * lut_len)] : 0.f;
+    }
+    uint64_t tq[QG];
+#pragma unroll
+    for (int g = 0; g < QG; ++g) tq[g] = (q0 + g < nq) ? tau[q0 + g] : ~0ull;
+    __syncthreads();
+    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_cta;
+    const uint64_t r1 = min(n_idx, r0 + rows_per_cta);
+    const bool vec = (m % 16) == 0;
+    const unsigned lane = threadIdx.x & 31u;
+    for (uint64_t base = r0; base < r1; base += PQ_THREADS) {     // block-uniform trip count (warp collectives below)
+        const uint64_t j = base + threadIdx.x;
+        const bool valid = j < r1;
+        float acc[QG];
+#pragma unroll
+        for (int g = 0; g < QG; ++g) acc[g] = 0.f;
+        if (valid) {
+            const uint8_t* cd = codes + j * m;
+            if (vec) {
+                for (uint32_t mi = 0; mi < m; mi += 16) {
+                    const uint4 w = *reinterpret_cast<const uint4*>(cd + mi);
+                    const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const uint32_t e = (mi + u * 4 + b) * k + ((ws[u] >> (8 * b)) & 0xFFu);
+#pragma unroll
+                            for (int g = 0; g < QG; ++g) acc[g] = __fadd_rn(acc[g], lut[g * lut_len + e]);
+                        }
+                }
+            } else {
+                for (uint32_t mi = 0; mi < m; ++mi) {
+                    const uint32_t e = mi * k + cd[mi];
+#pragma unroll
+                    for (int g = 0; g < QG; ++g) acc[g] = __fadd_rn(acc[g], lut[g * lut_len + e]);
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < QG; ++g) {
+            uint32_t b = __float_as_uint(acc[g]);
+            b = (acc[g] != acc[g]) ? 0u : ((b & 0x80000000u) ? ~b : (b | 0x80000000u));
+            const uint32_t th = (uint32_t)(tq[g] >> 32);
+            bool pass = valid && b >= th;           // tq = ~0 for the padding queries of the last group: never passes
+            uint32_t rank = 0;
+            if (pass) {
+                rank = tie_rank[j];
+                uint64_t key = ((uint64_t)b << 32) | (uint64_t)(0xFFFFFFFFu - rank);
+                if (key == 0) key = 1;
+                pass = key >= tq[g] && tq[g] != ~0ull;
+            }
+            const unsigned mask = __ballot_sync(0xffffffffu, pass);
+            if (mask) {
+                const int leader = __ffs(mask) - 1;
+                uint32_t pos = 0;
+                if ((int)lane == leader) pos = atomicAdd(&counts[q0 + g], (uint32_t)__popc(mask));
+                pos = __shfl_sync(0xffffffffu, pos, leader) + __popc(mask & ((1u << lane) - 1u));
+                if (pass && pos < list_cap) {
+                    Cand c;
+                    c.score = acc[g];
+                    c.row = rank;
+                    lists[(size_t)(q0 + g) * list_cap + pos] = c;
+                }
+            }
+        }
+    }
+}
+
+// counts[q] > cap: the filtered list dropped rows (a sample that misjudged the data): the caller re-runs the unfiltered scan
+__global__ void pq_overflow_kernel(const uint32_t* __restrict__ counts, uint32_t nq, uint32_t cap, uint32_t* __restrict__ flag) {
+    uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq && counts[q] > cap) atomicExch(flag, 1u);
 }
 
 // survivors carry tie ranks: back to corpus rows (rank -> indexed row -> corpus row)
@@ -309,7 +415,7 @@ struct yams_b200_pq {
     uint64_t n_idx = 0;
     DevBuf codebooks, codes, idx_rows, tie_rank, rank_to_idx;
     // search workspace
-    DevBuf q32, lut, valid, lists, counts, sel, exact, dout;
+    DevBuf q32, lut, valid, lists, counts, sel, exact, dout, tau;
     std::mutex mu;
 };
 
@@ -384,7 +490,7 @@ yams_status_t yams_b200_pq_build(yams_b200_corpus* c, uint32_t m, uint32_t k, co
 void yams_b200_pq_destroy(yams_b200_pq* p) {
     if (!p) return;
     for (DevBuf* b : {&p->codebooks, &p->codes, &p->idx_rows, &p->tie_rank, &p->rank_to_idx, &p->q32, &p->lut, &p->valid, &p->lists, &p->counts,
-                      &p->sel, &p->exact, &p->dout})
+                      &p->sel, &p->exact, &p->dout, &p->tau})
         b->release();
     delete p;
 }
@@ -433,26 +539,75 @@ yams_status_t yams_b200_pq_search(yams_b200_pq* p, const float* queries, uint32_
     yams_status_t rc;
     const uint32_t m = p->m, kc = p->k, d = p->dim;
     const uint32_t tiles = (uint32_t)((p->n_idx + PQ_TILE - 1) / PQ_TILE);
-    const uint32_t cap = tiles * approx;
+    // Two ways to the same exact top-approx by (score, tie-break key):
+    //   unfiltered: every tile keeps its own top-approx (bitonic network in shared memory) -> lists of tiles * approx entries;
+    //   filtered  : a strided sample of tiles goes through the unfiltered path and yields the sample's approx-th best key tau
+    //               (<= the global approx-th best key), then ONE pass over all rows appends the rows with key >= tau.
+    // The filtered pass does no sorting (the unfiltered kernel spends ~10x its lookup work in the network); it is used when
+    // the expected survivors (approx * tiles / sample tiles) fit the list with a 4x margin, and falls back when a list overflows.
+    static const int force_unfiltered = [] { const char* e = getenv("YAMS_B200_PQ_UNFILTERED"); return e ? atoi(e) : 0; }();
+    const uint32_t kFilterCap = 32768;
+    uint32_t sample_tiles = 16;
+    while ((uint64_t)approx * 4 * tiles > (uint64_t)kFilterCap * sample_tiles && sample_tiles < tiles) sample_tiles *= 2;
+    const bool filtered = !force_unfiltered && tiles >= 4 * sample_tiles;
+    const uint32_t cap_unf = tiles * approx;
+    const uint32_t cap = filtered ? std::max<uint32_t>(kFilterCap, sample_tiles * approx) : cap_unf;
     if ((rc = p->q32.reserve((size_t)nq * d * 4)) != YAMS_OK) return rc;
     if ((rc = p->lut.reserve((size_t)nq * m * kc * 4)) != YAMS_OK) return rc;
     if ((rc = p->valid.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
     if ((rc = p->lists.reserve((size_t)nq * cap * sizeof(Cand))) != YAMS_OK) return rc;
-    if ((rc = p->counts.reserve((size_t)nq * 4)) != YAMS_OK) return rc;
+    if ((rc = p->counts.reserve((size_t)nq * 4 + 16)) != YAMS_OK) return rc;
     if ((rc = p->sel.reserve((size_t)nq * approx * sizeof(Cand) + (size_t)nq * 4)) != YAMS_OK) return rc;
     if ((rc = p->exact.reserve((size_t)nq * approx * sizeof(PqExact))) != YAMS_OK) return rc;
     if ((rc = p->dout.reserve((size_t)nq * k * 12 + (size_t)nq * 12 + 64)) != YAMS_OK) return rc;
+    if ((rc = p->tau.reserve((size_t)nq * 8)) != YAMS_OK) return rc;
     Cand* d_sel = p->sel.as<Cand>();
     uint32_t* d_sel_n = reinterpret_cast<uint32_t*>(d_sel + (size_t)nq * approx);
+    uint32_t* d_counts = p->counts.as<uint32_t>();
+    uint32_t* d_overflow = d_counts + nq;
     YB_CUDA(cudaMemcpyAsync(p->q32.p, queries, (size_t)nq * d * 4, cudaMemcpyHostToDevice, st));
-    YB_CUDA(cudaMemsetAsync(p->counts.p, 0, (size_t)nq * 4, st));
     YB_CUDA(cudaFuncSetAttribute(pq_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(d * 4)));
     pq_lut_kernel<<<nq, 256, d * 4, st>>>(p->q32.as<float>(), d, p->codebooks.as<float>(), m, kc, p->lut.as<float>(), p->valid.as<uint32_t>());
-    const size_t smem = (((size_t)m * kc * 4 + 7) & ~(size_t)7) + (size_t)PQ_TILE * 8;
+    const size_t lut_bytes = (size_t)m * kc * 4;
+    const size_t smem = ((lut_bytes + 7) & ~(size_t)7) + (size_t)PQ_TILE * 8;
     YB_CUDA(cudaFuncSetAttribute(pq_adc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pq_adc_kernel<<<dim3(tiles, nq), PQ_THREADS, smem, st>>>(p->codes.as<uint8_t>(), p->n_idx, m, kc, p->lut.as<float>(), p->tie_rank.as<uint32_t>(),
-                                                             approx, p->lists.as<Cand>(), cap, p->counts.as<uint32_t>());
-    launch_topk_lists(p->lists.as<Cand>(), p->counts.as<uint32_t>(), cap, nq, approx, d_sel, d_sel_n, st);
+    auto unfiltered = [&](uint32_t ntiles, uint32_t stride, uint32_t list_cap) {
+        cudaMemsetAsync(d_counts, 0, (size_t)nq * 4 + 16, st);
+        pq_adc_kernel<<<dim3(ntiles, nq), PQ_THREADS, smem, st>>>(p->codes.as<uint8_t>(), p->n_idx, m, kc, p->lut.as<float>(), p->tie_rank.as<uint32_t>(),
+                                                                  approx, p->lists.as<Cand>(), list_cap, d_counts, stride);
+        launch_topk_lists(p->lists.as<Cand>(), d_counts, list_cap, nq, approx, d_sel, d_sel_n, st);
+    };
+    bool used_filter = false;
+    if (filtered) {
+        used_filter = true;
+        const uint32_t stride = tiles / sample_tiles;
+        unfiltered(sample_tiles, stride, cap);
+        pq_tau_kernel<<<(nq + 127) / 128, 128, 0, st>>>(d_sel, d_sel_n, approx, nq, p->tau.as<uint64_t>(), d_counts);
+        int qg = nq >= 4 ? 4 : (nq >= 2 ? 2 : 1);
+        while (qg > 1 && (size_t)qg * lut_bytes > 200 * 1024) qg >>= 1;
+        const uint32_t groups = (nq + qg - 1) / qg;
+        uint64_t chunks = std::max<uint64_t>(1, (uint64_t)c->dev->sm_count * 6 / groups);
+        chunks = std::min<uint64_t>(chunks, (p->n_idx + 2047) / 2048);
+        uint64_t rows_per_cta = ((p->n_idx + chunks - 1) / chunks + PQ_THREADS - 1) / PQ_THREADS * PQ_THREADS;
+        chunks = (p->n_idx + rows_per_cta - 1) / rows_per_cta;
+#define YB_PQF(G)                                                                                                                              \
+        YB_CUDA(cudaFuncSetAttribute(pq_adc_filter_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(G * lut_bytes)));             \
+        pq_adc_filter_kernel<G><<<dim3((unsigned)chunks, groups), PQ_THREADS, G * lut_bytes, st>>>(                                            \
+            p->codes.as<uint8_t>(), p->n_idx, m, kc, p->lut.as<float>(), p->tie_rank.as<uint32_t>(), p->tau.as<uint64_t>(), nq, rows_per_cta,   \
+            p->lists.as<Cand>(), cap, d_counts)
+        if (qg == 4) { YB_PQF(4); } else if (qg == 2) { YB_PQF(2); } else { YB_PQF(1); }
+#undef YB_PQF
+        pq_overflow_kernel<<<(nq + 127) / 128, 128, 0, st>>>(d_counts, nq, cap, d_overflow);
+        launch_topk_lists(p->lists.as<Cand>(), d_counts, cap, nq, approx, d_sel, d_sel_n, st);
+    } else {
+        unfiltered(tiles, 1, cap);
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+    if (attempt == 1) {
+        // a filtered list overflowed: redo the selection without the filter
+        if ((rc = p->lists.reserve((size_t)nq * cap_unf * sizeof(Cand))) != YAMS_OK) return rc;
+        unfiltered(tiles, 1, cap_unf);
+    }
     const uint32_t tot = nq * approx;
     pq_rank_to_row_kernel<<<(tot + 255) / 256, 256, 0, st>>>(d_sel, d_sel_n, approx, nq, p->rank_to_idx.as<uint32_t>(), p->idx_rows.as<uint32_t>());
     pq_rerank_kernel<<<(tot + 127) / 128, 128, 0, st>>>(c->rows.p, c->dtype, d, p->q32.as<float>(), d_sel, d_sel_n, p->valid.as<uint32_t>(), approx, nq,
@@ -467,7 +622,11 @@ yams_status_t yams_b200_pq_search(yams_b200_pq* p, const float* queries, uint32_
     YB_CUDA(cudaMemcpyAsync(out_scores, d_os, (size_t)nq * k * 4, cudaMemcpyDeviceToHost, st));
     YB_CUDA(cudaMemcpyAsync(out_counts, d_oc, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     if (out_flags) YB_CUDA(cudaMemcpyAsync(out_flags, d_of, (size_t)nq * 8, cudaMemcpyDeviceToHost, st));
+    uint32_t h_overflow = 0;
+    if (used_filter && attempt == 0) YB_CUDA(cudaMemcpyAsync(&h_overflow, d_overflow, 4, cudaMemcpyDeviceToHost, st));
     YB_CUDA(cudaStreamSynchronize(st));
+    if (!h_overflow) break;
+    }
     return YAMS_OK;
     YB_CATCH
 }

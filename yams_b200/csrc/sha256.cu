@@ -15,6 +15,7 @@
 // spans.  Lanes then read their row word-by-word; the byte misalignment of the chunk start and the
 // big-endian word order are both absorbed by ONE prmt per message word.
 // The kernel is INT32-ALU bound (~22 instr/byte), not HBM bound.
+#include <algorithm>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -74,7 +75,7 @@ template <bool MADD, int MINB>
 __global__ void __launch_bounds__(kShaWarpsPerCta * 32, MINB)
 sha256_chunks_kernel(const uint8_t* __restrict__ data, uint64_t base_pos,
                      yams_chunk_desc* __restrict__ descs, uint32_t first, uint32_t n,
-                     unsigned int* __restrict__ counter, uint32_t one) {
+                     unsigned int* __restrict__ counter, uint32_t one, const uint32_t* __restrict__ order) {
     __shared__ __align__(16) uint32_t smem[kShaWarpsPerCta][32 * kRowWords];
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -100,7 +101,7 @@ sha256_chunks_kernel(const uint8_t* __restrict__ data, uint64_t base_pos,
             if (want) {
                 uint32_t k = base + __popc(m & ((1u << lane) - 1u));
                 if (k < n) {
-                    idx = first + k;
+                    idx = order ? order[k] : first + k;
                     uint64_t off = descs[idx].offset;
                     uint64_t sz = descs[idx].size;
                     ptr = (uint64_t)data + (off - base_pos);
@@ -202,25 +203,89 @@ sha256_chunks_kernel(const uint8_t* __restrict__ data, uint64_t base_pos,
     }
 }
 
+// Longest-first order.  Every lane hashes whole chunks, so the launch ends when the lane that drew the last long chunk ends:
+// in index order that tail is 39 % of the ideal time on a 16 GiB / 700 k-chunk table (10 % at 64 GiB), sorted by size it is
+// 5 % / 1 % (simulation in DESIGN.md 3.3).  A 32-bucket counting sort by size (bucket = 6 * size / mean, largest first) is
+// close enough to a full sort; the order inside a bucket is whatever the atomics produce -- digests land in descs[idx], so
+// the result does not depend on it.
+constexpr int kShaBuckets = 32;
+__device__ __forceinline__ int sha_bucket(uint64_t size, uint64_t mean) {
+    const uint64_t t = mean ? (size * 6u) / mean : 0u;
+    return kShaBuckets - 1 - (int)(t < (uint64_t)(kShaBuckets - 1) ? t : (uint64_t)(kShaBuckets - 1));
+}
+__global__ void sha_order_count_kernel(const yams_chunk_desc* __restrict__ descs, uint32_t first, uint32_t n, uint64_t mean,
+                                       uint32_t* __restrict__ counts) {
+    __shared__ uint32_t h[kShaBuckets];
+    if (threadIdx.x < kShaBuckets) h[threadIdx.x] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        atomicAdd(&h[sha_bucket(descs[first + i].size, mean)], 1u);
+    __syncthreads();
+    if (threadIdx.x < kShaBuckets && h[threadIdx.x]) atomicAdd(&counts[threadIdx.x], h[threadIdx.x]);
+}
+__global__ void sha_order_scatter_kernel(const yams_chunk_desc* __restrict__ descs, uint32_t first, uint32_t n, uint64_t mean,
+                                         const uint32_t* __restrict__ counts, uint32_t* __restrict__ cursors,
+                                         uint32_t* __restrict__ order) {
+    __shared__ uint32_t base[kShaBuckets];
+    __shared__ uint32_t h[kShaBuckets];
+    __shared__ uint32_t got[kShaBuckets];
+    if (threadIdx.x < kShaBuckets) h[threadIdx.x] = 0;
+    if (threadIdx.x == 0) {
+        uint32_t acc = 0;
+        for (int b = 0; b < kShaBuckets; ++b) { base[b] = acc; acc += counts[b]; }
+    }
+    __syncthreads();
+    // one tile of blockDim.x chunks per iteration: rank inside the CTA by shared atomics, one global atomic per bucket per tile
+    for (uint32_t t0 = blockIdx.x * blockDim.x; t0 < n; t0 += gridDim.x * blockDim.x) {
+        const uint32_t i = t0 + threadIdx.x;
+        int b = -1;
+        uint32_t r = 0;
+        if (i < n) {
+            b = sha_bucket(descs[first + i].size, mean);
+            r = atomicAdd(&h[b], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x < kShaBuckets) {
+            got[threadIdx.x] = h[threadIdx.x] ? atomicAdd(&cursors[threadIdx.x], h[threadIdx.x]) : 0u;
+            h[threadIdx.x] = 0;
+        }
+        __syncthreads();
+        if (b >= 0) order[base[b] + got[b] + r] = first + i;
+        __syncthreads();
+    }
+}
+
 // Launch helper: hashes descs[first .. first+n). d_counter must point at a zeroed uint32.
 yams_status_t launch_sha256_chunks(const uint8_t* d_data, uint64_t base_pos, yams_chunk_desc* d_descs,
                                    uint32_t first, uint32_t n, unsigned int* d_counter, int sm_count,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, uint32_t* d_order_ws, uint64_t total_bytes, int variant_per_sm, int grid_per_sm) {
     if (n == 0) return YAMS_OK;
     YB_CUDA(cudaMemsetAsync(d_counter, 0, sizeof(unsigned int), st));
+    // d_order_ws: 64 counters + n indices (sha256_order_ws_bytes); tables that leave every lane under ~2 chunks are not worth it
+    static const int lpt = [] { const char* e = getenv("YAMS_B200_SHA_ORDER"); return e ? atoi(e) : 1; }();
+    const uint32_t* d_order = nullptr;
+    if (d_order_ws && lpt && n >= 4096) {
+        const uint64_t mean = std::max<uint64_t>(1, total_bytes / n);
+        YB_CUDA(cudaMemsetAsync(d_order_ws, 0, 64 * sizeof(uint32_t), st));
+        const unsigned g = (unsigned)std::min<uint32_t>((n + 255) / 256, (uint32_t)sm_count * 8u);
+        sha_order_count_kernel<<<g, 256, 0, st>>>(d_descs, first, n, mean, d_order_ws);
+        sha_order_scatter_kernel<<<g, 256, 0, st>>>(d_descs, first, n, mean, d_order_ws, d_order_ws + 32, d_order_ws + 64);
+        d_order = d_order_ws + 64;
+    }
+    static const int madd = [] { const char* e = getenv("YAMS_B200_SHA_MADD"); return e ? atoi(e) : 1; }();
+    static const int env_per_sm = [] { const char* e = getenv("YAMS_B200_SHA_CTAS"); int v = e ? atoi(e) : 4; return v < 3 ? 3 : (v > 6 ? 6 : v); }();
+    // experiment knob: grid CTAs per SM independent of the occupancy variant (co-residency with the candidate scan)
+    static const int env_grid = [] { const char* e = getenv("YAMS_B200_SHA_GRID"); return e ? atoi(e) : 0; }();
+    // variant_per_sm picks the register budget the kernel was compiled for (launch bounds 128 x per_sm); grid_per_sm how many
+    // CTAs per SM are launched - fewer than the variant allows leaves registers for a co-resident kernel
+    const int per_sm = variant_per_sm > 0 ? (variant_per_sm < 3 ? 3 : (variant_per_sm > 6 ? 6 : variant_per_sm)) : env_per_sm;
+    const int grid = grid_per_sm > 0 ? grid_per_sm : (env_grid > 0 ? env_grid : per_sm);
     uint32_t warps_needed = (n + 31) / 32;
     uint32_t ctas = (warps_needed + kShaWarpsPerCta - 1) / kShaWarpsPerCta;
-    uint32_t max_ctas = (uint32_t)sm_count * 4u;
+    uint32_t max_ctas = (uint32_t)sm_count * (uint32_t)grid;
     if (ctas > max_ctas) ctas = max_ctas;
-    static const int variant = [] { const char* e = getenv("YAMS_B200_SHA_MADD"); return e ? atoi(e) : 1; }();
-    static const int per_sm = [] { const char* e = getenv("YAMS_B200_SHA_CTAS"); int v = e ? atoi(e) : 4; return v < 3 ? 3 : (v > 6 ? 6 : v); }();
-    // experiment knob: grid CTAs per SM independent of the occupancy variant (co-residency with the candidate scan)
-    static const int grid_per_sm = [] { const char* e = getenv("YAMS_B200_SHA_GRID"); return e ? atoi(e) : 0; }();
-    max_ctas = (uint32_t)sm_count * (uint32_t)(grid_per_sm > 0 ? grid_per_sm : per_sm);
-    ctas = (warps_needed + kShaWarpsPerCta - 1) / kShaWarpsPerCta;
-    if (ctas > max_ctas) ctas = max_ctas;
-#define YB_SHA(M, B) sha256_chunks_kernel<M, B><<<ctas, kShaWarpsPerCta * 32, 0, st>>>(d_data, base_pos, d_descs, first, n, d_counter, 1u)
-    if (variant) {
+#define YB_SHA(M, B) sha256_chunks_kernel<M, B><<<ctas, kShaWarpsPerCta * 32, 0, st>>>(d_data, base_pos, d_descs, first, n, d_counter, 1u, d_order)
+    if (madd) {
         switch (per_sm) { case 3: YB_SHA(true, 3); break; case 4: YB_SHA(true, 4); break; case 5: YB_SHA(true, 5); break; default: YB_SHA(true, 6); break; }
     } else {
         YB_SHA(false, 4);
