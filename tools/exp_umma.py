@@ -90,10 +90,10 @@ def main():
         dict(ctas=2),
         dict(ctas=2, epi_relaxed=0),
         dict(ctas=2, nopf=1),
-        dict(ctas=1, mode=1),
-        dict(ctas=2, mode=1),
-        dict(ctas=1, mode=2),
-        dict(ctas=2, mode=2),
+        dict(ctas=1, mode=1, prof=1),   # the experiment modes live in the diagnostic (PROF) instantiation
+        dict(ctas=2, mode=1, prof=1),
+        dict(ctas=1, mode=2, prof=1),
+        dict(ctas=2, mode=2, prof=1),
         dict(ctas=2, stages=5),
         dict(ctas=2, stages=4),
         dict(ctas=2, stages=3),

@@ -215,6 +215,93 @@ __device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, u
         : "memory");
 }
 
+
+// ---- warp-uniform role loops -------------------------------------------------------------------------------------------
+// The producer and the MMA issuer run with the WHOLE warp converged (every lane polls the barriers) and only the
+// tcgen05 / TMA instructions sit under elect.sync.  A role written as `if (lane == 0) { loop }` compiles into a divergent
+// region: every UTCHMMA / UTMALDG gets its own elect-and-retry loop and the barrier waits carry their clock reads, ~165
+// issued instructions per 64-deep K block -- the single issuing thread then needs ~900 cycles per block for 512 cycles
+// of tensor work (tensor pipe 57 % active in profiles/r2_full_umma.md, and the same time per block at N = 128 as at
+// N = 256).  Converged, the loop state lives in uniform registers and a K block costs a fraction of that.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ bool mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+// fast path: one try_wait, no clock reads; the slow path keeps the "never hang the GPU" limit (checked every 1024 spins)
+template <bool PROF>
+__device__ __forceinline__ void mbar_wait_u(uint32_t addr, uint32_t parity, long long* waited) {
+    if (PROF) {
+        const long long t_begin = clock64();
+        while (!mbar_try(addr, parity))
+            if (clock64() - t_begin > UM_WAIT_LIMIT_CYCLES) __trap();
+        *waited += clock64() - t_begin;
+    } else {
+        if (mbar_try(addr, parity)) return;
+        long long t_begin = 0;
+        uint32_t spins = 0;
+        while (!mbar_try(addr, parity)) {
+            if ((++spins & 1023u) == 0) {
+                const long long now = clock64();
+                if (t_begin == 0) t_begin = now;
+                else if (now - t_begin > UM_WAIT_LIMIT_CYCLES) __trap();
+            }
+        }
+    }
+}
+__device__ __forceinline__ void mbar_expect_tx_u(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_u(uint32_t bar, uint32_t rank, bool relaxed) {
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(bar), "r"(rank));
+    if (relaxed) asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+    else asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+template <int CTAS>
+__device__ __forceinline__ void tma_load_u(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    if (CTAS == 2)
+        asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+            : "memory");
+    else
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+            : "memory");
+}
+template <int CTAS>
+__device__ __forceinline__ void umma_commit_u(uint32_t bar) {
+    if (CTAS == 2)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"((uint16_t)3) : "memory");
+    else
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int CTAS, bool TF32>
+__device__ __forceinline__ void umma_u(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (TF32) {
+        if (CTAS == 2) umma_tf32_2sm(tmem_d, adesc, bdesc, idesc, accumulate); else umma_tf32(tmem_d, adesc, bdesc, idesc, accumulate);
+    } else {
+        if (CTAS == 2) umma_f16_2sm(tmem_d, adesc, bdesc, idesc, accumulate); else umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+    }
+}
+
 __device__ __noinline__ void append_candidate(uint32_t* counts, Cand* cands, uint32_t cap, uint32_t q, uint32_t row, float sc) {
     uint32_t pos = atomicAdd(&counts[q], 1u);
     if (pos < cap) {
@@ -229,7 +316,7 @@ __device__ __noinline__ void append_candidate(uint32_t* counts, Cand* cands, uin
 // n_tile unit: each CTA stages its own 128 corpus rows and HALF of the query tile, the leader issues
 // tcgen05.mma.cta_group::2 (M = 256), each CTA's TMEM receives the accumulator rows of its own corpus rows.
 // Halving the query bytes each SM pulls through L2 is what lifts the L2-bound 1-CTA version.
-template <bool FILTER, int CTAS>
+template <bool FILTER, int CTAS, bool TF32, bool PROF>
 __global__ void __launch_bounds__(UM_THREADS, 1)
 stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, UmmaArgs u) {
     extern __shared__ uint8_t smem_raw[];
@@ -297,89 +384,94 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // experiment modes exist in the diagnostic build only (tools/exp_umma.py sets YAMS_B200_UMMA_PROF=1 with them)
+    const uint32_t mode = PROF ? u.mode : 0u;
+    const uint32_t tiles_u = smem_u32(tiles), full_u = smem_u32(full), empty_u = smem_u32(empty);
+    const uint32_t tfull_u = smem_u32(tfull), tempty_u = smem_u32(tempty);
     if (warp == 0) {
         // ===================== TMA producer (every CTA loads its own rows and its share of the queries) =====
-        if (lane == 0) {
-            uint32_t s = 0, ph = 0, iter = 0;
-            long long w_prod = 0;
-            // A CTA (pair) owns whole row tiles and runs every query tile against each: the corpus tile is fetched
-            // from HBM once and re-read from L2 by the same SM; the next row tile is prefetched into L2 meanwhile.
-            for (uint32_t rt = group; rt < u.nrt; rt += ngroups) {
-                const int a_row = (int)((rt * CTAS + rank) * UM_BLOCK_M);
-                const int a_next = (int)(((rt + ngroups) * CTAS + rank) * UM_BLOCK_M);
-                const bool have_next = rt + ngroups < u.nrt;
-                for (uint32_t qt = 0; qt < u.nqt; ++qt) {
-                    const int b_row = (int)(qt * u.n_tile + rank * (u.n_tile / CTAS));
-                    for (uint32_t kb = 0; kb < u.kblocks; ++kb) {
-                        mbar_wait(&empty[s], ph ^ 1, &w_prod);
-                        uint8_t* sa = tiles + (size_t)s * stage_bytes;
-                        uint8_t* sb = sa + UM_A_STAGE;
-                        if (u.mode == 2 && iter >= u.stages) {   // experiment: operands stay in place, barriers only
-                            if (leader) mbar_arrive(&full[s]);
-                            else if (u.peer_arrive) mbar_arrive_remote(&full[s], 0);
-                        } else if (CTAS == 2) {
-                            if (leader) mbar_expect_tx(&full[s], stage_bytes * 2);
-                            else if (u.peer_arrive) mbar_arrive_remote(&full[s], 0);
-                            tma_load_2d_2sm(sa, &tmA, &full[s], (int)(kb * u.block_k), a_row);
-                            tma_load_2d_2sm(sb, &tmB, &full[s], (int)(kb * u.block_k), b_row);
+        // A CTA (pair) owns whole row tiles and runs every query tile against each: the corpus tile is fetched
+        // from HBM once and re-read from L2 by the same SM; the next row tile is prefetched into L2 meanwhile.
+        uint32_t s = 0, ph = 0, iter = 0, sa = tiles_u;
+        long long w_prod = 0;
+        for (uint32_t rt = group; rt < u.nrt; rt += ngroups) {
+            const int a_row = (int)((rt * CTAS + rank) * UM_BLOCK_M);
+            const int a_next = (int)(((rt + ngroups) * CTAS + rank) * UM_BLOCK_M);
+            const bool have_next = rt + ngroups < u.nrt && !u.nopf;
+            for (uint32_t qt = 0; qt < u.nqt; ++qt) {
+                const int b_row = (int)(qt * u.n_tile + rank * (u.n_tile / CTAS));
+                const bool pf = qt == 0 && have_next;
+                int kc = 0;
+                for (uint32_t kb = 0; kb < u.kblocks; ++kb, kc += (int)u.block_k) {
+                    mbar_wait_u<PROF>(empty_u + 8u * s, ph ^ 1u, &w_prod);
+                    if (elect_one()) {
+                        const uint32_t fb = full_u + 8u * s;
+                        if (mode == 2 && iter >= u.stages) {   // experiment: operands stay in place, barriers only
+                            if (leader) mbar_arrive_u(fb);
+                            else if (u.peer_arrive) mbar_arrive_remote_u(fb, 0, false);
                         } else {
-                            mbar_expect_tx(&full[s], stage_bytes);
-                            tma_load_2d(sa, &tmA, &full[s], (int)(kb * u.block_k), a_row);
-                            tma_load_2d(sb, &tmB, &full[s], (int)(kb * u.block_k), b_row);
+                            if (CTAS == 2) {
+                                if (leader) mbar_expect_tx_u(fb, stage_bytes * 2);
+                                else if (u.peer_arrive) mbar_arrive_remote_u(fb, 0, false);
+                            } else {
+                                mbar_expect_tx_u(fb, stage_bytes);
+                            }
+                            tma_load_u<CTAS>(sa, &tmA, fb, kc, a_row);
+                            tma_load_u<CTAS>(sa + UM_A_STAGE, &tmB, fb, kc, b_row);
                         }
-                        ++iter;
-                        if (qt == 0 && have_next && !u.nopf) tma_prefetch_2d(&tmA, (int)(kb * u.block_k), a_next);
-                        if (++s == u.stages) { s = 0; ph ^= 1; }
+                        if (pf) tma_prefetch_2d(&tmA, kc, a_next);
                     }
+                    ++iter;
+                    sa += stage_bytes;
+                    if (++s == u.stages) { s = 0; ph ^= 1u; sa = tiles_u; }
                 }
             }
-            if (u.prof) u.prof[blockIdx.x * 8 + 0] = (unsigned long long)w_prod;
         }
+        if (PROF && lane == 0 && u.prof) u.prof[blockIdx.x * 8 + 0] = (unsigned long long)w_prod;
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
-        if (lane == 0 && leader) {
-            uint32_t s = 0, ph = 0, it = 0;
+        if (leader) {
+            uint32_t s = 0, ph = 0, it = 0, sa = tiles_u;
             long long w_full = 0, w_tempty = 0;
-            const long long t_start = clock64();
+            const long long t_start = PROF ? clock64() : 0;
+            // K-major operand tile, 128-byte swizzle (make_smem_desc): everything but the start address is constant
+            const uint64_t desc_hi = make_smem_desc(0);
             for (uint64_t unit = 0; unit < my_units; ++unit, ++it) {
-                const uint32_t as = it & 1, aph = (it >> 1) & 1;
-                mbar_wait(&tempty[as], aph ^ 1, &w_tempty);
+                const uint32_t as = it & 1u, aph = (it >> 1) & 1u;
+                mbar_wait_u<PROF>(tempty_u + 8u * as, aph ^ 1u, &w_tempty);
                 tcgen05_fence_after();
                 const uint32_t tmem_d = tmem_base + as * UM_MAX_N;
                 for (uint32_t kb = 0; kb < u.kblocks; ++kb) {
-                    mbar_wait(&full[s], ph, &w_full);
+                    mbar_wait_u<PROF>(full_u + 8u * s, ph, &w_full);
                     tcgen05_fence_after();
-                    const uint32_t sa = smem_u32(tiles + (size_t)s * stage_bytes);
-                    const uint64_t adesc = make_smem_desc(sa);
-                    const uint64_t bdesc = make_smem_desc(sa + UM_A_STAGE);
-                    if (u.mode == 1) {   // experiment: loads only
-                        mbar_arrive(&empty[s]);
-                        if (CTAS == 2) mbar_arrive_remote(&empty[s], 1);
-                        if (++s == u.stages) { s = 0; ph ^= 1; }
-                        continue;
-                    }
-#pragma unroll
-                    for (uint32_t k = 0; k < UM_MMAS_PER_KBLOCK; ++k) {
-                        // advance 32 bytes (16 fp16 / 8 tf32) along K inside the swizzle row: +2 in 16-byte units
-                        const uint32_t acc = (kb | k) != 0 ? 1u : 0u;
-                        if (u.tf32) {
-                            if (CTAS == 2) umma_tf32_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, acc);
-                            else umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, acc);
+                    if (elect_one()) {
+                        if (mode == 1) {   // experiment: loads only
+                            mbar_arrive_u(empty_u + 8u * s);
+                            if (CTAS == 2) mbar_arrive_remote_u(empty_u + 8u * s, 1, false);
                         } else {
-                            if (CTAS == 2) umma_f16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, acc);
-                            else umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, acc);
+                            const uint64_t adesc = desc_hi | (uint64_t)((sa >> 4) & 0x3FFFu);
+                            const uint64_t bdesc = desc_hi | (uint64_t)(((sa + UM_A_STAGE) >> 4) & 0x3FFFu);
+                            // advance 32 bytes (16 fp16 / 8 tf32) along K inside the swizzle row: +2 in 16-byte units
+                            umma_u<CTAS, TF32>(tmem_d, adesc, bdesc, u.idesc, kb != 0 ? 1u : 0u);
+#pragma unroll
+                            for (uint32_t k = 1; k < UM_MMAS_PER_KBLOCK; ++k) umma_u<CTAS, TF32>(tmem_d, adesc + 2 * k, bdesc + 2 * k, u.idesc, 1u);
+                            // smem stage reusable (in both CTAs) once these MMAs have read it
+                            umma_commit_u<CTAS>(empty_u + 8u * s);
                         }
                     }
-                    // smem stage reusable (in both CTAs) once these MMAs have read it
-                    if (CTAS == 2) umma_commit_2sm(&empty[s]); else umma_commit(&empty[s]);
-                    if (++s == u.stages) { s = 0; ph ^= 1; }
+                    sa += stage_bytes;
+                    if (++s == u.stages) { s = 0; ph ^= 1u; sa = tiles_u; }
                 }
-                if (u.mode == 1) {
-                    mbar_arrive(&tfull[as]);
-                    if (CTAS == 2) mbar_arrive_remote(&tfull[as], 1);
-                } else if (CTAS == 2) umma_commit_2sm(&tfull[as]); else umma_commit(&tfull[as]);   // accumulator complete
+                if (elect_one()) {
+                    if (mode == 1) {
+                        mbar_arrive_u(tfull_u + 8u * as);
+                        if (CTAS == 2) mbar_arrive_remote_u(tfull_u + 8u * as, 1, false);
+                    } else {
+                        umma_commit_u<CTAS>(tfull_u + 8u * as);   // accumulator complete
+                    }
+                }
             }
-            if (u.prof) {
+            if (PROF && lane == 0 && u.prof) {
                 u.prof[blockIdx.x * 8 + 1] = (unsigned long long)w_full;
                 u.prof[blockIdx.x * 8 + 2] = (unsigned long long)w_tempty;
                 u.prof[blockIdx.x * 8 + 5] = (unsigned long long)(clock64() - t_start);
@@ -394,8 +486,8 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         uint32_t it = 0;
         long long w_epi = 0, w_ld = 0, t_ldissue = 0, t_proc = 0, t_tail = 0, t_head = 0;
         unsigned long long n_slow = 0;
-        const long long e_start = clock64();
-        const bool profiling = u.prof != nullptr;
+        const long long e_start = PROF ? clock64() : 0;
+        constexpr bool profiling = PROF;
 
         auto append_global = [&](uint32_t q, uint32_t row, float sc) { append_candidate(u.a.counts, u.a.cands, u.a.cap, q, row, sc); };
         auto flush = [&]() {   // warp-uniform: drain the staged survivors with the atomics in flight together
@@ -436,7 +528,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint32_t q0 = qt * u.n_tile;
             const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + as * UM_MAX_N;
             if (profiling) t_head += clock64() - t_h0;
-            mbar_wait(&tfull[as], aph, &w_epi);
+            mbar_wait_u<PROF>(tfull_u + 8u * as, aph, &w_epi);
             tcgen05_fence_after();
             // score = acc * alpha + beta.  cosine: alpha = 1/|row| (0 marks a row the reference skips), beta = 0;
             // L2: alpha = 2, beta = -|row|^2 (the row slot holds |row|^2; +inf marks a non-finite row)
@@ -444,7 +536,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const float alpha = l2 ? 2.f : inr;
             const float beta = l2 ? -inr : 0.f;
             const bool rowok = rvalid && (l2 ? inr < INFINITY : inr > 0.f);
-            if (u.mode == 1) {
+            if (mode == 1) {
                 // experiment: no accumulators to read
             } else if (FILTER) {
                 const float* tau_t = tau_all + q0;
@@ -569,7 +661,7 @@ stage1_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             if (profiling) t_tail += clock64() - t_t0;
         }
         if (FILTER && !direct) flush();
-        if (u.prof && quad == 0 && lane == 0) {
+        if (PROF && u.prof && quad == 0 && lane == 0) {
             u.prof[blockIdx.x * 8 + 3] = (unsigned long long)w_epi;
             u.prof[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - e_start);
             u.prof[blockIdx.x * 8 + 6] = (unsigned long long)w_ld;
@@ -754,16 +846,22 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-#define YB_LAUNCH_UMMA(F, C)                                                                                          \
-    do {                                                                                                              \
-        YB_CUDA(cudaFuncSetAttribute(stage1_umma_kernel<F, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        YB_CUDA(cudaLaunchKernelEx(&cfg, stage1_umma_kernel<F, C>, tmA, tmB, u));                                     \
+#define YB_LAUNCH_UMMA(F, C, T, P)                                                                                          \
+    do {                                                                                                                    \
+        YB_CUDA(cudaFuncSetAttribute(stage1_umma_kernel<F, C, T, P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        YB_CUDA(cudaLaunchKernelEx(&cfg, stage1_umma_kernel<F, C, T, P>, tmA, tmB, u));                                     \
+    } while (0)
+#define YB_LAUNCH_UMMA_T(F, C)                                                                                              \
+    do {                                                                                                                    \
+        if (u.prof) { if (tf32) YB_LAUNCH_UMMA(F, C, true, true); else YB_LAUNCH_UMMA(F, C, false, true); }                 \
+        else { if (tf32) YB_LAUNCH_UMMA(F, C, true, false); else YB_LAUNCH_UMMA(F, C, false, false); }                      \
     } while (0)
     if (ctas == 2) {
-        if (filter) YB_LAUNCH_UMMA(true, 2); else YB_LAUNCH_UMMA(false, 2);
+        if (filter) YB_LAUNCH_UMMA_T(true, 2); else YB_LAUNCH_UMMA_T(false, 2);
     } else {
-        if (filter) YB_LAUNCH_UMMA(true, 1); else YB_LAUNCH_UMMA(false, 1);
+        if (filter) YB_LAUNCH_UMMA_T(true, 1); else YB_LAUNCH_UMMA_T(false, 1);
     }
+#undef YB_LAUNCH_UMMA_T
 #undef YB_LAUNCH_UMMA
     YB_CUDA(cudaGetLastError());
     if (u.prof) {
