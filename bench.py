@@ -259,8 +259,8 @@ def count_kernel_launches(fn):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="both", choices=["both", "knn", "ingest"])
     ap.add_argument("--rows", type=int, default=0, help="rows per GPU (default: 10M; 12.5M at 8 GPUs = config C4 as named)")
@@ -418,6 +418,7 @@ def main():
             res = step_e2e()
         torch.cuda.synchronize()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
+        tm_e2e = corpus.last_timings()                                  # device timings of the last end-to-end call
         clocks = sampler.stop() if rank == 0 else None
         e2e_qps = nq / (e2e_ms / 1e3) * (total_rows / REF_ROWS)
         launches_per_step = count_kernel_launches(lambda: (scan_into(0, q_dev.data_ptr()), corpus.sync())) if rank == 0 else None
@@ -483,7 +484,8 @@ def main():
             "dtype": "tf32" if f32 else "f16", "data": "synthetic", "config": knn_config(args, world, n),
             "roofline": roof,
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": nq * d * 4,
-                    "d2h_bytes_per_step": nq * k * 12 + (nq * 12 if not dist else 0), "ms_per_step": e2e_ms},
+                    "d2h_bytes_per_step": nq * k * 12 + (nq * 12 if not dist else 0), "ms_per_step": e2e_ms,
+                    "device_ms_last_call": tm_e2e["total_ms"], "scan_kernel_ms_last_call": tm_e2e["scan_kernel_ms"]},
             "gpu_launches": (launches_per_step + (1 if dist else 0)) * K if launches_per_step else (10 + (1 if dist else 0)) * K,
             "gpu_launches_source": "CUPTI (torch.profiler) count of one step's kernels x steps" if launches_per_step else "arithmetic (profiler unavailable)",
             "stage_ms": tm, "parity_full": parity_full,
