@@ -517,6 +517,15 @@ yams_status_t yams_b200_pq_codes(yams_b200_pq* p, uint8_t* out_codes, int64_t* o
     YB_CATCH
 }
 
+}  // extern "C"
+
+// the per-query lists (32 k entries each on the filtered path) bound the batch one pass can take: larger batches are sliced
+static constexpr uint32_t kPqMaxBatch = 512;
+static yams_status_t pq_search_batch(yams_b200_pq* p, const float* queries, uint32_t nq, uint32_t k, uint32_t rerank_factor, float threshold,
+                                     int64_t* out_rowids, float* out_scores, uint32_t* out_counts, uint64_t* out_flags);
+
+extern "C" {
+
 yams_status_t yams_b200_pq_search(yams_b200_pq* p, const float* queries, uint32_t nq, uint32_t k, uint32_t rerank_factor, float threshold,
                                   int64_t* out_rowids, float* out_scores, uint32_t* out_counts, uint64_t* out_flags) {
     YB_TRY
@@ -530,7 +539,23 @@ yams_status_t yams_b200_pq_search(yams_b200_pq* p, const float* queries, uint32_
     if (nq == 0 || k == 0 || p->n_idx == 0) return YAMS_OK;                           // :3873-3881
     YB_ARG(queries && out_rowids && out_scores, "null argument");
     YB_ARG(c->generation == p->corpus_generation, "the corpus changed after the PQ index was built: rebuild it (the reference marks the index dirty)");
-    YB_ARG(nq <= 65535, "at most 65535 queries per call");
+    for (uint32_t q0 = 0; q0 < nq; q0 += kPqMaxBatch) {
+        const uint32_t nb = std::min<uint32_t>(kPqMaxBatch, nq - q0);
+        yams_status_t rc = pq_search_batch(p, queries + (size_t)q0 * p->dim, nb, k, rerank_factor, threshold, out_rowids + (size_t)q0 * k,
+                                           out_scores + (size_t)q0 * k, out_counts + q0, out_flags ? out_flags + q0 : nullptr);
+        if (rc != YAMS_OK) return rc;
+    }
+    return YAMS_OK;
+    YB_CATCH
+}
+
+}  // extern "C"
+
+// one batch of <= kPqMaxBatch queries; the caller holds both locks and has bound the device
+static yams_status_t pq_search_batch(yams_b200_pq* p, const float* queries, uint32_t nq, uint32_t k, uint32_t rerank_factor, float threshold,
+                                     int64_t* out_rowids, float* out_scores, uint32_t* out_counts, uint64_t* out_flags) {
+    YB_TRY
+    yams_b200_corpus* c = p->corpus;
     if (rerank_factor == 0) rerank_factor = 1;                                        // :3670 max(1, rerank_factor)
     const uint64_t budget = (uint64_t)k * rerank_factor;
     const uint32_t approx = (uint32_t)std::min<uint64_t>(p->n_idx, std::max<uint64_t>(k, budget));   // :3956-3959
@@ -630,5 +655,3 @@ yams_status_t yams_b200_pq_search(yams_b200_pq* p, const float* queries, uint32_
     return YAMS_OK;
     YB_CATCH
 }
-
-}  // extern "C"
