@@ -556,6 +556,67 @@ def main():
         del corpus
         torch.cuda.empty_cache()
 
+        keep5 = []
+        if dist and not args.no_side and not f32:
+            # e2: config C5 on a row-sharded corpus -- every rank keeps the part of each allowed list that falls into
+            # its rowid range, re-ranks within it through the host entry point, the partial top-k are gathered and merged like the
+            # unfiltered scan; rank 0 also answers the same batch on an unsharded copy and compares bit for bit.
+            try:
+                from yams_b200.dist import split_allowed
+                c5n, c5q = 1_000_000, 256
+                per = c5n // world
+                lo5, hi5 = rank * per, (c5n if rank == world - 1 else (rank + 1) * per)
+                c5 = Y.Corpus(d, Y.F16, Y.COSINE, capacity_hint=hi5 - lo5)
+                c5.append_synthetic(42, lo5, hi5 - lo5)
+                q5 = q_host.numpy()[:c5q]
+                rec5 = c5q * k * 12
+                p5 = torch.empty(rec5, dtype=torch.uint8, device="cuda")
+                a5 = torch.empty(world * rec5, dtype=torch.uint8, device="cuda")
+                f5r = torch.empty((c5q, k), dtype=torch.int64, device="cuda")
+                f5s = torch.empty((c5q, k), dtype=torch.float32, device="cuda")
+                pts = []
+                for frac in (0.001, 0.01, 0.1):
+                    rng5 = np.random.default_rng(int(frac * 1e6))      # the same lists on every rank
+                    m5 = int(c5n * frac)
+                    allowed = [np.sort(rng5.choice(c5n, size=m5, replace=False)).astype(np.int64) for _ in range(c5q)]
+                    mine = split_allowed(allowed, lo5, hi5)
+
+                    def one():
+                        r, sc, _, _ = c5.search(q5, k, threshold=-1.0, allowed=mine)
+                        p5[:c5q * k * 8].copy_(torch.from_numpy(np.ascontiguousarray(r)).view(torch.uint8).reshape(-1), non_blocking=True)
+                        p5[c5q * k * 8:].copy_(torch.from_numpy(np.ascontiguousarray(sc)).view(torch.uint8).reshape(-1), non_blocking=True)
+                        dist.all_gather_into_tensor(a5, p5)
+                        c5.merge_packed_device(a5.data_ptr(), world, c5q, k, f5r.data_ptr(), f5s.data_ptr(), 0, torch.cuda.current_stream().cuda_stream)
+                        return f5r.cpu().numpy(), f5s.cpu().numpy()
+
+                    one()
+                    barrier_sync()
+                    t0 = time.perf_counter()
+                    for _ in range(3):
+                        rr, ss = one()
+                    dt = max_over_ranks((time.perf_counter() - t0) / 3)
+                    keep5.append((allowed, rr, ss))
+                    pts.append({"candidate_fraction": frac, "rows_per_list": m5, "ms_per_batch": dt * 1e3, "queries_per_s": c5q / dt})
+                if rank == 0:
+                    out["c5_sharded"] = {"workload": f"C5 on {world} row shards: {c5n} x {d} fp16, {c5q} queries, cosine top-{k}; host call per rank "
+                                                     "(list upload included) + packed all-gather + device merge + result copy", "points": pts}
+                c5.close()
+            except Exception as e:   # noqa: BLE001  (every rank runs the same code: a failure is symmetric, no collective is left half-entered)
+                if rank == 0:
+                    out["c5_sharded"] = {"error": repr(e)[:300]}
+            barrier_sync()
+            if rank == 0 and keep5:   # rank-local check, after the last collective of this block
+                try:
+                    whole = Y.Corpus(d, Y.F16, Y.COSINE, capacity_hint=1_000_000)
+                    whole.append_synthetic(42, 0, 1_000_000)
+                    same = True
+                    for allowed, rr, ss in keep5:
+                        wr, ws, _, _ = whole.search(q_host.numpy()[:256], k, threshold=-1.0, allowed=allowed)
+                        same = same and bool(np.array_equal(rr, wr) and np.array_equal(ss.view(np.uint32), ws.view(np.uint32)))
+                    whole.close()
+                    out["c5_sharded"]["equals_unsharded_bit_for_bit"] = same
+                except Exception as e:   # noqa: BLE001
+                    out["c5_sharded"]["check_error"] = repr(e)[:300]
         if rank == 0 and world == 1 and not args.no_side and not f32:
             try:   # C5: candidate-set re-rank within 1M x 768, 256 queries, host call incl. the rowid-list upload
                 c5n, c5q = 1_000_000, 256
