@@ -33,6 +33,20 @@ int main() {
     h.update(bytes("Hello "));
     h.update(bytes("World"));
     CHECK(h.finalize() == "a591a6d40bf420404a011733cfb7b190d62c65bf0bcda32b57b277d9ad9f146e");
+    {   // hashFile / hashFiles (sha256_hasher.cpp:111-150): file contents, empty file, missing file throws
+        namespace fs = std::filesystem;
+        const fs::path dir = fs::temp_directory_path() / "yams_b200_hashfile_test";
+        fs::create_directories(dir);
+        { std::ofstream(dir / "a.txt", std::ios::binary) << "Hello World"; }
+        { std::ofstream(dir / "empty.bin", std::ios::binary); }
+        CHECK(B200ContentHasher::hashFile(dir / "a.txt") == "a591a6d40bf420404a011733cfb7b190d62c65bf0bcda32b57b277d9ad9f146e");
+        auto many = B200ContentHasher::hashFiles({dir / "empty.bin", dir / "a.txt"});
+        CHECK(many.size() == 2 && many[0] == "e3b0c44298fc1c149afbf4c8996fb92427ae41e4649b934ca495991b7852b855" && many[1] == B200ContentHasher::hashFile(dir / "a.txt"));
+        bool threw = false;
+        try { B200ContentHasher::hashFile(dir / "does_not_exist"); } catch (const std::runtime_error&) { threw = true; }
+        CHECK(threw);
+        fs::remove_all(dir);
+    }
     // ---- chunker: pattern data, chunk invariants, per-chunk hash, lazy == full ----
     std::vector<std::byte> data(3 * 1024 * 1024 + 123);
     for (size_t i = 0; i < data.size(); ++i) data[i] = (std::byte)((i * 1315423911u + 0x9E3779B9u) & 0xFF);

@@ -235,6 +235,26 @@ public:
         return out;
     }
 
+    // IContentHasher::hashFile (src/crypto/sha256_hasher.cpp:111-150): same error behaviour (std::runtime_error when the file cannot be
+    // opened).  One file is one SHA-256 lane on the device (~80 MB/s): use hashFiles for more than a handful, it hashes all of
+    // them in one pass.
+    static std::string hashFile(const std::filesystem::path& path) { return hashFiles({path}).front(); }
+    static std::vector<std::string> hashFiles(const std::vector<std::filesystem::path>& paths) {
+        std::vector<std::vector<std::byte>> bufs(paths.size());
+        std::vector<std::span<const std::byte>> spans(paths.size());
+        for (size_t i = 0; i < paths.size(); ++i) {
+            std::ifstream f(paths[i], std::ios::binary);
+            if (!f) throw std::runtime_error("Failed to open file: " + paths[i].string());
+            f.seekg(0, std::ios::end);
+            const std::streamoff n = f.tellg();
+            f.seekg(0, std::ios::beg);
+            bufs[i].resize(n > 0 ? (size_t)n : 0);
+            if (n > 0) f.read(reinterpret_cast<char*>(bufs[i].data()), n);
+            spans[i] = std::span<const std::byte>(bufs[i].data(), bufs[i].size());
+        }
+        return hashSpans(spans);
+    }
+
 private:
     std::vector<std::byte> buf_;
 };
