@@ -342,3 +342,30 @@ def test_sha256_many_separate_messages(Y, oracle):
         assert bytes(got[i]) == O.sha256(m), (i, sizes[i])
     assert Y.sha256_many([]).shape == (0, 32)
     assert bytes(Y.sha256_many([b"abc"])[0]).hex() == "ba7816bf8f01cfea414140de5dae2223b00361a396177a9cb410ff61f20015ad"
+
+
+def test_sha256_longest_first_order_covers_every_bucket(Y, oracle):
+    """Tables of >= 4096 chunks are hashed longest first (32 size buckets, sha_order_*_kernel): sizes spanning every bucket, many
+    equal sizes, empty messages -- every digest must still land in its own slot."""
+    rng = np.random.default_rng(41)
+    n = 6000
+    sizes = np.concatenate([rng.integers(0, 200, 1500), rng.integers(200, 20000, 3000), rng.integers(20000, 90000, 1400),
+                            np.full(96, 4096), np.array([0, 0, 300000, 1 << 20])]).astype(np.int64)
+    rng.shuffle(sizes)
+    assert sizes.size == n
+    pool = rng.integers(0, 256, size=int(sizes.max()) + n, dtype=np.uint8)
+    msgs = [pool[i:i + int(s)] for i, s in enumerate(sizes)]          # overlapping windows of one pool: distinct contents, little memory
+    got = Y.sha256_many(msgs)
+    for i in list(range(0, n, 7)) + [int(np.argmax(sizes)), int(np.argmin(sizes))]:
+        assert bytes(got[i]) == hashlib.sha256(msgs[i].tobytes()).digest(), (i, int(sizes[i]))
+    # the chunker's own table: a device-resident stream with > 4096 chunks, every digest against hashlib
+    import torch
+    ln = 96 << 20
+    t = torch.empty(ln, dtype=torch.uint8, device="cuda")
+    Y.synth_bytes_device(77, 0, ln, t.data_ptr())
+    got = Y.chunk_and_hash_device(t.data_ptr(), ln, Y.default_config(min_chunk=2048, max_chunk=65536, mask=0x7FF))
+    host = t.cpu().numpy()
+    assert len(got) > 4096
+    for i in range(0, len(got), 5):
+        o, s = int(got["offset"][i]), int(got["size"][i])
+        assert bytes(got["digest"][i]) == hashlib.sha256(host[o:o + s].tobytes()).digest(), i
