@@ -376,8 +376,7 @@ def main():
         for i in range(max(W, 2)):
             step_resident(i)
         barrier_sync()
-        if rank == 0:
-            sampler.start()
+        sampler.start()                                                 # every rank samples its own GPU
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(S)
         for i in range(K):
@@ -419,7 +418,8 @@ def main():
         torch.cuda.synchronize()
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / K
         tm_e2e = corpus.last_timings()                                  # device timings of the last end-to-end call
-        clocks = sampler.stop() if rank == 0 else None
+        clocks_mine = sampler.stop()
+        clocks = clocks_mine if rank == 0 else None
         e2e_qps = nq / (e2e_ms / 1e3) * (total_rows / REF_ROWS)
         launches_per_step = count_kernel_launches(lambda: (scan_into(0, q_dev.data_ptr()), corpus.sync())) if rank == 0 else None
         if dist:
@@ -495,6 +495,11 @@ def main():
             out["multi_gpu"] = {"scan_kernel_ms_min_max": scan_ms_ranks, "allgather_ms_min_max": over_ranks(gm), "merge_ms_min_max": over_ranks(mm),
                                 "allgather_bytes_per_rank": rec, "overlap": "gather + merge of batch i run on a side stream behind the scan of batch i+1",
                                 "true_queries_per_s_against_full_corpus": nq / (ms_step / 1e3)}
+            # per-rank kernel time and SM clock under load: the step runs at the pace of the slowest (most power-limited) GPU
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, {"rank": rank, "scan_kernel_ms": tm["scan_kernel_ms"], "sm_mhz": clocks_mine.get("sm_mhz"),
+                                              "power_w": clocks_mine.get("power_w_median"), "reasons": clocks_mine.get("reasons")})
+            out["multi_gpu"]["per_rank"] = per_rank
         if clocks is not None:
             out["clocks"] = clocks
 

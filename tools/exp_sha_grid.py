@@ -26,9 +26,10 @@ print("total %%.2f ms = %%.0f GB/s ; sha256(tail) %%.2f scan %%.2f select %%.2f 
 ''' % (ROOT, GIB)
 CASES = [
     {},
+    {"YAMS_B200_SEGMENT_MIB": "8192"},
+    {"YAMS_B200_SEGMENT_MIB": "16384"},
+    {"YAMS_B200_SEGMENT_MIB": "2048"},
     {"YAMS_B200_SHA_ORDER": "0"},
-    {"YAMS_B200_SHA_GRID": "3"},
-    {"YAMS_B200_SHA_CTAS": "5"},
 ]
 for extra in CASES:
     env = dict(os.environ)
