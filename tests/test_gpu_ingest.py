@@ -176,7 +176,7 @@ def test_device_resident_matches_host_path_and_oracle(Y, oracle):
 
 def test_full_size_properties(Y, oracle):
     """BASELINE-size behaviour through size-independent properties: 6 GiB of the C3 stream resident in
-    HBM (crosses the 1 GiB segment boundaries and 32-bit offsets): coverage, sequential offsets, size bounds,
+    HBM (32-bit offsets overflow; segment boundaries are forced below): coverage, sequential offsets, size bounds,
     spot-checked digests, and equality of an interior window with the oracle re-run from a known cut."""
     import torch
     O = oracle
@@ -205,6 +205,16 @@ def test_full_size_properties(Y, oracle):
     got_cuts = offs[j + 1:][offs[j + 1:] <= start + span] - 1
     cand_abs = want.astype(np.int64) + (start - hist)
     assert np.isin(got_cuts[sizes[j:j + len(got_cuts)] < (1 << 20)], cand_abs).all()
+    # segmenting is invisible: the default (one 16 GiB segment here) and 1 / 2.5 GiB segments (the open chunk and the look-behind
+    # cross every segment boundary) give the same table, digests included
+    import os
+    for mib in ("1024", "2560"):
+        os.environ["YAMS_B200_SEGMENT_MIB"] = mib
+        try:
+            ch2 = Y.chunk_and_hash_device(t.data_ptr(), n, Y.default_config())
+        finally:
+            del os.environ["YAMS_B200_SEGMENT_MIB"]
+        assert np.array_equal(ch2["offset"], offs) and np.array_equal(ch2["size"], sizes) and np.array_equal(ch2["digest"], ch["digest"]), mib
 
 
 def test_dedup_stats_matches_reference_accounting(Y, oracle):

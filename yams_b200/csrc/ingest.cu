@@ -20,9 +20,12 @@
 namespace yb {
 
 constexpr uint32_t kTileBytesHost = kTileBytes;
-static uint64_t segment_bytes() {   // device-resident data is processed in segments (default 4 GiB)
+// Device-resident data is processed in segments (two host round trips each to size the selection buffers).  16 GiB: per 64 GiB the
+// candidate scan + selection cost 15.7 ms instead of 17.7 ms with 4 GiB segments (profiles/r2_sha_order.md); the candidate
+// workspace grows to ~1 GiB (2 x 16 B per 4 KiB tile x 16-entry slack).
+static uint64_t segment_bytes() {
     const char* e = getenv("YAMS_B200_SEGMENT_MIB");
-    uint64_t mib = e ? strtoull(e, nullptr, 10) : 4096;
+    uint64_t mib = e ? strtoull(e, nullptr, 10) : 16384;
     if (mib < 1) mib = 1;
     if (mib > 16384) mib = 16384;
     return mib << 20;
