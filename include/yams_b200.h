@@ -456,18 +456,31 @@ YAMS_B200_API void yams_b200_pq_destroy(yams_b200_pq* pq);
  * third_party/simeon Encoder::encode (src/simeon.cpp:190-262) for the profile YAMS runs (`simeon-v1-384`, src/simeon.cpp:75-93;
  * src/embedding_simeon/simeon_embedding_backend.cpp:118-135): byte n-grams of length ngram_min..ngram_max over the raw text,
  * SplitMix64 hashing, integer count sketch (+-2 per gram), Achlioptas sparse projection (int64 sums, one float scale),
- * L2 normalisation in the AVX2 tier's lane order.  Bit-identical to the reference encoder.  Other encoder modes (word /
- * sub-word tokens, ASCII lowering, IDF / PMI weighting, FWHT or Gaussian projections, matryoshka) are not served here. */
+ * L2 normalisation in the AVX2 tier's lane order.  Bit-identical to the reference encoder.  flags select the other recipe YAMS
+ * runs: word tokens (CharAndWord) and the Fwht projection.  Other encoder modes (sub-word tokens, ASCII lowering, word-bounded
+ * n-grams, IDF / PMI / sqrt-TF weighting, Gaussian / sparse-JL projections, matryoshka) are not served here. */
 typedef struct yams_simeon_config {
     uint32_t ngram_min, ngram_max;     /* 3, 5 */
     uint32_t sketch_dim, output_dim;   /* 4096, 384 */
     uint64_t hash_seed;                /* 0xA5A5A5A5A5A5A5A5 */
     uint64_t projection_seed;          /* 0xDEADBEEFCAFEBABE */
     int32_t l2_normalize;              /* 1 */
-    int32_t reserved;
+    int32_t flags;                     /* YAMS_SIMEON_* below; 0 = the simeon-v1-384 recipe */
 } yams_simeon_config;
+/* NGramMode::CharAndWord (third_party/simeon/src/tokenizer.cpp:40-52): besides the byte n-grams, every maximal [A-Za-z0-9_]+
+ * run is one feature of weight 0.5 (+-1 in the integer sketch) */
+#define YAMS_SIMEON_WORD_TOKENS 1
+/* ProjectionMode::Fwht (third_party/simeon/src/projection.cpp:149-186,359-374): sign diagonal, Walsh-Hadamard transform of the
+ * zero-padded sketch, output_dim sampled coordinates scaled by 1/sqrt(output_dim); requires output_dim <= next_pow2(sketch_dim).
+ * Without this flag the projection is AchlioptasSparse. */
+#define YAMS_SIMEON_PROJECTION_FWHT 2
 typedef struct yams_b200_encoder yams_b200_encoder;
+/* simeon_v1_384_config (third_party/simeon/src/simeon.cpp:75-93): EmbeddingConfig::SimeonEncoderProfile::FixedHash384 */
 YAMS_B200_API void yams_b200_simeon_default_config(yams_simeon_config* cfg);
+/* the encoder YAMS builds when [embeddings.simeon] is left unconfigured (SimeonEncoderProfile::Configurable, the default;
+ * /root/reference/src/embedding_simeon/simeon_embedding_backend.cpp:18-47,118-135): CharAndWord, n-grams 3..5, sketch 4096,
+ * Fwht, output_dim = embedding_dim (0 -> 1024, EmbeddingConfig's default), L2-normalised */
+YAMS_B200_API void yams_b200_simeon_yams_config(yams_simeon_config* cfg, uint32_t embedding_dim);
 YAMS_B200_API yams_status_t yams_b200_simeon_create(void* self, const yams_simeon_config* cfg /* NULL = default */,
                                                     yams_b200_encoder** out);
 /* IEmbeddingBackend::generateEmbeddings (simeon_embedding_backend.cpp:194-209): n HOST texts (bytes, not NUL-terminated)

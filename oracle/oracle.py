@@ -325,6 +325,27 @@ def simeon_encode_ref(texts, ngram_min=3, ngram_max=5, sketch_dim=4096, output_d
     return out
 
 
+def simeon_encode_modes_ref(texts, ngram_mode="CharAndWord", projection="Fwht", ngram_min=3, ngram_max=5, sketch_dim=4096, output_dim=1024,
+                            hash_seed=0xA5A5A5A5A5A5A5A5, projection_seed=0xDEADBEEFCAFEBABE, l2_normalize=1) -> np.ndarray:
+    """simeon::Encoder with an explicit n-gram mode and projection (the configurable profile of YAMS's Simeon backend)."""
+    R = ref()
+    R.ref_simeon_enum.argtypes = [C.c_char_p]
+    R.ref_simeon_enum.restype = C.c_int
+    R.ref_simeon_encode_modes.argtypes = [C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int,
+                                          C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, f32p]
+    nm, pm = R.ref_simeon_enum(ngram_mode.encode()), R.ref_simeon_enum(projection.encode())
+    assert nm >= 0 and pm >= 0
+    raw = [t.encode("utf-8") if isinstance(t, str) else bytes(t) for t in texts]
+    n = len(raw)
+    out = np.zeros((n, output_dim), dtype=np.float32)
+    if n:
+        ptrs = (C.c_char_p * n)(*raw)
+        lens = (C.c_size_t * n)(*[len(r) for r in raw])
+        R.ref_simeon_encode_modes(nm, pm, ngram_min, ngram_max, sketch_dim, output_dim, hash_seed, projection_seed, l2_normalize, ptrs, lens, n,
+                                  _p(out, f32p))
+    return out
+
+
 def _pq_fns():
     R = ref()
     R.ref_pq_encode.argtypes = [f32p, C.c_uint32, C.c_uint32, C.c_uint32, f32p, C.c_uint32, u8p]

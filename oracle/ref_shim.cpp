@@ -151,6 +151,34 @@ void ref_simeon_encode(uint32_t ngram_min, uint32_t ngram_max, uint32_t sketch_d
     simeon::Encoder enc(cfg);
     for (size_t i = 0; i < n; ++i) enc.encode(std::string_view(texts[i], lens[i]), out + i * enc.output_dim());
 }
+// The encoder YAMS builds when [embeddings.simeon] is left unconfigured (the "configurable" profile,
+// /root/reference/src/embedding_simeon/simeon_embedding_backend.cpp:118-135 with the parse_* defaults at :18-47): library defaults
+// plus the given ngram mode (0 CharOnly, 2 CharAndWord) and projection (1 AchlioptasSparse, 5 Fwht -- simeon.hpp enum values are
+// passed through as integers).
+void ref_simeon_encode_modes(int ngram_mode, int projection, uint32_t ngram_min, uint32_t ngram_max, uint32_t sketch_dim, uint32_t output_dim,
+                             uint64_t hash_seed, uint64_t projection_seed, int l2_normalize, const char* const* texts, const size_t* lens,
+                             size_t n, float* out) {
+    simeon::EncoderConfig cfg;
+    cfg.ngram_mode = static_cast<simeon::NGramMode>(ngram_mode);
+    cfg.projection = static_cast<simeon::ProjectionMode>(projection);
+    cfg.ngram_min = ngram_min;
+    cfg.ngram_max = ngram_max;
+    cfg.sketch_dim = sketch_dim;
+    cfg.output_dim = output_dim;
+    cfg.hash_seed = hash_seed;
+    cfg.projection_seed = projection_seed;
+    cfg.l2_normalize = l2_normalize != 0;
+    simeon::Encoder enc(cfg);
+    for (size_t i = 0; i < n; ++i) enc.encode(std::string_view(texts[i], lens[i]), out + i * enc.output_dim());
+}
+int ref_simeon_enum(const char* name) {
+    const std::string s(name);
+    if (s == "CharOnly") return (int)simeon::NGramMode::CharOnly;
+    if (s == "CharAndWord") return (int)simeon::NGramMode::CharAndWord;
+    if (s == "AchlioptasSparse") return (int)simeon::ProjectionMode::AchlioptasSparse;
+    if (s == "Fwht") return (int)simeon::ProjectionMode::Fwht;
+    return -1;
+}
 
 // Lloyd training of the reference (ProductQuantizer::train) -> codebooks, for realistic test indexes
 void ref_pq_train(uint32_t dim, uint32_t m, uint32_t k, const float* training, uint32_t n_train, float* out_codebooks) {

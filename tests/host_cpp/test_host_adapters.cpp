@@ -236,6 +236,17 @@ int main() {
         double n0 = 0, dot03 = 0, dot01 = 0, n2 = 0;
         for (int i = 0; i < 384; ++i) { n0 += embs[0][i] * embs[0][i]; dot03 += embs[0][i] * embs[3][i]; dot01 += embs[0][i] * embs[1][i]; n2 += embs[2][i] * embs[2][i]; }
         CHECK(std::fabs(n0 - 1.0) < 1e-5 && n2 == 0.0 && dot03 > 0.9 && dot01 < dot03);
+        CHECK(sb.getEmbeddingSpaceIdentity() == "simeon-v1-384");
+        // the profile of an unconfigured YAMS (Configurable): CharAndWord + Fwht, embedding_dim coordinates, its identity string
+        B200SimeonBackend yd(B200SimeonBackend::Profile::Configurable, 1024);
+        CHECK(yd.getEmbeddingDimension() == 1024);
+        CHECK(yd.getEmbeddingSpaceIdentity() == "simeon-config-v1:char_and_word:3-5:sketch=4096:output=1024:projection=fwht:l2=1");
+        auto e2 = yd.generateEmbeddings(texts);
+        double m0 = 0, d03 = 0, d01 = 0;
+        for (int i = 0; i < 1024; ++i) { m0 += e2[0][i] * e2[0][i]; d03 += e2[0][i] * e2[3][i]; d01 += e2[0][i] * e2[1][i]; }
+        CHECK(std::fabs(m0 - 1.0) < 1e-5 && d03 > 0.9 && d01 < d03);
+        B200SimeonBackend fixed(B200SimeonBackend::Profile::FixedHash384, 1024);
+        CHECK(fixed.getEmbeddingDimension() == 384 && fixed.generateEmbedding(texts[0]) == embs[0]);
     }
     std::puts("ALL OK");
     return 0;

@@ -69,3 +69,36 @@ def test_simeon_embeddings_feed_the_scan(Y, oracle):
     assert all(rid[i, 0] == i or sc[i, 0] == sc[i, 1] for i in range(50)) and np.all(sc[:, 0] > 0.9999)
     c.close()
     enc.close()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(profile="yams-default"),                                                     # unconfigured YAMS: CharAndWord + Fwht, 4096 -> 1024
+    dict(profile="yams-default", embedding_dim=384),
+    dict(profile="yams-default", embedding_dim=768, sketch_dim=8192),
+    dict(profile="yams-default", embedding_dim=100, sketch_dim=5000),                 # sketch padded 5000 -> 8192, modulo buckets
+    dict(profile="yams-default", embedding_dim=4096),                                 # output_dim == pad_n: every coordinate sampled
+    dict(flags=1),                                                                    # word tokens with the Achlioptas projection
+    dict(flags=2, output_dim=40, l2_normalize=0),                                     # Fwht without word tokens, raw output
+])
+def test_simeon_yams_default_profile_is_bit_identical(Y, oracle, cfg):
+    """The encoder an unconfigured YAMS builds (simeon_embedding_backend.cpp:18-47,118-135): byte n-grams + word tokens, count
+    sketch, FWHT projection, L2 -- against simeon's own Encoder with ngram_mode / projection set the same way."""
+    O = oracle
+    if not O.ref_available():
+        pytest.skip("needs simeon compiled in place")
+    rng = np.random.default_rng(123)
+    texts = corpus_of_texts(rng, 300) + [b"_", b"a_b c-d e.f 0x1F", b"word" * 3000, b"  leading and trailing  ", "Größe_42 naïve".encode()]
+    enc = Y.SimeonEncoder(**cfg)
+    got = enc.encode(texts)
+    c = enc.cfg
+    want = O.simeon_encode_modes_ref(texts, ngram_mode="CharAndWord" if c.flags & Y.SIMEON_WORD_TOKENS else "CharOnly",
+                                     projection="Fwht" if c.flags & Y.SIMEON_PROJECTION_FWHT else "AchlioptasSparse",
+                                     ngram_min=c.ngram_min, ngram_max=c.ngram_max, sketch_dim=c.sketch_dim, output_dim=c.output_dim,
+                                     hash_seed=c.hash_seed, projection_seed=c.projection_seed, l2_normalize=c.l2_normalize)
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(enc.encode([texts[7]])[0], got[7])
+    enc.close()
+    # the constraint of the reference constructor (projection.cpp:167-170)
+    with pytest.raises(Y.YamsB200Error):
+        Y.SimeonEncoder(profile="yams-default", embedding_dim=4096, sketch_dim=2048)

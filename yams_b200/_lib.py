@@ -47,8 +47,11 @@ class ManifestSummary(C.Structure):
 
 class SimeonConfig(C.Structure):
     _fields_ = [("ngram_min", C.c_uint32), ("ngram_max", C.c_uint32), ("sketch_dim", C.c_uint32), ("output_dim", C.c_uint32),
-                ("hash_seed", C.c_uint64), ("projection_seed", C.c_uint64), ("l2_normalize", C.c_int32), ("reserved", C.c_int32)]
+                ("hash_seed", C.c_uint64), ("projection_seed", C.c_uint64), ("l2_normalize", C.c_int32), ("flags", C.c_int32)]
 
+
+SIMEON_WORD_TOKENS = 1        # NGramMode::CharAndWord
+SIMEON_PROJECTION_FWHT = 2    # ProjectionMode::Fwht (default projection: AchlioptasSparse)
 
 CHUNK_REF_DTYPE = np.dtype([("hash", "S64"), ("offset", "<u8"), ("size", "<u4"), ("flags", "<u4")])
 assert CHUNK_REF_DTYPE.itemsize == 80
@@ -124,6 +127,7 @@ SYMBOLS = {
     "yams_b200_debug_stage1_scores": (C.c_int, [C.c_void_p, f32p, C.c_uint32, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
     "yams_b200_synth_rows_device": (C.c_int, [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
     "yams_b200_simeon_default_config": (None, [C.POINTER(SimeonConfig)]),
+    "yams_b200_simeon_yams_config": (None, [C.POINTER(SimeonConfig), C.c_uint32]),
     "yams_b200_simeon_create": (C.c_int, [C.c_void_p, C.POINTER(SimeonConfig), C.POINTER(C.c_void_p)]),
     "yams_b200_simeon_encode": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_size_t), C.c_size_t, f32p]),
     "yams_b200_simeon_destroy": (None, [C.c_void_p]),
@@ -521,11 +525,17 @@ class Corpus:
 
 
 class SimeonEncoder:
-    """The Simeon text encoder's default profile (byte n-grams -> count sketch -> Achlioptas projection -> L2)."""
+    """The Simeon text encoder: `profile="simeon-v1-384"` (byte n-grams -> count sketch -> Achlioptas projection -> L2) or
+    `profile="yams-default"` (what an unconfigured YAMS runs: byte n-grams + word tokens -> count sketch -> FWHT -> L2,
+    output_dim = embedding_dim)."""
 
-    def __init__(self, **overrides):
+    def __init__(self, profile: str = "simeon-v1-384", embedding_dim: int = 0, **overrides):
         cfg = SimeonConfig()
-        lib().yams_b200_simeon_default_config(C.byref(cfg))
+        if profile == "yams-default":
+            lib().yams_b200_simeon_yams_config(C.byref(cfg), embedding_dim)
+        else:
+            assert profile == "simeon-v1-384", profile
+            lib().yams_b200_simeon_default_config(C.byref(cfg))
         for k, v in overrides.items():
             setattr(cfg, k, v)
         self.cfg = cfg

@@ -1,4 +1,4 @@
-// simeon_encode.cu -- the Simeon text encoder's default profile on the device.
+// simeon_encode.cu -- the Simeon text encoder on the device: the two profiles YAMS runs.
 //
 // Reference (paths under /root/reference/third_party/simeon):
 //   Encoder::Impl::encode_one                       src/simeon.cpp:190-262
@@ -7,8 +7,11 @@
 //   SketchSink (integer count sketch, +-2 per gram) src/simeon.cpp:355-373, sketch_bucket :46-49
 //   Projection (AchlioptasSparse)                   src/projection.cpp:22-34 (entry), :326-343 (apply: int64 pos - neg, one float scale)
 //   simd::l2_normalize, AVX2 tier                   src/arch/avx2.cpp:31-60
-//   the profile YAMS runs (`simeon-v1-384` and the configurable default): src/simeon.cpp:75-93,
-//   /root/reference/src/embedding_simeon/simeon_embedding_backend.cpp:118-135
+//   emit_word_tokens (CharAndWord)                  src/tokenizer.cpp:40-52 (one +-1 feature per [A-Za-z0-9_]+ run)
+//   Projection (Fwht)                               src/projection.cpp:149-186 (signs, row sample), :359-374 (apply), fwht_inplace :50-70
+//   the profiles YAMS runs: `simeon-v1-384` = CharOnly + AchlioptasSparse (src/simeon.cpp:75-93); the "configurable" default of an
+//   unconfigured [embeddings.simeon] = CharAndWord + Fwht, sketch 4096, output = embedding_dim
+//   (/root/reference/src/embedding_simeon/simeon_embedding_backend.cpp:18-47,118-135)
 //
 // Everything up to the projection is integer arithmetic: every byte n-gram of length ngram_min..ngram_max is hashed
 // (splitmix64 over little-endian 8-byte words + a length-tagged tail), the low hash bits pick one of sketch_dim buckets, the top
@@ -17,6 +20,9 @@
 // multiplies ONCE by sqrt(3)/sqrt(output_dim) in float.  Only the L2 normalisation is a float reduction; it follows the lane
 // structure of the AVX2 kernel.  The output is therefore bit-identical to the reference encoder
 // (tests/test_gpu_simeon.py pins it against simeon's own sources compiled in place).
+// Fwht: the sketch, zero-padded to a power of two and multiplied by a +-1 diagonal, goes through the in-place Walsh-Hadamard
+// butterflies in shared memory (same stage order and the same x + y / x - y per butterfly as fwht_inplace, so every float is the
+// reference's), output_dim sampled coordinates are scaled by 1/sqrt(output_dim).
 //
 // One CTA per text.  The sign matrix is tabulated once per encoder, 2 bits per entry, column-major (for one sketch column the
 // 384 row signs are 96 contiguous bytes): the projection walks the NON-ZERO sketch columns only.
@@ -86,13 +92,25 @@ struct EncArgs {
     float scale;                // sqrt(3.0f) * (1.0f / sqrt((float)output_dim)), evaluated on the host in float like projection.cpp:128-129
     int l2_normalize;
     float* out;                 // n x output_dim
+    uint32_t flags;             // YAMS_SIMEON_WORD_TOKENS | YAMS_SIMEON_PROJECTION_FWHT
+    uint32_t pad_n;             // Fwht: next_pow2(sketch_dim)
+    const float* signs;         // Fwht: pad_n entries of +-1
+    const uint32_t* sample;     // Fwht: output_dim distinct coordinates of the transformed vector
+    float fwht_scale;           // Fwht: 1.0f / sqrt((float)output_dim)
 };
+
+// std::isalnum in the "C" locale, or '_' (tokenizer.cpp:13-15)
+__device__ __forceinline__ bool is_word_char(uint8_t c) {
+    return (c >= '0' && c <= '9') || (c >= 'A' && c <= 'Z') || (c >= 'a' && c <= 'z') || c == '_';
+}
 
 __global__ void __launch_bounds__(ENC_THREADS) simeon_encode_kernel(EncArgs a) {
     extern __shared__ unsigned char sm[];
     int32_t* sketch = reinterpret_cast<int32_t*>(sm);                      // sketch_dim
-    uint32_t* nz = reinterpret_cast<uint32_t*>(sketch + a.sketch_dim);     // sketch_dim: compacted non-zero columns
-    float* outv = reinterpret_cast<float*>(nz + a.sketch_dim);             // output_dim
+    uint32_t* nz = reinterpret_cast<uint32_t*>(sketch + a.sketch_dim);     // sketch_dim: compacted non-zero columns (Achlioptas)
+    float* wh = reinterpret_cast<float*>(nz);                              // pad_n: Walsh-Hadamard buffer (Fwht) -- same region
+    const uint32_t region2 = a.pad_n > a.sketch_dim ? a.pad_n : a.sketch_dim;
+    float* outv = reinterpret_cast<float*>(nz + region2);                  // output_dim
     __shared__ uint32_t s_nnz;
     __shared__ float s_inv;
     __shared__ int s_scale;
@@ -113,7 +131,37 @@ __global__ void __launch_bounds__(ENC_THREADS) simeon_encode_kernel(EncArgs a) {
                 atomicAdd(&sketch[bucket], (h >> 63) ? -2 : 2);            // char n-grams weigh 1.0 -> magnitude 2
             }
         }
+        // ---- word tokens (tokenizer.cpp:40-52): every maximal [A-Za-z0-9_]+ run is one feature of weight 0.5 -> magnitude 1;
+        //      the thread that sees a run's first byte hashes the whole run ----
+        if (a.flags & YAMS_SIMEON_WORD_TOKENS) {
+            for (uint64_t i = threadIdx.x; i < len; i += ENC_THREADS) {
+                if (!is_word_char(p[i]) || (i > 0 && is_word_char(p[i - 1]))) continue;
+                uint64_t e = i + 1;
+                while (e < len && is_word_char(p[e])) ++e;
+                const uint64_t h = gram_hash(p + i, (uint32_t)(e - i), a.h0);
+                const uint32_t low = (uint32_t)h;
+                const uint32_t bucket = (a.sketch_dim & (a.sketch_dim - 1)) == 0 ? (low & (a.sketch_dim - 1)) : (low % a.sketch_dim);
+                atomicAdd(&sketch[bucket], (h >> 63) ? -1 : 1);
+            }
+        }
         __syncthreads();
+        if (a.flags & YAMS_SIMEON_PROJECTION_FWHT) {
+            // ---- Fwht (projection.cpp:359-374): pad, sign diagonal, in-place butterflies, sample, scale ----
+            for (uint32_t i = threadIdx.x; i < a.pad_n; i += ENC_THREADS)
+                wh[i] = i < a.sketch_dim ? __fmul_rn((float)sketch[i], __ldg(&a.signs[i])) : 0.0f;
+            __syncthreads();
+            for (uint32_t h = 1; h < a.pad_n; h <<= 1) {
+                for (uint32_t tb = threadIdx.x; tb < a.pad_n / 2; tb += ENC_THREADS) {
+                    const uint32_t j = (tb / h) * (h << 1) + (tb % h);
+                    const float x = wh[j], y = wh[j + h];
+                    wh[j] = __fadd_rn(x, y);
+                    wh[j + h] = __fsub_rn(x, y);
+                }
+                __syncthreads();
+            }
+            for (uint32_t row = threadIdx.x; row < a.output_dim; row += ENC_THREADS)
+                outv[row] = __fmul_rn(wh[__ldg(&a.sample[row])], a.fwht_scale);
+        } else {
         // ---- non-zero columns, ascending order is irrelevant for an integer sum ----
         for (uint32_t i = threadIdx.x; i < a.sketch_dim; i += ENC_THREADS)
             if (sketch[i] != 0) nz[atomicAdd(&s_nnz, 1u)] = i;
@@ -131,6 +179,7 @@ __global__ void __launch_bounds__(ENC_THREADS) simeon_encode_kernel(EncArgs a) {
                 else if (code == 2) neg += v;
             }
             outv[row] = __fmul_rn((float)(pos - neg), a.scale);
+        }
         }
         __syncthreads();
         // ---- simd::l2_normalize, AVX2 tier (avx2.cpp:31-60): two 8-lane FMA accumulators over 16-element blocks ----
@@ -173,6 +222,10 @@ struct yams_b200_encoder {
     uint32_t words_per_col = 0;
     float scale = 0.f;
     DevBuf table;
+    // Fwht
+    uint32_t pad_n = 0;
+    float fwht_scale = 0.f;
+    DevBuf signs, sample;
     std::mutex mu;
 };
 
@@ -188,7 +241,16 @@ void yams_b200_simeon_default_config(yams_simeon_config* cfg) {
     cfg->hash_seed = 0xA5A5A5A5A5A5A5A5ULL;
     cfg->projection_seed = 0xDEADBEEFCAFEBABEULL;
     cfg->l2_normalize = 1;
-    cfg->reserved = 0;
+    cfg->flags = 0;
+}
+
+void yams_b200_simeon_yams_config(yams_simeon_config* cfg, uint32_t embedding_dim) {
+    if (!cfg) return;
+    // resolveEncoder with an unconfigured [embeddings.simeon] (simeon_embedding_backend.cpp:118-135): parse_ngram_mode("") ->
+    // CharAndWord (:18-29), parse_projection_mode("") -> Fwht (:31-46), n-grams 3..5, sketch 4096, output = embedding_dim
+    yams_b200_simeon_default_config(cfg);
+    cfg->output_dim = embedding_dim ? embedding_dim : 1024;   // EmbeddingConfig::embedding_dim default (embedding_generator.h:42)
+    cfg->flags = YAMS_SIMEON_WORD_TOKENS | YAMS_SIMEON_PROJECTION_FWHT;
 }
 
 yams_status_t yams_b200_simeon_create(void* self, const yams_simeon_config* cfg_in, yams_b200_encoder** out) {
@@ -201,6 +263,12 @@ yams_status_t yams_b200_simeon_create(void* self, const yams_simeon_config* cfg_
     YB_ARG(cfg.ngram_min >= 1 && cfg.ngram_min <= cfg.ngram_max && cfg.ngram_max <= 64, "ngram range must be 1 <= min <= max <= 64");
     YB_ARG(cfg.sketch_dim >= 1 && cfg.sketch_dim <= 16384, "sketch_dim must be in 1..16384");
     YB_ARG(cfg.output_dim >= 1 && cfg.output_dim <= 4096, "output_dim must be in 1..4096");
+    YB_ARG((cfg.flags & ~(YAMS_SIMEON_WORD_TOKENS | YAMS_SIMEON_PROJECTION_FWHT)) == 0, "unknown encoder flags");
+    const bool fwht = (cfg.flags & YAMS_SIMEON_PROJECTION_FWHT) != 0;
+    uint32_t pad_n = 1;
+    while (pad_n < cfg.sketch_dim) pad_n <<= 1;                                         // projection.cpp:72-80 next_pow2
+    // projection.cpp:167-170: "Fwht requires output_dim <= next_pow2(sketch_dim)"
+    YB_ARG(!fwht || cfg.output_dim <= pad_n, "Fwht requires output_dim <= next_pow2(sketch_dim)");
     DeviceCtx* dev = nullptr;
     yams_status_t rc = ensure_device(&dev);
     if (rc != YAMS_OK) return rc;
@@ -212,15 +280,44 @@ yams_status_t yams_b200_simeon_create(void* self, const yams_simeon_config* cfg_
     // projection.cpp:128-129: inv_scale_ = 1.0f / std::sqrt((float)output_dim); achlioptas_scale_ = std::sqrt(3.0f) * inv_scale_
     const float inv_scale = 1.0f / sqrtf((float)cfg.output_dim);
     e->scale = sqrtf(3.0f) * inv_scale;
+    cudaError_t ce = cudaSuccess;
+    if (fwht) {
+        // projection.cpp:149-186, evaluated once on the host: the sign diagonal is one splitmix64 chain over i, the row sample a
+        // partial Fisher-Yates over [0, pad_n) driven by a second chain -- both inherently sequential and tiny
+        e->pad_n = pad_n;
+        e->fwht_scale = 1.0f / sqrtf((float)cfg.output_dim);
+        std::vector<float> signs(pad_n);
+        uint64_t rng = sm64_mix(cfg.projection_seed ^ 0x9E3779B97F4A7C15ULL);
+        for (uint32_t i = 0; i < pad_n; ++i) {
+            rng = sm64_mix(rng + i);
+            signs[i] = (rng & 1ULL) ? -1.0f : 1.0f;
+        }
+        std::vector<uint32_t> idx(pad_n);
+        for (uint32_t i = 0; i < pad_n; ++i) idx[i] = i;
+        uint64_t srng = sm64_mix(cfg.projection_seed ^ 0xBF58476D1CE4E5B9ULL);
+        for (uint32_t i = 0; i < cfg.output_dim; ++i) {
+            srng = sm64_mix(srng + i);
+            const uint32_t pick = i + (uint32_t)(srng % (uint64_t)(pad_n - i));
+            std::swap(idx[i], idx[pick]);
+        }
+        if ((rc = e->signs.reserve((size_t)pad_n * 4)) != YAMS_OK || (rc = e->sample.reserve((size_t)cfg.output_dim * 4)) != YAMS_OK) {
+            e->signs.release(); e->sample.release();
+            delete e;
+            return rc;
+        }
+        ce = cudaMemcpy(e->signs.p, signs.data(), (size_t)pad_n * 4, cudaMemcpyHostToDevice);
+        if (ce == cudaSuccess) ce = cudaMemcpy(e->sample.p, idx.data(), (size_t)cfg.output_dim * 4, cudaMemcpyHostToDevice);
+    } else {
     const size_t words = (size_t)cfg.sketch_dim * e->words_per_col;
     rc = e->table.reserve(words * 4);
     if (rc != YAMS_OK) { delete e; return rc; }
     achlioptas_table_kernel<<<(unsigned)((words + 255) / 256), 256>>>(cfg.sketch_dim, cfg.output_dim, cfg.projection_seed, e->words_per_col,
                                                                       e->table.as<uint32_t>());
-    cudaError_t ce = cudaDeviceSynchronize();
+    }
+    if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
     if (ce != cudaSuccess) {
         set_last_error("encoder table build failed: %s", cudaGetErrorString(ce));
-        e->table.release();
+        e->table.release(); e->signs.release(); e->sample.release();
         delete e;
         return YAMS_ERR_INTERNAL;
     }
@@ -232,6 +329,8 @@ yams_status_t yams_b200_simeon_create(void* self, const yams_simeon_config* cfg_
 void yams_b200_simeon_destroy(yams_b200_encoder* e) {
     if (!e) return;
     e->table.release();
+    e->signs.release();
+    e->sample.release();
     delete e;
 }
 
@@ -274,7 +373,12 @@ yams_status_t yams_b200_simeon_encode(yams_b200_encoder* e, const char* const* t
     a.scale = e->scale;
     a.l2_normalize = e->cfg.l2_normalize;
     a.out = w->d[2].as<float>();
-    const size_t smem = (size_t)e->cfg.sketch_dim * 8 + (size_t)D * 4 + 64;
+    a.flags = (uint32_t)e->cfg.flags;
+    a.pad_n = e->pad_n;
+    a.signs = e->signs.as<float>();
+    a.sample = e->sample.as<uint32_t>();
+    a.fwht_scale = e->fwht_scale;
+    const size_t smem = (size_t)e->cfg.sketch_dim * 4 + (size_t)std::max(e->cfg.sketch_dim, e->pad_n) * 4 + (size_t)D * 4 + 64;
     YB_CUDA(cudaFuncSetAttribute(simeon_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const unsigned grid = (unsigned)std::min<size_t>(n, (size_t)e->dev->sm_count * 8);
     simeon_encode_kernel<<<grid, ENC_THREADS, smem, st>>>(a);

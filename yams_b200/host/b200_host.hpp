@@ -608,13 +608,22 @@ private:
 // Simeon profile only -- any other recipe stays on the reference's CPU encoder.
 class B200SimeonBackend {
 public:
+    // EmbeddingConfig::SimeonEncoderProfile (include/yams/vector/embedding_generator.h:29-37): Configurable is the default
+    enum class Profile { Configurable, FixedHash384 };
     explicit B200SimeonBackend(const yams_simeon_config* cfg = nullptr) {
         yams_simeon_config c;
         if (cfg) c = *cfg; else yams_b200_simeon_default_config(&c);
-        dim_ = c.output_dim;
-        yams_status_t st = yams_b200_simeon_create(nullptr, &c, &e_);
-        if (st != YAMS_OK) throw_status("simeon_create", st);
+        init(c);
     }
+    // resolveEncoder (simeon_embedding_backend.cpp:118-135) for an unconfigured [embeddings.simeon]: FixedHash384 -> simeon_v1_384_config,
+    // Configurable -> CharAndWord + Fwht with output_dim = embedding_dim
+    B200SimeonBackend(Profile profile, uint32_t embedding_dim) {
+        yams_simeon_config c;
+        if (profile == Profile::FixedHash384) yams_b200_simeon_default_config(&c);
+        else yams_b200_simeon_yams_config(&c, embedding_dim);
+        init(c);
+    }
+    std::string getEmbeddingSpaceIdentity() const { return identity_; }
     ~B200SimeonBackend() { yams_b200_simeon_destroy(e_); }
     B200SimeonBackend(const B200SimeonBackend&) = delete;
     B200SimeonBackend& operator=(const B200SimeonBackend&) = delete;
@@ -637,8 +646,22 @@ public:
     std::string getBackendName() const { return "Simeon"; }
 
 private:
+    void init(const yams_simeon_config& c) {
+        dim_ = c.output_dim;
+        const bool word = (c.flags & YAMS_SIMEON_WORD_TOKENS) != 0, fwht = (c.flags & YAMS_SIMEON_PROJECTION_FWHT) != 0;
+        if (!word && !fwht && c.ngram_min == 3 && c.ngram_max == 5 && c.sketch_dim == 4096 && c.output_dim == 384 && c.l2_normalize) {
+            identity_ = "simeon-v1-384";                                       // simeon.hpp:151
+        } else {                                                               // configurableSpaceIdentity, simeon_embedding_backend.cpp:100-116
+            identity_ = std::string("simeon-config-v1:") + (word ? "char_and_word" : "char") + ":" + std::to_string(c.ngram_min) + "-" +
+                        std::to_string(c.ngram_max) + ":sketch=" + std::to_string(c.sketch_dim) + ":output=" + std::to_string(c.output_dim) +
+                        ":projection=" + (fwht ? "fwht" : "achlioptas_sparse") + ":l2=" + (c.l2_normalize ? "1" : "0");
+        }
+        yams_status_t st = yams_b200_simeon_create(nullptr, &c, &e_);
+        if (st != YAMS_OK) throw_status("simeon_create", st);
+    }
     yams_b200_encoder* e_ = nullptr;
     size_t dim_ = 0;
+    std::string identity_;
 };
 
 // ManifestManager::createManifest (src/manifest/manifest_manager.cpp:411-436) over a chunk table: ChunkRefs + checksum in one device call
