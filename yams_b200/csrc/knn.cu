@@ -344,6 +344,8 @@ struct SelectIn {
     const uint32_t* qmap;   // nullable: CTA b handles query qmap[b] for the list/out side
     const float* tau;       // nullable (list mode): rows that never reached the list scored <= tau[q]
     float tau_margin;       // tau_only: subtracted from the selected score
+    int fast_tau;           // tau_only, K <= 16: one pass, the K-th largest of the per-thread maxima (a lower bound of the K-th
+                            // largest score: a threshold need not be exact, only close -- the certificate covers what it lets go)
 };
 
 __device__ __forceinline__ uint64_t sel_key(const SelectIn& in, uint32_t qsrc, uint64_t i) {
@@ -417,6 +419,28 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, u
             atomicMin(&s_want, mn);
             __syncthreads();
             if (threadIdx.x == 0) out_tau[qdst] = fkey_inv(s_want) - in.tau_margin;
+        } else if (in.fast_tau && K <= 16 && L >= 16 * SEL_THREADS) {
+            // One pass, no atomics: every thread keeps the best key of its strided share, the 256 maxima are sorted, the K-th of
+            // them is the threshold.  It equals the K-th best score unless two of the top K fall into one thread's share (11 % for
+            // K = 8), in which case it is the next one down: a slightly lower threshold, a few more survivors.
+            uint32_t* arr = reinterpret_cast<uint32_t*>(buf);
+            uint32_t mx = 0;
+            for (uint64_t i = threadIdx.x; i < L; i += SEL_THREADS) mx = max(mx, (uint32_t)(sel_key(in, qsrc, i) >> 32));
+            arr[threadIdx.x] = mx;
+            __syncthreads();
+            for (uint32_t size = 2; size <= SEL_THREADS; size <<= 1) {
+                for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+                    const uint32_t t = threadIdx.x;
+                    if (t < SEL_THREADS / 2) {
+                        uint32_t lo = (t / stride) * (stride * 2) + (t % stride), hi = lo + stride;
+                        bool desc = ((lo & size) == 0);
+                        uint32_t x = arr[lo], y = arr[hi];
+                        if ((x < y) == desc) { arr[lo] = y; arr[hi] = x; }
+                    }
+                    __syncthreads();
+                }
+            }
+            if (threadIdx.x == 0) out_tau[qdst] = fkey_inv(arr[K - 1]) - in.tau_margin;
         } else {
             // Two passes instead of four: a 4096-bin histogram of the top 12 key bits locates the bin that holds the K-th
             // best score; its (few) members are collected and sorted in shared memory.  A crowded bin (> 2048 members,
@@ -473,7 +497,7 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, u
         return;
     }
     uint64_t kth = 0;  // keys >= kth are selected
-    if (L > K) {
+    if (L > K && L > SEL_MAXK) {   // a list that fits the sort buffer is sorted whole (66 network steps for 2048 keys beat 8 radix passes)
         radix_select(8);
         kth = s_prefix;
     }
@@ -1312,6 +1336,7 @@ static yams_status_t scan_enqueue(Corpus* c, const ScanPlan& p, int64_t* d_out_r
             SelectIn in{};
             in.dense = c->sample_scores.as<float>(); in.ld = S; in.row_start = 0; in.row_stride = stride; in.dense_len = S;
             in.tau_margin = l2 ? 0.f : kTauMargin;
+            in.fast_tau = p.d_mask ? 0 : 1;   // candidate sets: masked sample rows are -inf, the exact rank matters there
             topk_select_kernel<<<nq, SEL_THREADS, 0, st>>>(in, m, 1, d_tau, nullptr, nullptr, nullptr);
         }
         if ((rc = c->cands.reserve((size_t)nq * cap * sizeof(Cand))) != YAMS_OK) return rc;
