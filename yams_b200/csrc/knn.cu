@@ -137,17 +137,31 @@ struct ScanStatus {
 
 // queries: invalid if non-finite or (cosine) |q|^2 < 1e-10 (sqlite_vec_backend.cpp:204-235,4127);
 // qnorm[q] = sqrt(sum (double)q^2) (:4204-4209), qinv[q] = 1/qnorm as float (1 for L2: queries stay unscaled)
-__global__ void query_prep_kernel(const float* __restrict__ q, uint32_t nq, uint32_t d, double* __restrict__ qnorm,
-                                  float* __restrict__ qinv, int metric, ScanStatus* __restrict__ status) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nq) return;
+constexpr int QP_THREADS = 64, QP_COLS = 64;
+__global__ void __launch_bounds__(QP_THREADS) query_prep_kernel(const float* __restrict__ q, uint32_t nq, uint32_t d, double* __restrict__ qnorm,
+                                                                float* __restrict__ qinv, int metric, ScanStatus* __restrict__ status) {
+    // thread = query, the reference's sequential double sum (sqlite_vec_backend.cpp:4140-4150); the values reach the thread through a
+    // shared-memory tile filled with coalesced loads (a thread walking its own 3 KB row was 64 us of dependent L2 round trips)
+    __shared__ float tile[QP_THREADS][QP_COLS + 1];
+    const uint32_t q0 = blockIdx.x * QP_THREADS;
+    const uint32_t i = q0 + threadIdx.x;
     double ss = 0.0;
     bool finite = true;
-    for (uint32_t c = 0; c < d; ++c) {
-        float v = q[(uint64_t)i * d + c];
-        if (!isfinite(v)) finite = false;
-        ss += (double)v * (double)v;
+    for (uint32_t c0 = 0; c0 < d; c0 += QP_COLS) {
+        const uint32_t w = min((uint32_t)QP_COLS, d - c0);
+        for (uint32_t e = threadIdx.x; e < QP_THREADS * QP_COLS; e += QP_THREADS) {
+            const uint32_t r = e / QP_COLS, c = e % QP_COLS;
+            tile[r][c] = (q0 + r < nq && c < w) ? q[(uint64_t)(q0 + r) * d + c0 + c] : 0.f;
+        }
+        __syncthreads();
+        for (uint32_t c = 0; c < w; ++c) {
+            const float v = tile[threadIdx.x][c];
+            if (!isfinite(v)) finite = false;
+            ss += (double)v * (double)v;
+        }
+        __syncthreads();
     }
+    if (i >= nq) return;
     bool bad = !finite || (metric == YAMS_B200_COSINE && ss < 1e-10);
     if (bad) atomicAdd(&status->n_invalid, 1u);
     double nrm = sqrt(ss);
@@ -425,7 +439,28 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, u
             // K = 8), in which case it is the next one down: a slightly lower threshold, a few more survivors.
             uint32_t* arr = reinterpret_cast<uint32_t*>(buf);
             uint32_t mx = 0;
-            for (uint64_t i = threadIdx.x; i < L; i += SEL_THREADS) mx = max(mx, (uint32_t)(sel_key(in, qsrc, i) >> 32));
+            const float* base = in.dense ? in.dense + (uint64_t)qsrc * in.ld : nullptr;
+            if (base && (reinterpret_cast<uintptr_t>(base) & 15u) == 0) {
+                // dense scores: 16-byte loads, four of them in flight per thread (one 4-byte load per trip was latency-bound:
+                // 1.2 TB/s over the Q x S score matrix)
+                const float4* b4 = reinterpret_cast<const float4*>(base);
+                const uint64_t n4 = L / 4;
+                uint64_t i = threadIdx.x;
+                for (; i + 3 * SEL_THREADS < n4; i += 4 * SEL_THREADS) {
+                    const float4 v0 = b4[i], v1 = b4[i + SEL_THREADS], v2 = b4[i + 2 * SEL_THREADS], v3 = b4[i + 3 * SEL_THREADS];
+                    mx = max(mx, max(max(fkey(v0.x), fkey(v0.y)), max(fkey(v0.z), fkey(v0.w))));
+                    mx = max(mx, max(max(fkey(v1.x), fkey(v1.y)), max(fkey(v1.z), fkey(v1.w))));
+                    mx = max(mx, max(max(fkey(v2.x), fkey(v2.y)), max(fkey(v2.z), fkey(v2.w))));
+                    mx = max(mx, max(max(fkey(v3.x), fkey(v3.y)), max(fkey(v3.z), fkey(v3.w))));
+                }
+                for (; i < n4; i += SEL_THREADS) {
+                    const float4 v = b4[i];
+                    mx = max(mx, max(max(fkey(v.x), fkey(v.y)), max(fkey(v.z), fkey(v.w))));
+                }
+                for (uint64_t j = n4 * 4 + threadIdx.x; j < L; j += SEL_THREADS) mx = max(mx, fkey(base[j]));
+            } else {
+                for (uint64_t i = threadIdx.x; i < L; i += SEL_THREADS) mx = max(mx, (uint32_t)(sel_key(in, qsrc, i) >> 32));
+            }
             arr[threadIdx.x] = mx;
             __syncthreads();
             for (uint32_t size = 2; size <= SEL_THREADS; size <<= 1) {
@@ -1143,7 +1178,7 @@ yams_status_t stage1_tcgen05(Corpus* c, const Stage1Args& a, bool filter, cudaSt
 bool tcgen05_supported(const Corpus* c, uint32_t nq);
 
 constexpr uint32_t kMaxK = 3072;          // K' = k + max(16, k/4) rounded to 32 must fit SEL_MAXK
-constexpr uint32_t kSampleRows = 65536;   // strided sample that calibrates the per-query thresholds
+constexpr uint32_t kSampleRows = 32768;   // strided sample that calibrates the per-query thresholds (dense fp32 scores: Q x 128 KiB)
 constexpr uint32_t kSampleRank = 8;       // threshold = 8th best score of the sample
 constexpr float kTauMargin = 2e-3f;       // cosine: keeps the candidate lists comfortably longer than K' (not needed for
                                           // exactness -- the certificate covers rows below the threshold)
@@ -1719,7 +1754,7 @@ static yams_status_t prepare_queries(yams_b200_corpus* c, const float* q_src, bo
     YB_CUDA(cudaMemsetAsync(c->status.p, 0, sizeof(ScanStatus), c->st));
     YB_CUDA(cudaMemcpyAsync(c->q32.p, q_src, qb, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->st));
     double* d_qnorm = reinterpret_cast<double*>(c->misc.as<uint8_t>());
-    query_prep_kernel<<<(nq + 63) / 64, 64, 0, c->st>>>(c->q32.as<float>(), nq, c->dim, d_qnorm, c->qinv.as<float>(), c->metric,
+    query_prep_kernel<<<(nq + QP_THREADS - 1) / QP_THREADS, QP_THREADS, 0, c->st>>>(c->q32.as<float>(), nq, c->dim, d_qnorm, c->qinv.as<float>(), c->metric,
                                                         status_of(c));
     YB_CUDA(cudaGetLastError());
     return YAMS_OK;
