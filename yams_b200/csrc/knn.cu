@@ -137,31 +137,39 @@ struct ScanStatus {
 
 // queries: invalid if non-finite or (cosine) |q|^2 < 1e-10 (sqlite_vec_backend.cpp:204-235,4127);
 // qnorm[q] = sqrt(sum (double)q^2) (:4204-4209), qinv[q] = 1/qnorm as float (1 for L2: queries stay unscaled)
-constexpr int QP_THREADS = 64, QP_COLS = 64;
+constexpr int QP_THREADS = 32;
 __global__ void __launch_bounds__(QP_THREADS) query_prep_kernel(const float* __restrict__ q, uint32_t nq, uint32_t d, double* __restrict__ qnorm,
                                                                 float* __restrict__ qinv, int metric, ScanStatus* __restrict__ status) {
-    // thread = query, the reference's sequential double sum (sqlite_vec_backend.cpp:4140-4150); the values reach the thread through a
-    // shared-memory tile filled with coalesced loads (a thread walking its own 3 KB row was 64 us of dependent L2 round trips)
-    __shared__ float tile[QP_THREADS][QP_COLS + 1];
-    const uint32_t q0 = blockIdx.x * QP_THREADS;
-    const uint32_t i = q0 + threadIdx.x;
+    // thread = query, the reference's sequential double sum (sqlite_vec_backend.cpp:4140-4150).  The row is read with 16-byte
+    // loads, four in flight (one 4-byte load per dependent trip cost 64 us for 1024 x 768 queries).
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq) return;
+    const float* row = q + (uint64_t)i * d;
     double ss = 0.0;
     bool finite = true;
-    for (uint32_t c0 = 0; c0 < d; c0 += QP_COLS) {
-        const uint32_t w = min((uint32_t)QP_COLS, d - c0);
-        for (uint32_t e = threadIdx.x; e < QP_THREADS * QP_COLS; e += QP_THREADS) {
-            const uint32_t r = e / QP_COLS, c = e % QP_COLS;
-            tile[r][c] = (q0 + r < nq && c < w) ? q[(uint64_t)(q0 + r) * d + c0 + c] : 0.f;
+    auto add = [&](float v) {
+        if (!isfinite(v)) finite = false;
+        ss += (double)v * (double)v;
+    };
+    uint32_t c = 0;
+    if ((reinterpret_cast<uintptr_t>(row) & 15u) == 0) {
+        const float4* r4 = reinterpret_cast<const float4*>(row);
+        const uint32_t n4 = d / 4;
+        uint32_t j = 0;
+        for (; j + 4 <= n4; j += 4) {
+            const float4 a0 = r4[j], a1 = r4[j + 1], a2 = r4[j + 2], a3 = r4[j + 3];
+            add(a0.x); add(a0.y); add(a0.z); add(a0.w);
+            add(a1.x); add(a1.y); add(a1.z); add(a1.w);
+            add(a2.x); add(a2.y); add(a2.z); add(a2.w);
+            add(a3.x); add(a3.y); add(a3.z); add(a3.w);
         }
-        __syncthreads();
-        for (uint32_t c = 0; c < w; ++c) {
-            const float v = tile[threadIdx.x][c];
-            if (!isfinite(v)) finite = false;
-            ss += (double)v * (double)v;
+        for (; j < n4; ++j) {
+            const float4 a0 = r4[j];
+            add(a0.x); add(a0.y); add(a0.z); add(a0.w);
         }
-        __syncthreads();
+        c = n4 * 4;
     }
-    if (i >= nq) return;
+    for (; c < d; ++c) add(row[c]);
     bool bad = !finite || (metric == YAMS_B200_COSINE && ss < 1e-10);
     if (bad) atomicAdd(&status->n_invalid, 1u);
     double nrm = sqrt(ss);
@@ -532,7 +540,51 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, u
         return;
     }
     uint64_t kth = 0;  // keys >= kth are selected
-    if (L > K && L > SEL_MAXK) {   // a list that fits the sort buffer is sorted whole (66 network steps for 2048 keys beat 8 radix passes)
+    constexpr int KPT = SEL_MAXK / SEL_THREADS;   // 16 keys per thread
+    if (L <= SEL_MAXK) {
+        // The normal case (a candidate list of 1-3 k entries): the keys are read ONCE into registers and the K-th largest is found
+        // bit by bit from the top -- 64 block-wide counts (compare, warp reduce, one barrier each), ~8 k cycles, where eight
+        // histogram passes over the list or a 4096-key sorting network cost 150-300 us per 1024 queries.
+        uint64_t kreg[KPT];
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) {
+            const uint64_t i = (uint64_t)threadIdx.x + (uint64_t)j * SEL_THREADS;
+            kreg[j] = i < L ? sel_key(in, qsrc, i) : 0ull;          // 0 is no key (a real key carries 0xFFFFFFFF - row != 0 below)
+        }
+        if (L > K && K > 0) {
+            uint32_t* part = reinterpret_cast<uint32_t*>(hist);      // [2][8] per-warp partial counts, double-buffered
+            uint64_t prefix = 0;
+            uint32_t want = K;
+            for (int bit = 63; bit >= 0; --bit) {
+                const uint64_t cand = prefix | (1ull << bit);
+                const uint64_t himask = ~((1ull << bit) - 1ull);
+                uint32_t cnt_t = 0;
+#pragma unroll
+                for (int j = 0; j < KPT; ++j) cnt_t += ((kreg[j] & himask) == cand) ? 1u : 0u;
+                const uint32_t wsum = __reduce_add_sync(0xffffffffu, cnt_t);
+                uint32_t* pb = part + (bit & 1) * 8;
+                if ((threadIdx.x & 31) == 0) pb[threadIdx.x >> 5] = wsum;
+                __syncthreads();
+                uint32_t tot = 0;
+#pragma unroll
+                for (int w = 0; w < SEL_THREADS / 32; ++w) tot += pb[w];
+                if (tot >= want) prefix = cand; else want -= tot;    // block-uniform
+            }
+            kth = prefix;
+        }
+        if (threadIdx.x == 0) s_cnt = 0;
+        for (int i = threadIdx.x; i < SEL_MAXK; i += SEL_THREADS) buf[i] = 0;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < KPT; ++j) {
+            if (kreg[j] != 0ull && kreg[j] >= kth) {
+                uint32_t pos = atomicAdd(&s_cnt, 1u);
+                if (pos < SEL_MAXK) buf[pos] = kreg[j];
+            }
+        }
+        __syncthreads();
+    } else {
+    if (L > K) {
         radix_select(8);
         kth = s_prefix;
     }
@@ -547,6 +599,7 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, u
         }
     }
     __syncthreads();
+    }
     uint32_t cnt = min(s_cnt, (uint32_t)SEL_MAXK);
     uint32_t np2 = 1;
     while (np2 < cnt) np2 <<= 1;
