@@ -29,13 +29,16 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
         c.search_device(q.data_ptr(), nq, k, -1.0, out.data_ptr(), out.data_ptr() + nq * k * 8)
     c.sync()
 agg = collections.OrderedDict()
+each = collections.defaultdict(list)     # individual durations, in launch order (the two selections of a step differ)
 first, last = None, None
 for e in prof.events():
     if e.device_type.name != "CUDA":
         continue
     a = agg.setdefault(e.name[:70], [0, 0.0])
     a[0] += 1
-    a[1] += e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
+    dur = e.device_time_total if hasattr(e, "device_time_total") else e.cuda_time_total
+    a[1] += dur
+    each[e.name[:70]].append((e.time_range.start, dur))
     t0 = e.time_range.start
     t1 = e.time_range.end
     first = t0 if first is None else min(first, t0)
@@ -44,3 +47,6 @@ tot = sum(v[1] for v in agg.values())
 print(f"{steps} steps: wall {(last - first) / steps / 1e3:.3f} ms/step, kernel time sum {tot / steps / 1e3:.3f} ms/step, gaps {(last - first - tot) / steps / 1e3:.3f} ms/step")
 for name, (cnt, us) in sorted(agg.items(), key=lambda x: -x[1][1]):
     print(f"{us / steps:10.1f} us/step  x{cnt / steps:.0f}  {name}")
+    if cnt / steps > 1:
+        seq = [d for _, d in sorted(each[name])][:int(2 * cnt / steps)]
+        print("            in launch order (us):", " ".join(f"{d:.0f}" for d in seq))
