@@ -552,25 +552,70 @@ __global__ void __launch_bounds__(SEL_THREADS) topk_select_kernel(SelectIn in, u
             kreg[j] = i < L ? sel_key(in, qsrc, i) : 0ull;          // 0 is no key (a real key carries 0xFFFFFFFF - row != 0 below)
         }
         if (L > K && K > 0) {
-            uint32_t* part = reinterpret_cast<uint32_t*>(hist);      // [2][8] per-warp partial counts, double-buffered
-            uint64_t prefix = 0;
-            uint32_t want = K;
-            for (int bit = 63; bit >= 0; --bit) {
-                const uint64_t cand = prefix | (1ull << bit);
-                const uint64_t himask = ~((1ull << bit) - 1ull);
-                uint32_t cnt_t = 0;
-#pragma unroll
-                for (int j = 0; j < KPT; ++j) cnt_t += ((kreg[j] & himask) == cand) ? 1u : 0u;
-                const uint32_t wsum = __reduce_add_sync(0xffffffffu, cnt_t);
-                uint32_t* pb = part + (bit & 1) * 8;
-                if ((threadIdx.x & 31) == 0) pb[threadIdx.x >> 5] = wsum;
+            // Block-wide helpers over 8 warps: one barrier per call, partials double-buffered by `slot`.
+            uint32_t* part = reinterpret_cast<uint32_t*>(hist);      // [4][8]
+            int slot = 0;
+            auto block_sum = [&](uint32_t v) {
+                const uint32_t w = __reduce_add_sync(0xffffffffu, v);
+                uint32_t* pb = part + (slot & 3) * 8;
+                ++slot;
+                if ((threadIdx.x & 31) == 0) pb[threadIdx.x >> 5] = w;
                 __syncthreads();
-                uint32_t tot = 0;
+                uint32_t t = 0;
 #pragma unroll
-                for (int w = 0; w < SEL_THREADS / 32; ++w) tot += pb[w];
-                if (tot >= want) prefix = cand; else want -= tot;    // block-uniform
+                for (int x = 0; x < SEL_THREADS / 32; ++x) t += pb[x];
+                return t;
+            };
+            // score words first (32-bit compares); the bits every valid key shares are skipped
+            uint32_t a_and = 0xFFFFFFFFu, a_or = 0u;
+#pragma unroll
+            for (int j = 0; j < KPT; ++j)
+                if (kreg[j] != 0ull) { a_and &= (uint32_t)(kreg[j] >> 32); a_or |= (uint32_t)(kreg[j] >> 32); }
+            {
+                const uint32_t wa = __reduce_and_sync(0xffffffffu, a_and), wo = __reduce_or_sync(0xffffffffu, a_or);
+                uint32_t* pb = part + 16;                              // slots 2,3 of the table: [8] ands, [8] ors
+                if ((threadIdx.x & 31) == 0) { pb[threadIdx.x >> 5] = wa; pb[8 + (threadIdx.x >> 5)] = wo; }
+                __syncthreads();
+                a_and = 0xFFFFFFFFu; a_or = 0u;
+#pragma unroll
+                for (int x = 0; x < SEL_THREADS / 32; ++x) { a_and &= pb[x]; a_or |= pb[8 + x]; }
+                __syncthreads();                                       // the table is reused by block_sum below
             }
-            kth = prefix;
+            const uint32_t diff = a_and ^ a_or;
+            uint32_t want = K;
+            uint32_t shi = a_or;                                       // all scores equal: that score
+            if (diff) {
+                const int top = 31 - __clz(diff);
+                shi = top == 31 ? 0u : (a_or & ~((2u << top) - 1u));   // the shared leading bits
+                for (int bit = top; bit >= 0; --bit) {
+                    const uint32_t cand = shi | (1u << bit);
+                    const uint32_t himask = ~((1u << bit) - 1u);
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int j = 0; j < KPT; ++j) c += (kreg[j] != 0ull && ((uint32_t)(kreg[j] >> 32) & himask) == cand) ? 1u : 0u;
+                    const uint32_t tot = block_sum(c);
+                    if (tot >= want) shi = cand; else want -= tot;    // block-uniform
+                }
+            }
+            // `want` of the keys whose score word equals shi are needed (those with the largest low words, i.e. the smallest rows)
+            uint32_t g = 0;
+#pragma unroll
+            for (int j = 0; j < KPT; ++j) g += (kreg[j] != 0ull && (uint32_t)(kreg[j] >> 32) == shi) ? 1u : 0u;
+            const uint32_t group = block_sum(g);
+            uint32_t slo = 0;                                          // group == want: the whole group is selected
+            if (group > want) {                                        // equal scores straddle the K-th place: resolve by the low words
+                for (int bit = 31; bit >= 0; --bit) {
+                    const uint32_t cand = slo | (1u << bit);
+                    const uint32_t lomask = ~((1u << bit) - 1u);
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int j = 0; j < KPT; ++j)
+                        c += (kreg[j] != 0ull && (uint32_t)(kreg[j] >> 32) == shi && ((uint32_t)kreg[j] & lomask) == cand) ? 1u : 0u;
+                    const uint32_t tot = block_sum(c);
+                    if (tot >= want) slo = cand; else want -= tot;
+                }
+            }
+            kth = ((uint64_t)shi << 32) | (uint64_t)slo;
         }
         if (threadIdx.x == 0) s_cnt = 0;
         for (int i = threadIdx.x; i < SEL_MAXK; i += SEL_THREADS) buf[i] = 0;
