@@ -102,3 +102,17 @@ def test_simeon_yams_default_profile_is_bit_identical(Y, oracle, cfg):
     # the constraint of the reference constructor (projection.cpp:167-170)
     with pytest.raises(Y.YamsB200Error):
         Y.SimeonEncoder(profile="yams-default", embedding_dim=4096, sketch_dim=2048)
+
+
+def test_simeon_matches_the_committed_golden_embeddings(Y):
+    """tests/golden/simeon_golden.json: simeon's own Encoder run in the build container (make_simeon_golden.py); needs no reference."""
+    import json
+    import os
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "simeon_golden.json")))
+    texts = g["texts"]
+    for key, kw in (("simeon_v1_384", dict()), ("yams_default_1024", dict(profile="yams-default")),
+                    ("yams_default_384", dict(profile="yams-default", embedding_dim=384))):
+        enc = Y.SimeonEncoder(**kw)
+        got = enc.encode(texts).view(np.uint32)
+        assert np.array_equal(got, np.array(g[key], dtype=np.uint32)), key
+        enc.close()
